@@ -1,0 +1,181 @@
+"""TEST INFRASTRUCTURE ONLY -- executes the *unmodified* reference files.
+
+This module imports walker-gym's own L1 "optimized flat" modules from a
+read-only checkout (default ``/root/reference/gym``) so that golden vectors
+can be generated from, and the C restatement (``walker_oracle.c``) validated
+against, the reference itself.  It only works where the checkout exists (the
+authoring container); it never travels to the GPU box and nothing in the
+product path, ``bench.py`` or the ``-m gpu`` tests may import it.
+
+The reference does not run as shipped.  The harness
+applies exactly three things, none of which touches the arithmetic:
+
+1. ``pygame`` and ``turtle`` are replaced by inert stubs in ``sys.modules``
+   (imported at ``gym/optimized_env.py:4,339`` and
+   ``gym/optimized_walker.py:2`` only for rendering).
+2. ``gym/optimized_walker.py`` is loaded *by path* under the module name
+   ``optimized_walker`` because the package directory of the same name
+   shadows it (``gym/optimized_env.py:5,281``).
+3. ``Point.forced`` (``gym/optimized_engine.py:104-106``) receives Python
+   lists from ``PhysicsEnv._run_physics`` (``gym/optimized_env.py:148-172``)
+   and would raise ``TypeError``; the shim converts with ``np.asarray`` and
+   zero-pads a 2-vector to the 3-vector ``a`` (2-D mode), then calls the
+   original.  The resulting dtype promotion (int64/float64 list -> float64
+   divide -> rounded into the float32 accumulator) is the reference's own.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+from unittest import mock
+
+import numpy as np
+
+DEFAULT_REF = os.environ.get("WALKER_GYM_REFERENCE", "/root/reference")
+
+_loaded = {}
+
+
+def available(ref_root: str = DEFAULT_REF) -> bool:
+    return os.path.isfile(os.path.join(ref_root, "gym", "optimized_env.py"))
+
+
+def load(ref_root: str = DEFAULT_REF):
+    """Return (engine, walker, env) reference modules, harnessed as above."""
+    if ref_root in _loaded:
+        return _loaded[ref_root]
+    gym_dir = os.path.join(ref_root, "gym")
+    if not available(ref_root):
+        raise FileNotFoundError(f"reference checkout not found under {ref_root}")
+    for name in ("pygame", "turtle"):
+        if name not in sys.modules:
+            sys.modules[name] = mock.MagicMock(name=name)
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.get(k) for k in
+                  ("optimized_engine", "optimized_renderer", "optimized_walker", "optimized_env")}
+    sys.path.insert(0, gym_dir)
+    try:
+        def by_path(modname, fname):
+            spec = importlib.util.spec_from_file_location(modname, os.path.join(gym_dir, fname))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[modname] = mod
+            spec.loader.exec_module(mod)
+            return mod
+
+        engine = by_path("optimized_engine", "optimized_engine.py")
+        by_path("optimized_renderer", "optimized_renderer.py")
+        walker = by_path("optimized_walker", "optimized_walker.py")
+        env = by_path("optimized_env", "optimized_env.py")
+    finally:
+        sys.path[:] = saved_path
+
+    orig_forced = engine.Point.forced
+
+    def forced(self, f):
+        f = np.asarray(f)
+        if f.shape[0] < self.a.shape[0]:
+            f = np.concatenate([f, np.zeros(self.a.shape[0] - f.shape[0], dtype=f.dtype)])
+        return orig_forced(self, f)
+
+    engine.Point.forced = forced
+    _loaded[ref_root] = (engine, walker, env)
+    return _loaded[ref_root]
+
+
+def build_creature(spec, ref_root: str = DEFAULT_REF):
+    """Build a reference ``Creature`` from a body spec (dict, see bodies.py).
+
+    spec: {"points": [(m, pos, fixed)], "muscles": [(i, j, kwargs)],
+           "skeletons": [(i, j, kwargs)]}
+    """
+    engine, walker, _ = load(ref_root)
+    engine.Point.clear()
+    pts = []
+    for m, pos, fixed in spec["points"]:
+        if fixed:
+            pts.append(engine.DingPoint(m, list(pos)))
+        else:
+            pts.append(engine.Point(m, list(pos), [0, 0, 0]))
+    mus = [walker.Muscle(pts[i], pts[j], **kw) for i, j, kw in spec["muscles"]]
+    sks = [walker.Skeleton(pts[i], pts[j], **kw) for i, j, kw in spec["skeletons"]]
+    return walker.Creature(pts, mus, sks)
+
+
+def snapshot(env):
+    """Copy the full observable state of a reference env into numpy arrays."""
+    c = env.creature
+    return dict(
+        pos=np.array([p.pos for p in c.phys], dtype=np.float32),
+        vel=np.array([p.v for p in c.phys], dtype=np.float32),
+        old_a=np.array([p.old_a for p in c.phys], dtype=np.float32),
+        x=np.array([float(m.x) for m in c.muscles], dtype=np.float64),
+        contact_pre=np.array([p.r == 3 for p in c.phys], dtype=np.bool_),
+    )
+
+
+def rollout(creature_or_id, actions, *, env_kwargs=None, seed=0, noise=None,
+            max_steps=None, ref_root: str = DEFAULT_REF):
+    """Run the reference ``PhysicsEnv`` for ``len(actions)`` steps.
+
+    ``actions``: float32 [T, M] (float32 keeps ``Muscle.x`` in float32,
+    SURVEY.md section 7.7).  ``noise``: optional [N, d] array that replaces
+    the ``np.random.normal`` draws of ``reset()`` (same call order: per point,
+    x then y then z) so that a kernel can be fed the identical jitter.
+    Returns a dict of per-step arrays with a leading T+1 (state) or T axis.
+    """
+    engine, walker, envmod = load(ref_root)
+    env_kwargs = dict(env_kwargs or {})
+    engine.Point.clear()
+    np.random.seed(seed)
+    draws = []
+
+    real_normal = np.random.normal
+
+    def fake_normal(loc=0.0, scale=1.0, size=None):
+        if noise is not None:
+            v = float(noise.reshape(-1)[len(draws)])
+        else:
+            v = real_normal(loc, scale, size)
+        draws.append(v)
+        return v
+
+    with mock.patch.object(np.random, "normal", fake_normal):
+        if isinstance(creature_or_id, str):
+            env = envmod.make_env(creature_or_id, **env_kwargs)
+        elif isinstance(creature_or_id, dict):
+            env = envmod.PhysicsEnv(build_creature(creature_or_id, ref_root), **env_kwargs)
+        else:
+            env = envmod.PhysicsEnv(creature_or_id, **env_kwargs)
+        obs0 = np.asarray(env._get_observation(), dtype=np.float64)
+    if max_steps is not None:
+        env.max_steps = max_steps
+    T = len(actions)
+    snaps = [snapshot(env)]
+    obs = [obs0]
+    rew, done, energy, centroid, steps = [], [], [], [], []
+    for t in range(T):
+        o, r, d, info = env.step(actions[t])
+        snaps.append(snapshot(env))
+        obs.append(np.asarray(o, dtype=np.float64))
+        rew.append(r)
+        done.append(bool(d))
+        energy.append(info["total_energy"])
+        centroid.append(info["centroid_position"])
+        steps.append(info["steps"])
+    out = {k: np.stack([s[k] for s in snaps]) for k in snaps[0]}
+    out["contact_pre"] = out["contact_pre"][1:]
+    out.update(
+        obs=np.stack(obs),
+        reward=np.asarray(rew, dtype=np.float64),
+        done=np.asarray(done, dtype=np.bool_),
+        energy=np.asarray(energy, dtype=np.float64),
+        centroid=np.asarray(centroid, dtype=np.float64).reshape(T, 3),
+        steps=np.asarray(steps, dtype=np.int64),
+        reset_noise=np.asarray(draws, dtype=np.float64),
+        masses=np.array([float(p.m) for p in env.creature.phys], dtype=np.float64),
+    )
+    out["reward_dtype"] = np.array(str(type(rew[0]).__name__) if rew else "")
+    engine.Point.clear()
+    return out

@@ -1,0 +1,209 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end of the C oracle.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this module.  The product
+package (``walker_gym_b200``) never does.
+
+A *body spec* is a plain dict (no product classes involved)::
+
+    {"points":    [(m, (x, y, z), fixed), ...],
+     "muscles":   [(i, j, {"k":..., "dampk":..., "minl":..., "maxl":..., "x":...}), ...],
+     "skeletons": [(i, j, {"k":..., "dampk":..., "x":...}), ...]}
+
+with the reference constructors' defaults (``gym/optimized_walker.py:8-9,70``:
+k=1000, dampk=20, minl=0.1, maxl=1.5, rest length = initial distance).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libwalker_oracle.so")
+MAX_MASS, MAX_SPRING = 32, 96
+
+
+class Body(C.Structure):
+    _fields_ = [
+        ("n_mass", C.c_int32), ("n_spring", C.c_int32), ("n_muscle", C.c_int32),
+        ("mass", C.c_double * MAX_MASS),
+        ("fixed", C.c_uint8 * MAX_MASS),
+        ("tmpl_pos", C.c_float * (MAX_MASS * 3)),
+        ("si", C.c_int32 * MAX_SPRING), ("sj", C.c_int32 * MAX_SPRING),
+        ("sk", C.c_float * MAX_SPRING), ("sdamp", C.c_float * MAX_SPRING),
+        ("srest", C.c_float * MAX_SPRING),
+        ("mlo", C.c_float * MAX_SPRING), ("mhi", C.c_float * MAX_SPRING),
+    ]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("g", C.c_double),
+        ("dampk", C.c_float), ("ground", C.c_float), ("fall_thresh", C.c_float),
+        ("ground_k", C.c_float), ("ground_damp", C.c_float), ("friction", C.c_float),
+        ("dt", C.c_float), ("sigma", C.c_float),
+        ("in3d", C.c_int32), ("max_steps", C.c_int32), ("k_sub", C.c_int32),
+        ("auto_reset", C.c_int32),
+        ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32),
+        ("step_index", C.c_uint32), ("env_offset", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc)."""
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(
+            os.path.join(_HERE, "walker_oracle.c")):
+        subprocess.run(["make", "-C", _HERE, "-B", "libwalker_oracle.so"], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        assert _lib.wgo_sizeof_body() == C.sizeof(Body)
+        assert _lib.wgo_sizeof_params() == C.sizeof(Params)
+        _lib.wgo_step.restype = C.c_int
+        _lib.wgo_reset.restype = C.c_int
+    return _lib
+
+
+def make_body(spec) -> Body:
+    """Evaluate the morphology exactly as the reference constructors would."""
+    b = Body()
+    pts = spec["points"]
+    mus, sks = spec["muscles"], spec["skeletons"]
+    b.n_mass, b.n_muscle, b.n_spring = len(pts), len(mus), len(mus) + len(sks)
+    assert b.n_mass <= MAX_MASS and b.n_spring <= MAX_SPRING
+    P = [np.array(p[1], dtype=np.float32) for p in pts]   # Point.pos  (optimized_engine.py:55)
+    for n, (m, pos, fixed) in enumerate(pts):
+        b.mass[n] = float(m)
+        b.fixed[n] = 1 if fixed else 0
+        for c in range(3):
+            b.tmpl_pos[n * 3 + c] = P[n][c]
+    for s, (i, j, kw) in enumerate(list(mus) + list(sks)):
+        b.si[s], b.sj[s] = i, j
+        b.sk[s] = np.float32(kw.get("k", 1000))
+        b.sdamp[s] = np.float32(kw.get("dampk", 20))
+        x = kw.get("x")
+        if x is None:
+            x = np.linalg.norm(P[i] - P[j])                # Muscle.distant (optimized_walker.py:23-25)
+        b.srest[s] = np.float32(x)
+        if s < len(mus):
+            b.mlo[s] = np.float32(x * kw.get("minl", 0.1))  # regulation (:27-30), python semantics
+            b.mhi[s] = np.float32(x * kw.get("maxl", 1.5))
+    return b
+
+
+def make_params(in3d=False, g=100, dampk=0, ground_high=0, ground_k=1000, ground_damp=100,
+                friction=100, rand_sigma=0.1, time_step=0.01, max_steps=1000, k_sub=1,
+                auto_reset=0, seed=0, step_index=0, env_offset=0) -> Params:
+    p = Params()
+    p.g = float(g)
+    p.dampk = np.float32(dampk)
+    p.ground = np.float32(ground_high)
+    p.fall_thresh = np.float32(ground_high - 50)
+    p.ground_k = np.float32(ground_k)
+    p.ground_damp = np.float32(ground_damp)
+    p.friction = np.float32(friction)
+    p.dt = np.float32(time_step)
+    p.sigma = np.float32(rand_sigma)
+    p.in3d, p.max_steps, p.k_sub = int(bool(in3d)), int(max_steps), int(k_sub)
+    p.auto_reset = int(auto_reset)
+    p.seed_lo, p.seed_hi = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    p.step_index, p.env_offset = step_index, env_offset
+    return p
+
+
+def obs_dim(body: Body, in3d) -> int:
+    return 3 * (3 if in3d else 2) * body.n_mass + body.n_muscle
+
+
+def _ptr(a, ctype):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "oracle arrays must be C-contiguous"
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def init_state(body: Body, E: int):
+    """Template state for E envs in the SoA layout [(n*3+c)][E]."""
+    N, M = body.n_mass, body.n_muscle
+    tp = np.array(body.tmpl_pos[: N * 3], dtype=np.float32)
+    st = dict(
+        pos=np.repeat(tp[:, None], E, axis=1).copy(),
+        vel=np.zeros((N * 3, E), np.float32),
+        old_a=np.zeros((N * 3, E), np.float32),
+        mx=np.repeat(np.array(body.srest[:M], dtype=np.float32)[:, None], E, axis=1).copy().reshape(M, E),
+        steps=np.zeros(E, np.int32),
+    )
+    return st
+
+
+def step(body: Body, prm: Params, st: dict, action: np.ndarray, *, want_info=True,
+         ep_ret=None, fin_stats=None, noise=None):
+    """One env-step, in place on ``st``.  Returns dict(obs, reward, done, ...)."""
+    E = st["pos"].shape[1]
+    D = obs_dim(body, prm.in3d)
+    action = np.ascontiguousarray(action, dtype=np.float32).reshape(E, -1)
+    out = dict(
+        obs=np.empty((E, D), np.float32), reward=np.empty(E, np.float32), done=np.empty(E, np.uint8),
+        contact_pre=np.empty(E, np.uint32), contact_post=np.empty(E, np.uint32),
+    )
+    if want_info:
+        out["energy"] = np.empty(E, np.float32)
+        out["centroid"] = np.empty((3, E), np.float32)
+    rc = lib().wgo_step(
+        C.byref(body), C.byref(prm), C.c_int64(E),
+        _ptr(st["pos"], C.c_float), _ptr(st["vel"], C.c_float), _ptr(st.get("old_a"), C.c_float),
+        _ptr(st["mx"], C.c_float), _ptr(st["steps"], C.c_int32),
+        _ptr(action, C.c_float), C.c_int32(action.shape[1]),
+        _ptr(out["obs"], C.c_float), _ptr(out["reward"], C.c_float), _ptr(out["done"], C.c_uint8),
+        _ptr(out["contact_pre"], C.c_uint32), _ptr(out["contact_post"], C.c_uint32),
+        _ptr(out.get("energy"), C.c_float), _ptr(out.get("centroid"), C.c_float),
+        _ptr(ep_ret, C.c_float), _ptr(fin_stats, C.c_float), _ptr(noise, C.c_float))
+    if rc != 0:
+        raise RuntimeError(f"wgo_step failed: {rc}")
+    return out
+
+
+def reset(body: Body, prm: Params, st: dict, *, mode=1, mask=None, noise=None):
+    """PhysicsEnv.reset for the masked envs (mode 1 = jitter, 2 = template). Returns obs."""
+    E = st["pos"].shape[1]
+    obs = np.zeros((E, obs_dim(body, prm.in3d)), np.float32)
+    rc = lib().wgo_reset(
+        C.byref(body), C.byref(prm), C.c_int64(E), C.c_int(mode),
+        _ptr(st["pos"], C.c_float), _ptr(st["vel"], C.c_float), _ptr(st.get("old_a"), C.c_float),
+        _ptr(st["mx"], C.c_float), _ptr(st["steps"], C.c_int32),
+        _ptr(obs, C.c_float), _ptr(mask, C.c_uint8), _ptr(noise, C.c_float))
+    if rc != 0:
+        raise RuntimeError(f"wgo_reset failed: {rc}")
+    return obs
+
+
+def normal3(seed: int, env: int, step: int, mass: int) -> np.ndarray:
+    out = (C.c_float * 3)()
+    lib().wgo_normal3(C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32((seed >> 32) & 0xFFFFFFFF),
+                      C.c_uint32(env), C.c_uint32(step), C.c_uint32(mass), out)
+    return np.array(out[:], dtype=np.float32)
+
+
+# The two morphologies of gym/optimized_walker.py:176-224 as specs (data only).
+BALANCE = {
+    "points": [(5, (-50, 100, 0), False), (5, (50, 100, 0), False), (1, (0, 0, 0), False), (3, (0, 100, 0), False)],
+    "muscles": [(0, 2, {}), (1, 2, {})],
+    "skeletons": [(0, 1, {}), (0, 3, {}), (1, 3, {})],
+}
+BOX = {
+    "points": [(1, (-50, 0, 0), False), (1, (-50, 100, 0), False), (1, (50, 100, 0), False), (1, (50, 0, 0), False)],
+    "muscles": [(0, 1, {}), (0, 2, {}), (3, 1, {}), (3, 2, {})],
+    "skeletons": [(1, 2, {})],
+}
