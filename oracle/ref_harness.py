@@ -116,13 +116,21 @@ def snapshot(env):
 
 
 def rollout(creature_or_id, actions, *, env_kwargs=None, seed=0, noise=None,
-            max_steps=None, ref_root: str = DEFAULT_REF):
+            max_steps=None, k_sub=1, reset_on_done=False, init_state=None,
+            ref_root: str = DEFAULT_REF):
     """Run the reference ``PhysicsEnv`` for ``len(actions)`` steps.
 
     ``actions``: float32 [T, M] (float32 keeps ``Muscle.x`` in float32,
-    SURVEY.md section 7.7).  ``noise``: optional [N, d] array that replaces
-    the ``np.random.normal`` draws of ``reset()`` (same call order: per point,
-    x then y then z) so that a kernel can be fed the identical jitter.
+    SURVEY.md section 7.7).  ``noise``: optional flat array that replaces the
+    ``np.random.normal`` draws of ``reset()`` in call order (per point: x, y,
+    then z if in3d) so a kernel can be fed the identical jitter.
+    ``k_sub``: physics substeps per env step: ``act`` once,
+    then ``k_sub`` x ``_run_physics``; k_sub == 1 calls ``env.step`` itself.
+    ``reset_on_done``: call ``env.reset()`` after a done step (the batched
+    library's "jitter" auto-reset); the recorded state/obs of that step are
+    then the post-reset ones, reward/done the pre-reset ones.
+    ``init_state``: optional dict(pos=[N,3], vel=[N,3]) written into the
+    creature's points after construction.
     Returns a dict of per-step arrays with a leading T+1 (state) or T axis.
     """
     engine, walker, envmod = load(ref_root)
@@ -135,7 +143,7 @@ def rollout(creature_or_id, actions, *, env_kwargs=None, seed=0, noise=None,
 
     def fake_normal(loc=0.0, scale=1.0, size=None):
         if noise is not None:
-            v = float(noise.reshape(-1)[len(draws)])
+            v = float(np.asarray(noise).reshape(-1)[len(draws)])
         else:
             v = real_normal(loc, scale, size)
         draws.append(v)
@@ -148,22 +156,39 @@ def rollout(creature_or_id, actions, *, env_kwargs=None, seed=0, noise=None,
             env = envmod.PhysicsEnv(build_creature(creature_or_id, ref_root), **env_kwargs)
         else:
             env = envmod.PhysicsEnv(creature_or_id, **env_kwargs)
+        if init_state is not None:
+            for n, p in enumerate(env.creature.phys):
+                p.pos[:] = np.asarray(init_state["pos"][n], dtype=np.float32)
+                p.v[:] = np.asarray(init_state["vel"][n], dtype=np.float32)
         obs0 = np.asarray(env._get_observation(), dtype=np.float64)
-    if max_steps is not None:
-        env.max_steps = max_steps
-    T = len(actions)
-    snaps = [snapshot(env)]
-    obs = [obs0]
-    rew, done, energy, centroid, steps = [], [], [], [], []
-    for t in range(T):
-        o, r, d, info = env.step(actions[t])
-        snaps.append(snapshot(env))
-        obs.append(np.asarray(o, dtype=np.float64))
-        rew.append(r)
-        done.append(bool(d))
-        energy.append(info["total_energy"])
-        centroid.append(info["centroid_position"])
-        steps.append(info["steps"])
+        if max_steps is not None:
+            env.max_steps = max_steps
+        T = len(actions)
+        snaps = [snapshot(env)]
+        obs = [obs0]
+        rew, done, energy, centroid, steps = [], [], [], [], []
+        for t in range(T):
+            if k_sub == 1:
+                o, r, d, info = env.step(actions[t])
+            else:
+                env.creature.act(actions[t])
+                for _ in range(k_sub):
+                    env._run_physics()
+                env.steps += 1
+                o, r, d, info = (env._get_observation(), env._get_reward(), env._is_done(),
+                                 env._get_info())
+            cpre = np.array([p.r == 3 for p in env.creature.phys], dtype=np.bool_)
+            if d and reset_on_done:
+                o = env.reset()
+            sn = snapshot(env)
+            sn["contact_pre"] = cpre
+            snaps.append(sn)
+            obs.append(np.asarray(o, dtype=np.float64))
+            rew.append(r)
+            done.append(bool(d))
+            energy.append(info["total_energy"])
+            centroid.append(info["centroid_position"])
+            steps.append(env.steps)
     out = {k: np.stack([s[k] for s in snaps]) for k in snaps[0]}
     out["contact_pre"] = out["contact_pre"][1:]
     out.update(
@@ -176,6 +201,5 @@ def rollout(creature_or_id, actions, *, env_kwargs=None, seed=0, noise=None,
         reset_noise=np.asarray(draws, dtype=np.float64),
         masses=np.array([float(p.m) for p in env.creature.phys], dtype=np.float64),
     )
-    out["reward_dtype"] = np.array(str(type(rew[0]).__name__) if rew else "")
     engine.Point.clear()
     return out

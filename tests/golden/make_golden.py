@@ -1,0 +1,172 @@
+"""Generate the golden fixtures in this directory from the reference itself.
+
+Run in the authoring container (needs the read-only reference checkout at
+/root/reference):
+
+    python tests/golden/make_golden.py
+
+Every ``*.npz`` here is the output of walker-gym's own ``PhysicsEnv``
+(``gym/optimized_env.py``), executed through ``oracle/ref_harness.py`` on
+seeded float32 actions.  They pin the C oracle (and through it the CUDA
+library) to the reference bit for bit.  Each file carries its inputs
+(actions, reset noise, body spec as JSON, env kwargs as JSON) so the tests
+need nothing else.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import ref_harness as rh  # noqa: E402
+import walker_oracle as wo  # noqa: E402  (only for the BALANCE / BOX specs)
+
+# gym/walker.py:255-293 `insect` as data (legacy constructor order is Phy(m, v, p)).
+INSECT = {
+    "points": [(1, p, False) for p in [
+        (-75, 100, 0), (-25, 100, 0), (25, 100, 0), (75, 100, 0),
+        (-100, 50, 0), (-50, 50, 0), (0, 50, 0), (50, 50, 0), (100, 50, 0),
+        (-75, 0, 0), (-25, 0, 0), (25, 0, 0), (75, 0, 0)]],
+    "muscles": [(9, 4, {}), (9, 5, {}), (10, 5, {}), (10, 6, {}), (11, 6, {}), (11, 7, {}), (12, 7, {}), (12, 8, {})],
+    "skeletons": [(0, 1, {}), (0, 4, {}), (0, 5, {}), (1, 2, {}), (1, 5, {}), (1, 6, {}), (2, 3, {}), (2, 6, {}),
+                  (2, 7, {}), (3, 7, {}), (3, 8, {}), (4, 5, {}), (5, 6, {}), (6, 7, {}), (7, 8, {})],
+}
+# An irregular body: float masses, a DingPoint, per-spring k/dampk, an explicit
+# python-float rest length, custom muscle limits, non-zero z.
+CUSTOM = {
+    "points": [(2.5, (-30, 40, 5), False), (0.1, (35, 60, -3), False), (7, (0, 5, 0), False),
+               (1, (10, 90, 2), True), (3, (-60, 20, 0), False)],
+    "muscles": [(0, 2, {"k": 800, "dampk": 15, "minl": 0.3, "maxl": 1.2}),
+                (1, 2, {"x": 70.0, "k": 1200, "dampk": 25}),
+                (4, 0, {"k": -300})],
+    "skeletons": [(0, 1, {"k": 500}), (1, 3, {"k": 2000, "dampk": 5}), (4, 2, {"x": 61.5})],
+}
+# Two free unit masses joined by a pure damper (k=0): settles on the ground.
+RESTING = {
+    "points": [(1, (-10, 0.5, 0), False), (1, (10, 0.25, 0), False)],
+    "muscles": [(0, 1, {"k": 0})],
+    "skeletons": [],
+}
+
+
+def n_muscles(body):
+    return len(body["muscles"]) if isinstance(body, dict) else {"balance-v0": 2, "box-v0": 4}[body.lower()]
+
+
+def save(name, out, body, env_kwargs, actions, extra=None):
+    spec = body if isinstance(body, dict) else {"balance-v0": wo.BALANCE, "box-v0": wo.BOX}[body.lower()]
+    arrs = dict(
+        pos=out["pos"].astype(np.float32), vel=out["vel"].astype(np.float32),
+        old_a=out["old_a"].astype(np.float32), x=out["x"].astype(np.float32),
+        obs=out["obs"].astype(np.float32), reward=out["reward"].astype(np.float32),
+        done=out["done"], contact_pre=out["contact_pre"],
+        energy=out["energy"].astype(np.float32), centroid=out["centroid"].astype(np.float32),
+        steps=out["steps"].astype(np.int32), reset_noise=out["reset_noise"].astype(np.float32),
+        actions=np.asarray(actions, np.float32),
+        spec=np.array(json.dumps(spec)), env_kwargs=np.array(json.dumps(env_kwargs)),
+    )
+    # every value the reference produced must be float32-representable (or non-finite)
+    for k in ("x", "obs", "reward", "energy", "centroid", "reset_noise"):
+        a64, a32 = np.asarray(out[k], np.float64), arrs[k].astype(np.float64)
+        assert np.array_equal(a64, a32, equal_nan=True), f"{name}:{k} not float32-representable"
+    if extra:
+        arrs.update(extra)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrs)
+    print(f"{name}: T={len(actions)} done={int(out['done'].sum())} "
+          f"contact={int(out['contact_pre'].sum())} nonfinite={int((~np.isfinite(out['pos'])).sum())}")
+
+
+def case(name, body, T, seed, env_kwargs=None, **kw):
+    env_kwargs = dict(env_kwargs or {})
+    rng = np.random.default_rng(1000 + seed)
+    actions = rng.uniform(-1, 1, (T, n_muscles(body))).astype(np.float32)
+    extra = {}
+    if "noise" not in kw:   # draw the reset jitter ourselves so it is float32-exact
+        nrng = np.random.default_rng(5000 + seed)
+        sigma = env_kwargs.get("rand_sigma", 0.1)
+        kw["noise"] = (nrng.standard_normal(4096) * sigma).astype(np.float32)
+    for k in ("k_sub", "max_steps", "reset_on_done"):
+        if k in kw:
+            extra[k] = np.array(int(kw[k]))
+    if "init_state" in kw:
+        extra["init_pos"] = np.asarray(kw["init_state"]["pos"], np.float32)
+        extra["init_vel"] = np.asarray(kw["init_state"]["vel"], np.float32)
+    out = rh.rollout(body, actions, env_kwargs=env_kwargs, seed=seed, **kw)
+    save(name, out, body, env_kwargs, actions, extra)
+
+
+def batch_case(name, body, E, seed, env_kwargs):
+    """E independent envs, one step each, from perturbed states (config-2 style)."""
+    spec = body if isinstance(body, dict) else {"balance-v0": wo.BALANCE, "box-v0": wo.BOX}[body.lower()]
+    N, M = len(spec["points"]), len(spec["muscles"])
+    rng = np.random.default_rng(9000 + seed)
+    tmpl = np.array([p[1] for p in spec["points"]], np.float32)
+    pos0 = (tmpl[None] + rng.normal(0, 8.0, (E, N, 3))).astype(np.float32)
+    pos0[:, :, 1] -= rng.uniform(0, 30, (E, 1)).astype(np.float32)      # push some masses under ground
+    vel0 = rng.normal(0, 20.0, (E, N, 3)).astype(np.float32)
+    if not env_kwargs.get("in3d", False):
+        pos0[:, :, 2] = 0
+        vel0[:, :, 2] = 0
+    actions = rng.uniform(-1, 1, (E, M)).astype(np.float32)
+    keys = ("pos", "vel", "old_a", "x", "obs", "reward", "done", "contact_pre", "energy", "centroid")
+    acc = {k: [] for k in keys}
+    for e in range(E):
+        out = rh.rollout(body, actions[e:e + 1], env_kwargs=env_kwargs, seed=seed,
+                         noise=np.zeros(64, np.float32), init_state=dict(pos=pos0[e], vel=vel0[e]))
+        for k in keys:
+            acc[k].append(out[k][-1])
+    arrs = {k: np.stack(v) for k, v in acc.items()}
+    for k in ("x", "obs", "reward", "energy", "centroid"):
+        a32 = arrs[k].astype(np.float32)
+        assert np.array_equal(arrs[k].astype(np.float64), a32.astype(np.float64), equal_nan=True)
+        arrs[k] = a32
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), init_pos=pos0, init_vel=vel0, actions=actions,
+                        spec=np.array(json.dumps(spec)), env_kwargs=np.array(json.dumps(env_kwargs)), **arrs)
+    print(f"{name}: E={E} done={int(arrs['done'].sum())} contact={int(arrs['contact_pre'].sum())}")
+
+
+def main():
+    assert rh.available(), "reference checkout missing"
+    # the two in-tree morphologies, 3-D and 2-D, two seeds
+    case("balance3d_s0", "Balance-v0", 120, 0, dict(in3d=True))
+    case("balance2d_s1", "Balance-v0", 120, 1, dict(in3d=False))
+    case("box3d_s0", "Box-v0", 120, 0, dict(in3d=True))
+    case("box2d_s1", "Box-v0", 120, 1, dict(in3d=False))
+    # long run through overflow to inf/NaN (as-written dynamics are unstable)
+    case("box3d_overflow", "Box-v0", 400, 2, dict(in3d=True))
+    # irregular body and non-default env parameters
+    case("custom3d", CUSTOM, 150, 3, dict(in3d=True, g=9.8, dampk=0.5, ground_high=-10, ground_k=500,
+                                          ground_damp=30, friction=20, rand_sigma=0.3))
+    case("custom2d", CUSTOM, 60, 4, dict(in3d=False, g=30, dampk=0.0, ground_high=2.5))
+    # N=13 body: exercises NumPy's 8-accumulator pairwise path
+    case("insect3d", INSECT, 100, 5, dict(in3d=True))
+    # termination branches
+    case("done_fall", "Balance-v0", 80, 6, dict(in3d=True, ground_k=0, ground_damp=0, friction=0))
+    case("done_stopped", RESTING, 130, 7, dict(in3d=True, rand_sigma=0.01))
+    case("done_maxsteps", "Box-v0", 30, 8, dict(in3d=True), max_steps=20)
+    # jitter auto-reset (env.reset() after done) and physics substeps
+    case("autoreset_jitter", "Balance-v0", 40, 9, dict(in3d=True), max_steps=7, reset_on_done=True)
+    case("autoreset_jitter2d", "Box-v0", 40, 10, dict(in3d=False), max_steps=5, reset_on_done=True)
+    case("substeps4_box", "Box-v0", 40, 11, dict(in3d=True), k_sub=4)
+    case("substeps8_insect", INSECT, 20, 12, dict(in3d=True), k_sub=8)
+    # physically-signed springs == negative k: stable for 300 steps
+    phys_box = json.loads(json.dumps(wo.BOX))
+    for grp in ("muscles", "skeletons"):
+        phys_box[grp] = [(i, j, {"k": -1000}) for i, j, _ in phys_box[grp]]
+    case("box3d_physical_sign", phys_box, 300, 13, dict(in3d=True))
+    # config-2 style batches: independent envs, one step from perturbed states
+    batch_case("batch_balance3d", "Balance-v0", 256, 20, dict(in3d=True))
+    batch_case("batch_box3d", "Box-v0", 256, 21, dict(in3d=True))
+    batch_case("batch_box2d", "Box-v0", 128, 22, dict(in3d=False))
+
+
+if __name__ == "__main__":
+    import warnings
+    warnings.filterwarnings("ignore", category=RuntimeWarning)
+    main()
