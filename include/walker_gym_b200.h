@@ -1,0 +1,161 @@
+/*
+ * walker_gym_b200.h -- C ABI of libwalkergym_b200.so
+ *
+ * The drop-in boundary for walker-gym's physics step on B200 (sm_100a).
+ * The reference has no FFI: its boundary is the Python class surface of
+ * gym/optimized_env.py (PhysicsEnv.reset/step, make_env), which the host
+ * package walker_gym_b200 keeps; these entry points are what that surface
+ * binds underneath (ctypes).  Plain pointers and sizes,
+ * no torch types, nothing owned by the library: every buffer is caller-owned
+ * device memory, every call is asynchronous on the caller's stream, the
+ * library keeps no global state except a thread-local error string.
+ *
+ * Data layout (device memory, float32 unless noted), E = n_env:
+ *   pos, vel, old_a : SoA  [(n*3 + c) * E + e]      n = mass, c = x/y/z
+ *   mx              : SoA  [m * E + e]              m = muscle (current length Muscle.x)
+ *   steps           : int32 [E]
+ *   action          : row-major [E][act_dim]        (what a policy emits)
+ *   obs             : row-major [E][D] (obs_layout 0) or feature-major [D][E] (obs_layout 1)
+ *   reward [E], done uint8 [E], contact_* uint32 bitmask [E] (bit n = mass n)
+ *   energy [E], centroid [3][E], ep_ret [E], fin_stats [4][E]
+ *   noise           : SoA like pos; already scaled by sigma
+ * D = 3 * (in3d ? 3 : 2) * n_mass + n_muscle   (Creature.getstat, gym/optimized_walker.py:129-162)
+ *
+ * Every function returns 0 on success or a negative wg_status; it never
+ * throws and never synchronises the device.
+ */
+#ifndef WALKER_GYM_B200_H
+#define WALKER_GYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WG_ABI_VERSION 1
+#define WG_MAX_MASS 32
+#define WG_MAX_SPRING 96
+
+typedef enum wg_status {
+    WG_OK = 0,
+    WG_ERR_BAD_ARG = -1,      /* null/ill-sized argument, N or S over the limits */
+    WG_ERR_UNSUPPORTED = -2,  /* e.g. no CUDA device / wrong architecture */
+    WG_ERR_CUDA = -3          /* a CUDA runtime call failed; see wg_last_error_string */
+} wg_status;
+
+/*
+ * One morphology shared by all envs.  Replaces the object graph
+ * Creature(phys, muscles, skeletons) of gym/optimized_walker.py:108-115 with
+ * Point (gym/optimized_engine.py:42-68), Muscle (:7-21) and Skeleton (:69-82).
+ * Springs [0, n_muscle) are the muscles in list order, [n_muscle, n_spring)
+ * the skeletons: the order Creature.run applies them (:117-127).
+ * Scalars are stored as the value NumPy would use at the point of use
+ * (float32 for "weak" python scalars multiplied into float32 arrays).
+ */
+typedef struct wg_topology {
+    int32_t n_mass, n_spring, n_muscle, reserved;
+    double  mass[WG_MAX_MASS];          /* Point.m */
+    uint8_t fixed[WG_MAX_MASS];         /* 1 = DingPoint: forced() ignored (gym/optimized_engine.py:414-416) */
+    float   tmpl_pos[WG_MAX_MASS * 3];  /* creation-time positions, [n*3+c] */
+    int32_t si[WG_MAX_SPRING], sj[WG_MAX_SPRING];   /* p1, p2 */
+    float   sk[WG_MAX_SPRING];          /* k      */
+    float   sdamp[WG_MAX_SPRING];       /* dampk  */
+    float   srest[WG_MAX_SPRING];       /* Skeleton.x / Muscle.originx */
+    float   mlo[WG_MAX_SPRING];         /* originx * minl   (Muscle.regulation, :27-30) */
+    float   mhi[WG_MAX_SPRING];         /* originx * maxl */
+} wg_topology;
+
+/*
+ * Environment constants.  Replaces the constructor arguments and attributes
+ * of PhysicsEnv (gym/optimized_env.py:15-44).
+ */
+typedef struct wg_params {
+    double   g;             /* gravity, applied as a force: a_y += (-g)/m in float64 (:148) */
+    float    dampk;         /* global velocity damping (:151,180-182) */
+    float    ground;        /* ground_high */
+    float    fall_thresh;   /* float32(ground_high - 50): done when mean(y) < this (:218) */
+    float    ground_k, ground_damp, friction;   /* contact spring, damper, friction (:162-172) */
+    float    dt;            /* time_step (:42) */
+    float    sigma;         /* rand_sigma of the in-kernel reset jitter (:59-62) */
+    int32_t  in3d;
+    int32_t  max_steps;     /* :44 */
+    int32_t  k_sub;         /* physics substeps per env step (>= 1) */
+    int32_t  auto_reset;    /* 0 none; 1 jitter-only = PhysicsEnv.reset (:53-68); 2 template = make_env again */
+    uint32_t seed_lo, seed_hi;   /* Philox key of the in-kernel jitter */
+    uint32_t step_index;    /* global step number (Philox counter word), set by the caller each step */
+    uint32_t env_offset;    /* global id of env 0 of this shard (multi-GPU invariance) */
+} wg_params;
+
+/* Caller-owned device buffers of one shard.  Optional ones may be NULL. */
+typedef struct wg_buffers {
+    float*       pos;           /* in/out */
+    float*       vel;           /* in/out */
+    float*       old_a;         /* out, optional: Point.old_a of the last substep */
+    float*       mx;            /* in/out */
+    int32_t*     steps;         /* in/out */
+    const float* action;        /* in */
+    int32_t      act_dim;       /* columns of action; only min(act_dim, n_muscle) are used (Creature.act :164-167) */
+    int32_t      obs_layout;    /* 0 = [E][D] row-major, 1 = [D][E] */
+    float*       obs;           /* out, optional */
+    float*       reward;        /* out, optional */
+    uint8_t*     done;          /* out, optional */
+    uint32_t*    contact_pre;   /* out, optional: force-phase contact of the last substep (:154) */
+    uint32_t*    contact_post;  /* out, optional: reward-phase contact (:200) */
+    float*       energy;        /* out, optional: _calculate_energy (:240-248) */
+    float*       centroid;      /* out, optional: info['centroid_position'] (:235) */
+    float*       ep_ret;        /* in/out, optional: running episode return */
+    float*       fin_stats;     /* in/out, optional: per-env sums over finished episodes:
+                                   [0] return, [1] return^2, [2] length, [3] count */
+    const float* noise;         /* in, optional: jitter used by auto-reset / wg_reset instead of Philox */
+} wg_buffers;
+
+int         wg_abi_version(void);
+const char* wg_last_error_string(void);
+
+/* Observation length for this morphology (len(PhysicsEnv._get_observation()), :184-187). */
+int wg_obs_dim(const wg_topology* topo, int in3d);
+
+/* Which kernel wg_step will launch: 0 = generic (runtime topology), >0 = id of a
+ * register-resident specialisation.  For tests and logs; not needed to call wg_step. */
+int wg_kernel_variant(const wg_topology* topo);
+/* Force the generic kernel (1) or restore automatic dispatch (0); returns the old value. */
+int wg_force_generic(int on);
+
+/*
+ * PhysicsEnv.step for n_env environments (gym/optimized_env.py:70-92):
+ * Creature.act -> k_sub x _run_physics -> steps += 1 -> reward, done, info ->
+ * optional auto-reset of done envs -> observation.  One kernel launch.
+ */
+int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf,
+            int64_t n_env, void* cuda_stream);
+
+/*
+ * PhysicsEnv.reset (gym/optimized_env.py:53-68) for the envs whose mask byte is
+ * non-zero (mask NULL = all).  mode 1 = jitter only (the reference's reset),
+ * mode 2 = restore the template first (what make_env does, :273-294).
+ * Writes obs if buf->obs is set.
+ */
+int wg_reset(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf,
+             int64_t n_env, int mode, const uint8_t* mask, void* cuda_stream);
+
+/*
+ * Sum the per-env finished-episode accumulators into out8 (device, 8 doubles):
+ * [sum return, sum return^2, sum length, count, 0, 0, 0, 0].  The caller
+ * all-reduces out8 across ranks (NCCL) -- the only collective on this path.
+ */
+int wg_stats_reduce(const float* fin_stats, int64_t n_env, double* out8, void* cuda_stream);
+
+/*
+ * Host-buffer convenience used for end-to-end timing: copies `action` from
+ * (pinned) host memory into buf->action, runs wg_step, and copies obs, reward
+ * and done back to the host pointers (any may be NULL), all on cuda_stream.
+ */
+int wg_step_host(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf,
+                 int64_t n_env, const float* h_action, float* h_obs, float* h_reward,
+                 uint8_t* h_done, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WALKER_GYM_B200_H */

@@ -1,0 +1,134 @@
+"""The CUDA library behind the oracle's calling convention (tests only).
+
+Every call uploads the numpy state, invokes ``wg_step`` / ``wg_reset`` through
+the C ABI on ``cuda:0`` and downloads the result, so the golden replay code in
+``test_oracle_golden.py`` can drive the oracle and the GPU identically.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from walker_gym_b200 import _lib
+from walker_gym_b200.batched import make_params as _make_params
+from walker_gym_b200.topology import topology_from_spec
+
+DEV = "cuda:0"
+obs_layout = 0          # module-level switches the tests flip
+force_generic = False
+
+
+class Body:
+    def __init__(self, spec):
+        self.topo = topology_from_spec(spec)
+        self.n_mass, self.n_muscle, self.n_spring = self.topo.n_mass, self.topo.n_muscle, self.topo.n_spring
+        self.srest = self.topo.srest
+        self.tmpl_pos = self.topo.tmpl_pos
+
+
+def make_body(spec):
+    return Body(spec)
+
+
+def make_params(**kw):
+    return _make_params(**kw)
+
+
+def obs_dim(body, in3d):
+    return 3 * (3 if in3d else 2) * body.n_mass + body.n_muscle
+
+
+def init_state(body, E):
+    N, M = body.n_mass, body.n_muscle
+    tp = np.array(body.tmpl_pos[: N * 3], dtype=np.float32)
+    return dict(pos=np.repeat(tp[:, None], E, axis=1).copy(), vel=np.zeros((N * 3, E), np.float32),
+                old_a=np.zeros((N * 3, E), np.float32),
+                mx=np.repeat(np.array(body.srest[:M], dtype=np.float32)[:, None], E, axis=1).copy().reshape(M, E),
+                steps=np.zeros(E, np.int32))
+
+
+def _dev(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream(torch.device(DEV)).cuda_stream)
+
+
+def _upload(st):
+    return {k: _dev(st[k]) for k in ("pos", "vel", "old_a", "mx", "steps")}
+
+
+def _download(st, d):
+    for k in ("pos", "vel", "old_a", "mx", "steps"):
+        st[k][...] = d[k].cpu().numpy()
+
+
+def step(body, prm, st, action, *, want_info=True, ep_ret=None, fin_stats=None, noise=None):
+    lib = _lib.load()
+    E = st["pos"].shape[1]
+    D = obs_dim(body, prm.in3d)
+    d = _upload(st)
+    act = _dev(np.ascontiguousarray(action, dtype=np.float32).reshape(E, -1))
+    f32 = dict(dtype=torch.float32, device=DEV)
+    out = dict(obs=torch.zeros((E, D) if obs_layout == 0 else (D, E), **f32), reward=torch.zeros(E, **f32),
+               done=torch.zeros(E, dtype=torch.uint8, device=DEV),
+               contact_pre=torch.zeros(E, dtype=torch.int32, device=DEV),
+               contact_post=torch.zeros(E, dtype=torch.int32, device=DEV))
+    if want_info:
+        out["energy"] = torch.zeros(E, **f32)
+        out["centroid"] = torch.zeros(3, E, **f32)
+    d_ep, d_fin, d_noise = _dev(ep_ret), _dev(fin_stats), _dev(noise)
+    b = _lib.WgBuffers()
+    b.pos, b.vel, b.old_a, b.mx, b.steps = (_ptr(d[k]) for k in ("pos", "vel", "old_a", "mx", "steps"))
+    if body.n_muscle == 0:
+        b.mx = b.steps
+    b.action, b.act_dim, b.obs_layout = _ptr(act), act.shape[1], obs_layout
+    b.obs, b.reward, b.done = _ptr(out["obs"]), _ptr(out["reward"]), _ptr(out["done"])
+    b.contact_pre, b.contact_post = _ptr(out["contact_pre"]), _ptr(out["contact_post"])
+    b.energy, b.centroid = _ptr(out.get("energy")), _ptr(out.get("centroid"))
+    b.ep_ret, b.fin_stats, b.noise = _ptr(d_ep), _ptr(d_fin), _ptr(d_noise)
+    old = lib.wg_force_generic(1 if force_generic else 0)
+    try:
+        rc = lib.wg_step(C.byref(body.topo), C.byref(prm), C.byref(b), E, _stream())
+    finally:
+        lib.wg_force_generic(old)
+    _lib.check(rc, "wg_step")
+    torch.cuda.synchronize()
+    _download(st, d)
+    if ep_ret is not None:
+        ep_ret[...] = d_ep.cpu().numpy()
+    if fin_stats is not None:
+        fin_stats[...] = d_fin.cpu().numpy()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    if obs_layout == 1:
+        res["obs"] = np.ascontiguousarray(res["obs"].T)
+    res["contact_pre"] = res["contact_pre"].astype(np.uint32)
+    res["contact_post"] = res["contact_post"].astype(np.uint32)
+    return res
+
+
+def reset(body, prm, st, *, mode=1, mask=None, noise=None):
+    lib = _lib.load()
+    E = st["pos"].shape[1]
+    D = obs_dim(body, prm.in3d)
+    d = _upload(st)
+    obs = torch.zeros((E, D) if obs_layout == 0 else (D, E), dtype=torch.float32, device=DEV)
+    d_noise, d_mask = _dev(noise), _dev(mask)
+    b = _lib.WgBuffers()
+    b.pos, b.vel, b.old_a, b.mx, b.steps = (_ptr(d[k]) for k in ("pos", "vel", "old_a", "mx", "steps"))
+    if body.n_muscle == 0:
+        b.mx = b.steps
+    b.obs, b.obs_layout, b.noise = _ptr(obs), obs_layout, _ptr(d_noise)
+    rc = lib.wg_reset(C.byref(body.topo), C.byref(prm), C.byref(b), E, mode, _ptr(d_mask), _stream())
+    _lib.check(rc, "wg_reset")
+    torch.cuda.synchronize()
+    _download(st, d)
+    o = obs.cpu().numpy()
+    return np.ascontiguousarray(o.T) if obs_layout == 1 else o

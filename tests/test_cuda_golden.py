@@ -1,0 +1,42 @@
+"""GPU: the CUDA library, called through its C ABI, must reproduce the reference's
+recorded outputs bit for bit -- every golden fixture, both kernels, both layouts."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from test_oracle_golden import replay_batch, replay_trajectory
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def stepper():
+    import cuda_stepper as cs
+    cs.obs_layout, cs.force_generic = 0, False
+    yield cs
+    cs.obs_layout, cs.force_generic = 0, False
+
+
+@pytest.mark.parametrize("name", gu.trajectory_names())
+def test_cuda_matches_reference_trajectory(stepper, name):
+    assert replay_trajectory(gu.load(name), stepper) is None
+
+
+@pytest.mark.parametrize("name", gu.trajectory_names())
+def test_cuda_generic_kernel_matches_reference_trajectory(stepper, name):
+    stepper.force_generic = True
+    assert replay_trajectory(gu.load(name), stepper) is None
+
+
+@pytest.mark.parametrize("name", ["balance3d_s0", "box2d_s1", "custom3d", "insect3d", "autoreset_jitter"])
+@pytest.mark.parametrize("generic", [False, True])
+def test_cuda_feature_major_obs(stepper, name, generic):
+    stepper.obs_layout, stepper.force_generic = 1, generic
+    assert replay_trajectory(gu.load(name), stepper) is None
+
+
+@pytest.mark.parametrize("name", gu.batch_names())
+@pytest.mark.parametrize("generic", [False, True])
+def test_cuda_matches_reference_batch(stepper, name, generic):
+    stepper.force_generic = generic
+    assert replay_batch(gu.load(name), stepper) == []

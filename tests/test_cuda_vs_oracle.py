@@ -1,0 +1,189 @@
+"""GPU: BatchedPhysicsEnv (public API -> C ABI -> CUDA) against the C oracle on the
+same seeded inputs, at sizes the oracle finishes in seconds, plus size-independent
+properties at BASELINE.json's full size.  Equality is exact (float32 bit patterns up
+to NaN payload / sign of zero): the kernel evaluates the reference's operations in
+the reference's order."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import walker_oracle as wo
+
+pytestmark = pytest.mark.gpu
+
+
+def spec_of(name):
+    from walker_gym_b200 import BODIES
+    b = BODIES[name]
+    ding = set(b.get("ding", ()))
+    return {"points": [(m, tuple(p), n in ding) for n, (m, p) in enumerate(b["points"])],
+            "muscles": b["muscles"], "skeletons": b["skeletons"]}
+
+
+def make_pair(name, E, *, env_kw=None, auto_reset=None, max_steps=1000, k_sub=1, seed=7, obs_layout="row", **extra):
+    """Build the CUDA env and the oracle state from the same template (no jitter yet)."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    env_kw = dict(env_kw or {})
+    env = BatchedPhysicsEnv(name, E, "cuda:0", auto_reset=auto_reset, max_steps=max_steps, k_sub=k_sub, seed=seed,
+                            obs_layout=obs_layout, keep_old_a=True, track_info=True, track_contacts=True,
+                            initial_reset=False, **env_kw, **extra)
+    body = wo.make_body(spec_of(name))
+    ar = {None: 0, "jitter": 1, "template": 2}[auto_reset]
+    prm = wo.make_params(max_steps=max_steps, k_sub=k_sub, auto_reset=ar, seed=seed,
+                         env_offset=extra.get("env_offset", 0), **env_kw)
+    st = wo.init_state(body, E)
+    return env, body, prm, st
+
+
+def assert_state_equal(env, st, N, what=""):
+    assert gu.same(env.pos.cpu().numpy(), st["pos"]), f"pos {what}"
+    assert gu.same(env.vel.cpu().numpy(), st["vel"]), f"vel {what}"
+    assert gu.same(env.old_a.cpu().numpy(), st["old_a"]), f"old_a {what}"
+    assert gu.same(env.mx.cpu().numpy(), st["mx"]), f"mx {what}"
+    assert gu.same(env.steps.cpu().numpy(), st["steps"]), f"steps {what}"
+
+
+def run_lockstep(env, body, prm, st, T, rng, *, noise_reset=True, ep=None):
+    import torch
+    E, M, N = env.num_envs, env.M, env.N
+    if noise_reset:
+        nz = (rng.standard_normal((3 * N, E)) * 0.1).astype(np.float32)
+        o_c = env.reset(noise=torch.from_numpy(nz).cuda(), mode="jitter")
+        o_o = wo.reset(body, prm, st, mode=1, noise=nz)
+        assert gu.same(o_c.cpu().numpy().reshape(o_o.shape) if env.obs_layout == "row" else o_c.cpu().numpy().T, o_o), "reset obs"
+    for t in range(T):
+        act = rng.uniform(-1, 1, (E, M)).astype(np.float32)
+        prm.step_index = env.step_count
+        obs, rew, done, info = env.step(torch.from_numpy(act).cuda())
+        out = wo.step(body, prm, st, act, ep_ret=None if ep is None else ep[0], fin_stats=None if ep is None else ep[1])
+        o = obs.cpu().numpy()
+        assert gu.same(o if env.obs_layout == "row" else o.T, out["obs"]), f"obs @ step {t}"
+        assert gu.same(rew.cpu().numpy(), out["reward"]), f"reward @ step {t}"
+        assert gu.same(done.cpu().numpy(), out["done"].astype(bool)), f"done @ step {t}"
+        assert gu.same(env.contact_pre.cpu().numpy().astype(np.uint32), out["contact_pre"]), f"contact_pre @ step {t}"
+        assert gu.same(env.contact_post.cpu().numpy().astype(np.uint32), out["contact_post"]), f"contact_post @ step {t}"
+        assert gu.same(info["total_energy"].cpu().numpy(), out["energy"]), f"energy @ step {t}"
+        assert gu.same(info["centroid_position"].cpu().numpy(), out["centroid"]), f"centroid @ step {t}"
+        assert_state_equal(env, st, N, f"@ step {t}")
+
+
+# ---- BASELINE config 2: optimized_walker bodies, 4096 envs, 100-step free-running trajectories ----
+@pytest.mark.parametrize("name", ["balance_v0", "box_v0"])
+@pytest.mark.parametrize("in3d", [True, False])
+def test_config2_4096_envs_100_steps_bit_exact(name, in3d):
+    env, body, prm, st = make_pair(name, 4096, env_kw=dict(in3d=in3d))
+    assert env.kernel_variant > 0
+    run_lockstep(env, body, prm, st, 100, np.random.default_rng(1))
+
+
+@pytest.mark.parametrize("E", [1, 2, 31, 129, 255, 4097])
+@pytest.mark.parametrize("name", ["balance_v0", "humanb"])
+def test_ragged_batch_sizes(name, E):
+    env, body, prm, st = make_pair(name, E, env_kw=dict(in3d=True))
+    run_lockstep(env, body, prm, st, 12, np.random.default_rng(E))
+
+
+@pytest.mark.parametrize("name", ["test", "leg2", "box", "box2", "balance", "balance2", "balance3", "intrian",
+                                  "humanb", "insect", "box4", "leg", "hat", "quad_balance"])
+def test_every_walker_py_body(name):
+    """BASELINE config 1 bodies (gym/walker.py tables) under the L1 semantics."""
+    env, body, prm, st = make_pair(name, 64, env_kw=dict(in3d=True))
+    run_lockstep(env, body, prm, st, 40, np.random.default_rng(3))
+
+
+def test_config4_enlarged_body_8_substeps():
+    env, body, prm, st = make_pair("quad_balance", 1024, env_kw=dict(in3d=True), k_sub=8)
+    assert env.kernel_variant == 3
+    run_lockstep(env, body, prm, st, 25, np.random.default_rng(4))
+
+
+@pytest.mark.parametrize("layout", ["row", "feature"])
+@pytest.mark.parametrize("mode", ["template", "jitter"])
+@pytest.mark.parametrize("name", ["balance_v0", "hat"])
+def test_auto_reset_with_in_kernel_philox_noise(name, mode, layout):
+    """done -> reset -> obs inside the kernel, jitter from the Philox stream both sides implement."""
+    env, body, prm, st = make_pair(name, 1000, env_kw=dict(in3d=True, rand_sigma=0.25), auto_reset=mode,
+                                   max_steps=9, obs_layout=layout, track_stats=True)
+    E = env.num_envs
+    ep = (np.zeros(E, np.float32), np.zeros((4, E), np.float32))
+    run_lockstep(env, body, prm, st, 30, np.random.default_rng(5), noise_reset=False, ep=ep)
+    assert gu.same(env.ep_ret.cpu().numpy(), ep[0])
+    assert gu.same(env.fin_stats.cpu().numpy(), ep[1])
+    stats = env.episode_stats()
+    assert stats["episodes"] == int(ep[1][3].sum()) == 3 * E
+    np.testing.assert_allclose(stats["return_sum"], ep[1][0].astype(np.float64).sum(), rtol=1e-12)
+    np.testing.assert_allclose(stats["length_sum"], ep[1][2].astype(np.float64).sum(), rtol=1e-12)
+
+
+def test_philox_reset_matches_oracle_and_is_normal():
+    import torch
+    env, body, prm, st = make_pair("box_v0", 1 << 16, env_kw=dict(in3d=True, rand_sigma=1.0))
+    prm.step_index = env.step_count
+    o_c = env.reset(mode="template")
+    o_o = wo.reset(body, prm, st, mode=2)
+    assert gu.same(o_c.cpu().numpy(), o_o)
+    v = env.vel.cpu().numpy().ravel().astype(np.float64)
+    assert abs(v.mean()) < 5e-3 and abs(v.std() - 1.0) < 5e-3
+    assert abs(((v - v.mean()) ** 4).mean() / v.var() ** 2 - 3.0) < 0.05      # kurtosis of a normal
+
+
+def test_sharding_is_invisible():
+    """shard k of the batch equals the same envs run in one piece, bit for bit."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    E, T = 8192, 30
+    kw = dict(in3d=True, auto_reset="template", max_steps=11, seed=123, track_stats=True)
+    whole = BatchedPhysicsEnv("balance_v0", E, "cuda:0", **kw)
+    halves = [BatchedPhysicsEnv("balance_v0", E // 2, "cuda:0", env_offset=k * E // 2, **kw) for k in range(2)]
+    g = torch.Generator(device="cuda:0").manual_seed(0)
+    for t in range(T):
+        act = torch.rand(E, 2, device="cuda:0", generator=g) * 2 - 1
+        whole.step(act)
+        for k, h in enumerate(halves):
+            h.step(act[k * E // 2:(k + 1) * E // 2].contiguous())
+    for name in ("pos", "vel", "mx", "fin_stats"):
+        cat = torch.cat([getattr(h, name) for h in halves], dim=1)
+        assert gu.same(getattr(whole, name).cpu().numpy(), cat.cpu().numpy()), name
+    assert gu.same(whole.obs.cpu().numpy(), torch.cat([h.obs for h in halves], 0).cpu().numpy())
+    a, b0, b1 = whole.episode_stats(), halves[0].episode_stats(), halves[1].episode_stats()
+    assert a["episodes"] == b0["episodes"] + b1["episodes"] > 0
+    np.testing.assert_allclose(a["return_sum"], b0["return_sum"] + b1["return_sum"], rtol=1e-9)
+
+
+def test_full_size_properties_1m_envs():
+    """BASELINE config 3 size (2^20 envs): determinism, agreement of both kernels and both
+    observation layouts, and a 2^14-env slice checked against the oracle."""
+    import ctypes as C
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv, _lib
+    E, T = 1 << 20, 20
+    kw = dict(in3d=True, auto_reset="template", max_steps=7, seed=5)
+    a = BatchedPhysicsEnv("balance_v0", E, "cuda:0", **kw)
+    b = BatchedPhysicsEnv("balance_v0", E, "cuda:0", obs_layout="feature", **kw)
+    lib = _lib.load()
+    g = torch.Generator(device="cuda:0").manual_seed(1)
+    for t in range(T):
+        act = torch.rand(E, 2, device="cuda:0", generator=g) * 2 - 1
+        a.step(act)
+        old = lib.wg_force_generic(1)           # b runs the generic shared-memory kernel
+        try:
+            b.step(act)
+        finally:
+            lib.wg_force_generic(old)
+    for name in ("pos", "vel", "mx", "steps", "reward"):
+        assert torch.equal(getattr(a, name).view(torch.int32), getattr(b, name).view(torch.int32)) or \
+            gu.same(getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy()), name
+    assert gu.same(a.obs.cpu().numpy(), b.obs.t().contiguous().cpu().numpy())
+    # oracle on the first 2^14 envs of the same run (env ids and Philox streams coincide)
+    Es = 1 << 14
+    env, body, prm, st = make_pair("balance_v0", Es, env_kw=dict(in3d=True), auto_reset="template", max_steps=7, seed=5)
+    g = torch.Generator(device="cuda:0").manual_seed(1)
+    prm.step_index = 0
+    wo.reset(body, prm, st, mode=2)
+    for t in range(T):
+        act = torch.rand(E, 2, device="cuda:0", generator=g) * 2 - 1
+        prm.step_index = t + 1
+        wo.step(body, prm, st, act[:Es].cpu().numpy())
+    assert gu.same(a.pos[:, :Es].cpu().numpy(), st["pos"])
+    assert gu.same(a.vel[:, :Es].cpu().numpy(), st["vel"])

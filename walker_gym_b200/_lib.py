@@ -1,0 +1,102 @@
+"""ctypes binding of ``libwalkergym_b200.so`` (C ABI: ``include/walker_gym_b200.h``).
+
+The library is the product: there is no CPU or PyTorch fallback.  If the
+shared object is missing, or was built for another ABI version, importing the
+binding raises -- it never degrades silently.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+MAX_MASS, MAX_SPRING = 32, 96
+ABI_VERSION = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwalkergym_b200.so")
+
+
+class WgTopology(C.Structure):
+    """``wg_topology``: replaces Creature(phys, muscles, skeletons) (gym/optimized_walker.py:108-115)."""
+    _fields_ = [
+        ("n_mass", C.c_int32), ("n_spring", C.c_int32), ("n_muscle", C.c_int32), ("reserved", C.c_int32),
+        ("mass", C.c_double * MAX_MASS),
+        ("fixed", C.c_uint8 * MAX_MASS),
+        ("tmpl_pos", C.c_float * (MAX_MASS * 3)),
+        ("si", C.c_int32 * MAX_SPRING), ("sj", C.c_int32 * MAX_SPRING),
+        ("sk", C.c_float * MAX_SPRING), ("sdamp", C.c_float * MAX_SPRING), ("srest", C.c_float * MAX_SPRING),
+        ("mlo", C.c_float * MAX_SPRING), ("mhi", C.c_float * MAX_SPRING),
+    ]
+
+
+class WgParams(C.Structure):
+    """``wg_params``: replaces PhysicsEnv's constructor arguments (gym/optimized_env.py:15-44)."""
+    _fields_ = [
+        ("g", C.c_double),
+        ("dampk", C.c_float), ("ground", C.c_float), ("fall_thresh", C.c_float),
+        ("ground_k", C.c_float), ("ground_damp", C.c_float), ("friction", C.c_float),
+        ("dt", C.c_float), ("sigma", C.c_float),
+        ("in3d", C.c_int32), ("max_steps", C.c_int32), ("k_sub", C.c_int32), ("auto_reset", C.c_int32),
+        ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("step_index", C.c_uint32), ("env_offset", C.c_uint32),
+    ]
+
+
+class WgBuffers(C.Structure):
+    _fields_ = [
+        ("pos", C.c_void_p), ("vel", C.c_void_p), ("old_a", C.c_void_p), ("mx", C.c_void_p), ("steps", C.c_void_p),
+        ("action", C.c_void_p), ("act_dim", C.c_int32), ("obs_layout", C.c_int32),
+        ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
+        ("contact_pre", C.c_void_p), ("contact_post", C.c_void_p),
+        ("energy", C.c_void_p), ("centroid", C.c_void_p),
+        ("ep_ret", C.c_void_p), ("fin_stats", C.c_void_p), ("noise", C.c_void_p),
+    ]
+
+
+EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
+           "wg_step", "wg_reset", "wg_stats_reduce", "wg_step_host")
+
+_lib = None
+
+
+class WalkerGymError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raise if it is absent (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WalkerGymError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  walker_gym_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise WalkerGymError(f"{LIB_PATH} does not export {name}")
+    lib.wg_abi_version.restype = C.c_int
+    if lib.wg_abi_version() != ABI_VERSION:
+        raise WalkerGymError(f"ABI mismatch: library {lib.wg_abi_version()} != binding {ABI_VERSION}")
+    lib.wg_last_error_string.restype = C.c_char_p
+    P = C.POINTER
+    lib.wg_obs_dim.argtypes = [P(WgTopology), C.c_int]
+    lib.wg_kernel_variant.argtypes = [P(WgTopology)]
+    lib.wg_force_generic.argtypes = [C.c_int]
+    lib.wg_step.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_void_p]
+    lib.wg_reset.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    lib.wg_stats_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.wg_step_host.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    for name in ("wg_obs_dim", "wg_kernel_variant", "wg_force_generic", "wg_step", "wg_reset",
+                 "wg_stats_reduce", "wg_step_host"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().wg_last_error_string().decode("utf-8", "replace")
+        exc = ValueError if rc == -1 else WalkerGymError
+        raise exc(f"{what} failed ({rc}): {msg}")

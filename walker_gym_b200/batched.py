@@ -1,0 +1,311 @@
+"""``BatchedPhysicsEnv``: millions of independent walkers stepped by one CUDA kernel.
+
+The per-env semantics are those of the reference's ``PhysicsEnv``
+(gym/optimized_env.py:8-269); this class only adds the env axis.  PyTorch is
+used for device memory and streams; every operation on the step path is a call
+into ``libwalkergym_b200.so`` through its C ABI.
+
+Layouts (float32, E = num_envs, N masses, M muscles, D = obs dim):
+  pos, vel : [3N, E]   row n*3+c, env fastest (coalesced per mass component)
+  mx       : [M, E]    current muscle rest lengths (Muscle.x)
+  steps    : int32 [E]
+  action   : [E, M]    row-major, what a policy emits
+  obs      : [E, D] (obs_layout="row") or [D, E] (obs_layout="feature")
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import WgBuffers, WgParams
+from .topology import topology_from_creature
+from .walker import Creature, create_balance_creature, create_box_creature, make_creature, BODIES
+
+AUTO_RESET = {None: 0, False: 0, "none": 0, "jitter": 1, "reference": 1, "template": 2, True: 2}
+
+
+def creature_from_id(env_id: str) -> Creature:
+    """The ids ``make_env`` accepts (gym/optimized_env.py:273-294), case-insensitive,
+    plus the names of the in-tree body tables."""
+    key = env_id.lower()
+    if key == "balance-v0":
+        return create_balance_creature()
+    if key == "box-v0":
+        return create_box_creature()
+    if key in BODIES:
+        return make_creature(key)
+    raise ValueError(f"Unknown environment ID: {key}")
+
+
+def make_params(*, in3d=False, g=100, dampk=0, ground_high=0, ground_k=1000, ground_damp=100, friction=100,
+                rand_sigma=0.1, time_step=0.01, max_steps=1000, k_sub=1, auto_reset=0, seed=0,
+                step_index=0, env_offset=0) -> WgParams:
+    """PhysicsEnv's constructor arguments -> ``wg_params``.  Scalars are converted
+    the way NumPy converts the reference's python numbers at their point of use."""
+    p = WgParams()
+    p.g = float(g)
+    p.dampk = np.float32(dampk)
+    p.ground = np.float32(ground_high)
+    p.fall_thresh = np.float32(ground_high - 50)
+    p.ground_k, p.ground_damp, p.friction = np.float32(ground_k), np.float32(ground_damp), np.float32(friction)
+    p.dt, p.sigma = np.float32(time_step), np.float32(rand_sigma)
+    p.in3d, p.max_steps, p.k_sub, p.auto_reset = int(bool(in3d)), int(max_steps), int(k_sub), int(auto_reset)
+    p.seed_lo, p.seed_hi = int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF
+    p.step_index, p.env_offset = int(step_index) & 0xFFFFFFFF, int(env_offset) & 0xFFFFFFFF
+    return p
+
+
+class BatchedPhysicsEnv:
+    def __init__(self, creature: Union[Creature, str], num_envs: int, device: Union[str, torch.device] = "cuda",
+                 in3d: bool = False, g=100, dampk=0, ground_high=0, ground_k=1000, ground_damp=100,
+                 friction=100, rand_sigma=0.1, *, max_steps: int = 1000, time_step: float = 0.01, k_sub: int = 1,
+                 auto_reset="template", obs_layout: str = "row", seed: int = 0, env_offset: int = 0,
+                 track_info: bool = False, track_stats: bool = True, track_contacts: bool = False,
+                 keep_old_a: bool = False, initial_reset: bool = True):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.WalkerGymError("walker_gym_b200 runs on CUDA devices only (no CPU fallback)")
+        if isinstance(creature, str):
+            creature = creature_from_id(creature)
+        self.creature = creature
+        self.topo = topology_from_creature(creature)
+        self.num_envs = E = int(num_envs)
+        self.in3d = bool(in3d)
+        if auto_reset not in AUTO_RESET:
+            raise ValueError(f"auto_reset must be one of {sorted(map(str, AUTO_RESET))}")
+        if obs_layout not in ("row", "feature"):
+            raise ValueError("obs_layout must be 'row' ([E, D]) or 'feature' ([D, E])")
+        self.params = make_params(in3d=in3d, g=g, dampk=dampk, ground_high=ground_high, ground_k=ground_k,
+                                  ground_damp=ground_damp, friction=friction, rand_sigma=rand_sigma,
+                                  time_step=time_step, max_steps=max_steps, k_sub=k_sub,
+                                  auto_reset=AUTO_RESET[auto_reset], seed=seed, env_offset=env_offset)
+        self.N, self.M = self.topo.n_mass, self.topo.n_muscle
+        self.obs_dim = self.lib.wg_obs_dim(C.byref(self.topo), int(self.in3d))
+        self.obs_layout = obs_layout
+        self.step_count = 0        # global step index: the Philox counter word of the in-kernel jitter
+        dev, f32 = self.device, torch.float32
+        tmpl = torch.tensor(list(self.topo.tmpl_pos[: 3 * self.N]), dtype=f32, device=dev)
+        self.pos = tmpl[:, None].repeat(1, E).contiguous()
+        self.vel = torch.zeros(3 * self.N, E, dtype=f32, device=dev)
+        x0 = torch.tensor([np.float32(m.x) for m in creature.muscles], dtype=f32, device=dev).reshape(self.M)
+        self.mx = x0[:, None].repeat(1, E).contiguous() if self.M else torch.zeros(0, E, dtype=f32, device=dev)
+        self.steps = torch.zeros(E, dtype=torch.int32, device=dev)
+        self.obs = torch.zeros((E, self.obs_dim) if obs_layout == "row" else (self.obs_dim, E), dtype=f32, device=dev)
+        self.reward = torch.zeros(E, dtype=f32, device=dev)
+        self._done_u8 = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self.done = self._done_u8.view(torch.bool)
+        self.old_a = torch.zeros(3 * self.N, E, dtype=f32, device=dev) if keep_old_a else None
+        self.energy = torch.zeros(E, dtype=f32, device=dev) if track_info else None
+        self.centroid = torch.zeros(3, E, dtype=f32, device=dev) if track_info else None
+        self.contact_pre = torch.zeros(E, dtype=torch.int32, device=dev) if track_contacts else None
+        self.contact_post = torch.zeros(E, dtype=torch.int32, device=dev) if track_contacts else None
+        self.ep_ret = torch.zeros(E, dtype=f32, device=dev) if track_stats else None
+        self.fin_stats = torch.zeros(4, E, dtype=f32, device=dev) if track_stats else None
+        self._stats_out = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._buf = WgBuffers()
+        self._bind()
+        if initial_reset:
+            self.reset()           # PhysicsEnv.__init__ ends with self.reset() (gym/optimized_env.py:51)
+
+    # ---- plumbing ----------------------------------------------------------------
+    @staticmethod
+    def _p(t: Optional[torch.Tensor]):
+        return None if t is None else t.data_ptr()
+
+    def _bind(self) -> None:
+        b = self._buf
+        b.pos, b.vel, b.old_a, b.mx, b.steps = map(self._p, (self.pos, self.vel, self.old_a, self.mx, self.steps))
+        if self.M == 0:
+            b.mx = self._p(self.steps)     # never dereferenced (M == 0); keeps validation simple
+        b.obs, b.reward, b.done = self._p(self.obs), self._p(self.reward), self._p(self._done_u8)
+        b.obs_layout = 0 if self.obs_layout == "row" else 1
+        b.contact_pre, b.contact_post = self._p(self.contact_pre), self._p(self.contact_post)
+        b.energy, b.centroid = self._p(self.energy), self._p(self.centroid)
+        b.ep_ret, b.fin_stats = self._p(self.ep_ret), self._p(self.fin_stats)
+        b.action, b.act_dim, b.noise = None, 0, None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_f32(self, t: torch.Tensor, shape, what: str) -> torch.Tensor:
+        if t.device != self.pos.device or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{what} must be a contiguous float32 tensor of shape {tuple(shape)} on {self.pos.device}")
+        return t
+
+    @property
+    def kernel_variant(self) -> int:
+        """0 = generic run-time-topology kernel, >0 = register-resident specialisation."""
+        return self.lib.wg_kernel_variant(C.byref(self.topo))
+
+    # ---- gym surface -------------------------------------------------------------
+    def reset(self, mask: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+              mode: Optional[str] = None) -> torch.Tensor:
+        """``PhysicsEnv.reset`` for every env (or those in ``mask``).
+
+        mode "jitter" is the reference's reset (velocities += N(0, sigma), steps = 0;
+        positions persist, gym/optimized_env.py:53-68); "template" first restores the
+        creation-time body, which is what calling ``make_env`` again does.  Default:
+        the env's ``auto_reset`` mode, or "jitter" if auto-reset is off.
+        ``noise``: optional [3N, E] jitter (already scaled) instead of the Philox stream."""
+        m = AUTO_RESET[mode] if mode is not None else (self.params.auto_reset or 1)
+        if m not in (1, 2):
+            raise ValueError("reset mode must be 'jitter' or 'template'")
+        self._buf.noise = self._p(self._check_f32(noise, (3 * self.N, self.num_envs), "noise")) if noise is not None else None
+        mptr = None
+        if mask is not None:
+            if mask.dtype == torch.bool:
+                mask = mask.view(torch.uint8)
+            if mask.dtype != torch.uint8 or mask.numel() != self.num_envs or not mask.is_contiguous():
+                raise ValueError("mask must be a contiguous bool/uint8 tensor of length num_envs")
+            mptr = mask.data_ptr()
+        self.params.step_index = self.step_count & 0xFFFFFFFF
+        with torch.cuda.device(self.device):
+            rc = self.lib.wg_reset(C.byref(self.topo), C.byref(self.params), C.byref(self._buf),
+                                   self.num_envs, m, mptr, self._stream())
+        self._buf.noise = None
+        _lib.check(rc, "wg_reset")
+        self.step_count += 1
+        return self.obs
+
+    def step(self, action: Optional[torch.Tensor], noise: Optional[torch.Tensor] = None):
+        """``PhysicsEnv.step`` for every env, one kernel launch.
+
+        ``action``: float32 [E, A]; only the first min(A, M) columns drive muscles
+        (Creature.act, gym/optimized_walker.py:164-167); ``None`` applies no action.
+        Returns ``(obs, reward, done, info)``: views of buffers that the next call overwrites.
+        With auto-reset on, ``obs`` of a done env is its post-reset observation while
+        ``reward``/``done`` describe the step that ended the episode."""
+        b = self._buf
+        if action is None:
+            b.action, b.act_dim = None, 0
+        else:
+            if action.dim() != 2 or action.shape[0] != self.num_envs:
+                raise ValueError(f"action must have shape [{self.num_envs}, A]")
+            self._check_f32(action, action.shape, "action")
+            b.action, b.act_dim = action.data_ptr(), int(action.shape[1])
+        b.noise = self._p(self._check_f32(noise, (3 * self.N, self.num_envs), "noise")) if noise is not None else None
+        self.params.step_index = self.step_count & 0xFFFFFFFF
+        with torch.cuda.device(self.device):
+            rc = self.lib.wg_step(C.byref(self.topo), C.byref(self.params), C.byref(b), self.num_envs, self._stream())
+        b.noise = None
+        _lib.check(rc, "wg_step")
+        self.step_count += 1
+        info = {}
+        if self.energy is not None:
+            info = {"steps": self.steps, "centroid_position": self.centroid, "total_energy": self.energy}
+        return self.obs, self.reward, self.done, info
+
+    def step_host(self, h_action: torch.Tensor, d_action: torch.Tensor, h_obs: Optional[torch.Tensor] = None,
+                  h_reward: Optional[torch.Tensor] = None, h_done: Optional[torch.Tensor] = None) -> None:
+        """End-to-end step on HOST buffers (``wg_step_host``): copies the pinned host
+        ``h_action`` [E, A] into the device staging tensor ``d_action``, launches the
+        step, and copies obs / reward / done back into the pinned host tensors, all
+        asynchronously on the current stream."""
+        for t, name in ((h_action, "h_action"), (h_obs, "h_obs"), (h_reward, "h_reward"), (h_done, "h_done")):
+            if t is not None and (t.device.type != "cpu" or not t.is_contiguous()):
+                raise ValueError(f"{name} must be a contiguous host tensor (pinned for async copies)")
+        if h_action.dtype != torch.float32 or h_action.dim() != 2 or h_action.shape[0] != self.num_envs:
+            raise ValueError(f"h_action must be float32 [{self.num_envs}, A]")
+        self._check_f32(d_action, h_action.shape, "d_action")
+        if h_obs is not None and (h_obs.dtype != torch.float32 or h_obs.numel() != self.obs.numel()):
+            raise ValueError("h_obs must be float32 with as many elements as obs")
+        if h_reward is not None and (h_reward.dtype != torch.float32 or h_reward.numel() != self.num_envs):
+            raise ValueError("h_reward must be float32 [E]")
+        if h_done is not None and (h_done.element_size() != 1 or h_done.numel() != self.num_envs):
+            raise ValueError("h_done must be a 1-byte dtype of length E")
+        b = self._buf
+        b.action, b.act_dim, b.noise = d_action.data_ptr(), int(d_action.shape[1]), None
+        self.params.step_index = self.step_count & 0xFFFFFFFF
+        with torch.cuda.device(self.device):
+            rc = self.lib.wg_step_host(C.byref(self.topo), C.byref(self.params), C.byref(b), self.num_envs,
+                                       h_action.data_ptr(), self._p(h_obs), self._p(h_reward), self._p(h_done),
+                                       self._stream())
+        _lib.check(rc, "wg_step_host")
+        self.step_count += 1
+
+    def get_action_space(self):
+        return {"shape": (self.M,), "type": "continuous", "low": -1.0, "high": 1.0}
+
+    def get_observation_space(self):
+        return {"shape": (self.obs_dim,), "type": "continuous", "low": -np.inf, "high": np.inf}
+
+    # ---- episode statistics (K3) ---------------------------------------------------
+    def episode_stats(self, all_reduce: bool = False, clear: bool = False) -> dict:
+        """Sum of finished-episode returns / squared returns / lengths / count over
+        this shard; with ``all_reduce`` the 8-double vector is summed across ranks
+        (NCCL) -- the only collective anywhere near the step path."""
+        if self.fin_stats is None:
+            raise RuntimeError("construct the env with track_stats=True")
+        with torch.cuda.device(self.device):
+            rc = self.lib.wg_stats_reduce(self.fin_stats.data_ptr(), self.num_envs, self._stats_out.data_ptr(), self._stream())
+        _lib.check(rc, "wg_stats_reduce")
+        out = self._stats_out
+        if all_reduce:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                out = out.clone()
+                dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        s = out.tolist()
+        if clear:
+            self.fin_stats.zero_()
+        n = s[3]
+        mean = s[0] / n if n else float("nan")
+        var = max(s[1] / n - mean * mean, 0.0) if n else float("nan")
+        return {"episodes": int(n), "return_mean": mean, "return_std": var ** 0.5 if n else float("nan"),
+                "length_mean": s[2] / n if n else float("nan"), "return_sum": s[0], "return_sqsum": s[1], "length_sum": s[2]}
+
+    # ---- checkpoint / state.pkl ------------------------------------------------------
+    def state_dict(self) -> dict:
+        d = {"pos": self.pos, "vel": self.vel, "mx": self.mx, "steps": self.steps, "obs": self.obs,
+             "step_count": self.step_count}
+        for k in ("old_a", "ep_ret", "fin_stats"):
+            if getattr(self, k) is not None:
+                d[k] = getattr(self, k)
+        return d
+
+    def load_state_dict(self, d: dict) -> None:
+        for k, v in d.items():
+            if k == "step_count":
+                self.step_count = int(v)
+            elif getattr(self, k, None) is not None:
+                getattr(self, k).copy_(v)
+
+    def save_state(self, path: str, env_index: int = 0) -> None:
+        """Write env ``env_index`` as a reference-compatible ``state.pkl``
+        (gym/engine.py:199-204): the reference's ``Point.backup`` can load it."""
+        from .engine import Point
+        from .state_io import save_points
+        pos = self.pos[:, env_index].reshape(self.N, 3).cpu().numpy()
+        vel = self.vel[:, env_index].reshape(self.N, 3).cpu().numpy()
+        old = self.old_a[:, env_index].reshape(self.N, 3).cpu().numpy() if self.old_a is not None else np.zeros((self.N, 3), np.float32)
+        saved, pts = list(Point.points), []
+        try:
+            for n, p in enumerate(self.creature.phys):
+                q = type(p).__new__(type(p))
+                q.__dict__.update(p.__dict__)
+                q.pos, q.v, q.old_a, q.a = pos[n].copy(), vel[n].copy(), old[n].copy(), np.zeros(3, np.float32)
+                pts.append(q)
+        finally:
+            Point.points = saved
+        save_points(path, pts, {})
+
+    def load_state(self, path: str, env_index: Optional[int] = None) -> None:
+        """Load point positions/velocities from a reference ``state.pkl`` into one env
+        (or broadcast to all envs when ``env_index`` is None)."""
+        from .state_io import load_points
+        pts, _ = load_points(path)
+        if len(pts) != self.N:
+            raise ValueError(f"snapshot has {len(pts)} points, this body has {self.N}")
+        pos = torch.tensor(np.stack([p.pos for p in pts]).reshape(-1), dtype=torch.float32, device=self.device)
+        vel = torch.tensor(np.stack([p.v for p in pts]).reshape(-1), dtype=torch.float32, device=self.device)
+        if env_index is None:
+            self.pos.copy_(pos[:, None].expand_as(self.pos))
+            self.vel.copy_(vel[:, None].expand_as(self.vel))
+        else:
+            self.pos[:, env_index] = pos
+            self.vel[:, env_index] = vel

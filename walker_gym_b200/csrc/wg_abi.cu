@@ -1,0 +1,140 @@
+// wg_abi.cu -- C ABI (include/walker_gym_b200.h): validation and kernel dispatch.
+// Built by plain nvcc for sm_100a only; no torch headers, no globals besides a
+// thread-local error string and the "force generic" test switch.
+#include <atomic>
+#include <cstdarg>
+
+#include "wg_launch.cuh"
+
+namespace wg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int> g_force_generic{0};
+
+int fail(int code, const char* fmt, const char* a) {
+    snprintf(g_err, sizeof(g_err), fmt, a);
+    return code;
+}
+
+template <class Topo>
+static bool topo_matches(const wg_topology* t) {
+    if (t->n_mass != Topo::N || t->n_spring != Topo::S || t->n_muscle != Topo::M) return false;
+    for (int s = 0; s < Topo::S; s++)
+        if (t->si[s] != Topo::si(s) || t->sj[s] != Topo::sj(s)) return false;
+    return true;
+}
+
+static int pick_variant(const wg_topology* t) {
+    if (g_force_generic.load()) return 0;
+    if (topo_matches<TopoBalance>(t)) return TopoBalance::kId;
+    if (topo_matches<TopoBox>(t)) return TopoBox::kId;
+    if (topo_matches<TopoQuad>(t)) return TopoQuad::kId;
+    if (topo_matches<TopoInsect>(t)) return TopoInsect::kId;
+    return 0;
+}
+
+static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E) {
+    if (!t || !p || !b) return fail(WG_ERR_BAD_ARG, "null argument%s");
+    if (t->n_mass < 1 || t->n_mass > WG_MAX_MASS) return fail(WG_ERR_BAD_ARG, "n_mass out of range [1, 32]%s");
+    if (t->n_spring < 0 || t->n_spring > WG_MAX_SPRING) return fail(WG_ERR_BAD_ARG, "n_spring out of range [0, 96]%s");
+    if (t->n_muscle < 0 || t->n_muscle > t->n_spring) return fail(WG_ERR_BAD_ARG, "n_muscle out of range%s");
+    for (int s = 0; s < t->n_spring; s++)
+        if (t->si[s] < 0 || t->si[s] >= t->n_mass || t->sj[s] < 0 || t->sj[s] >= t->n_mass || t->si[s] == t->sj[s])
+            return fail(WG_ERR_BAD_ARG, "spring endpoint out of range or degenerate%s");
+    if (E < 0 || E > ((int64_t)1 << 31) - 1) return fail(WG_ERR_BAD_ARG, "n_env out of range%s");
+    if (p->k_sub < 1) return fail(WG_ERR_BAD_ARG, "k_sub must be >= 1%s");
+    if (p->auto_reset < 0 || p->auto_reset > 2) return fail(WG_ERR_BAD_ARG, "auto_reset must be 0, 1 or 2%s");
+    if (!b->pos || !b->vel || !b->steps || (t->n_muscle > 0 && !b->mx))
+        return fail(WG_ERR_BAD_ARG, "pos/vel/mx/steps must be set%s");
+    if (b->obs_layout != 0 && b->obs_layout != 1) return fail(WG_ERR_BAD_ARG, "obs_layout must be 0 or 1%s");
+    if (b->action && b->act_dim < 0) return fail(WG_ERR_BAD_ARG, "act_dim < 0%s");
+    return WG_OK;
+}
+
+static bool aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
+
+// can EPT consecutive envs be moved as one vector for every buffer?
+static bool vec_ok(const wg_buffers* b, int64_t E, int ept) {
+    if (ept == 1) return true;
+    if (E % ept) return false;
+    const size_t a4 = 4 * ept;
+    const void* f[] = { b->pos, b->vel, b->old_a, b->mx, b->steps, b->reward, b->contact_pre, b->contact_post,
+                        b->energy, b->centroid, b->ep_ret };
+    for (const void* p : f) if (p && !aligned(p, a4)) return false;
+    if (b->done && !aligned(b->done, ept)) return false;
+    return true;
+}
+
+}  // namespace wg
+
+using namespace wg;
+
+extern "C" {
+
+int wg_abi_version(void) { return WG_ABI_VERSION; }
+const char* wg_last_error_string(void) { return g_err; }
+
+int wg_obs_dim(const wg_topology* topo, int in3d) {
+    if (!topo) return fail(WG_ERR_BAD_ARG, "null topology%s");
+    return 3 * (in3d ? 3 : 2) * topo->n_mass + topo->n_muscle;
+}
+
+int wg_kernel_variant(const wg_topology* topo) {
+    if (!topo) return fail(WG_ERR_BAD_ARG, "null topology%s");
+    return pick_variant(topo);
+}
+
+int wg_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
+
+int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf, int64_t n_env, void* cuda_stream) {
+    int rc = validate(topo, prm, buf, n_env);
+    if (rc != WG_OK) return rc;
+    if (n_env == 0) return WG_OK;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    // small bodies move two envs per thread as 8-byte vectors; the big ones are register-bound
+    const int ept = vec_ok(buf, n_env, 2) ? 2 : 1;
+    switch (pick_variant(topo)) {
+        case TopoBalance::kId: return launch_balance(topo, prm, buf, n_env, ept, s);
+        case TopoBox::kId:     return launch_box(topo, prm, buf, n_env, ept, s);
+        case TopoQuad::kId:    return launch_quad(topo, prm, buf, n_env, 1, s);
+        case TopoInsect::kId:  return launch_insect(topo, prm, buf, n_env, 1, s);
+        default:               return launch_generic_step(topo, prm, buf, n_env, s);
+    }
+}
+
+int wg_reset(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf, int64_t n_env, int mode,
+             const uint8_t* mask, void* cuda_stream) {
+    int rc = validate(topo, prm, buf, n_env);
+    if (rc != WG_OK) return rc;
+    if (mode != 1 && mode != 2) return fail(WG_ERR_BAD_ARG, "reset mode must be 1 (jitter) or 2 (template)%s");
+    if (n_env == 0) return WG_OK;
+    return launch_reset(topo, prm, buf, n_env, mode, mask, (cudaStream_t)cuda_stream);
+}
+
+int wg_stats_reduce(const float* fin_stats, int64_t n_env, double* out8, void* cuda_stream) {
+    if (!fin_stats || !out8 || n_env < 0) return fail(WG_ERR_BAD_ARG, "bad argument to wg_stats_reduce%s");
+    return launch_stats(fin_stats, n_env, out8, (cudaStream_t)cuda_stream);
+}
+
+int wg_step_host(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf, int64_t n_env,
+                 const float* h_action, float* h_obs, float* h_reward, uint8_t* h_done, void* cuda_stream) {
+    int rc = validate(topo, prm, buf, n_env);
+    if (rc != WG_OK) return rc;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    cudaError_t e = cudaSuccess;
+    if (h_action) {
+        if (!buf->action) return fail(WG_ERR_BAD_ARG, "wg_step_host: device action buffer missing%s");
+        e = cudaMemcpyAsync((void*)buf->action, h_action, sizeof(float) * n_env * buf->act_dim, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return fail(WG_ERR_CUDA, "H2D action: %s", cudaGetErrorString(e));
+    }
+    rc = wg_step(topo, prm, buf, n_env, cuda_stream);
+    if (rc != WG_OK) return rc;
+    const int D = wg_obs_dim(topo, prm->in3d);
+    if (h_obs && buf->obs) e = cudaMemcpyAsync(h_obs, buf->obs, sizeof(float) * n_env * D, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && h_reward && buf->reward) e = cudaMemcpyAsync(h_reward, buf->reward, sizeof(float) * n_env, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && h_done && buf->done) e = cudaMemcpyAsync(h_done, buf->done, n_env, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "D2H results: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
+}  // extern "C"

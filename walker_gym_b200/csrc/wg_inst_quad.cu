@@ -1,0 +1,8 @@
+// wg_inst_quad.cu -- instantiates the register-resident step kernel for TopoQuad.
+#include "wg_launch.cuh"
+namespace wg {
+int launch_quad(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int ept, cudaStream_t s) {
+    (void)ept;
+    return launch_static_flags<TopoQuad, 1>(t, p, b, E, s);
+}
+}  // namespace wg

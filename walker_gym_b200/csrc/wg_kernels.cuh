@@ -1,0 +1,438 @@
+// wg_kernels.cuh -- the fused step kernel (K1), the reset kernel (K2) and the
+// episode-statistics reduction (K3).
+//
+// K1 performs, in ONE launch and with ONE read and ONE write of the state per
+// env step: Creature.act, k_sub x (_run_physics + Point.run1), steps += 1,
+// reward, done, info, episode statistics, auto-reset and the observation.
+// HBM-bound by design (sparse per-env stencil, no tensor cores): all global
+// accesses are coalesced SoA vectors of EPT consecutive envs per thread; the
+// row-major [E][D] observation is transposed through a padded shared-memory
+// tile and written back as fully coalesced rows.
+#pragma once
+#include "wg_physics.cuh"
+
+namespace wg {
+
+constexpr int kBlock = 128;
+
+template <int MAXN, int MAXS>
+struct StepArgs {
+    BodyVals<MAXN, MAXS> bv;
+    EnvConst ec;
+    float* pos; float* vel; float* old_a; float* mx; int32_t* steps;
+    const float* action; float* obs; float* reward; uint8_t* done;
+    uint32_t* contact_pre; uint32_t* contact_post; float* energy; float* centroid;
+    float* ep_ret; float* fin_stats; const float* noise;
+    int64_t E;
+    int32_t act_dim;
+};
+
+// ---- vector access of EPT consecutive envs --------------------------------------
+template <int EPT> struct Vec;
+template <> struct Vec<1> { using F = float;  using I = int32_t; using U = uint32_t; using B = uint8_t; };
+template <> struct Vec<2> { using F = float2; using I = int2;    using U = uint2;    using B = uchar2; };
+template <> struct Vec<4> { using F = float4; using I = int4;    using U = uint4;    using B = uchar4; };
+
+template <int EPT, class T, class V>
+__device__ __forceinline__ void ld_vec(const T* p, T (&out)[EPT]) {
+    V v = *reinterpret_cast<const V*>(p);
+    const T* s = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int j = 0; j < EPT; j++) out[j] = s[j];
+}
+template <int EPT, class T, class V>
+__device__ __forceinline__ void st_vec(T* p, const T (&in)[EPT]) {
+    V v;
+    T* s = reinterpret_cast<T*>(&v);
+#pragma unroll
+    for (int j = 0; j < EPT; j++) s[j] = in[j];
+    *reinterpret_cast<V*>(p) = v;
+}
+#define WG_LDF(ptr, arr) ld_vec<EPT, float, typename Vec<EPT>::F>(ptr, arr)
+#define WG_STF(ptr, arr) st_vec<EPT, float, typename Vec<EPT>::F>(ptr, arr)
+
+// ---- per-env epilogue: reward, done, info, stats, auto-reset (shared by both kernels) ----
+struct EpiOut { float reward; uint32_t cpost; int done; float energy; float cen[3]; };
+
+template <bool IN3D, class Topo, class BV, class Store, class YS, class SP>
+__device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const EnvConst& ec, Store& st,
+                                         int32_t steps_now, bool want_energy, bool want_centroid,
+                                         YS ys, SP sp, EpiOut& o) {
+    const int N = topo.n();
+    uint32_t cpost = 0; int ncon = 0;
+#pragma unroll
+    for (int n = 0; n < N; n++) {                               // _get_reward (optimized_env.py:189-205)
+        ys(n) = st.pos(n, 1);
+        sp(n) = np_norm3(st.vel(n, 0), st.vel(n, 1), st.vel(n, 2));
+        if (st.pos(n, 1) - ec.ground < 0.0f) { cpost |= 1u << n; ncon++; }
+    }
+    const float fn = (float)N;
+    const float cy = div_rn(np_pairwise_sum(N, [&](int i) { return ys(i); }), fn);
+    const float avgv = div_rn(np_pairwise_sum(N, [&](int i) { return sp(i); }), fn);
+    const float vpen = (-avgv) * 0.1f;
+    const float cpen = -0.5f * (float)ncon;
+    o.reward = (cy + vpen) + cpen;
+    o.cpost = cpost;
+    int dn = 0;                                                  // _is_done (:207-230)
+    if (steps_now >= ec.max_steps) dn = 1;
+    else if (cy < ec.fall_thresh) dn = 1;
+    else {
+        bool all_stopped = true;
+#pragma unroll
+        for (int n = 0; n < N; n++) all_stopped = all_stopped && (sp(n) < 0.1f);
+        if (all_stopped && steps_now > 100) dn = 1;
+    }
+    o.done = dn;
+    if (want_energy) {                                           // _calculate_energy (:240-248)
+        const float ke = np_pairwise_sum(N, [&](int i) { return bv.mass_f[i] * (sp(i) * sp(i)); });
+        const float pe = np_pairwise_sum(N, [&](int i) { return bv.mg_f[i] * (st.pos(i, 1) - ec.ground); });
+        o.energy = 0.5f * ke + pe;
+    }
+    if (want_centroid) {                                         // np.mean(axis=0): sequential
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float acc = st.pos(0, c);
+#pragma unroll
+            for (int n = 1; n < N; n++) acc = acc + st.pos(n, c);
+            o.cen[c] = div_rn(acc, fn);
+        }
+    }
+}
+
+// =================================================================================
+// K1, register-resident specialisation: Topo is compile-time, EPT envs per thread.
+// =================================================================================
+template <class Topo, bool IN3D, bool ROWMAJOR, int EPT>
+__global__ void __launch_bounds__(kBlock)
+step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
+    constexpr int N = Topo::N, M = Topo::M;
+    constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;
+    constexpr int STRIDE = D | 1;                 // odd row pitch: conflict-free tile writes
+    constexpr int TILE_ENVS = kBlock * EPT;
+    extern __shared__ float tile[];
+    const Topo topo;
+    const int tid = threadIdx.x;
+    const int64_t E = A.E;
+    const int64_t e0 = (int64_t)blockIdx.x * TILE_ENVS;
+    const int64_t e = e0 + (int64_t)tid * EPT;    // first env of this thread (E % EPT == 0 is guaranteed)
+    const bool valid = e < E;
+
+    if (valid) {
+        RegStore<N, M> st[EPT];
+        int32_t stp[EPT];
+        // ---- single HBM read of the state: coalesced vectors of EPT envs ----
+#pragma unroll
+        for (int n = 0; n < N; n++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float t[EPT];
+                WG_LDF(A.pos + (int64_t)(n * 3 + c) * E + e, t);
+#pragma unroll
+                for (int j = 0; j < EPT; j++) st[j].pos(n, c) = t[j];
+                WG_LDF(A.vel + (int64_t)(n * 3 + c) * E + e, t);
+#pragma unroll
+                for (int j = 0; j < EPT; j++) st[j].vel(n, c) = t[j];
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            float t[EPT];
+            WG_LDF(A.mx + (int64_t)m * E + e, t);
+#pragma unroll
+            for (int j = 0; j < EPT; j++) st[j].mx(m) = t[j];
+        }
+        ld_vec<EPT, int32_t, typename Vec<EPT>::I>(A.steps + e, stp);
+        float epr[EPT];
+        if (A.ep_ret) WG_LDF(A.ep_ret + e, epr);
+
+        float rew[EPT]; uint8_t dnb[EPT]; uint32_t cpre[EPT], cpost[EPT];
+        float eng[EPT], cen[3][EPT];
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+            // ---- Creature.act (optimized_walker.py:164-167; Muscle.act/regulation :27-35) ----
+            const int na = A.act_dim < M ? A.act_dim : M;
+#pragma unroll
+            for (int m = 0; m < M; m++) {
+                if (m < na) {
+                    float x = st[j].mx(m) + A.action[(e + j) * A.act_dim + m];
+                    if (A.bv.mlo[m] > x) x = A.bv.mlo[m];       // python max(x, lo)
+                    if (A.bv.mhi[m] < x) x = A.bv.mhi[m];       // python min(x, hi)
+                    st[j].mx(m) = x;
+                }
+            }
+            // ---- k_sub x (_run_physics + run1) ----
+            uint32_t cp = 0;
+            for (int k = 0; k < A.ec.k_sub; k++) cp = run_physics<IN3D>(topo, A.bv, A.ec, st[j]);
+            cpre[j] = cp;
+            // ---- reward / done / info ----
+            const int32_t sn = stp[j] + 1;
+            float ysr[N], spr[N];
+            EpiOut o;
+            epilogue<IN3D>(topo, A.bv, A.ec, st[j], sn, A.energy != nullptr, A.centroid != nullptr,
+                           [&](int i) -> float& { return ysr[i]; }, [&](int i) -> float& { return spr[i]; }, o);
+            rew[j] = o.reward; dnb[j] = (uint8_t)o.done; cpost[j] = o.cpost;
+            eng[j] = o.energy; cen[0][j] = o.cen[0]; cen[1][j] = o.cen[1]; cen[2][j] = o.cen[2];
+            stp[j] = sn;
+            if (A.ep_ret) {
+                const float r = epr[j] + o.reward;
+                if (o.done && A.fin_stats) {
+                    A.fin_stats[0 * E + e + j] += r;
+                    A.fin_stats[1 * E + e + j] += r * r;
+                    A.fin_stats[2 * E + e + j] += (float)sn;
+                    A.fin_stats[3 * E + e + j] += 1.0f;
+                }
+                epr[j] = (o.done && A.ec.auto_reset) ? 0.0f : r;
+            }
+            if (o.done && A.ec.auto_reset) {
+                apply_reset<IN3D>(topo, A.bv, A.ec, st[j], A.ec.auto_reset, A.noise, E, e + j);
+                stp[j] = 0;
+            }
+            // ---- observation of the (possibly reset) state ----
+            if (A.obs) {
+                if (ROWMAJOR) {
+                    float* row = tile + (tid * EPT + j) * STRIDE;
+                    get_obs<IN3D>(topo, st[j], [&](int k, float v) { row[k] = v; });
+                } else {
+                    get_obs<IN3D>(topo, st[j], [&](int k, float v) { A.obs[(int64_t)k * E + e + j] = v; });
+                }
+            }
+        }
+        // ---- single HBM write of the state ----
+#pragma unroll
+        for (int n = 0; n < N; n++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float t[EPT];
+#pragma unroll
+                for (int j = 0; j < EPT; j++) t[j] = st[j].pos(n, c);
+                WG_STF(A.pos + (int64_t)(n * 3 + c) * E + e, t);
+#pragma unroll
+                for (int j = 0; j < EPT; j++) t[j] = st[j].vel(n, c);
+                WG_STF(A.vel + (int64_t)(n * 3 + c) * E + e, t);
+                if (A.old_a) {
+#pragma unroll
+                    for (int j = 0; j < EPT; j++) t[j] = st[j].acc(n, c);
+                    WG_STF(A.old_a + (int64_t)(n * 3 + c) * E + e, t);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            float t[EPT];
+#pragma unroll
+            for (int j = 0; j < EPT; j++) t[j] = st[j].mx(m);
+            WG_STF(A.mx + (int64_t)m * E + e, t);
+        }
+        st_vec<EPT, int32_t, typename Vec<EPT>::I>(A.steps + e, stp);
+        if (A.ep_ret) WG_STF(A.ep_ret + e, epr);
+        if (A.reward) WG_STF(A.reward + e, rew);
+        if (A.done) st_vec<EPT, uint8_t, typename Vec<EPT>::B>(A.done + e, dnb);
+        if (A.contact_pre) st_vec<EPT, uint32_t, typename Vec<EPT>::U>(A.contact_pre + e, cpre);
+        if (A.contact_post) st_vec<EPT, uint32_t, typename Vec<EPT>::U>(A.contact_post + e, cpost);
+        if (A.energy) WG_STF(A.energy + e, eng);
+        if (A.centroid) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) WG_STF(A.centroid + (int64_t)c * E + e, cen[c]);
+        }
+    }
+    // ---- row-major observation: the block's rows are one contiguous span of global memory ----
+    if (ROWMAJOR && A.obs) {
+        __syncthreads();
+        const int64_t rem = E - e0;
+        const int nvalid = rem < TILE_ENVS ? (int)rem : TILE_ENVS;
+        const int total = nvalid * D;
+        float* out = A.obs + e0 * D;
+        for (int idx = tid; idx < total; idx += kBlock) {
+            const int el = idx / D, k = idx - el * D;
+            out[idx] = tile[el * STRIDE + k];
+        }
+    }
+}
+
+// =================================================================================
+// K1, generic: run-time topology, per-env state in a shared-memory tile that stays
+// resident across the k_sub substeps; one thread per env.
+// =================================================================================
+template <bool IN3D, bool ROWMAJOR>
+__global__ void __launch_bounds__(kBlock)
+step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A) {
+    extern __shared__ float smem[];
+    const int N = A.bv.n_mass, S = A.bv.n_spring, M = A.bv.n_muscle;
+    constexpr int d = IN3D ? 3 : 2;
+    const int D = 3 * d * N + M;
+    constexpr int PITCH = kBlock + 1;             // odd pitch: row-wise and column-wise access conflict-free
+    RuntimeTopo topo{ N, S, M, A.bv.si, A.bv.sj };
+    const int tid = threadIdx.x;
+    const int64_t E = A.E;
+    const int64_t e0 = (int64_t)blockIdx.x * kBlock;
+    const int64_t e = e0 + tid;
+    const bool valid = e < E;
+    SmemStore st{ smem + tid, PITCH, N };
+    // scratch rows: [0,N) ys, [N,2N) speeds, [2N,2N+3) centroid used by the obs copy-out
+    if (valid) {
+        for (int r = 0; r < 3 * N; r++) {
+            st.base[r * PITCH] = A.pos[(int64_t)r * E + e];
+            st.base[(3 * N + r) * PITCH] = A.vel[(int64_t)r * E + e];
+        }
+        for (int m = 0; m < M; m++) st.mx(m) = A.mx[(int64_t)m * E + e];
+        const int na = A.act_dim < M ? A.act_dim : M;
+        for (int m = 0; m < na; m++) {
+            float x = st.mx(m) + A.action[e * A.act_dim + m];
+            if (A.bv.mlo[m] > x) x = A.bv.mlo[m];
+            if (A.bv.mhi[m] < x) x = A.bv.mhi[m];
+            st.mx(m) = x;
+        }
+        uint32_t cp = 0;
+        for (int k = 0; k < A.ec.k_sub; k++) cp = run_physics<IN3D>(topo, A.bv, A.ec, st);
+        int32_t sn = A.steps[e] + 1;
+        EpiOut o;
+        epilogue<IN3D>(topo, A.bv, A.ec, st, sn, A.energy != nullptr, A.centroid != nullptr,
+                       [&](int i) -> float& { return st.scratch(M, i); },
+                       [&](int i) -> float& { return st.scratch(M, N + i); }, o);
+        if (A.reward) A.reward[e] = o.reward;
+        if (A.done) A.done[e] = (uint8_t)o.done;
+        if (A.contact_pre) A.contact_pre[e] = cp;
+        if (A.contact_post) A.contact_post[e] = o.cpost;
+        if (A.energy) A.energy[e] = o.energy;
+        if (A.centroid) { A.centroid[e] = o.cen[0]; A.centroid[E + e] = o.cen[1]; A.centroid[2 * E + e] = o.cen[2]; }
+        if (A.ep_ret) {
+            const float r = A.ep_ret[e] + o.reward;
+            if (o.done && A.fin_stats) {
+                A.fin_stats[0 * E + e] += r;
+                A.fin_stats[1 * E + e] += r * r;
+                A.fin_stats[2 * E + e] += (float)sn;
+                A.fin_stats[3 * E + e] += 1.0f;
+            }
+            A.ep_ret[e] = (o.done && A.ec.auto_reset) ? 0.0f : r;
+        }
+        if (o.done && A.ec.auto_reset) {
+            apply_reset<IN3D>(topo, A.bv, A.ec, st, A.ec.auto_reset, A.noise, E, e);
+            sn = 0;
+        }
+        A.steps[e] = sn;
+        for (int r = 0; r < 3 * N; r++) {
+            A.pos[(int64_t)r * E + e] = st.base[r * PITCH];
+            A.vel[(int64_t)r * E + e] = st.base[(3 * N + r) * PITCH];
+            if (A.old_a) A.old_a[(int64_t)r * E + e] = st.base[(6 * N + r) * PITCH];
+        }
+        for (int m = 0; m < M; m++) A.mx[(int64_t)m * E + e] = st.mx(m);
+        if (A.obs) {
+            if (ROWMAJOR) {
+                // centroid of getstat (sequential sum, then / N) for the cooperative copy-out below
+                float mid[3] = { 0.0f, 0.0f, 0.0f };
+                for (int n = 0; n < N; n++) { mid[0] = mid[0] + st.pos(n, 0); mid[1] = mid[1] + st.pos(n, 1); mid[2] = mid[2] + st.pos(n, 2); }
+                const float fn = (float)N;
+                st.scratch(M, 2 * N + 0) = div_rn(mid[0], fn);
+                st.scratch(M, 2 * N + 1) = div_rn(mid[1], fn);
+                st.scratch(M, 2 * N + 2) = div_rn(mid[2], fn);
+            } else {
+                get_obs<IN3D>(topo, st, [&](int k, float v) { A.obs[(int64_t)k * E + e] = v; });
+            }
+        }
+    }
+    if (ROWMAJOR && A.obs) {
+        // Each warp streams whole observation rows straight out of the state tile:
+        // lanes run over the D entries of one env, so global stores are coalesced
+        // and the (row, env) shared-memory reads hit distinct banks (odd pitch).
+        __syncthreads();
+        const int64_t rem = E - e0;
+        const int nvalid = rem < kBlock ? (int)rem : kBlock;
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int el = warp; el < nvalid; el += kBlock / 32) {
+            const float* col = smem + el;
+            float* out = A.obs + (e0 + el) * D;
+            for (int k = lane; k < D; k += 32) {
+                float v;
+                if (k < 3 * d * N) {
+                    const int n = k / (3 * d), r = k - n * 3 * d, part = r / d, c = r - part * d;
+                    v = col[(part * 3 * N + n * 3 + c) * PITCH];
+                    if (part == 0) v = v - col[(9 * N + M + 2 * N + c) * PITCH];
+                } else {
+                    v = col[(9 * N + (k - 3 * d * N)) * PITCH];
+                }
+                out[k] = v;
+            }
+        }
+    }
+}
+
+// =================================================================================
+// K2: PhysicsEnv.reset for masked envs.  Not on the hot path: generic, local-memory state.
+// =================================================================================
+struct LocalStore {
+    float p_[kMaxMass][3], v_[kMaxMass][3], a_[kMaxMass][3], mx_[kMaxSpring];
+    __device__ __forceinline__ float& pos(int n, int c) { return p_[n][c]; }
+    __device__ __forceinline__ float& vel(int n, int c) { return v_[n][c]; }
+    __device__ __forceinline__ float& acc(int n, int c) { return a_[n][c]; }
+    __device__ __forceinline__ float& mx(int m) { return mx_[m]; }
+};
+
+template <bool IN3D>
+__global__ void __launch_bounds__(kBlock)
+reset_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A, int mode, const uint8_t* mask, int obs_layout) {
+    const int N = A.bv.n_mass, S = A.bv.n_spring, M = A.bv.n_muscle;
+    constexpr int d = IN3D ? 3 : 2;
+    const int D = 3 * d * N + M;
+    const int64_t E = A.E;
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= E) return;
+    if (mask && !mask[e]) return;
+    RuntimeTopo topo{ N, S, M, A.bv.si, A.bv.sj };
+    LocalStore st;
+    for (int r = 0; r < 3 * N; r++) {
+        st.p_[r / 3][r % 3] = A.pos[(int64_t)r * E + e];
+        st.v_[r / 3][r % 3] = A.vel[(int64_t)r * E + e];
+        st.a_[r / 3][r % 3] = A.old_a ? A.old_a[(int64_t)r * E + e] : 0.0f;
+    }
+    for (int m = 0; m < M; m++) st.mx_[m] = A.mx[(int64_t)m * E + e];
+    apply_reset<IN3D>(topo, A.bv, A.ec, st, mode, A.noise, E, e);
+    A.steps[e] = 0;
+    if (A.ep_ret) A.ep_ret[e] = 0.0f;
+    for (int r = 0; r < 3 * N; r++) {
+        A.pos[(int64_t)r * E + e] = st.p_[r / 3][r % 3];
+        A.vel[(int64_t)r * E + e] = st.v_[r / 3][r % 3];
+        if (A.old_a) A.old_a[(int64_t)r * E + e] = st.a_[r / 3][r % 3];
+    }
+    for (int m = 0; m < M; m++) A.mx[(int64_t)m * E + e] = st.mx_[m];
+    if (A.obs) {
+        // jitter-only reset without an old_a buffer: the acceleration slots of the
+        // observation still hold Point.old_a of the last step -- leave them alone.
+        const bool keep_acc = (mode == 1) && (A.old_a == nullptr);
+        get_obs<IN3D>(topo, st, [&](int k, float v) {
+            if (keep_acc && k < 3 * d * N && (k % (3 * d)) >= 2 * d) return;
+            if (obs_layout == 0) A.obs[e * D + k] = v; else A.obs[(int64_t)k * E + e] = v;
+        });
+    }
+}
+
+// =================================================================================
+// K3: deterministic single-block reduction of the finished-episode accumulators.
+// =================================================================================
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) stats_reduce_kernel(const float* __restrict__ fin, int64_t E, double* out8) {
+    __shared__ double part[4][32];
+    double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+    for (int64_t i = threadIdx.x; i < E; i += blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[q] += (double)fin[(int64_t)q * E + i];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_down_sync(0xffffffffu, acc[q], off);
+        if (lane == 0) part[q][warp] = acc[q];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double v = lane < (int)(blockDim.x >> 5) ? part[q][lane] : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0) { out8[q] = v; out8[4 + q] = 0.0; }
+        }
+    }
+}
+
+}  // namespace wg

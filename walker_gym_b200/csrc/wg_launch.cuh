@@ -1,0 +1,97 @@
+// wg_launch.cuh -- host-side launch helpers shared by the per-morphology translation units.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include "../../include/walker_gym_b200.h"
+#include "wg_kernels.cuh"
+
+namespace wg {
+
+int fail(int code, const char* fmt, const char* a = "");
+
+// ---- register-resident specialisations --------------------------------------------
+// endpoints listed as (p1, p2) pairs, muscles first then skeletons (Creature.run order)
+// Balance-v0: gym/optimized_walker.py:176-199 (also walker.py balance/balance2/balance3)
+WG_STATIC_TOPO(TopoBalance, 1, 4, 5, 2, 0,2, 1,2, 0,1, 0,3, 1,3)
+// Box-v0: gym/optimized_walker.py:201-224 (== walker.py box2)
+WG_STATIC_TOPO(TopoBox, 2, 4, 5, 4, 0,1, 0,2, 3,1, 3,2, 1,2)
+// 4x Balance in one env (N=16, S=20, M=8): the enlarged morphology of BASELINE config 4.
+// muscles of unit u: (4u+0,4u+2),(4u+1,4u+2); skeletons: (4u+0,4u+1),(4u+0,4u+3),(4u+1,4u+3)
+WG_STATIC_TOPO(TopoQuad, 3, 16, 20, 8,
+               0,2, 1,2, 4,6, 5,6, 8,10, 9,10, 12,14, 13,14,
+               0,1, 0,3, 1,3, 4,5, 4,7, 5,7, 8,9, 8,11, 9,11, 12,13, 12,15, 13,15)
+// walker.py insect (:255-293): N=13, 8 muscles, 15 skeletons
+WG_STATIC_TOPO(TopoInsect, 4, 13, 23, 8,
+               9,4, 9,5, 10,5, 10,6, 11,6, 11,7, 12,7, 12,8,
+               0,1, 0,4, 0,5, 1,2, 1,5, 1,6, 2,3, 2,6, 2,7, 3,7, 3,8, 4,5, 5,6, 6,7, 7,8)
+
+// one entry point per translation unit (ept = envs per thread the caller verified as legal)
+int launch_balance(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
+int launch_box(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
+int launch_quad(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
+int launch_insect(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
+int launch_generic_step(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
+int launch_reset(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int mode, const uint8_t* mask, cudaStream_t);
+int launch_stats(const float* fin_stats, int64_t E, double* out8, cudaStream_t);
+
+template <int MAXN, int MAXS>
+inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E) {
+    memset(&A, 0, sizeof(A));
+    auto& bv = A.bv;
+    bv.n_mass = t->n_mass; bv.n_spring = t->n_spring; bv.n_muscle = t->n_muscle;
+    for (int n = 0; n < t->n_mass; n++) {
+        bv.mass_d[n] = t->mass[n];
+        bv.mass_f[n] = (float)t->mass[n];
+        bv.gm[n] = (-p->g) / t->mass[n];                  // np.asarray([0,-g,0]) / m  (float64)
+        bv.mg_f[n] = (float)(t->mass[n] * p->g);          // python m*g, then float32 at the multiply
+        if (t->fixed[n]) bv.fixed_mask |= 1u << n;
+        if (t->mass[n] == 1.0) bv.unit_mask |= 1u << n;
+        for (int c = 0; c < 3; c++) bv.tmpl[n * 3 + c] = t->tmpl_pos[n * 3 + c];
+    }
+    for (int s = 0; s < t->n_spring; s++) {
+        bv.si[s] = t->si[s]; bv.sj[s] = t->sj[s];
+        bv.sk[s] = t->sk[s]; bv.sdamp[s] = t->sdamp[s]; bv.srest[s] = t->srest[s];
+        bv.mlo[s] = t->mlo[s]; bv.mhi[s] = t->mhi[s];
+    }
+    auto& ec = A.ec;
+    ec.ndampk = -p->dampk;
+    ec.dampk_is_zero = (p->dampk == 0.0f);
+    ec.ground = p->ground; ec.fall_thresh = p->fall_thresh;
+    ec.nground_k = -p->ground_k; ec.nground_damp = -p->ground_damp; ec.friction = p->friction;
+    ec.dt = p->dt; ec.sigma = p->sigma;
+    ec.max_steps = p->max_steps; ec.k_sub = p->k_sub; ec.auto_reset = p->auto_reset;
+    ec.seed_lo = p->seed_lo; ec.seed_hi = p->seed_hi; ec.step_index = p->step_index; ec.env_offset = p->env_offset;
+    A.pos = b->pos; A.vel = b->vel; A.old_a = b->old_a; A.mx = b->mx; A.steps = b->steps;
+    A.action = b->action; A.obs = b->obs; A.reward = b->reward; A.done = b->done;
+    A.contact_pre = b->contact_pre; A.contact_post = b->contact_post; A.energy = b->energy; A.centroid = b->centroid;
+    A.ep_ret = b->ep_ret; A.fin_stats = b->fin_stats; A.noise = b->noise;
+    A.E = E; A.act_dim = b->action ? b->act_dim : 0;
+}
+
+template <class Topo, bool IN3D, bool ROWMAJOR, int EPT>
+inline int launch_static(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
+    StepArgs<Topo::N, Topo::S> A;
+    fill_args(A, t, p, b, E);
+    constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
+    const size_t smem = (ROWMAJOR && b->obs) ? sizeof(float) * kBlock * EPT * (D | 1) : 0;
+    auto kern = step_static_kernel<Topo, IN3D, ROWMAJOR, EPT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    const int64_t tile = (int64_t)kBlock * EPT;
+    const unsigned grid = (unsigned)((E + tile - 1) / tile);
+    kern<<<grid, kBlock, smem, s>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
+template <class Topo, int EPT>
+inline int launch_static_flags(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
+    const bool rm = b->obs_layout == 0;
+    if (p->in3d) return rm ? launch_static<Topo, true, true, EPT>(t, p, b, E, s) : launch_static<Topo, true, false, EPT>(t, p, b, E, s);
+    return rm ? launch_static<Topo, false, true, EPT>(t, p, b, E, s) : launch_static<Topo, false, false, EPT>(t, p, b, E, s);
+}
+
+}  // namespace wg

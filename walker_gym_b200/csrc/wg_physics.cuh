@@ -1,0 +1,261 @@
+// wg_physics.cuh -- the per-env physics of walker-gym's PhysicsEnv.step, written
+// once as templates over
+//   Topo  : the spring/muscle topology (compile-time tables for the register-
+//           resident specialisations, run-time tables for the generic kernel),
+//   Store : where the per-env state lives (registers or a shared-memory tile).
+// One thread owns one env; springs are applied strictly in the reference's list
+// order with its four separate accumulations per endpoint, so the float32
+// result is bit-identical to the reference (gym/optimized_walker.py:45-127,
+// gym/optimized_env.py:140-230, gym/optimized_engine.py:104-106,258-272).
+#pragma once
+#include "wg_math.cuh"
+
+namespace wg {
+
+constexpr int kMaxMass = 32;
+constexpr int kMaxSpring = 96;
+
+// Per-morphology scalars, passed by value in the kernel parameters (constant bank).
+template <int MAXN, int MAXS>
+struct BodyVals {
+    double gm[MAXN];        // (-g) / m  in float64: gravity "force" per unit mass (optimized_env.py:148)
+    double mass_d[MAXN];    // Point.m
+    float mass_f[MAXN];     // float32(m): divisor of float32 forces
+    float mg_f[MAXN];       // float32(m * g): potential-energy weight (:245)
+    float tmpl[MAXN * 3];   // creation-time positions
+    float sk[MAXS], sdamp[MAXS], srest[MAXS];
+    float mlo[MAXS], mhi[MAXS];
+    uint32_t fixed_mask;    // DingPoint bits
+    uint32_t unit_mask;     // bit n: m == 1 (x / 1 is exact, division skipped)
+    int32_t si[MAXS], sj[MAXS];   // only read by the run-time topology
+    int32_t n_mass, n_spring, n_muscle;
+};
+
+struct EnvConst {
+    float ndampk;           // -dampk
+    float ground, fall_thresh;
+    float nground_k, nground_damp, friction;
+    float dt, sigma;
+    int32_t max_steps, k_sub, auto_reset;
+    uint32_t seed_lo, seed_hi, step_index, env_offset;
+    int32_t dampk_is_zero;
+};
+
+// ---- state stores -------------------------------------------------------------
+template <int N, int M>
+struct RegStore {
+    float p_[N][3], v_[N][3], a_[N][3];
+    float mx_[M > 0 ? M : 1];
+    __device__ __forceinline__ float& pos(int n, int c) { return p_[n][c]; }
+    __device__ __forceinline__ float& vel(int n, int c) { return v_[n][c]; }
+    __device__ __forceinline__ float& acc(int n, int c) { return a_[n][c]; }
+    __device__ __forceinline__ float& mx(int m) { return mx_[m]; }
+};
+// shared-memory tile: element (row, thread) at base[row * stride + tid], conflict-free per warp
+struct SmemStore {
+    float* base; int stride; int N;
+    __device__ __forceinline__ float& pos(int n, int c) { return base[(n * 3 + c) * stride]; }
+    __device__ __forceinline__ float& vel(int n, int c) { return base[(3 * N + n * 3 + c) * stride]; }
+    __device__ __forceinline__ float& acc(int n, int c) { return base[(6 * N + n * 3 + c) * stride]; }
+    __device__ __forceinline__ float& mx(int m) { return base[(9 * N + m) * stride]; }
+    // scratch rows after the muscles: 2*N floats (ys / speeds)
+    __device__ __forceinline__ float& scratch(int M, int i) { return base[(9 * N + M + i) * stride]; }
+};
+
+// ---- topologies ---------------------------------------------------------------
+struct RuntimeTopo {
+    static constexpr bool kStatic = false;
+    static constexpr int kId = 0;
+    int N_, S_, M_;
+    const int32_t* si_; const int32_t* sj_;
+    __device__ __forceinline__ int n() const { return N_; }
+    __device__ __forceinline__ int s() const { return S_; }
+    __device__ __forceinline__ int m() const { return M_; }
+    __device__ __forceinline__ int si(int k) const { return si_[k]; }
+    __device__ __forceinline__ int sj(int k) const { return sj_[k]; }
+};
+
+#define WG_STATIC_TOPO(NAME, ID, NN, SS, MM, ...)                                               \
+    struct NAME {                                                                               \
+        static constexpr bool kStatic = true;                                                   \
+        static constexpr int kId = ID, N = NN, S = SS, M = MM;                                  \
+        __host__ __device__ static constexpr int n() { return NN; }                             \
+        __host__ __device__ static constexpr int s() { return SS; }                             \
+        __host__ __device__ static constexpr int m() { return MM; }                             \
+        __host__ __device__ static constexpr int ep(int k) {                                    \
+            constexpr int t[2 * SS] = { __VA_ARGS__ };                                          \
+            return t[k];                                                                        \
+        }                                                                                       \
+        __host__ __device__ static constexpr int si(int k) { return ep(2 * k); }                \
+        __host__ __device__ static constexpr int sj(int k) { return ep(2 * k + 1); }            \
+    };
+
+// ---- physics ------------------------------------------------------------------
+
+// a += f / m   (Point.forced, float32 ndarray force)
+template <class BV>
+__device__ __forceinline__ float forced_f32(float a, float f, const BV& bv, int n) {
+    float q = ((bv.unit_mask >> n) & 1u) ? f : div_rn(f, bv.mass_f[n]);
+    return a + q;
+}
+
+// Muscle.run / Skeleton.run (optimized_walker.py:45-67 == :84-106)
+template <class Topo, class BV, class Store>
+__device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store& st, int sp, float x) {
+    const int i = topo.si(sp), j = topo.sj(sp);
+    const float pix = st.pos(i, 0), piy = st.pos(i, 1), piz = st.pos(i, 2);
+    const float pjx = st.pos(j, 0), pjy = st.pos(j, 1), pjz = st.pos(j, 2);
+    const float L = np_norm3(pix - pjx, piy - pjy, piz - pjz);            // distant(p1, p2)
+    const float dx = L - x;
+    const float fs = (-dx) * bv.sk[sp];                                   // -dx * k (sign as written)
+    float d0 = pjx - pix, d1 = pjy - piy, d2 = pjz - piz;                 // direction = p2 - p1
+    if (L > 0.0f) { d0 = div_rn(d0, L); d1 = div_rn(d1, L); d2 = div_rn(d2, L); }
+    const float F0 = fs * d0, F1 = fs * d1, F2 = fs * d2;
+    const bool fi = (bv.fixed_mask >> i) & 1u, fj = (bv.fixed_mask >> j) & 1u;
+    const float dk = np_dot3(st.vel(i, 0) - st.vel(j, 0), st.vel(i, 1) - st.vel(j, 1),
+                             st.vel(i, 2) - st.vel(j, 2), d0, d1, d2);
+    const float cd = dk * bv.sdamp[sp];
+    const float D0 = cd * d0, D1 = cd * d1, D2 = cd * d2;
+    if (!fi) {                                                            // p1.forced(force); p1.forced(-damp)
+        st.acc(i, 0) = forced_f32(forced_f32(st.acc(i, 0), F0, bv, i), -D0, bv, i);
+        st.acc(i, 1) = forced_f32(forced_f32(st.acc(i, 1), F1, bv, i), -D1, bv, i);
+        st.acc(i, 2) = forced_f32(forced_f32(st.acc(i, 2), F2, bv, i), -D2, bv, i);
+    }
+    if (!fj) {                                                            // p2.forced(-force); p2.forced(damp)
+        st.acc(j, 0) = forced_f32(forced_f32(st.acc(j, 0), -F0, bv, j), D0, bv, j);
+        st.acc(j, 1) = forced_f32(forced_f32(st.acc(j, 1), -F1, bv, j), D1, bv, j);
+        st.acc(j, 2) = forced_f32(forced_f32(st.acc(j, 2), -F2, bv, j), D2, bv, j);
+    }
+}
+
+// PhysicsEnv._run_physics + Point.run1: one substep.  Returns the force-phase contact mask.
+template <bool IN3D, class Topo, class BV, class Store>
+__device__ __forceinline__ uint32_t run_physics(const Topo& topo, const BV& bv, const EnvConst& ec, Store& st) {
+    const int N = topo.n(), S = topo.s(), M = topo.m();
+    // Creature.run: zero, muscles, skeletons
+#pragma unroll
+    for (int n = 0; n < N; n++) { st.acc(n, 0) = 0.0f; st.acc(n, 1) = 0.0f; st.acc(n, 2) = 0.0f; }
+#pragma unroll
+    for (int sp = 0; sp < M; sp++) spring_run(topo, bv, st, sp, st.mx(sp));
+#pragma unroll
+    for (int sp = M; sp < S; sp++) spring_run(topo, bv, st, sp, bv.srest[sp]);
+    uint32_t contact = 0;
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        const bool fixed = (bv.fixed_mask >> n) & 1u;
+        const bool unit = (bv.unit_mask >> n) & 1u;
+        float ax = st.acc(n, 0), ay = st.acc(n, 1), az = st.acc(n, 2);
+        const float vx = st.vel(n, 0), vy = st.vel(n, 1), vz = st.vel(n, 2);
+        const float deep = st.pos(n, 1) - ec.ground;
+        const bool hit = deep < 0.0f;
+        if (hit) contact |= 1u << n;
+        if (!fixed) {
+            ay = (float)((double)ay + bv.gm[n]);                 // forced([0, -g, 0])
+            if (ec.dampk_is_zero) {                               // forced(-0 * v): +-0, or NaN for non-finite v
+                ax = ax + ec.ndampk * vx; ay = ay + ec.ndampk * vy; az = az + ec.ndampk * vz;
+            } else {
+                ax = forced_f32(ax, ec.ndampk * vx, bv, n);
+                ay = forced_f32(ay, ec.ndampk * vy, bv, n);
+                az = forced_f32(az, ec.ndampk * vz, bv, n);
+            }
+            if (hit) {
+                const double m = bv.mass_d[n];
+                ay = forced_list(ay, ec.nground_k * deep, m, unit);      // ground spring
+                ay = forced_list(ay, ec.nground_damp * vy, m, unit);     // ground damper
+                const float ff = fabsf(deep) * ec.friction;             // friction
+                ax = forced_list(ax, (-vx) * ff, m, unit);
+                if (IN3D) az = forced_list(az, (-vz) * ff, m, unit);
+            }
+        }
+        // Point.run1: v += a*t; pos += v*t   (old_a = a stays in acc)
+        const float nvx = vx + ax * ec.dt, nvy = vy + ay * ec.dt, nvz = vz + az * ec.dt;
+        st.vel(n, 0) = nvx; st.vel(n, 1) = nvy; st.vel(n, 2) = nvz;
+        st.pos(n, 0) = st.pos(n, 0) + nvx * ec.dt;
+        st.pos(n, 1) = st.pos(n, 1) + nvy * ec.dt;
+        st.pos(n, 2) = st.pos(n, 2) + nvz * ec.dt;
+        st.acc(n, 0) = ax; st.acc(n, 1) = ay; st.acc(n, 2) = az;
+    }
+    return contact;
+}
+
+// NumPy float32 pairwise sum over n values produced by get(i)
+template <class Get>
+__device__ __forceinline__ float np_pairwise_sum(int n, Get get) {
+    if (n < 8) {
+        float r = -0.0f;
+#pragma unroll
+        for (int i = 0; i < n; i++) r = r + get(i);
+        return r;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = get(j);
+    int i = 8;
+    const int lim = n - (n % 8);
+#pragma unroll
+    for (; i < lim; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = r[j] + get(i + j);
+    }
+    float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+    for (; i < n; i++) res = res + get(i);
+    return res;
+}
+
+// Template reset + jitter (PhysicsEnv.reset, optimized_env.py:53-68; make_env :273-294)
+template <bool IN3D, class Topo, class BV, class Store>
+__device__ __forceinline__ void apply_reset(const Topo& topo, const BV& bv, const EnvConst& ec, Store& st,
+                                            int mode, const float* __restrict__ noise, int64_t E, int64_t e) {
+    const int N = topo.n(), M = topo.m();
+    if (mode == 2) {
+#pragma unroll
+        for (int n = 0; n < N; n++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { st.pos(n, c) = bv.tmpl[n * 3 + c]; st.vel(n, c) = 0.0f; st.acc(n, c) = 0.0f; }
+        }
+#pragma unroll
+        for (int m = 0; m < M; m++) st.mx(m) = bv.srest[m];
+    }
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        float z[3];
+        if (noise) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) z[c] = noise[(int64_t)(n * 3 + c) * E + e];
+        } else {
+            normal3(ec.seed_lo, ec.seed_hi, ec.env_offset + (uint32_t)e, ec.step_index, (uint32_t)n, z);
+#pragma unroll
+            for (int c = 0; c < 3; c++) z[c] = ec.sigma * z[c];
+        }
+        st.vel(n, 0) = st.vel(n, 0) + z[0];
+        st.vel(n, 1) = st.vel(n, 1) + z[1];
+        if (IN3D) st.vel(n, 2) = st.vel(n, 2) + z[2];
+    }
+}
+
+// Creature.getstat with PhysicsEnv's defaults; emit(k, value) receives the D entries in order.
+template <bool IN3D, class Topo, class Store, class Emit>
+__device__ __forceinline__ void get_obs(const Topo& topo, Store& st, Emit emit) {
+    const int N = topo.n(), M = topo.m();
+    constexpr int d = IN3D ? 3 : 2;
+    float mid[3] = { 0.0f, 0.0f, 0.0f };
+#pragma unroll
+    for (int n = 0; n < N; n++) { mid[0] = mid[0] + st.pos(n, 0); mid[1] = mid[1] + st.pos(n, 1); mid[2] = mid[2] + st.pos(n, 2); }
+    const float fn = (float)N;
+    mid[0] = div_rn(mid[0], fn); mid[1] = div_rn(mid[1], fn); mid[2] = div_rn(mid[2], fn);
+    int k = 0;
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+#pragma unroll
+        for (int c = 0; c < d; c++) emit(k++, st.pos(n, c) - mid[c]);
+#pragma unroll
+        for (int c = 0; c < d; c++) emit(k++, st.vel(n, c));
+#pragma unroll
+        for (int c = 0; c < d; c++) emit(k++, st.acc(n, c));
+    }
+#pragma unroll
+    for (int m = 0; m < M; m++) emit(k++, st.mx(m));
+}
+
+}  // namespace wg

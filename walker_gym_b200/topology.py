@@ -1,0 +1,60 @@
+"""Creature -> ``wg_topology``: evaluate the morphology the way the reference's
+constructors and NumPy would, once, on the host."""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import MAX_MASS, MAX_SPRING, WgTopology
+from .walker import Creature
+
+
+def topology_from_creature(creature: Creature) -> WgTopology:
+    """Springs are emitted muscles-first then skeletons -- the order ``Creature.run``
+    applies them (gym/optimized_walker.py:117-127), which fixes the float32
+    accumulation order on the device."""
+    phys = list(creature.phys)
+    index = {id(p): n for n, p in enumerate(phys)}
+    springs = list(creature.muscles) + list(creature.skeletons)
+    if not 1 <= len(phys) <= MAX_MASS:
+        raise ValueError(f"a creature needs 1..{MAX_MASS} points, got {len(phys)}")
+    if len(springs) > MAX_SPRING:
+        raise ValueError(f"at most {MAX_SPRING} springs are supported, got {len(springs)}")
+    t = WgTopology()
+    t.n_mass, t.n_muscle, t.n_spring = len(phys), len(creature.muscles), len(springs)
+    for n, p in enumerate(phys):
+        t.mass[n] = float(p.m)
+        t.fixed[n] = 1 if getattr(p, "fixed", False) else 0
+        tp = getattr(p, "original_pos", None) if getattr(p, "fixed", False) else None
+        src = p.pos if tp is None else tp
+        for c in range(3):
+            t.tmpl_pos[n * 3 + c] = np.float32(src[c])
+    for s, sp in enumerate(springs):
+        try:
+            t.si[s], t.sj[s] = index[id(sp.p1)], index[id(sp.p2)]
+        except KeyError:
+            raise ValueError("a spring references a point that is not in creature.phys") from None
+        if t.si[s] == t.sj[s]:
+            raise ValueError("a spring must join two different points")
+        t.sk[s] = np.float32(sp.k)
+        t.sdamp[s] = np.float32(sp.dampk)
+        if s < t.n_muscle:
+            t.srest[s] = np.float32(sp.originx)
+            t.mlo[s] = np.float32(sp.originx * sp.minl)     # Muscle.regulation operands, python semantics
+            t.mhi[s] = np.float32(sp.originx * sp.maxl)
+        else:
+            t.srest[s] = np.float32(sp.x)
+    return t
+
+
+def topology_from_spec(spec) -> WgTopology:
+    """Same, from a plain dict spec {"points": [(m, pos, fixed)], "muscles": [(i, j, kw)], "skeletons": [...]}."""
+    from .engine import DingPoint, Point
+    from .walker import Muscle, Skeleton
+    saved = list(Point.points)
+    try:
+        pts = [DingPoint(m, list(pos)) if fixed else Point(m, list(pos), [0, 0, 0]) for m, pos, fixed in spec["points"]]
+        mus = [Muscle(pts[i], pts[j], **kw) for i, j, kw in spec["muscles"]]
+        sks = [Skeleton(pts[i], pts[j], **kw) for i, j, kw in spec["skeletons"]]
+        return topology_from_creature(Creature(pts, mus, sks))
+    finally:
+        Point.points = saved
