@@ -3,6 +3,7 @@
 // thread-local error string and the "force generic" test switch.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 
 #include "wg_launch.cuh"
 
@@ -91,8 +92,9 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
     if (rc != WG_OK) return rc;
     if (n_env == 0) return WG_OK;
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    // small bodies move two envs per thread as 8-byte vectors; the big ones are register-bound
-    const int ept = vec_ok(buf, n_env, 2) ? 2 : 1;
+    // one env per thread measured fastest on B200 (80 registers, 24 warps/SM); EPT=2 kept as a knob
+    static const int ept_cap = [] { const char* v = getenv("WG_EPT"); return v ? atoi(v) : 1; }();   // tuning knob
+    const int ept = (ept_cap >= 2 && vec_ok(buf, n_env, 2)) ? 2 : 1;
     switch (pick_variant(topo)) {
         case TopoBalance::kId: return launch_balance(topo, prm, buf, n_env, ept, s);
         case TopoBox::kId:     return launch_box(topo, prm, buf, n_env, ept, s);

@@ -66,9 +66,9 @@ __device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const E
         sp(n) = np_norm3(st.vel(n, 0), st.vel(n, 1), st.vel(n, 2));
         if (st.pos(n, 1) - ec.ground < 0.0f) { cpost |= 1u << n; ncon++; }
     }
-    const float fn = (float)N;
-    const float cy = div_rn(np_pairwise_sum(N, [&](int i) { return ys(i); }), fn);
-    const float avgv = div_rn(np_pairwise_sum(N, [&](int i) { return sp(i); }), fn);
+    const ConstDiv nd = bv.ndiv;
+    const float cy = div_const(np_pairwise_sum(N, [&](int i) { return ys(i); }), nd.m, nd.r, nd.kind);
+    const float avgv = div_const(np_pairwise_sum(N, [&](int i) { return sp(i); }), nd.m, nd.r, nd.kind);
     const float vpen = (-avgv) * 0.1f;
     const float cpen = -0.5f * (float)ncon;
     o.reward = (cy + vpen) + cpen;
@@ -94,7 +94,7 @@ __device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const E
             float acc = st.pos(0, c);
 #pragma unroll
             for (int n = 1; n < N; n++) acc = acc + st.pos(n, c);
-            o.cen[c] = div_rn(acc, fn);
+            o.cen[c] = div_const(acc, nd.m, nd.r, nd.kind);
         }
     }
 }
@@ -145,6 +145,23 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
         float epr[EPT];
         if (A.ep_ret) WG_LDF(A.ep_ret + e, epr);
 
+        // actions: when the row has exactly M columns the EPT rows of this thread are one aligned vector
+        constexpr int AV = EPT * M;
+        constexpr bool kVecOk = (M > 0) && (AV == 2 || AV == 4 || AV == 8);
+        float actv[kVecOk ? AV : 1];
+        const bool act_vec = kVecOk && A.act_dim == M && ((reinterpret_cast<uintptr_t>(A.action) & 15u) == 0);
+        if (act_vec) {
+            const float* ap = A.action + e * M;
+            if (AV == 2) { const float2 v = *reinterpret_cast<const float2*>(ap); actv[0] = v.x; actv[AV > 1 ? 1 : 0] = v.y; }
+            else {
+#pragma unroll
+                for (int q = 0; q < AV / 4; q++) {
+                    const float4 v = *reinterpret_cast<const float4*>(ap + 4 * q);
+                    actv[(4 * q + 0) % AV] = v.x; actv[(4 * q + 1) % AV] = v.y;
+                    actv[(4 * q + 2) % AV] = v.z; actv[(4 * q + 3) % AV] = v.w;
+                }
+            }
+        }
         float rew[EPT]; uint8_t dnb[EPT]; uint32_t cpre[EPT], cpost[EPT];
         float eng[EPT], cen[3][EPT];
 #pragma unroll
@@ -154,7 +171,7 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
 #pragma unroll
             for (int m = 0; m < M; m++) {
                 if (m < na) {
-                    float x = st[j].mx(m) + A.action[(e + j) * A.act_dim + m];
+                    float x = st[j].mx(m) + (act_vec ? actv[j * M + m] : A.action[(e + j) * A.act_dim + m]);
                     if (A.bv.mlo[m] > x) x = A.bv.mlo[m];       // python max(x, lo)
                     if (A.bv.mhi[m] < x) x = A.bv.mhi[m];       // python min(x, hi)
                     st[j].mx(m) = x;
@@ -191,9 +208,9 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
             if (A.obs) {
                 if (ROWMAJOR) {
                     float* row = tile + (tid * EPT + j) * STRIDE;
-                    get_obs<IN3D>(topo, st[j], [&](int k, float v) { row[k] = v; });
+                    get_obs<IN3D>(topo, A.bv.ndiv, st[j], [&](int k, float v) { row[k] = v; });
                 } else {
-                    get_obs<IN3D>(topo, st[j], [&](int k, float v) { A.obs[(int64_t)k * E + e + j] = v; });
+                    get_obs<IN3D>(topo, A.bv.ndiv, st[j], [&](int k, float v) { A.obs[(int64_t)k * E + e + j] = v; });
                 }
             }
         }
@@ -242,9 +259,13 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
         const int nvalid = rem < TILE_ENVS ? (int)rem : TILE_ENVS;
         const int total = nvalid * D;
         float* out = A.obs + e0 * D;
+        // idx -> (row el, column k) is advanced incrementally: kBlock = QD * D + RD
+        constexpr int QD = kBlock / D, RD = kBlock % D;
+        int el = tid / D, k = tid - el * D;
         for (int idx = tid; idx < total; idx += kBlock) {
-            const int el = idx / D, k = idx - el * D;
             out[idx] = tile[el * STRIDE + k];
+            el += QD; k += RD;
+            if (k >= D) { k -= D; el += 1; }
         }
     }
 }
@@ -321,12 +342,12 @@ step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A) {
                 // centroid of getstat (sequential sum, then / N) for the cooperative copy-out below
                 float mid[3] = { 0.0f, 0.0f, 0.0f };
                 for (int n = 0; n < N; n++) { mid[0] = mid[0] + st.pos(n, 0); mid[1] = mid[1] + st.pos(n, 1); mid[2] = mid[2] + st.pos(n, 2); }
-                const float fn = (float)N;
-                st.scratch(M, 2 * N + 0) = div_rn(mid[0], fn);
-                st.scratch(M, 2 * N + 1) = div_rn(mid[1], fn);
-                st.scratch(M, 2 * N + 2) = div_rn(mid[2], fn);
+                const ConstDiv nd = A.bv.ndiv;
+                st.scratch(M, 2 * N + 0) = div_const(mid[0], nd.m, nd.r, nd.kind);
+                st.scratch(M, 2 * N + 1) = div_const(mid[1], nd.m, nd.r, nd.kind);
+                st.scratch(M, 2 * N + 2) = div_const(mid[2], nd.m, nd.r, nd.kind);
             } else {
-                get_obs<IN3D>(topo, st, [&](int k, float v) { A.obs[(int64_t)k * E + e] = v; });
+                get_obs<IN3D>(topo, A.bv.ndiv, st, [&](int k, float v) { A.obs[(int64_t)k * E + e] = v; });
             }
         }
     }
@@ -398,7 +419,7 @@ reset_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A, int mode,
         // jitter-only reset without an old_a buffer: the acceleration slots of the
         // observation still hold Point.old_a of the last step -- leave them alone.
         const bool keep_acc = (mode == 1) && (A.old_a == nullptr);
-        get_obs<IN3D>(topo, st, [&](int k, float v) {
+        get_obs<IN3D>(topo, A.bv.ndiv, st, [&](int k, float v) {
             if (keep_acc && k < 3 * d * N && (k % (3 * d)) >= 2 * d) return;
             if (obs_layout == 0) A.obs[e * D + k] = v; else A.obs[(int64_t)k * E + e] = v;
         });

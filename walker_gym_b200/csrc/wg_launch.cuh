@@ -1,5 +1,6 @@
 // wg_launch.cuh -- host-side launch helpers shared by the per-morphology translation units.
 #pragma once
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include "../../include/walker_gym_b200.h"
@@ -34,6 +35,17 @@ int launch_generic_step(const wg_topology*, const wg_params*, const wg_buffers*,
 int launch_reset(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int mode, const uint8_t* mask, cudaStream_t);
 int launch_stats(const float* fin_stats, int64_t E, double* out8, cudaStream_t);
 
+// classify a host-known divisor for div_const (see wg_math.cuh)
+inline ConstDiv make_const_div(float m) {
+    ConstDiv c; c.m = m; c.r = 1.0f / m; c.kind = 3;
+    int ex = 0;
+    const float fr = frexpf(m, &ex);
+    if (m == 1.0f) c.kind = 0;
+    else if (fr == 0.5f && ex > -100 && ex < 100) c.kind = 1;              // power of two: reciprocal exact
+    else if (m >= 2.0f && m <= 2048.0f && m == floorf(m)) c.kind = 2;       // small integer
+    return c;
+}
+
 template <int MAXN, int MAXS>
 inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E) {
     memset(&A, 0, sizeof(A));
@@ -42,6 +54,8 @@ inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_pa
     for (int n = 0; n < t->n_mass; n++) {
         bv.mass_d[n] = t->mass[n];
         bv.mass_f[n] = (float)t->mass[n];
+        const ConstDiv cd = make_const_div(bv.mass_f[n]);
+        bv.mass_r[n] = cd.r; bv.mass_kind[n] = cd.kind;
         bv.gm[n] = (-p->g) / t->mass[n];                  // np.asarray([0,-g,0]) / m  (float64)
         bv.mg_f[n] = (float)(t->mass[n] * p->g);          // python m*g, then float32 at the multiply
         if (t->fixed[n]) bv.fixed_mask |= 1u << n;
@@ -53,6 +67,7 @@ inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_pa
         bv.sk[s] = t->sk[s]; bv.sdamp[s] = t->sdamp[s]; bv.srest[s] = t->srest[s];
         bv.mlo[s] = t->mlo[s]; bv.mhi[s] = t->mhi[s];
     }
+    bv.ndiv = make_const_div((float)t->n_mass);
     auto& ec = A.ec;
     ec.ndampk = -p->dampk;
     ec.dampk_is_zero = (p->dampk == 0.0f);

@@ -21,12 +21,15 @@ struct BodyVals {
     double gm[MAXN];        // (-g) / m  in float64: gravity "force" per unit mass (optimized_env.py:148)
     double mass_d[MAXN];    // Point.m
     float mass_f[MAXN];     // float32(m): divisor of float32 forces
+    float mass_r[MAXN];     // RN(1 / float32(m))
+    int32_t mass_kind[MAXN];// div_const kind of each mass (0 unit, 1 pow2, 2 small integer, 3 general)
+    ConstDiv ndiv;          // division by the number of masses (centroid / means)
     float mg_f[MAXN];       // float32(m * g): potential-energy weight (:245)
     float tmpl[MAXN * 3];   // creation-time positions
     float sk[MAXS], sdamp[MAXS], srest[MAXS];
     float mlo[MAXS], mhi[MAXS];
     uint32_t fixed_mask;    // DingPoint bits
-    uint32_t unit_mask;     // bit n: m == 1 (x / 1 is exact, division skipped)
+    uint32_t unit_mask;     // bit n: m == 1 (x / 1 is exact, float64 division skipped)
     int32_t si[MAXS], sj[MAXS];   // only read by the run-time topology
     int32_t n_mass, n_spring, n_muscle;
 };
@@ -95,8 +98,7 @@ struct RuntimeTopo {
 // a += f / m   (Point.forced, float32 ndarray force)
 template <class BV>
 __device__ __forceinline__ float forced_f32(float a, float f, const BV& bv, int n) {
-    float q = ((bv.unit_mask >> n) & 1u) ? f : div_rn(f, bv.mass_f[n]);
-    return a + q;
+    return a + div_const(f, bv.mass_f[n], bv.mass_r[n], bv.mass_kind[n]);
 }
 
 // Muscle.run / Skeleton.run (optimized_walker.py:45-67 == :84-106)
@@ -109,7 +111,7 @@ __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store
     const float dx = L - x;
     const float fs = (-dx) * bv.sk[sp];                                   // -dx * k (sign as written)
     float d0 = pjx - pix, d1 = pjy - piy, d2 = pjz - piz;                 // direction = p2 - p1
-    if (L > 0.0f) { d0 = div_rn(d0, L); d1 = div_rn(d1, L); d2 = div_rn(d2, L); }
+    if (L > 0.0f) div3_len(d0, d1, d2, L);
     const float F0 = fs * d0, F1 = fs * d1, F2 = fs * d2;
     const bool fi = (bv.fixed_mask >> i) & 1u, fj = (bv.fixed_mask >> j) & 1u;
     const float dk = np_dot3(st.vel(i, 0) - st.vel(j, 0), st.vel(i, 1) - st.vel(j, 1),
@@ -236,14 +238,15 @@ __device__ __forceinline__ void apply_reset(const Topo& topo, const BV& bv, cons
 
 // Creature.getstat with PhysicsEnv's defaults; emit(k, value) receives the D entries in order.
 template <bool IN3D, class Topo, class Store, class Emit>
-__device__ __forceinline__ void get_obs(const Topo& topo, Store& st, Emit emit) {
+__device__ __forceinline__ void get_obs(const Topo& topo, const ConstDiv& nd, Store& st, Emit emit) {
     const int N = topo.n(), M = topo.m();
     constexpr int d = IN3D ? 3 : 2;
     float mid[3] = { 0.0f, 0.0f, 0.0f };
 #pragma unroll
     for (int n = 0; n < N; n++) { mid[0] = mid[0] + st.pos(n, 0); mid[1] = mid[1] + st.pos(n, 1); mid[2] = mid[2] + st.pos(n, 2); }
-    const float fn = (float)N;
-    mid[0] = div_rn(mid[0], fn); mid[1] = div_rn(mid[1], fn); mid[2] = div_rn(mid[2], fn);
+    mid[0] = div_const(mid[0], nd.m, nd.r, nd.kind);
+    mid[1] = div_const(mid[1], nd.m, nd.r, nd.kind);
+    mid[2] = div_const(mid[2], nd.m, nd.r, nd.kind);
     int k = 0;
 #pragma unroll
     for (int n = 0; n < N; n++) {
