@@ -102,9 +102,14 @@ __device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const E
 // =================================================================================
 // K1, register-resident specialisation: Topo is compile-time, EPT envs per thread.
 // =================================================================================
-template <class Topo, bool IN3D, bool ROWMAJOR, int EPT>
+// OBS: 0 = feature-major [D][E] (stores coalesced straight from registers),
+//      1 = row-major [E][D] staged through a padded shared-memory tile, each warp streaming its
+//          own 32*EPT rows (one contiguous span of global memory) with only a __syncwarp,
+//      2 = row-major written directly as 8-byte pieces of each thread's own row (no shared memory).
+template <class Topo, bool IN3D, int OBS, int EPT, int MM>
 __global__ void __launch_bounds__(kBlock)
 step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
+    constexpr bool ROWMAJOR = (OBS == 1);
     constexpr int N = Topo::N, M = Topo::M;
     constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;
     constexpr int STRIDE = D | 1;                 // odd row pitch: conflict-free tile writes
@@ -179,7 +184,7 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
             }
             // ---- k_sub x (_run_physics + run1) ----
             uint32_t cp = 0;
-            for (int k = 0; k < A.ec.k_sub; k++) cp = run_physics<IN3D>(topo, A.bv, A.ec, st[j]);
+            for (int k = 0; k < A.ec.k_sub; k++) cp = run_physics<IN3D, MM>(topo, A.bv, A.ec, st[j]);
             cpre[j] = cp;
             // ---- reward / done / info ----
             const int32_t sn = stp[j] + 1;
@@ -206,9 +211,16 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
             }
             // ---- observation of the (possibly reset) state ----
             if (A.obs) {
-                if (ROWMAJOR) {
+                if (OBS == 1) {
                     float* row = tile + (tid * EPT + j) * STRIDE;
                     get_obs<IN3D>(topo, A.bv.ndiv, st[j], [&](int k, float v) { row[k] = v; });
+                } else if (OBS == 2) {
+                    static_assert(OBS != 2 || D % 2 == 0, "direct row-major stores need an even obs dim");
+                    float2* row = reinterpret_cast<float2*>(A.obs + (e + j) * D);
+                    float hold = 0.0f;
+                    get_obs<IN3D>(topo, A.bv.ndiv, st[j], [&](int k, float v) {
+                        if (k & 1) row[k >> 1] = make_float2(hold, v); else hold = v;
+                    });
                 } else {
                     get_obs<IN3D>(topo, A.bv.ndiv, st[j], [&](int k, float v) { A.obs[(int64_t)k * E + e + j] = v; });
                 }
@@ -252,20 +264,34 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
             for (int c = 0; c < 3; c++) WG_STF(A.centroid + (int64_t)c * E + e, cen[c]);
         }
     }
-    // ---- row-major observation: the block's rows are one contiguous span of global memory ----
+    // ---- row-major observation: each warp owns 32*EPT consecutive rows = one contiguous span ----
     if (ROWMAJOR && A.obs) {
-        __syncthreads();
-        const int64_t rem = E - e0;
-        const int nvalid = rem < TILE_ENVS ? (int)rem : TILE_ENVS;
-        const int total = nvalid * D;
-        float* out = A.obs + e0 * D;
-        // idx -> (row el, column k) is advanced incrementally: kBlock = QD * D + RD
-        constexpr int QD = kBlock / D, RD = kBlock % D;
-        int el = tid / D, k = tid - el * D;
-        for (int idx = tid; idx < total; idx += kBlock) {
-            out[idx] = tile[el * STRIDE + k];
-            el += QD; k += RD;
-            if (k >= D) { k -= D; el += 1; }
+        static_assert(D >= 16, "copy-out assumes at most two row wraps per 32 lanes");
+        __syncwarp();
+        constexpr int RW = 32 * EPT;                       // rows per warp
+        constexpr int PAD = STRIDE - D;
+        const int warp = tid >> 5, lane = tid & 31;
+        const int64_t ew = e0 + (int64_t)warp * RW;         // first env of this warp
+        const int64_t rem = E - ew;
+        if (rem > 0) {
+            const float* src = tile + warp * RW * STRIDE + lane;
+            float* out = A.obs + ew * D + lane;
+            if (rem >= RW) {
+#pragma unroll
+                for (int i = 0; i < EPT * D; i++) {         // idx = 32*i + lane -> row el, column idx - el*D
+                    constexpr int dummy = 0; (void)dummy;
+                    const int base = (32 * i) / D, r0 = (32 * i) % D;
+                    const int t = lane + r0;
+                    const int el = base + (t >= D ? 1 : 0) + (t >= 2 * D ? 1 : 0);
+                    out[32 * i] = src[32 * i + el * PAD];
+                }
+            } else {
+                const int total = (int)rem * D;
+                for (int idx = lane; idx < total; idx += 32) {
+                    const int el = idx / D;
+                    out[idx - lane] = src[idx - lane + el * PAD];
+                }
+            }
         }
     }
 }
@@ -304,7 +330,7 @@ step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A) {
             st.mx(m) = x;
         }
         uint32_t cp = 0;
-        for (int k = 0; k < A.ec.k_sub; k++) cp = run_physics<IN3D>(topo, A.bv, A.ec, st);
+        for (int k = 0; k < A.ec.k_sub; k++) cp = run_physics<IN3D, 2>(topo, A.bv, A.ec, st);
         int32_t sn = A.steps[e] + 1;
         EpiOut o;
         epilogue<IN3D>(topo, A.bv, A.ec, st, sn, A.energy != nullptr, A.centroid != nullptr,

@@ -2,6 +2,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "../../include/walker_gym_b200.h"
 #include "wg_kernels.cuh"
@@ -83,13 +84,30 @@ inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_pa
     A.E = E; A.act_dim = b->action ? b->act_dim : 0;
 }
 
-template <class Topo, bool IN3D, bool ROWMAJOR, int EPT>
+// body-wide mass mode (see forced2): 0 all unit, 1 unit / power of two / small integer, 2 general
+inline int mass_mode(const wg_topology* t) {
+    int mode = 0;
+    for (int n = 0; n < t->n_mass; n++) {
+        const int k = make_const_div((float)t->mass[n]).kind;
+        if (k == 3) return 2;
+        if (k != 0) mode = 1;
+    }
+    return mode;
+}
+
+inline int obs_mode(const wg_buffers* b, int D) {
+    static const int direct = [] { const char* v = getenv("WG_OBS_DIRECT"); return v ? atoi(v) : 0; }();   // tuning knob
+    if (b->obs_layout == 1) return 0;
+    return (direct && D % 2 == 0) ? 2 : 1;
+}
+
+template <class Topo, bool IN3D, int OBS, int EPT, int MM>
 inline int launch_static(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
     StepArgs<Topo::N, Topo::S> A;
     fill_args(A, t, p, b, E);
     constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
-    const size_t smem = (ROWMAJOR && b->obs) ? sizeof(float) * kBlock * EPT * (D | 1) : 0;
-    auto kern = step_static_kernel<Topo, IN3D, ROWMAJOR, EPT>;
+    const size_t smem = (OBS == 1 && b->obs) ? sizeof(float) * kBlock * EPT * (D | 1) : 0;
+    auto kern = step_static_kernel<Topo, IN3D, OBS, EPT, MM>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -102,11 +120,22 @@ inline int launch_static(const wg_topology* t, const wg_params* p, const wg_buff
     return WG_OK;
 }
 
+template <class Topo, bool IN3D, int EPT, int MM>
+inline int launch_static_obs(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
+    constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
+    switch (obs_mode(b, D)) {
+        case 0: return launch_static<Topo, IN3D, 0, EPT, MM>(t, p, b, E, s);
+        case 2: if constexpr (D % 2 == 0) return launch_static<Topo, IN3D, 2, EPT, MM>(t, p, b, E, s);
+        default: return launch_static<Topo, IN3D, 1, EPT, MM>(t, p, b, E, s);
+    }
+}
+
+// static kernels exist for mass modes 0 and 1; bodies with arbitrary masses use the generic kernel
 template <class Topo, int EPT>
 inline int launch_static_flags(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
-    const bool rm = b->obs_layout == 0;
-    if (p->in3d) return rm ? launch_static<Topo, true, true, EPT>(t, p, b, E, s) : launch_static<Topo, true, false, EPT>(t, p, b, E, s);
-    return rm ? launch_static<Topo, false, true, EPT>(t, p, b, E, s) : launch_static<Topo, false, false, EPT>(t, p, b, E, s);
+    const int mm = mass_mode(t);
+    if (p->in3d) return mm == 0 ? launch_static_obs<Topo, true, EPT, 0>(t, p, b, E, s) : launch_static_obs<Topo, true, EPT, 1>(t, p, b, E, s);
+    return mm == 0 ? launch_static_obs<Topo, false, EPT, 0>(t, p, b, E, s) : launch_static_obs<Topo, false, EPT, 1>(t, p, b, E, s);
 }
 
 }  // namespace wg

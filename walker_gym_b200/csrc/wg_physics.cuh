@@ -95,14 +95,35 @@ struct RuntimeTopo {
 
 // ---- physics ------------------------------------------------------------------
 
-// a += f / m   (Point.forced, float32 ndarray force)
-template <class BV>
-__device__ __forceinline__ float forced_f32(float a, float f, const BV& bv, int n) {
-    return a + div_const(f, bv.mass_f[n], bv.mass_r[n], bv.mass_kind[n]);
+// Two successive Point.forced calls on mass n with float32 ndarray forces:
+//   a += f / m;  a += g / m        (gym/optimized_engine.py:104-106)
+// MM is the body-wide mass mode chosen at launch: 0 = every mass is 1 (x / 1 == x, no division at
+// all), 1 = every mass is 1, a power of two or a small integer (exact 3-instruction division),
+// 2 = arbitrary masses.  The per-mass choice is a warp-uniform branch on a kernel parameter.
+template <int MM, class BV>
+__device__ __forceinline__ void forced2(float (&a)[3], const float (&f)[3], const float (&g)[3], const BV& bv, int n) {
+    if (MM == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) a[c] = (a[c] + f[c]) + g[c];
+        return;
+    }
+    const int kind = bv.mass_kind[n];
+    if (kind == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) a[c] = (a[c] + f[c]) + g[c];
+    } else if (MM == 1 || kind <= 2) {
+        const float m = bv.mass_f[n], r = bv.mass_r[n];
+#pragma unroll
+        for (int c = 0; c < 3; c++) a[c] = (a[c] + div_smallint(f[c], m, r)) + div_smallint(g[c], m, r);
+    } else {
+        const float m = bv.mass_f[n];
+#pragma unroll
+        for (int c = 0; c < 3; c++) a[c] = (a[c] + div_rn(f[c], m)) + div_rn(g[c], m);
+    }
 }
 
 // Muscle.run / Skeleton.run (optimized_walker.py:45-67 == :84-106)
-template <class Topo, class BV, class Store>
+template <int MM, class Topo, class BV, class Store>
 __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store& st, int sp, float x) {
     const int i = topo.si(sp), j = topo.sj(sp);
     const float pix = st.pos(i, 0), piy = st.pos(i, 1), piz = st.pos(i, 2);
@@ -112,35 +133,35 @@ __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store
     const float fs = (-dx) * bv.sk[sp];                                   // -dx * k (sign as written)
     float d0 = pjx - pix, d1 = pjy - piy, d2 = pjz - piz;                 // direction = p2 - p1
     if (L > 0.0f) div3_len(d0, d1, d2, L);
-    const float F0 = fs * d0, F1 = fs * d1, F2 = fs * d2;
-    const bool fi = (bv.fixed_mask >> i) & 1u, fj = (bv.fixed_mask >> j) & 1u;
+    const float F[3] = { fs * d0, fs * d1, fs * d2 };
     const float dk = np_dot3(st.vel(i, 0) - st.vel(j, 0), st.vel(i, 1) - st.vel(j, 1),
                              st.vel(i, 2) - st.vel(j, 2), d0, d1, d2);
     const float cd = dk * bv.sdamp[sp];
-    const float D0 = cd * d0, D1 = cd * d1, D2 = cd * d2;
-    if (!fi) {                                                            // p1.forced(force); p1.forced(-damp)
-        st.acc(i, 0) = forced_f32(forced_f32(st.acc(i, 0), F0, bv, i), -D0, bv, i);
-        st.acc(i, 1) = forced_f32(forced_f32(st.acc(i, 1), F1, bv, i), -D1, bv, i);
-        st.acc(i, 2) = forced_f32(forced_f32(st.acc(i, 2), F2, bv, i), -D2, bv, i);
+    const float D[3] = { cd * d0, cd * d1, cd * d2 };
+    const float nF[3] = { -F[0], -F[1], -F[2] }, nD[3] = { -D[0], -D[1], -D[2] };
+    if (!((bv.fixed_mask >> i) & 1u)) {                                   // p1.forced(force); p1.forced(-damp)
+        float a[3] = { st.acc(i, 0), st.acc(i, 1), st.acc(i, 2) };
+        forced2<MM>(a, F, nD, bv, i);
+        st.acc(i, 0) = a[0]; st.acc(i, 1) = a[1]; st.acc(i, 2) = a[2];
     }
-    if (!fj) {                                                            // p2.forced(-force); p2.forced(damp)
-        st.acc(j, 0) = forced_f32(forced_f32(st.acc(j, 0), -F0, bv, j), D0, bv, j);
-        st.acc(j, 1) = forced_f32(forced_f32(st.acc(j, 1), -F1, bv, j), D1, bv, j);
-        st.acc(j, 2) = forced_f32(forced_f32(st.acc(j, 2), -F2, bv, j), D2, bv, j);
+    if (!((bv.fixed_mask >> j) & 1u)) {                                   // p2.forced(-force); p2.forced(damp)
+        float a[3] = { st.acc(j, 0), st.acc(j, 1), st.acc(j, 2) };
+        forced2<MM>(a, nF, D, bv, j);
+        st.acc(j, 0) = a[0]; st.acc(j, 1) = a[1]; st.acc(j, 2) = a[2];
     }
 }
 
 // PhysicsEnv._run_physics + Point.run1: one substep.  Returns the force-phase contact mask.
-template <bool IN3D, class Topo, class BV, class Store>
+template <bool IN3D, int MM, class Topo, class BV, class Store>
 __device__ __forceinline__ uint32_t run_physics(const Topo& topo, const BV& bv, const EnvConst& ec, Store& st) {
     const int N = topo.n(), S = topo.s(), M = topo.m();
     // Creature.run: zero, muscles, skeletons
 #pragma unroll
     for (int n = 0; n < N; n++) { st.acc(n, 0) = 0.0f; st.acc(n, 1) = 0.0f; st.acc(n, 2) = 0.0f; }
 #pragma unroll
-    for (int sp = 0; sp < M; sp++) spring_run(topo, bv, st, sp, st.mx(sp));
+    for (int sp = 0; sp < M; sp++) spring_run<MM>(topo, bv, st, sp, st.mx(sp));
 #pragma unroll
-    for (int sp = M; sp < S; sp++) spring_run(topo, bv, st, sp, bv.srest[sp]);
+    for (int sp = M; sp < S; sp++) spring_run<MM>(topo, bv, st, sp, bv.srest[sp]);
     uint32_t contact = 0;
 #pragma unroll
     for (int n = 0; n < N; n++) {
@@ -155,10 +176,11 @@ __device__ __forceinline__ uint32_t run_physics(const Topo& topo, const BV& bv, 
             ay = (float)((double)ay + bv.gm[n]);                 // forced([0, -g, 0])
             if (ec.dampk_is_zero) {                               // forced(-0 * v): +-0, or NaN for non-finite v
                 ax = ax + ec.ndampk * vx; ay = ay + ec.ndampk * vy; az = az + ec.ndampk * vz;
-            } else {
-                ax = forced_f32(ax, ec.ndampk * vx, bv, n);
-                ay = forced_f32(ay, ec.ndampk * vy, bv, n);
-                az = forced_f32(az, ec.ndampk * vz, bv, n);
+            } else {                                              // forced(-k * v): float32 force / m
+                const ConstDiv md{ bv.mass_f[n], bv.mass_r[n], bv.mass_kind[n] };
+                ax = ax + div_const(ec.ndampk * vx, md.m, md.r, md.kind);
+                ay = ay + div_const(ec.ndampk * vy, md.m, md.r, md.kind);
+                az = az + div_const(ec.ndampk * vz, md.m, md.r, md.kind);
             }
             if (hit) {
                 const double m = bv.mass_d[n];
