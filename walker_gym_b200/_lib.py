@@ -13,7 +13,7 @@ MAX_MASS, MAX_SPRING = 32, 96
 ABI_VERSION = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwalkergym_b200.so")
+LIB_PATH = os.environ.get("WG_LIB_PATH", os.path.join(_HERE, "libwalkergym_b200.so"))   # override: tuning experiments
 
 
 class WgTopology(C.Structure):

@@ -16,11 +16,12 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-OUT = os.path.join(HERE, "libwalkergym_b200.so")
-OBJ_DIR = os.path.join(HERE, "build")
+OUT = os.environ.get("WG_LIB_OUT", os.path.join(HERE, "libwalkergym_b200.so"))
+OBJ_DIR = os.environ.get("WG_OBJ_DIR", os.path.join(HERE, "build"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+NVCC_FLAGS += os.environ.get("WG_EXTRA_NVCC_FLAGS", "").split()      # tuning experiments only
 
 
 def _nvcc() -> str:

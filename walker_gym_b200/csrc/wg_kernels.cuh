@@ -13,7 +13,13 @@
 
 namespace wg {
 
-constexpr int kBlock = 128;
+#ifndef WG_BLOCK
+#define WG_BLOCK 128
+#endif
+#ifndef WG_MIN_BLOCKS
+#define WG_MIN_BLOCKS 6
+#endif
+constexpr int kBlock = WG_BLOCK;
 
 template <int MAXN, int MAXS>
 struct StepArgs {
@@ -107,7 +113,7 @@ __device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const E
 //          own 32*EPT rows (one contiguous span of global memory) with only a __syncwarp,
 //      2 = row-major written directly as 8-byte pieces of each thread's own row (no shared memory).
 template <class Topo, bool IN3D, int OBS, int EPT, int MM>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, (Topo::N <= 4 && EPT == 1) ? WG_MIN_BLOCKS : 1)
 step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
     constexpr bool ROWMAJOR = (OBS == 1);
     constexpr int N = Topo::N, M = Topo::M;
