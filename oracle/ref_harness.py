@@ -203,3 +203,33 @@ def rollout(creature_or_id, actions, *, env_kwargs=None, seed=0, noise=None,
     )
     engine.Point.clear()
     return out
+
+
+def rollout_compat(spec_or_id, actions, t_step, *, env_kwargs=None, noise=None, ref_root: str = DEFAULT_REF):
+    """Legacy-signature ``Environment`` (gym/optimized_env.py:298-334): per step the caller does
+    ``creature.act(a)`` then ``env.step(t)`` (= run() + Point.run1(t)); returns the point states."""
+    engine, walker, envmod = load(ref_root)
+    engine.Point.clear()
+    draws = []
+
+    def fake_normal(loc=0.0, scale=1.0, size=None):
+        v = float(np.asarray(noise).reshape(-1)[len(draws)])
+        draws.append(v)
+        return v
+
+    with mock.patch.object(np.random, "normal", fake_normal):
+        if isinstance(spec_or_id, dict):
+            creature = build_creature(spec_or_id, ref_root)
+        else:
+            creature = {"balance-v0": walker.create_balance_creature, "box-v0": walker.create_box_creature}[spec_or_id.lower()]()
+        env = envmod.Environment([creature], **dict(env_kwargs or {}))
+        snaps = [snapshot(env)]
+        for a in actions:
+            creature.act(a)
+            env.step(t_step)
+            snaps.append(snapshot(env))
+    out = {k: np.stack([s[k] for s in snaps]) for k in snaps[0]}
+    out["contact_pre"] = out["contact_pre"][1:]
+    out["reset_noise"] = np.asarray(draws, dtype=np.float64)
+    engine.Point.clear()
+    return out

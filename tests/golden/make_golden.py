@@ -164,6 +164,25 @@ def main():
     batch_case("batch_balance3d", "Balance-v0", 256, 20, dict(in3d=True))
     batch_case("batch_box3d", "Box-v0", 256, 21, dict(in3d=True))
     batch_case("batch_box2d", "Box-v0", 128, 22, dict(in3d=False))
+    # legacy-signature Environment: creature.act(a); env.step(t) with a caller-chosen t
+    rng = np.random.default_rng(31)
+    acts = rng.uniform(-1, 1, (50, 4)).astype(np.float32)
+    nz = (rng.standard_normal(64) * 0.1).astype(np.float32)
+    kw = dict(in3d=True, g=50, groundk=800)
+    out = rh.rollout_compat("Box-v0", acts, 0.005, env_kwargs=kw, noise=nz)
+    np.savez_compressed(os.path.join(HERE, "compat_environment.npz"), pos=out["pos"], vel=out["vel"],
+                        old_a=out["old_a"], x=out["x"].astype(np.float32), contact_pre=out["contact_pre"],
+                        reset_noise=out["reset_noise"].astype(np.float32), actions=acts, t_step=np.array(0.005),
+                        spec=np.array(json.dumps(wo.BOX)), env_kwargs=np.array(json.dumps(kw)))
+    print("compat_environment: T=50")
+    # a snapshot written by the reference's own Point.snapshot (gym/optimized_engine.py:319-324)
+    engine, walker, _ = rh.load()
+    engine.Point.clear()
+    c = walker.create_box_creature()
+    c.phys[0].v[:] = [1.5, -2.0, 0.25]
+    c.phys[2].pos[:] = [51.0, 99.5, -0.5]
+    engine.Point.snapshot(os.path.join(HERE, "state_ref_box.pkl"))
+    engine.Point.clear()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,157 @@
+"""GPU: the drop-in single-env surface (make_env / PhysicsEnv / Environment) replayed
+against the reference's recorded trajectories.  Written the way a reference test
+would read: build the env, seed, step, compare what step() returns and what the
+creature's Point/Muscle objects show afterwards."""
+from unittest import mock
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def feed_normal(draws):
+    it = iter(np.asarray(draws, np.float64).tolist())
+    return mock.patch.object(np.random, "normal", lambda loc=0.0, scale=1.0, size=None: next(it))
+
+
+@pytest.mark.parametrize("name,env_id", [("balance3d_s0", "Balance-v0"), ("balance2d_s1", "Balance-v0"),
+                                         ("box3d_s0", "Box-v0"), ("box2d_s1", "Box-v0"), ("box3d_overflow", "Box-v0"),
+                                         ("done_fall", "Balance-v0"), ("done_maxsteps", "Box-v0")])
+def test_make_env_step_matches_reference(name, env_id):
+    from walker_gym_b200 import Point, make_env
+    g = gu.load(name)
+    Point.clear()
+    with feed_normal(g["reset_noise"]):
+        env = make_env(env_id, **g["env_kwargs"])
+    if g["max_steps"] is not None:
+        env.max_steps = g["max_steps"]
+    assert env.time_step == 0.01 and env.steps == 0
+    obs0 = env._body.core.obs[0].cpu().numpy()
+    assert gu.same(obs0, g["obs"][0])
+    assert env.get_observation_space()["shape"] == (g["obs"].shape[1],)
+    assert env.get_action_space()["shape"] == (g["actions"].shape[1],)
+    T = min(len(g["actions"]), 150)
+    for t in range(T):
+        obs, reward, done, info = env.step(g["actions"][t])
+        assert isinstance(obs, np.ndarray) and obs.dtype == np.float64 and isinstance(done, bool)
+        assert gu.same(obs.astype(np.float32), g["obs"][t + 1]), f"obs @ {t}"
+        assert gu.same(np.float32(reward), g["reward"][t]), f"reward @ {t}"
+        assert done == bool(g["done"][t]), f"done @ {t}"
+        assert info["steps"] == t + 1 == env.steps
+        assert gu.same(np.float32(info["total_energy"]), g["energy"][t]), f"energy @ {t}"
+        assert gu.same(np.float32(info["centroid_position"]), g["centroid"][t]), f"centroid @ {t}"
+        c = env.creature
+        assert gu.same(np.stack([p.pos for p in c.phys]), g["pos"][t + 1])
+        assert gu.same(np.stack([p.v for p in c.phys]), g["vel"][t + 1])
+        assert gu.same(np.stack([p.old_a for p in c.phys]), g["old_a"][t + 1])
+        assert gu.same(np.float32([m.x for m in c.muscles]), g["x"][t + 1])
+        assert [p.r == 3 for p in c.phys] == list(g["contact_pre"][t])
+        assert [p.color == "red" for p in c.phys] == list(g["contact_pre"][t])
+        assert gu.same(np.array(c.getstat(env.in3d), np.float32), g["obs"][t + 1])
+    Point.clear()
+
+
+def test_reset_is_jitter_only_like_the_reference():
+    from walker_gym_b200 import Point, make_env
+    g = gu.load("autoreset_jitter")
+    Point.clear()
+    with feed_normal(g["reset_noise"]):
+        env = make_env("Balance-v0", **g["env_kwargs"])
+        env.max_steps = g["max_steps"]
+        for t in range(len(g["actions"])):
+            obs, reward, done, info = env.step(g["actions"][t])
+            assert done == bool(g["done"][t])
+            if done:
+                obs = env.reset()
+                assert env.steps == 0
+            assert gu.same(obs.astype(np.float32), g["obs"][t + 1]), f"obs @ {t}"
+            assert gu.same(np.stack([p.pos for p in env.creature.phys]), g["pos"][t + 1])
+    assert env.seed(5) == [5] and env.seed() == []
+    Point.clear()
+
+
+def test_user_mutations_between_steps_are_honoured():
+    """The reference mutates the caller's Point objects in place, and reads them on every step."""
+    from walker_gym_b200 import Point, make_env
+    g = gu.load("batch_box3d")
+    Point.clear()
+    with feed_normal(np.zeros(64)):
+        env = make_env("Box-v0", in3d=True)
+    for e in range(8):
+        for n, p in enumerate(env.creature.phys):
+            p.pos[:], p.v[:] = g["init_pos"][e][n], g["init_vel"][e][n]
+        for m in env.creature.muscles:
+            m.x = m.originx
+        env.steps = 0
+        obs, reward, done, info = env.step(g["actions"][e])
+        assert gu.same(obs.astype(np.float32), g["obs"][e]) and gu.same(np.float32(reward), g["reward"][e])
+        assert gu.same(np.stack([p.pos for p in env.creature.phys]), g["pos"][e])
+    Point.clear()
+
+
+def test_compat_environment_step_t():
+    from walker_gym_b200 import Environment, Point, create_box_creature
+    g = gu.load("compat_environment") if False else None
+    z = np.load(gu.GOLDEN_DIR + "/compat_environment.npz")
+    import json
+    kw = json.loads(str(z["env_kwargs"]))
+    Point.clear()
+    c = create_box_creature()
+    with feed_normal(z["reset_noise"]):
+        env = Environment([c], **kw)
+    t_step = float(z["t_step"])
+    for t, a in enumerate(z["actions"]):
+        c.act(a)
+        if t % 2 == 0:
+            assert env.step(t_step) is None
+        else:                       # the legacy two-call form
+            env.run()
+            Point.run1(t_step)
+        assert gu.same(np.stack([p.pos for p in c.phys]), z["pos"][t + 1]), f"pos @ {t}"
+        assert gu.same(np.stack([p.v for p in c.phys]), z["vel"][t + 1]), f"vel @ {t}"
+        assert gu.same(np.stack([p.old_a for p in c.phys]), z["old_a"][t + 1]), f"old_a @ {t}"
+        assert gu.same(np.float32([m.x for m in c.muscles]), z["x"][t + 1])
+    Point.clear()
+
+
+def test_batched_save_state_roundtrip(tmp_path):
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    from walker_gym_b200.state_io import load_points
+    env = BatchedPhysicsEnv("Box-v0", 64, "cuda:0", in3d=True, keep_old_a=True)
+    for _ in range(5):
+        env.step(torch.rand(64, 4, device="cuda:0") * 2 - 1)
+    path = str(tmp_path / "state.pkl")
+    env.save_state(path, env_index=17)
+    pts, _ = load_points(path)
+    assert gu.same(np.stack([p.pos for p in pts]).reshape(-1), env.pos[:, 17].cpu().numpy())
+    assert gu.same(np.stack([p.v for p in pts]).reshape(-1), env.vel[:, 17].cpu().numpy())
+    other = BatchedPhysicsEnv("Box-v0", 8, "cuda:0", in3d=True)
+    other.load_state(path)
+    assert gu.same(other.pos[:, 3].cpu().numpy(), env.pos[:, 17].cpu().numpy())
+    sd = env.state_dict()
+    env2 = BatchedPhysicsEnv("Box-v0", 64, "cuda:0", in3d=True, keep_old_a=True)
+    env2.load_state_dict(sd)
+    a = torch.rand(64, 4, device="cuda:0") * 2 - 1
+    env.step(a); env2.step(a)
+    assert gu.same(env.pos.cpu().numpy(), env2.pos.cpu().numpy()) and gu.same(env.obs.cpu().numpy(), env2.obs.cpu().numpy())
+
+
+def test_step_host_end_to_end_buffers():
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    E = 4096
+    a = BatchedPhysicsEnv("Balance-v0", E, "cuda:0", in3d=True, seed=3)
+    b = BatchedPhysicsEnv("Balance-v0", E, "cuda:0", in3d=True, seed=3)
+    h_act = (torch.rand(E, 2) * 2 - 1).pin_memory()
+    h_obs = torch.empty(E, a.obs_dim).pin_memory()
+    h_rew, h_done = torch.empty(E).pin_memory(), torch.empty(E, dtype=torch.uint8).pin_memory()
+    d_act = torch.empty(E, 2, device="cuda:0")
+    a.step_host(h_act, d_act, h_obs, h_rew, h_done)
+    obs, rew, done, _ = b.step(h_act.cuda())
+    torch.cuda.synchronize()
+    assert gu.same(h_obs.numpy(), obs.cpu().numpy()) and gu.same(h_rew.numpy(), rew.cpu().numpy())
+    assert gu.same(h_done.numpy().astype(bool), done.cpu().numpy())

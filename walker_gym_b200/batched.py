@@ -244,20 +244,12 @@ class BatchedPhysicsEnv:
         with torch.cuda.device(self.device):
             rc = self.lib.wg_stats_reduce(self.fin_stats.data_ptr(), self.num_envs, self._stats_out.data_ptr(), self._stream())
         _lib.check(rc, "wg_stats_reduce")
-        out = self._stats_out
-        if all_reduce:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                out = out.clone()
-                dist.all_reduce(out, op=dist.ReduceOp.SUM)
-        s = out.tolist()
+        from .dist import all_reduce_stats, finalize_stats
+        out = all_reduce_stats(self._stats_out) if all_reduce else self._stats_out
+        stats = finalize_stats(out)
         if clear:
             self.fin_stats.zero_()
-        n = s[3]
-        mean = s[0] / n if n else float("nan")
-        var = max(s[1] / n - mean * mean, 0.0) if n else float("nan")
-        return {"episodes": int(n), "return_mean": mean, "return_std": var ** 0.5 if n else float("nan"),
-                "length_mean": s[2] / n if n else float("nan"), "return_sum": s[0], "return_sqsum": s[1], "length_sum": s[2]}
+        return stats
 
     # ---- checkpoint / state.pkl ------------------------------------------------------
     def state_dict(self) -> dict:
