@@ -121,6 +121,11 @@ def cpu_run(n_env: int, steps: int, warmup: int, seed: int = 0):
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import walker_oracle as wo
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    threads = wo.set_threads(ncpu)          # all host threads (torchrun would pin OMP_NUM_THREADS=1)
     body = wo.make_body(wo.BALANCE)
     prm = wo.make_params(in3d=True, auto_reset=2, seed=seed)
     st = wo.init_state(body, n_env)
@@ -136,7 +141,7 @@ def cpu_run(n_env: int, steps: int, warmup: int, seed: int = 0):
         prm.step_index = warmup + t + 1
         wo.step(body, prm, st, ring[t % 8], want_info=False)
     dt = time.perf_counter() - t0
-    return n_env * steps / dt, dt, os.cpu_count() or 1
+    return n_env * steps / dt, dt, threads
 
 
 def cpu_baseline(target_seconds: float):
@@ -264,7 +269,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if tr is None else tr * E, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
-                         "kernel": "wg::step_static_kernel<TopoBalance,3D,rowmajor,EPT=2>",
+                         "kernel": "wg::step_static_kernel<TopoBalance, in3d, OBS=row-major staged, EPT=1, MM=1>",
                          "kernel_us": per_launch_s * 1e6},
             "e2e": e2e, "gpu_launches": K, "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "return_mean", "length_mean")},

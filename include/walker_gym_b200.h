@@ -14,7 +14,7 @@
  *   pos, vel, old_a : SoA  [(n*3 + c) * E + e]      n = mass, c = x/y/z
  *   mx              : SoA  [m * E + e]              m = muscle (current length Muscle.x)
  *   steps           : int32 [E]
- *   action          : row-major [E][act_dim]        (what a policy emits)
+ *   action          : row-major [E][act_dim] (act_layout 0) or feature-major [act_dim][E] (act_layout 1)
  *   obs             : row-major [E][D] (obs_layout 0) or feature-major [D][E] (obs_layout 1)
  *   reward [E], done uint8 [E], contact_* uint32 bitmask [E] (bit n = mass n)
  *   energy [E], centroid [3][E], ep_ret [E], fin_stats [4][E]
@@ -97,6 +97,8 @@ typedef struct wg_buffers {
     const float* action;        /* in */
     int32_t      act_dim;       /* columns of action; only min(act_dim, n_muscle) are used (Creature.act :164-167) */
     int32_t      obs_layout;    /* 0 = [E][D] row-major, 1 = [D][E] */
+    int32_t      act_layout;    /* 0 = [E][act_dim] row-major, 1 = [act_dim][E] (what a feature-major policy emits) */
+    int32_t      reserved0;
     float*       obs;           /* out, optional */
     float*       reward;        /* out, optional */
     uint8_t*     done;          /* out, optional */
@@ -108,6 +110,8 @@ typedef struct wg_buffers {
     float*       fin_stats;     /* in/out, optional: per-env sums over finished episodes:
                                    [0] return, [1] return^2, [2] length, [3] count */
     const float* noise;         /* in, optional: jitter used by auto-reset / wg_reset instead of Philox */
+    const uint32_t* step_counter; /* in, optional: device scalar added to prm->step_index; lets a CUDA graph
+                                   that replays wg_step advance the Philox counter without new parameters */
 } wg_buffers;
 
 int         wg_abi_version(void);
@@ -121,6 +125,14 @@ int wg_obs_dim(const wg_topology* topo, int in3d);
 int wg_kernel_variant(const wg_topology* topo);
 /* Force the generic kernel (1) or restore automatic dispatch (0); returns the old value. */
 int wg_force_generic(int on);
+/* Kernel-selection knobs for experiments and tests; results never depend on them.
+ *   WG_TUNE_TMA (0): 1 = use the persistent TMA-pipelined variant of the specialised kernels when
+ *                    the buffers allow it (E % 4 == 0, 16-byte aligned); default 0.
+ *   WG_TUNE_EPT (1): envs per thread of the non-TMA specialised kernel, 1 (default) or 2.
+ * Returns the previous value, or WG_ERR_BAD_ARG. */
+#define WG_TUNE_TMA 0
+#define WG_TUNE_EPT 1
+int wg_set_tuning(int key, int value);
 
 /*
  * PhysicsEnv.step for n_env environments (gym/optimized_env.py:70-92):

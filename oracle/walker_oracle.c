@@ -423,5 +423,14 @@ int wgo_reset(const wgo_body *b, const wgo_params *p, int64_t E, int mode,
     return 0;
 }
 
+#ifdef _OPENMP
+#include <omp.h>
+void wgo_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int wgo_get_max_threads(void) { return omp_get_max_threads(); }
+#else
+void wgo_set_num_threads(int n) { (void)n; }
+int wgo_get_max_threads(void) { return 1; }
+#endif
+
 int wgo_sizeof_body(void) { return (int)sizeof(wgo_body); }
 int wgo_sizeof_params(void) { return (int)sizeof(wgo_params); }

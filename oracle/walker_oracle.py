@@ -76,6 +76,12 @@ def lib():
     return _lib
 
 
+def set_threads(n: int) -> int:
+    """Set the OpenMP team size of the oracle (torchrun exports OMP_NUM_THREADS=1); returns the size in effect."""
+    lib().wgo_set_num_threads(C.c_int(int(n)))
+    return int(lib().wgo_get_max_threads())
+
+
 def make_body(spec) -> Body:
     """Evaluate the morphology exactly as the reference constructors would."""
     b = Body()

@@ -45,14 +45,19 @@ class WgBuffers(C.Structure):
     _fields_ = [
         ("pos", C.c_void_p), ("vel", C.c_void_p), ("old_a", C.c_void_p), ("mx", C.c_void_p), ("steps", C.c_void_p),
         ("action", C.c_void_p), ("act_dim", C.c_int32), ("obs_layout", C.c_int32),
+        ("act_layout", C.c_int32), ("reserved0", C.c_int32),
         ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
         ("contact_pre", C.c_void_p), ("contact_post", C.c_void_p),
         ("energy", C.c_void_p), ("centroid", C.c_void_p),
         ("ep_ret", C.c_void_p), ("fin_stats", C.c_void_p), ("noise", C.c_void_p),
+        ("step_counter", C.c_void_p),
     ]
 
 
+TUNE_TMA, TUNE_EPT = 0, 1
+
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
+           "wg_set_tuning",
            "wg_step", "wg_reset", "wg_stats_reduce", "wg_step_host")
 
 _lib = None
@@ -83,6 +88,8 @@ def load():
     lib.wg_obs_dim.argtypes = [P(WgTopology), C.c_int]
     lib.wg_kernel_variant.argtypes = [P(WgTopology)]
     lib.wg_force_generic.argtypes = [C.c_int]
+    lib.wg_set_tuning.argtypes = [C.c_int, C.c_int]
+    lib.wg_set_tuning.restype = C.c_int
     lib.wg_step.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_void_p]
     lib.wg_reset.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     lib.wg_stats_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]

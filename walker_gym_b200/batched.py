@@ -63,7 +63,8 @@ class BatchedPhysicsEnv:
     def __init__(self, creature: Union[Creature, str], num_envs: int, device: Union[str, torch.device] = "cuda",
                  in3d: bool = False, g=100, dampk=0, ground_high=0, ground_k=1000, ground_damp=100,
                  friction=100, rand_sigma=0.1, *, max_steps: int = 1000, time_step: float = 0.01, k_sub: int = 1,
-                 auto_reset="template", obs_layout: str = "row", seed: int = 0, env_offset: int = 0,
+                 auto_reset="template", obs_layout: str = "row", act_layout: str = "row", seed: int = 0,
+                 env_offset: int = 0, graph_safe: bool = False,
                  track_info: bool = False, track_stats: bool = True, track_contacts: bool = False,
                  keep_old_a: bool = False, initial_reset: bool = True):
         self.lib = _lib.load()
@@ -80,6 +81,9 @@ class BatchedPhysicsEnv:
             raise ValueError(f"auto_reset must be one of {sorted(map(str, AUTO_RESET))}")
         if obs_layout not in ("row", "feature"):
             raise ValueError("obs_layout must be 'row' ([E, D]) or 'feature' ([D, E])")
+        if act_layout not in ("row", "feature"):
+            raise ValueError("act_layout must be 'row' ([E, A]) or 'feature' ([A, E])")
+        self.act_layout = act_layout
         self.params = make_params(in3d=in3d, g=g, dampk=dampk, ground_high=ground_high, ground_k=ground_k,
                                   ground_damp=ground_damp, friction=friction, rand_sigma=rand_sigma,
                                   time_step=time_step, max_steps=max_steps, k_sub=k_sub,
@@ -107,6 +111,9 @@ class BatchedPhysicsEnv:
         self.ep_ret = torch.zeros(E, dtype=f32, device=dev) if track_stats else None
         self.fin_stats = torch.zeros(4, E, dtype=f32, device=dev) if track_stats else None
         self._stats_out = torch.zeros(8, dtype=torch.float64, device=dev)
+        # graph_safe: the Philox step index lives in a device scalar advanced by a device op, so a
+        # captured CUDA graph that replays step() keeps drawing fresh reset jitter
+        self._counter = torch.zeros(1, dtype=torch.int32, device=dev) if graph_safe else None
         self._buf = WgBuffers()
         self._bind()
         if initial_reset:
@@ -128,6 +135,17 @@ class BatchedPhysicsEnv:
         b.energy, b.centroid = self._p(self.energy), self._p(self.centroid)
         b.ep_ret, b.fin_stats = self._p(self.ep_ret), self._p(self.fin_stats)
         b.action, b.act_dim, b.noise = None, 0, None
+        b.act_layout = 0 if self.act_layout == "row" else 1
+        b.step_counter = self._p(self._counter)
+
+    def _advance(self) -> None:
+        if self._counter is not None:
+            self._counter.add_(1)
+        else:
+            self.step_count += 1
+
+    def _stamp(self) -> None:
+        self.params.step_index = 0 if self._counter is not None else (self.step_count & 0xFFFFFFFF)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -163,20 +181,21 @@ class BatchedPhysicsEnv:
             if mask.dtype != torch.uint8 or mask.numel() != self.num_envs or not mask.is_contiguous():
                 raise ValueError("mask must be a contiguous bool/uint8 tensor of length num_envs")
             mptr = mask.data_ptr()
-        self.params.step_index = self.step_count & 0xFFFFFFFF
+        self._stamp()
         with torch.cuda.device(self.device):
             rc = self.lib.wg_reset(C.byref(self.topo), C.byref(self.params), C.byref(self._buf),
                                    self.num_envs, m, mptr, self._stream())
         self._buf.noise = None
         _lib.check(rc, "wg_reset")
-        self.step_count += 1
+        self._advance()
         return self.obs
 
     def step(self, action: Optional[torch.Tensor], noise: Optional[torch.Tensor] = None):
         """``PhysicsEnv.step`` for every env, one kernel launch.
 
-        ``action``: float32 [E, A]; only the first min(A, M) columns drive muscles
-        (Creature.act, gym/optimized_walker.py:164-167); ``None`` applies no action.
+        ``action``: float32 [E, A] (or [A, E] with ``act_layout="feature"``); only the first
+        min(A, M) columns drive muscles (Creature.act, gym/optimized_walker.py:164-167);
+        ``None`` applies no action.
         Returns ``(obs, reward, done, info)``: views of buffers that the next call overwrites.
         With auto-reset on, ``obs`` of a done env is its post-reset observation while
         ``reward``/``done`` describe the step that ended the episode."""
@@ -184,17 +203,18 @@ class BatchedPhysicsEnv:
         if action is None:
             b.action, b.act_dim = None, 0
         else:
-            if action.dim() != 2 or action.shape[0] != self.num_envs:
-                raise ValueError(f"action must have shape [{self.num_envs}, A]")
+            env_axis = 0 if self.act_layout == "row" else 1
+            if action.dim() != 2 or action.shape[env_axis] != self.num_envs:
+                raise ValueError(f"action must have shape [{self.num_envs}, A] (row) or [A, {self.num_envs}] (feature)")
             self._check_f32(action, action.shape, "action")
-            b.action, b.act_dim = action.data_ptr(), int(action.shape[1])
+            b.action, b.act_dim = action.data_ptr(), int(action.shape[1 - env_axis])
         b.noise = self._p(self._check_f32(noise, (3 * self.N, self.num_envs), "noise")) if noise is not None else None
-        self.params.step_index = self.step_count & 0xFFFFFFFF
+        self._stamp()
         with torch.cuda.device(self.device):
             rc = self.lib.wg_step(C.byref(self.topo), C.byref(self.params), C.byref(b), self.num_envs, self._stream())
         b.noise = None
         _lib.check(rc, "wg_step")
-        self.step_count += 1
+        self._advance()
         info = {}
         if self.energy is not None:
             info = {"steps": self.steps, "centroid_position": self.centroid, "total_energy": self.energy}
@@ -219,14 +239,16 @@ class BatchedPhysicsEnv:
         if h_done is not None and (h_done.element_size() != 1 or h_done.numel() != self.num_envs):
             raise ValueError("h_done must be a 1-byte dtype of length E")
         b = self._buf
+        if self.act_layout != "row":
+            raise ValueError("step_host needs act_layout='row'")
         b.action, b.act_dim, b.noise = d_action.data_ptr(), int(d_action.shape[1]), None
-        self.params.step_index = self.step_count & 0xFFFFFFFF
+        self._stamp()
         with torch.cuda.device(self.device):
             rc = self.lib.wg_step_host(C.byref(self.topo), C.byref(self.params), C.byref(b), self.num_envs,
                                        h_action.data_ptr(), self._p(h_obs), self._p(h_reward), self._p(h_done),
                                        self._stream())
         _lib.check(rc, "wg_step_host")
-        self.step_count += 1
+        self._advance()
 
     def get_action_space(self):
         return {"shape": (self.M,), "type": "continuous", "low": -1.0, "high": 1.0}

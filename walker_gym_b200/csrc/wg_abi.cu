@@ -11,6 +11,9 @@ namespace wg {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_force_generic{0};
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+static std::atomic<int> g_tune[2] = { {env_int("WG_TMA", 0)}, {env_int("WG_EPT", 1)} };
+int tuning(int key) { return g_tune[key].load(std::memory_order_relaxed); }
 
 int fail(int code, const char* fmt, const char* a) {
     snprintf(g_err, sizeof(g_err), fmt, a);
@@ -49,6 +52,7 @@ static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* 
     if (!b->pos || !b->vel || !b->steps || (t->n_muscle > 0 && !b->mx))
         return fail(WG_ERR_BAD_ARG, "pos/vel/mx/steps must be set%s");
     if (b->obs_layout != 0 && b->obs_layout != 1) return fail(WG_ERR_BAD_ARG, "obs_layout must be 0 or 1%s");
+    if (b->act_layout != 0 && b->act_layout != 1) return fail(WG_ERR_BAD_ARG, "act_layout must be 0 or 1%s");
     if (b->action && b->act_dim < 0) return fail(WG_ERR_BAD_ARG, "act_dim < 0%s");
     return WG_OK;
 }
@@ -88,14 +92,19 @@ int wg_kernel_variant(const wg_topology* topo) {
 
 int wg_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
 
+int wg_set_tuning(int key, int value) {
+    if (key < 0 || key > 1) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
+    if (key == WG_TUNE_EPT && value != 1 && value != 2) return fail(WG_ERR_BAD_ARG, "EPT must be 1 or 2%s");
+    return g_tune[key].exchange(value);
+}
+
 int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf, int64_t n_env, void* cuda_stream) {
     int rc = validate(topo, prm, buf, n_env);
     if (rc != WG_OK) return rc;
     if (n_env == 0) return WG_OK;
     cudaStream_t s = (cudaStream_t)cuda_stream;
     // one env per thread measured fastest on B200 (80 registers, 24 warps/SM); EPT=2 kept as a knob
-    static const int ept_cap = [] { const char* v = getenv("WG_EPT"); return v ? atoi(v) : 1; }();   // tuning knob
-    const int ept = (ept_cap >= 2 && vec_ok(buf, n_env, 2)) ? 2 : 1;
+    const int ept = (tuning(WG_TUNE_EPT) >= 2 && vec_ok(buf, n_env, 2)) ? 2 : 1;
     switch (pick_variant(topo)) {
         case TopoBalance::kId: return launch_balance(topo, prm, buf, n_env, ept, s);
         case TopoBox::kId:     return launch_box(topo, prm, buf, n_env, ept, s);

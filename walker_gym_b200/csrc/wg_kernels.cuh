@@ -29,9 +29,16 @@ struct StepArgs {
     const float* action; float* obs; float* reward; uint8_t* done;
     uint32_t* contact_pre; uint32_t* contact_post; float* energy; float* centroid;
     float* ep_ret; float* fin_stats; const float* noise;
+    const uint32_t* step_counter;
     int64_t E;
-    int32_t act_dim;
+    int32_t act_dim, act_layout;
 };
+
+// Philox counter word of this launch: the by-value step index plus the optional device-side counter
+template <class Args>
+__device__ __forceinline__ uint32_t step_index_of(const Args& A) {
+    return A.ec.step_index + (A.step_counter ? __ldg(A.step_counter) : 0u);
+}
 
 // ---- vector access of EPT consecutive envs --------------------------------------
 template <int EPT> struct Vec;
@@ -160,7 +167,7 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
         constexpr int AV = EPT * M;
         constexpr bool kVecOk = (M > 0) && (AV == 2 || AV == 4 || AV == 8);
         float actv[kVecOk ? AV : 1];
-        const bool act_vec = kVecOk && A.act_dim == M && ((reinterpret_cast<uintptr_t>(A.action) & 15u) == 0);
+        const bool act_vec = kVecOk && A.act_layout == 0 && A.act_dim == M && ((reinterpret_cast<uintptr_t>(A.action) & 15u) == 0);
         if (act_vec) {
             const float* ap = A.action + e * M;
             if (AV == 2) { const float2 v = *reinterpret_cast<const float2*>(ap); actv[0] = v.x; actv[AV > 1 ? 1 : 0] = v.y; }
@@ -182,7 +189,8 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
 #pragma unroll
             for (int m = 0; m < M; m++) {
                 if (m < na) {
-                    float x = st[j].mx(m) + (act_vec ? actv[j * M + m] : A.action[(e + j) * A.act_dim + m]);
+                    float x = st[j].mx(m) + (act_vec ? actv[j * M + m]
+                                             : A.act_layout ? A.action[(int64_t)m * E + e + j] : A.action[(e + j) * A.act_dim + m]);
                     if (A.bv.mlo[m] > x) x = A.bv.mlo[m];       // python max(x, lo)
                     if (A.bv.mhi[m] < x) x = A.bv.mhi[m];       // python min(x, hi)
                     st[j].mx(m) = x;
@@ -212,7 +220,7 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
                 epr[j] = (o.done && A.ec.auto_reset) ? 0.0f : r;
             }
             if (o.done && A.ec.auto_reset) {
-                apply_reset<IN3D>(topo, A.bv, A.ec, st[j], A.ec.auto_reset, A.noise, E, e + j);
+                apply_reset<IN3D>(topo, A.bv, A.ec, st[j], A.ec.auto_reset, A.noise, E, e + j, step_index_of(A));
                 stp[j] = 0;
             }
             // ---- observation of the (possibly reset) state ----
@@ -330,7 +338,7 @@ step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A) {
         for (int m = 0; m < M; m++) st.mx(m) = A.mx[(int64_t)m * E + e];
         const int na = A.act_dim < M ? A.act_dim : M;
         for (int m = 0; m < na; m++) {
-            float x = st.mx(m) + A.action[e * A.act_dim + m];
+            float x = st.mx(m) + (A.act_layout ? A.action[(int64_t)m * E + e] : A.action[e * A.act_dim + m]);
             if (A.bv.mlo[m] > x) x = A.bv.mlo[m];
             if (A.bv.mhi[m] < x) x = A.bv.mhi[m];
             st.mx(m) = x;
@@ -359,7 +367,7 @@ step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A) {
             A.ep_ret[e] = (o.done && A.ec.auto_reset) ? 0.0f : r;
         }
         if (o.done && A.ec.auto_reset) {
-            apply_reset<IN3D>(topo, A.bv, A.ec, st, A.ec.auto_reset, A.noise, E, e);
+            apply_reset<IN3D>(topo, A.bv, A.ec, st, A.ec.auto_reset, A.noise, E, e, step_index_of(A));
             sn = 0;
         }
         A.steps[e] = sn;
@@ -438,7 +446,7 @@ reset_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A, int mode,
         st.a_[r / 3][r % 3] = A.old_a ? A.old_a[(int64_t)r * E + e] : 0.0f;
     }
     for (int m = 0; m < M; m++) st.mx_[m] = A.mx[(int64_t)m * E + e];
-    apply_reset<IN3D>(topo, A.bv, A.ec, st, mode, A.noise, E, e);
+    apply_reset<IN3D>(topo, A.bv, A.ec, st, mode, A.noise, E, e, step_index_of(A));
     A.steps[e] = 0;
     if (A.ep_ret) A.ep_ret[e] = 0.0f;
     for (int r = 0; r < 3 * N; r++) {

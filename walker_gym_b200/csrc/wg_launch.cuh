@@ -6,10 +6,12 @@
 #include <cstring>
 #include "../../include/walker_gym_b200.h"
 #include "wg_kernels.cuh"
+#include "wg_kernels_tma.cuh"
 
 namespace wg {
 
 int fail(int code, const char* fmt, const char* a = "");
+int tuning(int key);      // current value of a WG_TUNE_* knob (wg_abi.cu)
 
 // ---- register-resident specialisations --------------------------------------------
 // endpoints listed as (p1, p2) pairs, muscles first then skeletons (Creature.run order)
@@ -57,6 +59,7 @@ inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_pa
         bv.mass_f[n] = (float)t->mass[n];
         const ConstDiv cd = make_const_div(bv.mass_f[n]);
         bv.mass_r[n] = cd.r; bv.mass_kind[n] = cd.kind;
+        bv.mass_rd[n] = 1.0 / t->mass[n];
         bv.gm[n] = (-p->g) / t->mass[n];                  // np.asarray([0,-g,0]) / m  (float64)
         bv.mg_f[n] = (float)(t->mass[n] * p->g);          // python m*g, then float32 at the multiply
         if (t->fixed[n]) bv.fixed_mask |= 1u << n;
@@ -81,7 +84,8 @@ inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_pa
     A.action = b->action; A.obs = b->obs; A.reward = b->reward; A.done = b->done;
     A.contact_pre = b->contact_pre; A.contact_post = b->contact_post; A.energy = b->energy; A.centroid = b->centroid;
     A.ep_ret = b->ep_ret; A.fin_stats = b->fin_stats; A.noise = b->noise;
-    A.E = E; A.act_dim = b->action ? b->act_dim : 0;
+    A.step_counter = b->step_counter;
+    A.E = E; A.act_dim = b->action ? b->act_dim : 0; A.act_layout = b->act_layout;
 }
 
 // body-wide mass mode (see forced2): 0 all unit, 1 unit / power of two / small integer, 2 general
@@ -120,10 +124,53 @@ inline int launch_static(const wg_topology* t, const wg_params* p, const wg_buff
     return WG_OK;
 }
 
+// ---- persistent TMA-pipelined variant ----------------------------------------------------------
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// every bulk copy needs 16-byte aligned addresses and sizes: E % 4 == 0 and aligned base pointers
+inline bool tma_ok(const wg_buffers* b, int64_t E) {
+    if (!tuning(WG_TUNE_TMA) || (E % 4) != 0) return false;
+    return aligned16(b->pos) && aligned16(b->vel) && aligned16(b->mx) && aligned16(b->steps) &&
+           aligned16(b->ep_ret) && aligned16(b->action) && aligned16(b->obs);
+}
+
+template <class Topo, bool IN3D, int OBS, int MM>
+inline int launch_static_tma(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
+    using LY = TmaLayout<Topo, IN3D>;
+    StepArgs<Topo::N, Topo::S> A;
+    fill_args(A, t, p, b, E);
+    const size_t smem = LY::smem_bytes(OBS == 1 && b->obs);
+    auto kern = step_static_tma_kernel<Topo, IN3D, OBS, MM>;
+    static thread_local int cached_dev = -1, ctas_per_sm = 0, n_sm = 0;
+    static thread_local size_t cached_smem = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev || smem != cached_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kBlock, smem);
+        if (e != cudaSuccess || ctas_per_sm < 1) return fail(WG_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+        cached_dev = dev; cached_smem = smem;
+    }
+    const int64_t n_tiles = (E + kBlock - 1) / kBlock;
+    const int64_t resident = (int64_t)n_sm * ctas_per_sm;        // persistent grid: a multiple of the SM count
+    const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+    kern<<<grid, kBlock, smem, s>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (tma) launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
 template <class Topo, bool IN3D, int EPT, int MM>
 inline int launch_static_obs(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
     constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
-    switch (obs_mode(b, D)) {
+    const int om = obs_mode(b, D);
+    if constexpr (EPT == 1 && Topo::N <= 4) {
+        if (om != 2 && tma_ok(b, E))
+            return om == 0 ? launch_static_tma<Topo, IN3D, 0, MM>(t, p, b, E, s) : launch_static_tma<Topo, IN3D, 1, MM>(t, p, b, E, s);
+    }
+    switch (om) {
         case 0: return launch_static<Topo, IN3D, 0, EPT, MM>(t, p, b, E, s);
         case 2: if constexpr (D % 2 == 0) return launch_static<Topo, IN3D, 2, EPT, MM>(t, p, b, E, s);
         default: return launch_static<Topo, IN3D, 1, EPT, MM>(t, p, b, E, s);

@@ -22,6 +22,7 @@ struct BodyVals {
     double mass_d[MAXN];    // Point.m
     float mass_f[MAXN];     // float32(m): divisor of float32 forces
     float mass_r[MAXN];     // RN(1 / float32(m))
+    double mass_rd[MAXN];   // RN(1 / m) in float64
     int32_t mass_kind[MAXN];// div_const kind of each mass (0 unit, 1 pow2, 2 small integer, 3 general)
     ConstDiv ndiv;          // division by the number of masses (centroid / means)
     float mg_f[MAXN];       // float32(m * g): potential-energy weight (:245)
@@ -166,7 +167,6 @@ __device__ __forceinline__ uint32_t run_physics(const Topo& topo, const BV& bv, 
 #pragma unroll
     for (int n = 0; n < N; n++) {
         const bool fixed = (bv.fixed_mask >> n) & 1u;
-        const bool unit = (bv.unit_mask >> n) & 1u;
         float ax = st.acc(n, 0), ay = st.acc(n, 1), az = st.acc(n, 2);
         const float vx = st.vel(n, 0), vy = st.vel(n, 1), vz = st.vel(n, 2);
         const float deep = st.pos(n, 1) - ec.ground;
@@ -183,12 +183,13 @@ __device__ __forceinline__ uint32_t run_physics(const Topo& topo, const BV& bv, 
                 az = az + div_const(ec.ndampk * vz, md.m, md.r, md.kind);
             }
             if (hit) {
-                const double m = bv.mass_d[n];
-                ay = forced_list(ay, ec.nground_k * deep, m, unit);      // ground spring
-                ay = forced_list(ay, ec.nground_damp * vy, m, unit);     // ground damper
+                const double m = bv.mass_d[n], rd = bv.mass_rd[n];
+                const int kd = MM == 0 ? 0 : bv.mass_kind[n];
+                ay = forced_list(ay, ec.nground_k * deep, m, rd, kd);    // ground spring
+                ay = forced_list(ay, ec.nground_damp * vy, m, rd, kd);   // ground damper
                 const float ff = fabsf(deep) * ec.friction;             // friction
-                ax = forced_list(ax, (-vx) * ff, m, unit);
-                if (IN3D) az = forced_list(az, (-vz) * ff, m, unit);
+                ax = forced_list(ax, (-vx) * ff, m, rd, kd);
+                if (IN3D) az = forced_list(az, (-vz) * ff, m, rd, kd);
             }
         }
         // Point.run1: v += a*t; pos += v*t   (old_a = a stays in acc)
@@ -230,7 +231,8 @@ __device__ __forceinline__ float np_pairwise_sum(int n, Get get) {
 // Template reset + jitter (PhysicsEnv.reset, optimized_env.py:53-68; make_env :273-294)
 template <bool IN3D, class Topo, class BV, class Store>
 __device__ __forceinline__ void apply_reset(const Topo& topo, const BV& bv, const EnvConst& ec, Store& st,
-                                            int mode, const float* __restrict__ noise, int64_t E, int64_t e) {
+                                            int mode, const float* __restrict__ noise, int64_t E, int64_t e,
+                                            uint32_t step_index) {
     const int N = topo.n(), M = topo.m();
     if (mode == 2) {
 #pragma unroll
@@ -248,7 +250,7 @@ __device__ __forceinline__ void apply_reset(const Topo& topo, const BV& bv, cons
 #pragma unroll
             for (int c = 0; c < 3; c++) z[c] = noise[(int64_t)(n * 3 + c) * E + e];
         } else {
-            normal3(ec.seed_lo, ec.seed_hi, ec.env_offset + (uint32_t)e, ec.step_index, (uint32_t)n, z);
+            normal3(ec.seed_lo, ec.seed_hi, ec.env_offset + (uint32_t)e, step_index, (uint32_t)n, z);
 #pragma unroll
             for (int c = 0; c < 3; c++) z[c] = ec.sigma * z[c];
         }
