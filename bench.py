@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
+                    help="BASELINE.json config: 3 = Balance-v0 throughput (headline, default), 4 = enlarged body "
+                         "(4x masses/springs) with 8 substeps, 5 = PPO rollout collection (torch MLP policy + step kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -194,9 +197,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     W, K = max(args.warmup, 3), args.steps
     E = args.envs_per_gpu
+    if args.config == 5:
+        return run_rollout(args, rank, world, dev)
+    body, k_sub = (ENV_ID, 1) if args.config == 3 else ("quad_balance", 8)
 
-    env = BatchedPhysicsEnv(ENV_ID, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
-                            track_stats=True)
+    env = BatchedPhysicsEnv(body, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
+                            track_stats=True, k_sub=k_sub)
+    bytes_per_env_step = 48 * env.N + 12 * env.M + 13 + 36 * env.N + 4 * env.M
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     ring = [(torch.rand(E, env.M, device=dev, generator=g) * 2 - 1) for _ in range(16)]
 
@@ -253,29 +260,93 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = hbm_peak()
         per_launch_s = ms * 1e-3 / K
-        achieved = E * BYTES_PER_ENV_STEP / per_launch_s / 1e9
+        achieved = E * bytes_per_env_step / per_launch_s / 1e9
         tr = ncu_traffic_per_env_step()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{ENV_ID} (gym/optimized_walker.py create_balance_creature), in3d=True, "
-                                   f"{E} envs per GPU, 1 kernel launch per env-step, K_sub=1, template auto-reset, "
-                                   "reference semantics as written, U(-1,1) f32 actions from a 16-deep device ring",
-                       "envs_per_gpu": E, "global_envs": world * E, "obs": "row-major [E,38] materialised",
-                       "l2": f"state+obs+actions per step = {E * BYTES_PER_ENV_STEP / 1e6:.0f} MB > 126 MB L2 "
+            "config": {"workload": (f"{ENV_ID} (gym/optimized_walker.py create_balance_creature)" if args.config == 3 else
+                                    "quad_balance (4x Balance-v0: N=16, S=20, M=8; BASELINE config 4)") +
+                                   f", in3d=True, {E} envs per GPU, 1 kernel launch per env-step, K_sub={k_sub}, template "
+                                   "auto-reset, reference semantics as written, U(-1,1) f32 actions from a 16-deep device ring",
+                       "baseline_config": args.config,
+                       "envs_per_gpu": E, "global_envs": world * E, "obs": f"row-major [E,{env.obs_dim}] materialised",
+                       "l2": f"state+obs+actions per step = {E * bytes_per_env_step / 1e6:.0f} MB > 126 MB L2 "
                              "(inputs larger than L2, no flush needed)",
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if tr is None else tr * E, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
-                         "kernel": "wg::step_static_kernel<TopoBalance, in3d, OBS=row-major staged, EPT=1, MM=1>",
+                         "algorithmic_bytes_per_env_step": bytes_per_env_step,
+                         "kernel": ("wg::step_static_kernel<TopoBalance, in3d, OBS=row-major staged, EPT=1, MM=1>" if args.config == 3
+                                    else "wg::step_static_kernel<TopoQuad, in3d, OBS=row-major staged, EPT=1, MM=1>"),
                          "kernel_us": per_launch_s * 1e6},
             "e2e": e2e, "gpu_launches": K, "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "return_mean", "length_mean")},
         }
-        if not args.no_cpu_baseline and world == 1:
+        if args.config == 4:
+            line["roofline"]["note"] = ("config 4 is fp32-issue bound, not HBM bound: ~8 substeps x 20 springs per env-step "
+                                        "against 1485 bytes (SURVEY 7.5); the HBM fraction is reported for completeness")
+        if not args.no_cpu_baseline and world == 1 and args.config == 3:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_rollout(args, rank, world, dev):
+    """BASELINE config 5: PPO rollout collection -- torch MLP policy (obs->64->64->M, tanh) + the step kernel,
+    262144 envs per GPU, T=32 steps per CUDA-graph replay, episode-return statistics all-reduced over NCCL."""
+    import torch
+    import torch.distributed as dist
+    from walker_gym_b200 import BatchedPhysicsEnv
+    from walker_gym_b200.rollout import FeatureMajorMLP, RolloutCollector
+    E = args.envs_per_gpu if args.envs_per_gpu != (1 << 20) else (1 << 18)
+    T = 32
+    torch.manual_seed(7 + rank)
+    env = BatchedPhysicsEnv(ENV_ID, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
+                            obs_layout="feature", act_layout="feature", graph_safe=True)
+    pol = FeatureMajorMLP(env.obs_dim, env.M).to(dev)
+    col = RolloutCollector(env, pol, T)
+    n_roll = max(1, args.steps // T)
+    n_warm = max(3, args.warmup // T)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(n_warm):
+        col.collect()
+    barrier()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(n_roll):
+        col.collect()
+    stats = col.episode_stats(all_reduce=True)         # K3 + NCCL all-reduce of 8 doubles, once per timed region
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    tmax = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    steps = n_roll * T
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": world * E * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": n_warm * T, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"PPO rollout collection (BASELINE config 5): torch MLP policy {env.obs_dim}->64->64->{env.M} "
+                                   f"(tanh, gaussian head, value head) + fused step kernel, {ENV_ID} in3d, {E} envs per GPU, "
+                                   f"T={T} steps per CUDA-graph replay, GAE on device, feature-major obs/actions",
+                       "baseline_config": 5, "envs_per_gpu": E, "global_envs": world * E,
+                       "parallelism": f"env-sharded x{world}; one NCCL all-reduce of 8 doubles (episode-return stats) per timed region"},
+            "gpu_launches": steps, "clocks": clocks,
+            "episode_stats": {k: stats[k] for k in ("episodes", "return_mean", "length_mean")},
+        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
