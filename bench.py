@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
                     help="BASELINE.json config: 3 = Balance-v0 throughput (headline, default), 4 = enlarged body "
                          "(4x masses/springs) with 8 substeps, 5 = PPO rollout collection (torch MLP policy + step kernel)")
+    ap.add_argument("--generic", action="store_true", help="measure the run-time-topology kernel instead of the specialisation")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -197,6 +198,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     W, K = max(args.warmup, 3), args.steps
     E = args.envs_per_gpu
+    if args.generic:
+        from walker_gym_b200 import _lib
+        _lib.load().wg_force_generic(1)
     if args.config == 5:
         return run_rollout(args, rank, world, dev)
     body, k_sub = (ENV_ID, 1) if args.config == 3 else ("quad_balance", 8)

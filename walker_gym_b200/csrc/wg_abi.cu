@@ -31,6 +31,7 @@ static bool topo_matches(const wg_topology* t) {
 static int pick_variant(const wg_topology* t) {
     if (g_force_generic.load()) return 0;
     if (mass_mode(t) == 2) return 0;       // arbitrary masses: only the generic kernel carries full IEEE division
+    for (int n = 0; n < t->n_mass; n++) if (t->fixed[n]) return 0;   // DingPoints: generic kernel only
     if (topo_matches<TopoBalance>(t)) return TopoBalance::kId;
     if (topo_matches<TopoBox>(t)) return TopoBox::kId;
     if (topo_matches<TopoQuad>(t)) return TopoQuad::kId;

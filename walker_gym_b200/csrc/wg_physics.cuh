@@ -133,19 +133,20 @@ __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store
     const float dx = L - x;
     const float fs = (-dx) * bv.sk[sp];                                   // -dx * k (sign as written)
     float d0 = pjx - pix, d1 = pjy - piy, d2 = pjz - piz;                 // direction = p2 - p1
-    if (L > 0.0f) div3_len(d0, d1, d2, L);
+    div3_len(d0, d1, d2, L);
     const float F[3] = { fs * d0, fs * d1, fs * d2 };
     const float dk = np_dot3(st.vel(i, 0) - st.vel(j, 0), st.vel(i, 1) - st.vel(j, 1),
                              st.vel(i, 2) - st.vel(j, 2), d0, d1, d2);
     const float cd = dk * bv.sdamp[sp];
     const float D[3] = { cd * d0, cd * d1, cd * d2 };
     const float nF[3] = { -F[0], -F[1], -F[2] }, nD[3] = { -D[0], -D[1], -D[2] };
-    if (!((bv.fixed_mask >> i) & 1u)) {                                   // p1.forced(force); p1.forced(-damp)
+    // DingPoints (fixed masses) only occur with MM == 2: bodies that have them run the generic kernel
+    if (MM != 2 || !((bv.fixed_mask >> i) & 1u)) {                        // p1.forced(force); p1.forced(-damp)
         float a[3] = { st.acc(i, 0), st.acc(i, 1), st.acc(i, 2) };
         forced2<MM>(a, F, nD, bv, i);
         st.acc(i, 0) = a[0]; st.acc(i, 1) = a[1]; st.acc(i, 2) = a[2];
     }
-    if (!((bv.fixed_mask >> j) & 1u)) {                                   // p2.forced(-force); p2.forced(damp)
+    if (MM != 2 || !((bv.fixed_mask >> j) & 1u)) {                        // p2.forced(-force); p2.forced(damp)
         float a[3] = { st.acc(j, 0), st.acc(j, 1), st.acc(j, 2) };
         forced2<MM>(a, nF, D, bv, j);
         st.acc(j, 0) = a[0]; st.acc(j, 1) = a[1]; st.acc(j, 2) = a[2];
@@ -166,7 +167,7 @@ __device__ __forceinline__ uint32_t run_physics(const Topo& topo, const BV& bv, 
     uint32_t contact = 0;
 #pragma unroll
     for (int n = 0; n < N; n++) {
-        const bool fixed = (bv.fixed_mask >> n) & 1u;
+        const bool fixed = (MM == 2) && ((bv.fixed_mask >> n) & 1u);
         float ax = st.acc(n, 0), ay = st.acc(n, 1), az = st.acc(n, 2);
         const float vx = st.vel(n, 0), vy = st.vel(n, 1), vz = st.vel(n, 2);
         const float deep = st.pos(n, 1) - ec.ground;
