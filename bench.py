@@ -259,7 +259,25 @@ def run_ours(args):
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": world * E * Ke / (float(t2.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": E * env.M * 4, "d2h_bytes_per_step": E * (env.obs_dim * 4 + 4 + 1),
-               "steps": Ke}
+               "steps": Ke,
+               "what": "wg_step_host: pinned host actions in; observations, rewards and dones out to pinned host memory "
+                       "every step (the reference-facing call); PCIe-bound by the 152-byte observation rows"}
+        # the other usage mode: policy on the device -- observations stay in HBM, only reward/done go to the host
+        Kd = max(Ke, 50)
+        for _ in range(3):
+            env.step_host(h_act, d_act, None, h_rew, h_done)
+        barrier()
+        e0.record()
+        for _ in range(Kd):
+            env.step_host(h_act, d_act, None, h_rew, h_done)
+        e1.record()
+        barrier()
+        t3 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        e2e["device_policy_mode"] = {"value": world * E * Kd / (float(t3.item()) * 1e-3), "unit": UNIT,
+                                     "h2d_bytes_per_step": E * env.M * 4, "d2h_bytes_per_step": E * 5, "steps": Kd,
+                                     "what": "same call with h_obs = NULL: observations stay on the device"}
 
     if rank == 0:
         peak, peak_src = hbm_peak()

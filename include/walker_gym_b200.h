@@ -77,11 +77,14 @@ typedef struct wg_params {
     float    fall_thresh;   /* float32(ground_high - 50): done when mean(y) < this (:218) */
     float    ground_k, ground_damp, friction;   /* contact spring, damper, friction (:162-172) */
     float    dt;            /* time_step (:42) */
+    float    dt2;           /* float32(time_step ** 2): only used by integrator 1 */
     float    sigma;         /* rand_sigma of the in-kernel reset jitter (:59-62) */
     int32_t  in3d;
     int32_t  max_steps;     /* :44 */
     int32_t  k_sub;         /* physics substeps per env step (>= 1) */
     int32_t  auto_reset;    /* 0 none; 1 jitter-only = PhysicsEnv.reset (:53-68); 2 template = make_env again */
+    int32_t  integrator;    /* 0 = Point.run1, semi-implicit Euler (gym/optimized_engine.py:258-272, what PhysicsEnv uses);
+                               1 = Point.run2 (:274-288): pos += v*t + 0.5*a*t^2, then v += a*t */
     uint32_t seed_lo, seed_hi;   /* Philox key of the in-kernel jitter */
     uint32_t step_index;    /* global step number (Philox counter word), set by the caller each step */
     uint32_t env_offset;    /* global id of env 0 of this shard (multi-GPU invariance) */

@@ -116,7 +116,7 @@ def snapshot(env):
 
 
 def rollout(creature_or_id, actions, *, env_kwargs=None, seed=0, noise=None,
-            max_steps=None, k_sub=1, reset_on_done=False, init_state=None,
+            max_steps=None, k_sub=1, reset_on_done=False, init_state=None, integrator="run1",
             ref_root: str = DEFAULT_REF):
     """Run the reference ``PhysicsEnv`` for ``len(actions)`` steps.
 
@@ -138,6 +138,11 @@ def rollout(creature_or_id, actions, *, env_kwargs=None, seed=0, noise=None,
     engine.Point.clear()
     np.random.seed(seed)
     draws = []
+    # integrator="run2": PhysicsEnv._run_physics calls Point.run1 (gym/optimized_env.py:178); route that
+    # call to the reference's own Point.run2 (gym/optimized_engine.py:274-288) for the duration of the rollout
+    run1_saved = engine.Point.__dict__["run1"]
+    if integrator == "run2":
+        engine.Point.run1 = engine.Point.__dict__["run2"]
 
     real_normal = np.random.normal
 
@@ -189,6 +194,7 @@ def rollout(creature_or_id, actions, *, env_kwargs=None, seed=0, noise=None,
             energy.append(info["total_energy"])
             centroid.append(info["centroid_position"])
             steps.append(env.steps)
+    engine.Point.run1 = run1_saved
     out = {k: np.stack([s[k] for s in snaps]) for k in snaps[0]}
     out["contact_pre"] = out["contact_pre"][1:]
     out.update(

@@ -50,9 +50,11 @@ typedef struct {
     float fall_thresh;       /* float32(ground_high - 50)  (optimized_env.py:218) */
     float ground_k, ground_damp, friction;
     float dt;                /* float32(time_step) */
+    float dt2;               /* float32(time_step ** 2), integrator 1 only */
     float sigma;             /* rand_sigma for in-kernel reset noise */
     int32_t in3d, max_steps, k_sub;
     int32_t auto_reset;      /* 0 = none, 1 = jitter-only (reference reset()), 2 = template (make_env again) */
+    int32_t integrator;      /* 0 = Point.run1, 1 = Point.run2 (optimized_engine.py:274-288) */
     uint32_t seed_lo, seed_hi;
     uint32_t step_index;     /* global step counter, part of the Philox counter */
     uint32_t env_offset;     /* global id of env 0 of this shard */
@@ -238,10 +240,18 @@ static uint32_t run_physics(const wgo_body *b, const wgo_params *p, env_state *s
     /* Point.run1: v += a*t; pos += v*t; old_a = a  (two roundings each, no FMA) */
     for (int n = 0; n < N; n++)
         for (int c = 0; c < 3; c++) {
-            float at = s->acc[n][c] * p->dt;
-            s->vel[n][c] = s->vel[n][c] + at;
-            float vt = s->vel[n][c] * p->dt;
-            s->pos[n][c] = s->pos[n][c] + vt;
+            if (p->integrator == 0) {
+                float at = s->acc[n][c] * p->dt;
+                s->vel[n][c] = s->vel[n][c] + at;
+                float vt = s->vel[n][c] * p->dt;
+                s->pos[n][c] = s->pos[n][c] + vt;
+            } else {   /* Point.run2: p.pos += p.v*t + 0.5*p.a*t**2; p.v += p.a*t */
+                float vt = s->vel[n][c] * p->dt;
+                float ha = (0.5f * s->acc[n][c]) * p->dt2;
+                s->pos[n][c] = s->pos[n][c] + (vt + ha);
+                float at = s->acc[n][c] * p->dt;
+                s->vel[n][c] = s->vel[n][c] + at;
+            }
             s->old_a[n][c] = s->acc[n][c];
         }
     return contact;

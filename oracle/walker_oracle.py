@@ -44,9 +44,9 @@ class Params(C.Structure):
         ("g", C.c_double),
         ("dampk", C.c_float), ("ground", C.c_float), ("fall_thresh", C.c_float),
         ("ground_k", C.c_float), ("ground_damp", C.c_float), ("friction", C.c_float),
-        ("dt", C.c_float), ("sigma", C.c_float),
+        ("dt", C.c_float), ("dt2", C.c_float), ("sigma", C.c_float),
         ("in3d", C.c_int32), ("max_steps", C.c_int32), ("k_sub", C.c_int32),
-        ("auto_reset", C.c_int32),
+        ("auto_reset", C.c_int32), ("integrator", C.c_int32),
         ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32),
         ("step_index", C.c_uint32), ("env_offset", C.c_uint32),
     ]
@@ -111,7 +111,7 @@ def make_body(spec) -> Body:
 
 def make_params(in3d=False, g=100, dampk=0, ground_high=0, ground_k=1000, ground_damp=100,
                 friction=100, rand_sigma=0.1, time_step=0.01, max_steps=1000, k_sub=1,
-                auto_reset=0, seed=0, step_index=0, env_offset=0) -> Params:
+                auto_reset=0, seed=0, step_index=0, env_offset=0, integrator=0) -> Params:
     p = Params()
     p.g = float(g)
     p.dampk = np.float32(dampk)
@@ -121,6 +121,8 @@ def make_params(in3d=False, g=100, dampk=0, ground_high=0, ground_k=1000, ground
     p.ground_damp = np.float32(ground_damp)
     p.friction = np.float32(friction)
     p.dt = np.float32(time_step)
+    p.dt2 = np.float32(time_step ** 2)
+    p.integrator = 1 if integrator in (1, "run2") else 0
     p.sigma = np.float32(rand_sigma)
     p.in3d, p.max_steps, p.k_sub = int(bool(in3d)), int(max_steps), int(k_sub)
     p.auto_reset = int(auto_reset)

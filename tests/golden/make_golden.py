@@ -94,6 +94,8 @@ def case(name, body, T, seed, env_kwargs=None, **kw):
     for k in ("k_sub", "max_steps", "reset_on_done"):
         if k in kw:
             extra[k] = np.array(int(kw[k]))
+    if "integrator" in kw:
+        extra["integrator"] = np.array(1 if kw["integrator"] == "run2" else 0)
     if "init_state" in kw:
         extra["init_pos"] = np.asarray(kw["init_state"]["pos"], np.float32)
         extra["init_vel"] = np.asarray(kw["init_state"]["vel"], np.float32)
@@ -155,6 +157,8 @@ def main():
     case("autoreset_jitter2d", "Box-v0", 40, 10, dict(in3d=False), max_steps=5, reset_on_done=True)
     case("substeps4_box", "Box-v0", 40, 11, dict(in3d=True), k_sub=4)
     case("substeps8_insect", INSECT, 20, 12, dict(in3d=True), k_sub=8)
+    # the reference's second integrator, Point.run2, in place of run1
+    case("run2_balance3d", "Balance-v0", 60, 14, dict(in3d=True), integrator="run2")
     # physically-signed springs == negative k: stable for 300 steps
     phys_box = json.loads(json.dumps(wo.BOX))
     for grp in ("muscles", "skeletons"):

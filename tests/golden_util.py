@@ -37,7 +37,7 @@ def load(name):
     g["spec"]["muscles"] = [(i, j, dict(kw)) for i, j, kw in g["spec"]["muscles"]]
     g["spec"]["skeletons"] = [(i, j, dict(kw)) for i, j, kw in g["spec"]["skeletons"]]
     g["env_kwargs"] = json.loads(str(g["env_kwargs"]))
-    for k in ("k_sub", "max_steps", "reset_on_done"):
+    for k in ("k_sub", "max_steps", "reset_on_done", "integrator"):
         g[k] = int(g[k]) if k in g else None
     return g
 

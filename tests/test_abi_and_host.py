@@ -245,3 +245,26 @@ def test_oracle_against_live_reference_random_bodies():
             for k in ("obs", "reward", "energy", "centroid", "x"):
                 g[k] = np.asarray(out[k], np.float32)
             assert replay_trajectory(g, wo) is None, f"trial {trial}"
+
+
+@pytest.mark.reference
+def test_config1_walker_py_body_1000_steps_oracle_vs_live_reference():
+    """BASELINE config 1 on the CPU: a gym/walker.py body, 1000 random-action steps, oracle == reference."""
+    import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference checkout not present")
+    import warnings
+    from test_oracle_golden import replay_trajectory
+    spec = spec_of("humanb")
+    rng = np.random.default_rng(123)
+    acts = rng.uniform(-1, 1, (1000, 4)).astype(np.float32)
+    noise = (rng.standard_normal(64) * 0.1).astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = rh.rollout(spec, acts, env_kwargs=dict(in3d=True), noise=noise)
+    g = dict(out, spec=spec, env_kwargs=dict(in3d=True), actions=acts, k_sub=None, max_steps=None, reset_on_done=None)
+    g["reset_noise"] = out["reset_noise"].astype(np.float32)
+    for k in ("obs", "reward", "energy", "centroid", "x"):
+        g[k] = np.asarray(out[k], np.float32)
+    assert replay_trajectory(g, wo) is None
+    assert bool(out["done"][-1]) and not out["done"][:-1].any()

@@ -256,3 +256,18 @@ def test_rollout_collector_cuda_graph_and_eager():
     assert torch.equal(outs[0]["obs"][0], outs[1]["obs"][0])
     for o in outs:
         assert torch.isfinite(o["rewards"]).all() and torch.isfinite(o["logp"]).all()
+
+
+@pytest.mark.parametrize("name", ["box2", "humanb"])
+def test_config1_single_walker_1000_steps(name):
+    """BASELINE config 1: one gym/walker.py body, 1000 steps of random actions; the CPU side is the oracle
+    (the legacy walker.py/engine.py/env.py trio is not executable as shipped; L1 semantics apply)."""
+    env, body, prm, st = make_pair(name, 1, env_kw=dict(in3d=True))
+    run_lockstep(env, body, prm, st, 1000, np.random.default_rng(0))
+    assert int(env.steps.item()) == 1000 and bool(env.done.item())
+
+
+def test_run2_integrator_batched():
+    env, body, prm, st = make_pair("box_v0", 512, env_kw=dict(in3d=True), integrator="run2")
+    prm.integrator = 1
+    run_lockstep(env, body, prm, st, 40, np.random.default_rng(8))

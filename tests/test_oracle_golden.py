@@ -18,6 +18,8 @@ def replay_trajectory(g, stepper):
         prm_kw["max_steps"] = g["max_steps"]
     if g["k_sub"] is not None:
         prm_kw["k_sub"] = g["k_sub"]
+    if g.get("integrator"):
+        prm_kw["integrator"] = g["integrator"]
     auto = 1 if g["reset_on_done"] else 0
     prm = stepper.make_params(auto_reset=auto, **prm_kw)
     st = stepper.init_state(body, 1)

@@ -35,8 +35,9 @@ class WgParams(C.Structure):
         ("g", C.c_double),
         ("dampk", C.c_float), ("ground", C.c_float), ("fall_thresh", C.c_float),
         ("ground_k", C.c_float), ("ground_damp", C.c_float), ("friction", C.c_float),
-        ("dt", C.c_float), ("sigma", C.c_float),
+        ("dt", C.c_float), ("dt2", C.c_float), ("sigma", C.c_float),
         ("in3d", C.c_int32), ("max_steps", C.c_int32), ("k_sub", C.c_int32), ("auto_reset", C.c_int32),
+        ("integrator", C.c_int32),
         ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("step_index", C.c_uint32), ("env_offset", C.c_uint32),
     ]
 

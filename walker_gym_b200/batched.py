@@ -43,7 +43,7 @@ def creature_from_id(env_id: str) -> Creature:
 
 def make_params(*, in3d=False, g=100, dampk=0, ground_high=0, ground_k=1000, ground_damp=100, friction=100,
                 rand_sigma=0.1, time_step=0.01, max_steps=1000, k_sub=1, auto_reset=0, seed=0,
-                step_index=0, env_offset=0) -> WgParams:
+                step_index=0, env_offset=0, integrator="run1") -> WgParams:
     """PhysicsEnv's constructor arguments -> ``wg_params``.  Scalars are converted
     the way NumPy converts the reference's python numbers at their point of use."""
     p = WgParams()
@@ -53,6 +53,10 @@ def make_params(*, in3d=False, g=100, dampk=0, ground_high=0, ground_k=1000, gro
     p.fall_thresh = np.float32(ground_high - 50)
     p.ground_k, p.ground_damp, p.friction = np.float32(ground_k), np.float32(ground_damp), np.float32(friction)
     p.dt, p.sigma = np.float32(time_step), np.float32(rand_sigma)
+    p.dt2 = np.float32(time_step ** 2)            # python `t ** 2`, cast where NumPy would cast it
+    if integrator not in ("run1", "run2", 0, 1):
+        raise ValueError("integrator must be 'run1' (Point.run1) or 'run2' (Point.run2)")
+    p.integrator = 1 if integrator in ("run2", 1) else 0
     p.in3d, p.max_steps, p.k_sub, p.auto_reset = int(bool(in3d)), int(max_steps), int(k_sub), int(auto_reset)
     p.seed_lo, p.seed_hi = int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF
     p.step_index, p.env_offset = int(step_index) & 0xFFFFFFFF, int(env_offset) & 0xFFFFFFFF
@@ -64,7 +68,7 @@ class BatchedPhysicsEnv:
                  in3d: bool = False, g=100, dampk=0, ground_high=0, ground_k=1000, ground_damp=100,
                  friction=100, rand_sigma=0.1, *, max_steps: int = 1000, time_step: float = 0.01, k_sub: int = 1,
                  auto_reset="template", obs_layout: str = "row", act_layout: str = "row", seed: int = 0,
-                 env_offset: int = 0, graph_safe: bool = False,
+                 env_offset: int = 0, graph_safe: bool = False, integrator: str = "run1",
                  track_info: bool = False, track_stats: bool = True, track_contacts: bool = False,
                  keep_old_a: bool = False, initial_reset: bool = True):
         self.lib = _lib.load()
@@ -87,7 +91,8 @@ class BatchedPhysicsEnv:
         self.params = make_params(in3d=in3d, g=g, dampk=dampk, ground_high=ground_high, ground_k=ground_k,
                                   ground_damp=ground_damp, friction=friction, rand_sigma=rand_sigma,
                                   time_step=time_step, max_steps=max_steps, k_sub=k_sub,
-                                  auto_reset=AUTO_RESET[auto_reset], seed=seed, env_offset=env_offset)
+                                  auto_reset=AUTO_RESET[auto_reset], seed=seed, env_offset=env_offset,
+                                  integrator=integrator)
         self.N, self.M = self.topo.n_mass, self.topo.n_muscle
         self.obs_dim = self.lib.wg_obs_dim(C.byref(self.topo), int(self.in3d))
         self.obs_layout = obs_layout

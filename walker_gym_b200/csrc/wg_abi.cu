@@ -50,6 +50,7 @@ static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* 
     if (E < 0 || E > ((int64_t)1 << 31) - 1) return fail(WG_ERR_BAD_ARG, "n_env out of range%s");
     if (p->k_sub < 1) return fail(WG_ERR_BAD_ARG, "k_sub must be >= 1%s");
     if (p->auto_reset < 0 || p->auto_reset > 2) return fail(WG_ERR_BAD_ARG, "auto_reset must be 0, 1 or 2%s");
+    if (p->integrator < 0 || p->integrator > 1) return fail(WG_ERR_BAD_ARG, "integrator must be 0 (run1) or 1 (run2)%s");
     if (!b->pos || !b->vel || !b->steps || (t->n_muscle > 0 && !b->mx))
         return fail(WG_ERR_BAD_ARG, "pos/vel/mx/steps must be set%s");
     if (b->obs_layout != 0 && b->obs_layout != 1) return fail(WG_ERR_BAD_ARG, "obs_layout must be 0 or 1%s");

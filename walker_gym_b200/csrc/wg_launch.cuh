@@ -77,7 +77,7 @@ inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_pa
     ec.dampk_is_zero = (p->dampk == 0.0f);
     ec.ground = p->ground; ec.fall_thresh = p->fall_thresh;
     ec.nground_k = -p->ground_k; ec.nground_damp = -p->ground_damp; ec.friction = p->friction;
-    ec.dt = p->dt; ec.sigma = p->sigma;
+    ec.dt = p->dt; ec.dt2 = p->dt2; ec.sigma = p->sigma; ec.integrator = p->integrator;
     ec.max_steps = p->max_steps; ec.k_sub = p->k_sub; ec.auto_reset = p->auto_reset;
     ec.seed_lo = p->seed_lo; ec.seed_hi = p->seed_hi; ec.step_index = p->step_index; ec.env_offset = p->env_offset;
     A.pos = b->pos; A.vel = b->vel; A.old_a = b->old_a; A.mx = b->mx; A.steps = b->steps;

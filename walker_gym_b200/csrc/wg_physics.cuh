@@ -39,8 +39,8 @@ struct EnvConst {
     float ndampk;           // -dampk
     float ground, fall_thresh;
     float nground_k, nground_damp, friction;
-    float dt, sigma;
-    int32_t max_steps, k_sub, auto_reset;
+    float dt, dt2, sigma;
+    int32_t max_steps, k_sub, auto_reset, integrator;
     uint32_t seed_lo, seed_hi, step_index, env_offset;
     int32_t dampk_is_zero;
 };
@@ -193,12 +193,20 @@ __device__ __forceinline__ uint32_t run_physics(const Topo& topo, const BV& bv, 
                 if (IN3D) az = forced_list(az, (-vz) * ff, m, rd, kd);
             }
         }
-        // Point.run1: v += a*t; pos += v*t   (old_a = a stays in acc)
-        const float nvx = vx + ax * ec.dt, nvy = vy + ay * ec.dt, nvz = vz + az * ec.dt;
-        st.vel(n, 0) = nvx; st.vel(n, 1) = nvy; st.vel(n, 2) = nvz;
-        st.pos(n, 0) = st.pos(n, 0) + nvx * ec.dt;
-        st.pos(n, 1) = st.pos(n, 1) + nvy * ec.dt;
-        st.pos(n, 2) = st.pos(n, 2) + nvz * ec.dt;
+        if (ec.integrator == 0) {
+            // Point.run1: v += a*t; pos += v*t   (old_a = a stays in acc)
+            const float nvx = vx + ax * ec.dt, nvy = vy + ay * ec.dt, nvz = vz + az * ec.dt;
+            st.vel(n, 0) = nvx; st.vel(n, 1) = nvy; st.vel(n, 2) = nvz;
+            st.pos(n, 0) = st.pos(n, 0) + nvx * ec.dt;
+            st.pos(n, 1) = st.pos(n, 1) + nvy * ec.dt;
+            st.pos(n, 2) = st.pos(n, 2) + nvz * ec.dt;
+        } else {
+            // Point.run2 (gym/optimized_engine.py:274-288): pos += v*t + (0.5*a)*t**2; then v += a*t
+            st.pos(n, 0) = st.pos(n, 0) + (vx * ec.dt + (0.5f * ax) * ec.dt2);
+            st.pos(n, 1) = st.pos(n, 1) + (vy * ec.dt + (0.5f * ay) * ec.dt2);
+            st.pos(n, 2) = st.pos(n, 2) + (vz * ec.dt + (0.5f * az) * ec.dt2);
+            st.vel(n, 0) = vx + ax * ec.dt; st.vel(n, 1) = vy + ay * ec.dt; st.vel(n, 2) = vz + az * ec.dt;
+        }
         st.acc(n, 0) = ax; st.acc(n, 1) = ay; st.acc(n, 2) = az;
     }
     return contact;
