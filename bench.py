@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
                     help="BASELINE.json config: 3 = Balance-v0 throughput (headline, default), 4 = enlarged body "
                          "(4x masses/springs) with 8 substeps, 5 = PPO rollout collection (torch MLP policy + step kernel)")
+    ap.add_argument("--obs-layout", default="row", choices=["row", "feature"],
+                    help="observation layout written by the kernel: row-major [E,D] (default) or feature-major [D,E]")
     ap.add_argument("--generic", action="store_true", help="measure the run-time-topology kernel instead of the specialisation")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -206,7 +208,7 @@ def run_ours(args):
     body, k_sub = (ENV_ID, 1) if args.config == 3 else ("quad_balance", 8)
 
     env = BatchedPhysicsEnv(body, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
-                            track_stats=True, k_sub=k_sub)
+                            track_stats=True, k_sub=k_sub, obs_layout=args.obs_layout)
     bytes_per_env_step = 48 * env.N + 12 * env.M + 13 + 36 * env.N + 4 * env.M
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     ring = [(torch.rand(E, env.M, device=dev, generator=g) * 2 - 1) for _ in range(16)]
@@ -238,7 +240,7 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer C-ABI call: pinned host action in, obs/reward/done out ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.obs_layout == "row":
         h_act = torch.empty(E, env.M, dtype=torch.float32).uniform_(-1, 1).pin_memory()
         h_obs = torch.empty(E, env.obs_dim, dtype=torch.float32).pin_memory()
         h_rew = torch.empty(E, dtype=torch.float32).pin_memory()
@@ -283,7 +285,7 @@ def run_ours(args):
         peak, peak_src = hbm_peak()
         per_launch_s = ms * 1e-3 / K
         achieved = E * bytes_per_env_step / per_launch_s / 1e9
-        tr = ncu_traffic_per_env_step()
+        tr = ncu_traffic_per_env_step() if (args.config == 3 and args.obs_layout == "row" and not args.generic) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -293,7 +295,8 @@ def run_ours(args):
                                    f", in3d=True, {E} envs per GPU, 1 kernel launch per env-step, K_sub={k_sub}, template "
                                    "auto-reset, reference semantics as written, U(-1,1) f32 actions from a 16-deep device ring",
                        "baseline_config": args.config,
-                       "envs_per_gpu": E, "global_envs": world * E, "obs": f"row-major [E,{env.obs_dim}] materialised",
+                       "envs_per_gpu": E, "global_envs": world * E, "obs": (f"row-major [E,{env.obs_dim}] materialised" if args.obs_layout == "row"
+                               else f"feature-major [{env.obs_dim},E] materialised"),
                        "l2": f"state+obs+actions per step = {E * bytes_per_env_step / 1e6:.0f} MB > 126 MB L2 "
                              "(inputs larger than L2, no flush needed)",
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
@@ -301,7 +304,7 @@ def run_ours(args):
                          "traffic": None if tr is None else tr * E, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_per_env_step,
                          "kernel": ("wg::step_static_kernel<TopoBalance, in3d, OBS=row-major staged, EPT=1, MM=1>" if args.config == 3
-                                    else "wg::step_static_kernel<TopoQuad, in3d, OBS=row-major staged, EPT=1, MM=1>"),
+                                    else "wg::step_part_kernel<in3d, P=4 lanes per env, row-major, MM=1>"),
                          "kernel_us": per_launch_s * 1e6},
             "e2e": e2e, "gpu_launches": K, "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "return_mean", "length_mean")},

@@ -132,9 +132,12 @@ int wg_force_generic(int on);
  *   WG_TUNE_TMA (0): 1 = use the persistent TMA-pipelined variant of the specialised kernels when
  *                    the buffers allow it (E % 4 == 0, 16-byte aligned); default 0.
  *   WG_TUNE_EPT (1): envs per thread of the non-TMA specialised kernel, 1 (default) or 2.
+ *   WG_TUNE_PART (2): lanes per env of the mass-partitioned kernel used for larger bodies:
+ *                    -1 = automatic (default), 0 = never, 2 / 4 / 8 = force that many parts.
  * Returns the previous value, or WG_ERR_BAD_ARG. */
 #define WG_TUNE_TMA 0
 #define WG_TUNE_EPT 1
+#define WG_TUNE_PART 2
 int wg_set_tuning(int key, int value);
 
 /*

@@ -271,3 +271,34 @@ def test_run2_integrator_batched():
     env, body, prm, st = make_pair("box_v0", 512, env_kw=dict(in3d=True), integrator="run2")
     prm.integrator = 1
     run_lockstep(env, body, prm, st, 40, np.random.default_rng(8))
+
+
+@pytest.mark.parametrize("parts", [2, 4, 8])
+@pytest.mark.parametrize("name,layout", [("quad_balance", "row"), ("insect", "feature"), ("humanb", "row"),
+                                         ("balance3", "row"), ("leg", "feature")])
+def test_mass_partitioned_kernel_matches_oracle(name, layout, parts):
+    """P lanes per env (WG_TUNE_PART): crossing springs are evaluated by both owners; bits must not change.
+    Covers disjoint units, a connected body, DingPoints / float masses, auto-reset and ragged tails."""
+    from walker_gym_b200 import _lib
+    lib = _lib.load()
+    old = lib.wg_set_tuning(_lib.TUNE_PART, parts)
+    try:
+        env, body, prm, st = make_pair(name, 1000 + parts, env_kw=dict(in3d=True, rand_sigma=0.3), auto_reset="template",
+                                       max_steps=7, k_sub=2, obs_layout=layout, track_stats=True)
+        E = env.num_envs
+        ep = (np.zeros(E, np.float32), np.zeros((4, E), np.float32))
+        run_lockstep(env, body, prm, st, 16, np.random.default_rng(parts), noise_reset=False, ep=ep)
+        assert gu.same(env.fin_stats.cpu().numpy(), ep[1])
+    finally:
+        lib.wg_set_tuning(_lib.TUNE_PART, old)
+
+
+def test_partition_off_uses_one_thread_per_env():
+    from walker_gym_b200 import _lib
+    lib = _lib.load()
+    old = lib.wg_set_tuning(_lib.TUNE_PART, 0)
+    try:
+        env, body, prm, st = make_pair("quad_balance", 256, env_kw=dict(in3d=True), k_sub=3)
+        run_lockstep(env, body, prm, st, 6, np.random.default_rng(1))
+    finally:
+        lib.wg_set_tuning(_lib.TUNE_PART, old)

@@ -12,7 +12,7 @@ namespace wg {
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_force_generic{0};
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
-static std::atomic<int> g_tune[2] = { {env_int("WG_TMA", 0)}, {env_int("WG_EPT", 1)} };
+static std::atomic<int> g_tune[3] = { {env_int("WG_TMA", 0)}, {env_int("WG_EPT", 1)}, {env_int("WG_PART", -1)} };
 int tuning(int key) { return g_tune[key].load(std::memory_order_relaxed); }
 
 int fail(int code, const char* fmt, const char* a) {
@@ -95,7 +95,9 @@ int wg_kernel_variant(const wg_topology* topo) {
 int wg_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
 
 int wg_set_tuning(int key, int value) {
-    if (key < 0 || key > 1) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
+    if (key < 0 || key > 2) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
+    if (key == WG_TUNE_PART && value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
+        return fail(WG_ERR_BAD_ARG, "PART must be -1, 0, 2, 4 or 8%s");
     if (key == WG_TUNE_EPT && value != 1 && value != 2) return fail(WG_ERR_BAD_ARG, "EPT must be 1 or 2%s");
     return g_tune[key].exchange(value);
 }
@@ -107,6 +109,11 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
     cudaStream_t s = (cudaStream_t)cuda_stream;
     // one env per thread measured fastest on B200 (80 registers, 24 warps/SM); EPT=2 kept as a knob
     const int ept = (tuning(WG_TUNE_EPT) >= 2 && vec_ok(buf, n_env, 2)) ? 2 : 1;
+    // larger bodies: several lanes per env (mass partition); automatic choice by body size
+    int parts = tuning(WG_TUNE_PART);
+    if (parts < 0) parts = topo->n_mass >= 12 ? 4 : (topo->n_mass >= 6 ? 2 : 0);
+    if (parts > topo->n_mass) parts = 0;
+    if (parts >= 2 && !g_force_generic.load()) return launch_part_step(topo, prm, buf, n_env, parts, s);
     switch (pick_variant(topo)) {
         case TopoBalance::kId: return launch_balance(topo, prm, buf, n_env, ept, s);
         case TopoBox::kId:     return launch_box(topo, prm, buf, n_env, ept, s);

@@ -67,18 +67,14 @@ __device__ __forceinline__ void st_vec(T* p, const T (&in)[EPT]) {
 // ---- per-env epilogue: reward, done, info, stats, auto-reset (shared by both kernels) ----
 struct EpiOut { float reward; uint32_t cpost; int done; float energy; float cen[3]; };
 
-template <bool IN3D, class Topo, class BV, class Store, class YS, class SP>
-__device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const EnvConst& ec, Store& st,
-                                         int32_t steps_now, bool want_energy, bool want_centroid,
-                                         YS ys, SP sp, EpiOut& o) {
-    const int N = topo.n();
+// reward, done and info from the per-mass heights ys(i) and speeds sp(i) (already filled in)
+template <class BV, class Store, class YS, class SP>
+__device__ __forceinline__ void epilogue_reduce(int N, const BV& bv, const EnvConst& ec, Store& st, int32_t steps_now,
+                                                bool want_energy, bool want_centroid, YS ys, SP sp, EpiOut& o) {
     uint32_t cpost = 0; int ncon = 0;
 #pragma unroll
-    for (int n = 0; n < N; n++) {                               // _get_reward (optimized_env.py:189-205)
-        ys(n) = st.pos(n, 1);
-        sp(n) = np_norm3(st.vel(n, 0), st.vel(n, 1), st.vel(n, 2));
-        if (st.pos(n, 1) - ec.ground < 0.0f) { cpost |= 1u << n; ncon++; }
-    }
+    for (int n = 0; n < N; n++)
+        if (ys(n) - ec.ground < 0.0f) { cpost |= 1u << n; ncon++; }
     const ConstDiv nd = bv.ndiv;
     const float cy = div_const(np_pairwise_sum(N, [&](int i) { return ys(i); }), nd.m, nd.r, nd.kind);
     const float avgv = div_const(np_pairwise_sum(N, [&](int i) { return sp(i); }), nd.m, nd.r, nd.kind);
@@ -98,7 +94,7 @@ __device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const E
     o.done = dn;
     if (want_energy) {                                           // _calculate_energy (:240-248)
         const float ke = np_pairwise_sum(N, [&](int i) { return bv.mass_f[i] * (sp(i) * sp(i)); });
-        const float pe = np_pairwise_sum(N, [&](int i) { return bv.mg_f[i] * (st.pos(i, 1) - ec.ground); });
+        const float pe = np_pairwise_sum(N, [&](int i) { return bv.mg_f[i] * (ys(i) - ec.ground); });
         o.energy = 0.5f * ke + pe;
     }
     if (want_centroid) {                                         // np.mean(axis=0): sequential
@@ -110,6 +106,19 @@ __device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const E
             o.cen[c] = div_const(acc, nd.m, nd.r, nd.kind);
         }
     }
+}
+
+template <bool IN3D, class Topo, class BV, class Store, class YS, class SP>
+__device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const EnvConst& ec, Store& st,
+                                         int32_t steps_now, bool want_energy, bool want_centroid,
+                                         YS ys, SP sp, EpiOut& o) {
+    const int N = topo.n();
+#pragma unroll
+    for (int n = 0; n < N; n++) {                               // _get_reward (optimized_env.py:189-205)
+        ys(n) = st.pos(n, 1);
+        sp(n) = np_norm3(st.vel(n, 0), st.vel(n, 1), st.vel(n, 2));
+    }
+    epilogue_reduce(N, bv, ec, st, steps_now, want_energy, want_centroid, ys, sp, o);
 }
 
 // =================================================================================

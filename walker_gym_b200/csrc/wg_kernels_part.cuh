@@ -1,0 +1,200 @@
+// wg_kernels_part.cuh -- K1 for larger bodies: P adjacent lanes share one env ("mass partition").
+//
+// A body with N >= 8 masses costs ~750 bytes of per-env state and tens of thousands of instructions
+// per env-step; with one thread per env a B200 SM holds too few envs to hide latency, and the fully
+// unrolled specialisation does not fit the instruction caches.  Here the masses of a body are split
+// into P parts (host side: breadth-first order of the spring graph cut into P chunks, so connected
+// pieces stay together) and lane `part` of an env
+//   * evaluates, in the reference's list order, every spring that touches one of its masses and
+//     accumulates only into ITS masses' accelerations (a spring that crosses two parts is evaluated by
+//     both owners -- same inputs, same operations, same bits);
+//   * applies the environment forces and integrates its own masses.
+// Per-mass accumulation order is therefore exactly the reference's, so the result is bit-identical to
+// the one-thread-per-env kernels, while an env exposes P-fold parallelism.  The state of the block's
+// envs lives in a shared-memory tile [row][env] (odd pitch) for the whole step: one coalesced read and
+// one coalesced write of HBM per env-step, rolled loops (small code), two __syncwarp per substep.
+#pragma once
+#include "wg_kernels.cuh"
+
+namespace wg {
+
+constexpr int kMaxPart = 8;
+
+struct PartTables {
+    uint8_t spring[kMaxPart][kMaxSpring];   // springs touching part p, ascending (= list order)
+    uint8_t mass[kMaxPart][kMaxMass];       // masses owned by part p
+    uint8_t n_spring[kMaxPart], n_mass[kMaxPart];
+    uint32_t own_mask[kMaxPart];
+};
+
+struct PartArgs {
+    StepArgs<kMaxMass, kMaxSpring> A;
+    PartTables pt;
+};
+
+template <bool IN3D, int P, bool ROWMAJOR, int MM>
+__global__ void __launch_bounds__(kBlock)
+step_part_kernel(const __grid_constant__ PartArgs PA) {
+    const auto& A = PA.A;
+    extern __shared__ float smem[];
+    // lanes of one warp work on different springs and masses: per-spring / per-mass constants would be
+    // divergent constant-bank reads (serialised per distinct address), so the tables are staged once per
+    // block in shared memory
+    __shared__ BodyVals<kMaxMass, kMaxSpring> bv;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&A.bv);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&bv);
+        for (int i = threadIdx.x; i < (int)(sizeof(bv) / 4); i += kBlock) dst[i] = src[i];
+    }
+    constexpr int EB = kBlock / P;                 // envs per block
+    constexpr int PITCH = EB + 1;
+    constexpr int d = IN3D ? 3 : 2;
+    const int N = A.bv.n_mass, S = A.bv.n_spring, M = A.bv.n_muscle;
+    const int D = 3 * d * N + M;
+    const int ROWS = 11 * N + M + 3;               // pos, vel, acc, mx, ys, speeds, centroid
+    RuntimeTopo topo{ N, S, M, bv.si, bv.sj };
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int el = tid / P, part = tid % P;        // env within the block, lane's part
+    const int64_t E = A.E;
+    const int64_t e0 = (int64_t)blockIdx.x * EB;
+    const int64_t e = e0 + el;
+    const bool valid = e < E;
+    const int64_t rem = E - e0;
+    const int nvalid = rem < EB ? (int)rem : EB;
+    SmemStore st{ smem + el, PITCH, N };
+    // per-part tables in shared memory (lanes of a warp read different parts)
+    uint8_t* tab = reinterpret_cast<uint8_t*>(smem + ROWS * PITCH);
+    uint8_t* my_springs = tab + part * kMaxSpring;
+    uint8_t* my_masses = tab + P * kMaxSpring + part * kMaxMass;
+    for (int i = tid; i < P * kMaxSpring; i += kBlock) tab[i] = PA.pt.spring[i / kMaxSpring][i % kMaxSpring];
+    for (int i = tid; i < P * kMaxMass; i += kBlock) tab[P * kMaxSpring + i] = PA.pt.mass[i / kMaxMass][i % kMaxMass];
+    const int n_my_springs = PA.pt.n_spring[part], n_my_masses = PA.pt.n_mass[part];
+    const uint32_t skip = A.bv.fixed_mask | ~PA.pt.own_mask[part];
+    __syncthreads();                               // staged tables visible
+
+    // ---- single HBM read: the block's EB envs of every state row, coalesced ----
+    for (int idx = tid; idx < 6 * N * EB; idx += kBlock) {
+        const int r = idx / EB, c = idx - r * EB;
+        if (c < nvalid) smem[r * PITCH + c] = r < 3 * N ? A.pos[(int64_t)r * E + e0 + c] : A.vel[(int64_t)(r - 3 * N) * E + e0 + c];
+    }
+    {   // Creature.act while loading the muscle lengths
+        const int na = A.act_dim < M ? A.act_dim : M;
+        for (int idx = tid; idx < M * EB; idx += kBlock) {
+            const int m = idx / EB, c = idx - m * EB;
+            if (c < nvalid) {
+                float x = A.mx[(int64_t)m * E + e0 + c];
+                if (m < na) {
+                    x = x + (A.act_layout ? A.action[(int64_t)m * E + e0 + c] : A.action[(e0 + c) * A.act_dim + m]);
+                    if (bv.mlo[m] > x) x = bv.mlo[m];
+                    if (bv.mhi[m] < x) x = bv.mhi[m];
+                }
+                smem[(9 * N + m) * PITCH + c] = x;
+            }
+        }
+    }
+    __syncthreads();
+
+    uint32_t cpre = 0;
+    for (int k = 0; k < A.ec.k_sub; k++) {
+        if (valid) {
+            for (int q = 0; q < n_my_masses; q++) { const int n = my_masses[q]; st.acc(n, 0) = 0.0f; st.acc(n, 1) = 0.0f; st.acc(n, 2) = 0.0f; }
+            for (int q = 0; q < n_my_springs; q++) {
+                const int sp = my_springs[q];
+                spring_run<MM, true>(topo, bv, st, sp, sp < M ? st.mx(sp) : bv.srest[sp], skip);
+            }
+        }
+        __syncwarp();                              // everyone has read the old positions / velocities
+        cpre = 0;
+        if (valid)
+            for (int q = 0; q < n_my_masses; q++) { const int n = my_masses[q]; if (point_step<IN3D, MM>(bv, A.ec, st, n)) cpre |= 1u << n; }
+        __syncwarp();                              // new positions / velocities visible to the env's other lanes
+    }
+    // ---- reward / done / info: speeds in parallel, the reduction on the env's first lane ----
+    if (valid)
+        for (int q = 0; q < n_my_masses; q++) {
+            const int n = my_masses[q];
+            st.scratch(M, n) = st.pos(n, 1);
+            st.scratch(M, N + n) = np_norm3(st.vel(n, 0), st.vel(n, 1), st.vel(n, 2));
+        }
+#pragma unroll
+    for (int off = 1; off < P; off <<= 1) cpre |= __shfl_xor_sync(0xffffffffu, cpre, off);
+    __syncwarp();
+    int do_reset = 0;
+    if (valid && part == 0) {
+        const int32_t sn = A.steps[e] + 1;
+        EpiOut o;
+        epilogue_reduce(N, bv, A.ec, st, sn, A.energy != nullptr, A.centroid != nullptr,
+                        [&](int i) -> float& { return st.scratch(M, i); },
+                        [&](int i) -> float& { return st.scratch(M, N + i); }, o);
+        if (A.reward) A.reward[e] = o.reward;
+        if (A.done) A.done[e] = (uint8_t)o.done;
+        if (A.contact_pre) A.contact_pre[e] = cpre;
+        if (A.contact_post) A.contact_post[e] = o.cpost;
+        if (A.energy) A.energy[e] = o.energy;
+        if (A.centroid) { A.centroid[e] = o.cen[0]; A.centroid[E + e] = o.cen[1]; A.centroid[2 * E + e] = o.cen[2]; }
+        if (A.ep_ret) {
+            const float r = A.ep_ret[e] + o.reward;
+            if (o.done && A.fin_stats) {
+                A.fin_stats[0 * E + e] += r;
+                A.fin_stats[1 * E + e] += r * r;
+                A.fin_stats[2 * E + e] += (float)sn;
+                A.fin_stats[3 * E + e] += 1.0f;
+            }
+            A.ep_ret[e] = (o.done && A.ec.auto_reset) ? 0.0f : r;
+        }
+        do_reset = (o.done && A.ec.auto_reset) ? 1 : 0;
+        A.steps[e] = do_reset ? 0 : sn;
+        if (do_reset && A.ec.auto_reset == 2)
+            for (int m = 0; m < M; m++) st.mx(m) = bv.srest[m];
+    }
+    do_reset = __shfl_sync(0xffffffffu, do_reset, lane - part);
+    if (valid && do_reset) {                       // each lane resets its own masses (Philox keyed per mass)
+        const uint32_t si = step_index_of(A);
+        for (int q = 0; q < n_my_masses; q++) reset_mass<IN3D>(bv, A.ec, st, my_masses[q], A.ec.auto_reset, A.noise, E, e, si);
+    }
+    __syncwarp();
+    if (valid && part == 0 && A.obs && ROWMAJOR) {  // getstat centroid: sequential sum over the masses, then / N
+        float mid[3] = { 0.0f, 0.0f, 0.0f };
+        for (int n = 0; n < N; n++) { mid[0] = mid[0] + st.pos(n, 0); mid[1] = mid[1] + st.pos(n, 1); mid[2] = mid[2] + st.pos(n, 2); }
+        const ConstDiv nd = bv.ndiv;
+        st.scratch(M, 2 * N + 0) = div_const(mid[0], nd.m, nd.r, nd.kind);
+        st.scratch(M, 2 * N + 1) = div_const(mid[1], nd.m, nd.r, nd.kind);
+        st.scratch(M, 2 * N + 2) = div_const(mid[2], nd.m, nd.r, nd.kind);
+    }
+    if (valid && part == 0 && A.obs && !ROWMAJOR)
+        get_obs<IN3D>(topo, bv.ndiv, st, [&](int k, float v) { A.obs[(int64_t)k * E + e] = v; });
+    __syncthreads();
+    // ---- single HBM write of the state, coalesced ----
+    for (int idx = tid; idx < 3 * N * EB; idx += kBlock) {
+        const int r = idx / EB, c = idx - r * EB;
+        if (c < nvalid) {
+            A.pos[(int64_t)r * E + e0 + c] = smem[r * PITCH + c];
+            A.vel[(int64_t)r * E + e0 + c] = smem[(3 * N + r) * PITCH + c];
+            if (A.old_a) A.old_a[(int64_t)r * E + e0 + c] = smem[(6 * N + r) * PITCH + c];
+        }
+    }
+    for (int idx = tid; idx < M * EB; idx += kBlock) {
+        const int m = idx / EB, c = idx - m * EB;
+        if (c < nvalid) A.mx[(int64_t)m * E + e0 + c] = smem[(9 * N + m) * PITCH + c];
+    }
+    if (ROWMAJOR && A.obs) {                        // whole warps stream observation rows out of the tile
+        const int warp = tid >> 5;
+        for (int r = warp; r < nvalid; r += kBlock / 32) {
+            const float* col = smem + r;
+            float* out = A.obs + (e0 + r) * D;
+            for (int k = lane; k < D; k += 32) {
+                float v;
+                if (k < 3 * d * N) {
+                    const int n = k / (3 * d), rr = k - n * 3 * d, sec = rr / d, c = rr - sec * d;
+                    v = col[(sec * 3 * N + n * 3 + c) * PITCH];
+                    if (sec == 0) v = v - col[(9 * N + M + 2 * N + c) * PITCH];
+                } else {
+                    v = col[(9 * N + (k - 3 * d * N)) * PITCH];
+                }
+                out[k] = v;
+            }
+        }
+    }
+}
+
+}  // namespace wg

@@ -7,6 +7,7 @@
 #include "../../include/walker_gym_b200.h"
 #include "wg_kernels.cuh"
 #include "wg_kernels_tma.cuh"
+#include "wg_kernels_part.cuh"
 
 namespace wg {
 
@@ -35,6 +36,7 @@ int launch_box(const wg_topology*, const wg_params*, const wg_buffers*, int64_t 
 int launch_quad(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
 int launch_insect(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
 int launch_generic_step(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
+int launch_part_step(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int parts, cudaStream_t);
 int launch_reset(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int mode, const uint8_t* mask, cudaStream_t);
 int launch_stats(const float* fin_stats, int64_t E, double* out8, cudaStream_t);
 

@@ -124,8 +124,8 @@ __device__ __forceinline__ void forced2(float (&a)[3], const float (&f)[3], cons
 }
 
 // Muscle.run / Skeleton.run (optimized_walker.py:45-67 == :84-106)
-template <int MM, class Topo, class BV, class Store>
-__device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store& st, int sp, float x) {
+template <int MM, bool USE_SKIP = (MM == 2), class Topo, class BV, class Store>
+__device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store& st, int sp, float x, uint32_t skip_mask) {
     const int i = topo.si(sp), j = topo.sj(sp);
     const float pix = st.pos(i, 0), piy = st.pos(i, 1), piz = st.pos(i, 2);
     const float pjx = st.pos(j, 0), pjy = st.pos(j, 1), pjz = st.pos(j, 2);
@@ -140,17 +140,66 @@ __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store
     const float cd = dk * bv.sdamp[sp];
     const float D[3] = { cd * d0, cd * d1, cd * d2 };
     const float nF[3] = { -F[0], -F[1], -F[2] }, nD[3] = { -D[0], -D[1], -D[2] };
-    // DingPoints (fixed masses) only occur with MM == 2: bodies that have them run the generic kernel
-    if (MM != 2 || !((bv.fixed_mask >> i) & 1u)) {                        // p1.forced(force); p1.forced(-damp)
+    // skip_mask: masses whose accumulator this thread must not touch -- DingPoints (forced() is a no-op)
+    // and, in the mass-partitioned kernel, masses owned by another lane.  Compiled out (USE_SKIP false)
+    // in the one-thread-per-env kernels for bodies without DingPoints.
+    if (!USE_SKIP || !((skip_mask >> i) & 1u)) {                            // p1.forced(force); p1.forced(-damp)
         float a[3] = { st.acc(i, 0), st.acc(i, 1), st.acc(i, 2) };
         forced2<MM>(a, F, nD, bv, i);
         st.acc(i, 0) = a[0]; st.acc(i, 1) = a[1]; st.acc(i, 2) = a[2];
     }
-    if (MM != 2 || !((bv.fixed_mask >> j) & 1u)) {                        // p2.forced(-force); p2.forced(damp)
+    if (!USE_SKIP || !((skip_mask >> j) & 1u)) {                            // p2.forced(-force); p2.forced(damp)
         float a[3] = { st.acc(j, 0), st.acc(j, 1), st.acc(j, 2) };
         forced2<MM>(a, nF, D, bv, j);
         st.acc(j, 0) = a[0]; st.acc(j, 1) = a[1]; st.acc(j, 2) = a[2];
     }
+}
+
+// Environment forces on mass n (gravity, damping, ground contact: gym/optimized_env.py:146-175) followed by
+// the integrator (Point.run1 / run2).  Returns the force-phase contact flag.
+template <bool IN3D, int MM, class BV, class Store>
+__device__ __forceinline__ bool point_step(const BV& bv, const EnvConst& ec, Store& st, int n) {
+    const bool fixed = (MM == 2) && ((bv.fixed_mask >> n) & 1u);
+    float ax = st.acc(n, 0), ay = st.acc(n, 1), az = st.acc(n, 2);
+    const float vx = st.vel(n, 0), vy = st.vel(n, 1), vz = st.vel(n, 2);
+    const float deep = st.pos(n, 1) - ec.ground;
+    const bool hit = deep < 0.0f;
+    if (!fixed) {
+        ay = (float)((double)ay + bv.gm[n]);                 // forced([0, -g, 0])
+        if (ec.dampk_is_zero) {                               // forced(-0 * v): +-0, or NaN for non-finite v
+            ax = ax + ec.ndampk * vx; ay = ay + ec.ndampk * vy; az = az + ec.ndampk * vz;
+        } else {                                              // forced(-k * v): float32 force / m
+            const ConstDiv md{ bv.mass_f[n], bv.mass_r[n], bv.mass_kind[n] };
+            ax = ax + div_const(ec.ndampk * vx, md.m, md.r, md.kind);
+            ay = ay + div_const(ec.ndampk * vy, md.m, md.r, md.kind);
+            az = az + div_const(ec.ndampk * vz, md.m, md.r, md.kind);
+        }
+        if (hit) {
+            const double m = bv.mass_d[n], rd = bv.mass_rd[n];
+            const int kd = MM == 0 ? 0 : bv.mass_kind[n];
+            ay = forced_list(ay, ec.nground_k * deep, m, rd, kd);    // ground spring
+            ay = forced_list(ay, ec.nground_damp * vy, m, rd, kd);   // ground damper
+            const float ff = fabsf(deep) * ec.friction;             // friction
+            ax = forced_list(ax, (-vx) * ff, m, rd, kd);
+            if (IN3D) az = forced_list(az, (-vz) * ff, m, rd, kd);
+        }
+    }
+    if (ec.integrator == 0) {
+        // Point.run1: v += a*t; pos += v*t   (old_a = a stays in acc)
+        const float nvx = vx + ax * ec.dt, nvy = vy + ay * ec.dt, nvz = vz + az * ec.dt;
+        st.vel(n, 0) = nvx; st.vel(n, 1) = nvy; st.vel(n, 2) = nvz;
+        st.pos(n, 0) = st.pos(n, 0) + nvx * ec.dt;
+        st.pos(n, 1) = st.pos(n, 1) + nvy * ec.dt;
+        st.pos(n, 2) = st.pos(n, 2) + nvz * ec.dt;
+    } else {
+        // Point.run2 (gym/optimized_engine.py:274-288): pos += v*t + (0.5*a)*t**2; then v += a*t
+        st.pos(n, 0) = st.pos(n, 0) + (vx * ec.dt + (0.5f * ax) * ec.dt2);
+        st.pos(n, 1) = st.pos(n, 1) + (vy * ec.dt + (0.5f * ay) * ec.dt2);
+        st.pos(n, 2) = st.pos(n, 2) + (vz * ec.dt + (0.5f * az) * ec.dt2);
+        st.vel(n, 0) = vx + ax * ec.dt; st.vel(n, 1) = vy + ay * ec.dt; st.vel(n, 2) = vz + az * ec.dt;
+    }
+    st.acc(n, 0) = ax; st.acc(n, 1) = ay; st.acc(n, 2) = az;
+    return hit;
 }
 
 // PhysicsEnv._run_physics + Point.run1: one substep.  Returns the force-phase contact mask.
@@ -161,54 +210,13 @@ __device__ __forceinline__ uint32_t run_physics(const Topo& topo, const BV& bv, 
 #pragma unroll
     for (int n = 0; n < N; n++) { st.acc(n, 0) = 0.0f; st.acc(n, 1) = 0.0f; st.acc(n, 2) = 0.0f; }
 #pragma unroll
-    for (int sp = 0; sp < M; sp++) spring_run<MM>(topo, bv, st, sp, st.mx(sp));
+    for (int sp = 0; sp < M; sp++) spring_run<MM>(topo, bv, st, sp, st.mx(sp), bv.fixed_mask);
 #pragma unroll
-    for (int sp = M; sp < S; sp++) spring_run<MM>(topo, bv, st, sp, bv.srest[sp]);
+    for (int sp = M; sp < S; sp++) spring_run<MM>(topo, bv, st, sp, bv.srest[sp], bv.fixed_mask);
     uint32_t contact = 0;
 #pragma unroll
-    for (int n = 0; n < N; n++) {
-        const bool fixed = (MM == 2) && ((bv.fixed_mask >> n) & 1u);
-        float ax = st.acc(n, 0), ay = st.acc(n, 1), az = st.acc(n, 2);
-        const float vx = st.vel(n, 0), vy = st.vel(n, 1), vz = st.vel(n, 2);
-        const float deep = st.pos(n, 1) - ec.ground;
-        const bool hit = deep < 0.0f;
-        if (hit) contact |= 1u << n;
-        if (!fixed) {
-            ay = (float)((double)ay + bv.gm[n]);                 // forced([0, -g, 0])
-            if (ec.dampk_is_zero) {                               // forced(-0 * v): +-0, or NaN for non-finite v
-                ax = ax + ec.ndampk * vx; ay = ay + ec.ndampk * vy; az = az + ec.ndampk * vz;
-            } else {                                              // forced(-k * v): float32 force / m
-                const ConstDiv md{ bv.mass_f[n], bv.mass_r[n], bv.mass_kind[n] };
-                ax = ax + div_const(ec.ndampk * vx, md.m, md.r, md.kind);
-                ay = ay + div_const(ec.ndampk * vy, md.m, md.r, md.kind);
-                az = az + div_const(ec.ndampk * vz, md.m, md.r, md.kind);
-            }
-            if (hit) {
-                const double m = bv.mass_d[n], rd = bv.mass_rd[n];
-                const int kd = MM == 0 ? 0 : bv.mass_kind[n];
-                ay = forced_list(ay, ec.nground_k * deep, m, rd, kd);    // ground spring
-                ay = forced_list(ay, ec.nground_damp * vy, m, rd, kd);   // ground damper
-                const float ff = fabsf(deep) * ec.friction;             // friction
-                ax = forced_list(ax, (-vx) * ff, m, rd, kd);
-                if (IN3D) az = forced_list(az, (-vz) * ff, m, rd, kd);
-            }
-        }
-        if (ec.integrator == 0) {
-            // Point.run1: v += a*t; pos += v*t   (old_a = a stays in acc)
-            const float nvx = vx + ax * ec.dt, nvy = vy + ay * ec.dt, nvz = vz + az * ec.dt;
-            st.vel(n, 0) = nvx; st.vel(n, 1) = nvy; st.vel(n, 2) = nvz;
-            st.pos(n, 0) = st.pos(n, 0) + nvx * ec.dt;
-            st.pos(n, 1) = st.pos(n, 1) + nvy * ec.dt;
-            st.pos(n, 2) = st.pos(n, 2) + nvz * ec.dt;
-        } else {
-            // Point.run2 (gym/optimized_engine.py:274-288): pos += v*t + (0.5*a)*t**2; then v += a*t
-            st.pos(n, 0) = st.pos(n, 0) + (vx * ec.dt + (0.5f * ax) * ec.dt2);
-            st.pos(n, 1) = st.pos(n, 1) + (vy * ec.dt + (0.5f * ay) * ec.dt2);
-            st.pos(n, 2) = st.pos(n, 2) + (vz * ec.dt + (0.5f * az) * ec.dt2);
-            st.vel(n, 0) = vx + ax * ec.dt; st.vel(n, 1) = vy + ay * ec.dt; st.vel(n, 2) = vz + az * ec.dt;
-        }
-        st.acc(n, 0) = ax; st.acc(n, 1) = ay; st.acc(n, 2) = az;
-    }
+    for (int n = 0; n < N; n++)
+        if (point_step<IN3D, MM>(bv, ec, st, n)) contact |= 1u << n;
     return contact;
 }
 
@@ -237,6 +245,28 @@ __device__ __forceinline__ float np_pairwise_sum(int n, Get get) {
     return res;
 }
 
+// Reset of one mass: optional template restore, then the velocity jitter of PhysicsEnv.reset.
+template <bool IN3D, class BV, class Store>
+__device__ __forceinline__ void reset_mass(const BV& bv, const EnvConst& ec, Store& st, int n, int mode,
+                                           const float* __restrict__ noise, int64_t E, int64_t e, uint32_t step_index) {
+    if (mode == 2) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { st.pos(n, c) = bv.tmpl[n * 3 + c]; st.vel(n, c) = 0.0f; st.acc(n, c) = 0.0f; }
+    }
+    float z[3];
+    if (noise) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) z[c] = noise[(int64_t)(n * 3 + c) * E + e];
+    } else {
+        normal3(ec.seed_lo, ec.seed_hi, ec.env_offset + (uint32_t)e, step_index, (uint32_t)n, z);
+#pragma unroll
+        for (int c = 0; c < 3; c++) z[c] = ec.sigma * z[c];
+    }
+    st.vel(n, 0) = st.vel(n, 0) + z[0];
+    st.vel(n, 1) = st.vel(n, 1) + z[1];
+    if (IN3D) st.vel(n, 2) = st.vel(n, 2) + z[2];
+}
+
 // Template reset + jitter (PhysicsEnv.reset, optimized_env.py:53-68; make_env :273-294)
 template <bool IN3D, class Topo, class BV, class Store>
 __device__ __forceinline__ void apply_reset(const Topo& topo, const BV& bv, const EnvConst& ec, Store& st,
@@ -245,28 +275,10 @@ __device__ __forceinline__ void apply_reset(const Topo& topo, const BV& bv, cons
     const int N = topo.n(), M = topo.m();
     if (mode == 2) {
 #pragma unroll
-        for (int n = 0; n < N; n++) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) { st.pos(n, c) = bv.tmpl[n * 3 + c]; st.vel(n, c) = 0.0f; st.acc(n, c) = 0.0f; }
-        }
-#pragma unroll
         for (int m = 0; m < M; m++) st.mx(m) = bv.srest[m];
     }
 #pragma unroll
-    for (int n = 0; n < N; n++) {
-        float z[3];
-        if (noise) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) z[c] = noise[(int64_t)(n * 3 + c) * E + e];
-        } else {
-            normal3(ec.seed_lo, ec.seed_hi, ec.env_offset + (uint32_t)e, step_index, (uint32_t)n, z);
-#pragma unroll
-            for (int c = 0; c < 3; c++) z[c] = ec.sigma * z[c];
-        }
-        st.vel(n, 0) = st.vel(n, 0) + z[0];
-        st.vel(n, 1) = st.vel(n, 1) + z[1];
-        if (IN3D) st.vel(n, 2) = st.vel(n, 2) + z[2];
-    }
+    for (int n = 0; n < N; n++) reset_mass<IN3D>(bv, ec, st, n, mode, noise, E, e, step_index);
 }
 
 // Creature.getstat with PhysicsEnv's defaults; emit(k, value) receives the D entries in order.
