@@ -138,6 +138,7 @@ int wg_force_generic(int on);
 #define WG_TUNE_TMA 0
 #define WG_TUNE_EPT 1
 #define WG_TUNE_PART 2
+#define WG_TUNE_PREFETCH 3   /* 0 = off; 2 / 4 = tiles per CTA of the per-thread cp.async prefetch variant */
 int wg_set_tuning(int key, int value);
 
 /*

@@ -12,7 +12,8 @@ namespace wg {
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_force_generic{0};
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
-static std::atomic<int> g_tune[3] = { {env_int("WG_TMA", 0)}, {env_int("WG_EPT", 1)}, {env_int("WG_PART", -1)} };
+static std::atomic<int> g_tune[4] = { {env_int("WG_TMA", 0)}, {env_int("WG_EPT", 1)}, {env_int("WG_PART", -1)},
+                                      {env_int("WG_PREFETCH", 0)} };
 int tuning(int key) { return g_tune[key].load(std::memory_order_relaxed); }
 
 int fail(int code, const char* fmt, const char* a) {
@@ -95,7 +96,8 @@ int wg_kernel_variant(const wg_topology* topo) {
 int wg_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
 
 int wg_set_tuning(int key, int value) {
-    if (key < 0 || key > 2) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
+    if (key < 0 || key > 3) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
+    if (key == WG_TUNE_PREFETCH && value != 0 && value != 2 && value != 4) return fail(WG_ERR_BAD_ARG, "PREFETCH must be 0, 2 or 4%s");
     if (key == WG_TUNE_PART && value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
         return fail(WG_ERR_BAD_ARG, "PART must be -1, 0, 2, 4 or 8%s");
     if (key == WG_TUNE_EPT && value != 1 && value != 2) return fail(WG_ERR_BAD_ARG, "EPT must be 1 or 2%s");
