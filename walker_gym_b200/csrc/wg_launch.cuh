@@ -112,7 +112,8 @@ inline int launch_static(const wg_topology* t, const wg_params* p, const wg_buff
     StepArgs<Topo::N, Topo::S> A;
     fill_args(A, t, p, b, E);
     constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
-    const size_t smem = (OBS == 1 && b->obs) ? sizeof(float) * kBlock * EPT * (D | 1) : 0;
+    constexpr bool bulk = (OBS == 1) && (EPT == 1) && gcd_c(D, 32) <= 2;      // must mirror the kernel's OBS_BULK
+    const size_t smem = (OBS == 1 && b->obs) ? sizeof(float) * kBlock * EPT * (bulk ? D : (D | 1)) : 0;
     auto kern = step_static_kernel<Topo, IN3D, OBS, EPT, MM>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
