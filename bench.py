@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
                     help="BASELINE.json config: 3 = Balance-v0 throughput (headline, default), 4 = enlarged body "
                          "(4x masses/springs) with 8 substeps, 5 = PPO rollout collection (torch MLP policy + step kernel)")
+    ap.add_argument("--body", default="balance", choices=["balance", "box"],
+                    help="config 3 body: Balance-v0 (headline) or Box-v0, both from gym/optimized_walker.py:176-224")
     ap.add_argument("--obs-layout", default="row", choices=["row", "feature"],
                     help="observation layout written by the kernel: row-major [E,D] (default) or feature-major [D,E]")
     ap.add_argument("--generic", action="store_true", help="measure the run-time-topology kernel instead of the specialisation")
@@ -205,7 +207,8 @@ def run_ours(args):
         _lib.load().wg_force_generic(1)
     if args.config == 5:
         return run_rollout(args, rank, world, dev)
-    body, k_sub = (ENV_ID, 1) if args.config == 3 else ("quad_balance", 8)
+    env_id = ENV_ID if args.body == "balance" else "Box-v0"
+    body, k_sub = (env_id, 1) if args.config == 3 else ("quad_balance", 8)
 
     env = BatchedPhysicsEnv(body, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
                             track_stats=True, k_sub=k_sub, obs_layout=args.obs_layout)
@@ -285,12 +288,13 @@ def run_ours(args):
         peak, peak_src = hbm_peak()
         per_launch_s = ms * 1e-3 / K
         achieved = E * bytes_per_env_step / per_launch_s / 1e9
-        tr = ncu_traffic_per_env_step() if (args.config == 3 and args.obs_layout == "row" and not args.generic) else None
+        tr = ncu_traffic_per_env_step() if (args.config == 3 and args.obs_layout == "row" and not args.generic
+                                            and args.body == "balance") else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (f"{ENV_ID} (gym/optimized_walker.py create_balance_creature)" if args.config == 3 else
+            "config": {"workload": (f"{env_id} (gym/optimized_walker.py create_{args.body}_creature)" if args.config == 3 else
                                     "quad_balance (4x Balance-v0: N=16, S=20, M=8; BASELINE config 4)") +
                                    f", in3d=True, {E} envs per GPU, 1 kernel launch per env-step, K_sub={k_sub}, template "
                                    "auto-reset, reference semantics as written, U(-1,1) f32 actions from a 16-deep device ring",
@@ -312,7 +316,7 @@ def run_ours(args):
         if args.config == 4:
             line["roofline"]["note"] = ("config 4 is fp32-issue bound, not HBM bound: ~8 substeps x 20 springs per env-step "
                                         "against 1485 bytes (SURVEY 7.5); the HBM fraction is reported for completeness")
-        if not args.no_cpu_baseline and world == 1 and args.config == 3:
+        if not args.no_cpu_baseline and world == 1 and args.config == 3 and args.body == "balance":
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if world > 1:

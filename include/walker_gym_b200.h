@@ -115,7 +115,19 @@ typedef struct wg_buffers {
     const float* noise;         /* in, optional: jitter used by auto-reset / wg_reset instead of Philox */
     const uint32_t* step_counter; /* in, optional: device scalar added to prm->step_index; lets a CUDA graph
                                    that replays wg_step advance the Philox counter without new parameters */
+    float*       state_packed;  /* in/out, optional: the packed state layout (see below).  When set, pos / vel /
+                                   mx / steps / ep_ret are ignored (they live inside it) */
 } wg_buffers;
+
+/*
+ * Packed state layout (only for bodies with a register-resident specialisation, wg_kernel_variant() in {1, 2}).
+ * The R = 6*n_mass + n_muscle + 2 per-env scalars k -- pos rows 0..3N-1 (n*3+c), vel rows 3N..6N-1, muscle
+ * lengths 6N..6N+M-1, steps (int32 bits) 6N+M, ep_ret 6N+M+1 -- are stored as [tile][k/4][128 envs][4]:
+ *     index(e, k) = ((e >> 7) * R4 + (k >> 2)) * 512 + (e & 127) * 4 + (k & 3),   R4 = ceil(R / 4)
+ * so a thread moves four scalars of its env with one 16-byte access, a warp moves 512 contiguous bytes, and a
+ * tile of 128 envs is one contiguous R4 * 2 KiB block.  The buffer holds ceil(E / 128) * R4 * 512 floats.
+ */
+int64_t wg_packed_state_floats(const wg_topology* topo, int64_t n_env);
 
 int         wg_abi_version(void);
 const char* wg_last_error_string(void);

@@ -160,7 +160,7 @@ def test_full_size_properties_1m_envs():
     E, T = 1 << 20, 20
     kw = dict(in3d=True, auto_reset="template", max_steps=7, seed=5)
     a = BatchedPhysicsEnv("balance_v0", E, "cuda:0", **kw)
-    b = BatchedPhysicsEnv("balance_v0", E, "cuda:0", obs_layout="feature", **kw)
+    b = BatchedPhysicsEnv("balance_v0", E, "cuda:0", obs_layout="feature", state_layout="soa", **kw)
     lib = _lib.load()
     g = torch.Generator(device="cuda:0").manual_seed(1)
     for t in range(T):
@@ -197,7 +197,8 @@ def test_tma_pipelined_kernel_matches_oracle(name, E):
     lib = _lib.load()
     old = lib.wg_set_tuning(_lib.TUNE_TMA, 1)
     try:
-        env, body, prm, st = make_pair(name, E, env_kw=dict(in3d=True), auto_reset="template", max_steps=6, track_stats=True)
+        env, body, prm, st = make_pair(name, E, env_kw=dict(in3d=True), auto_reset="template", max_steps=6, track_stats=True,
+                                       state_layout="soa")
         ep = (np.zeros(E, np.float32), np.zeros((4, E), np.float32))
         run_lockstep(env, body, prm, st, 15, np.random.default_rng(E), noise_reset=False, ep=ep)
         assert gu.same(env.fin_stats.cpu().numpy(), ep[1])
@@ -244,7 +245,7 @@ def test_rollout_collector_cuda_graph_and_eager():
             sd = {k: v.clone() if torch.is_tensor(v) else v for k, v in env.state_dict().items()}
             ctr = env._counter.clone()
             col.collect()
-            env.load_state_dict(sd); env._counter.copy_(ctr); env.fin_stats.zero_(); env.ep_ret.zero_()
+            env.load_state_dict(sd); env._counter.copy_(ctr); env.fin_stats.zero_(); env.set_state(ep_ret=torch.zeros(E))
             torch.cuda.manual_seed(0)
         batch = col.collect()
         torch.cuda.synchronize()
@@ -314,9 +315,32 @@ def test_prefetch_kernel_matches_oracle(name, layout, E, tpc):
     old = lib.wg_set_tuning(_lib.TUNE_PREFETCH, tpc)
     try:
         env, body, prm, st = make_pair(name, E, env_kw=dict(in3d=True), auto_reset="template", max_steps=6,
-                                       obs_layout=layout, track_stats=True)
+                                       obs_layout=layout, track_stats=True, state_layout="soa")
         ep = (np.zeros(E, np.float32), np.zeros((4, E), np.float32))
         run_lockstep(env, body, prm, st, 14, np.random.default_rng(E + tpc), noise_reset=False, ep=ep)
         assert gu.same(env.fin_stats.cpu().numpy(), ep[1])
     finally:
         lib.wg_set_tuning(_lib.TUNE_PREFETCH, old)
+
+
+@pytest.mark.parametrize("state_layout", ["soa", "packed"])
+@pytest.mark.parametrize("E", [1, 127, 128, 129, 1000, 4096])
+@pytest.mark.parametrize("name,in3d,layout", [("balance_v0", True, "row"), ("box_v0", True, "feature"),
+                                               ("balance", False, "row"), ("box2", False, "feature")])
+def test_state_layouts_match_oracle(name, in3d, layout, E, state_layout):
+    """Both state layouts -- separate SoA rows and the packed [tile][k/4][128][4] float4 layout -- against the
+    oracle: full and ragged tiles, 2-D and 3-D, unit and integer masses, auto-reset with episode statistics."""
+    env, body, prm, st = make_pair(name, E, env_kw=dict(in3d=in3d), auto_reset="template", max_steps=5,
+                                   obs_layout=layout, track_stats=True, state_layout=state_layout)
+    assert env.state_layout == state_layout
+    ep = (np.zeros(E, np.float32), np.zeros((4, E), np.float32))
+    run_lockstep(env, body, prm, st, 12, np.random.default_rng(E), noise_reset=True, ep=ep)
+    assert gu.same(env.ep_ret.cpu().numpy(), ep[0]) and gu.same(env.fin_stats.cpu().numpy(), ep[1])
+
+
+def test_packed_layout_rejected_for_bodies_without_a_specialised_kernel():
+    from walker_gym_b200 import BatchedPhysicsEnv
+    with pytest.raises(ValueError):
+        BatchedPhysicsEnv("humanb", 64, "cuda:0", state_layout="packed")
+    assert BatchedPhysicsEnv("humanb", 64, "cuda:0").state_layout == "soa"
+    assert BatchedPhysicsEnv("Balance-v0", 64, "cuda:0").state_layout == "packed"

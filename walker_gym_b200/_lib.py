@@ -51,14 +51,14 @@ class WgBuffers(C.Structure):
         ("contact_pre", C.c_void_p), ("contact_post", C.c_void_p),
         ("energy", C.c_void_p), ("centroid", C.c_void_p),
         ("ep_ret", C.c_void_p), ("fin_stats", C.c_void_p), ("noise", C.c_void_p),
-        ("step_counter", C.c_void_p),
+        ("step_counter", C.c_void_p), ("state_packed", C.c_void_p),
     ]
 
 
 TUNE_TMA, TUNE_EPT, TUNE_PART, TUNE_PREFETCH = 0, 1, 2, 3
 
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
-           "wg_set_tuning",
+           "wg_set_tuning", "wg_packed_state_floats",
            "wg_step", "wg_reset", "wg_stats_reduce", "wg_step_host")
 
 _lib = None
@@ -91,6 +91,8 @@ def load():
     lib.wg_force_generic.argtypes = [C.c_int]
     lib.wg_set_tuning.argtypes = [C.c_int, C.c_int]
     lib.wg_set_tuning.restype = C.c_int
+    lib.wg_packed_state_floats.argtypes = [P(WgTopology), C.c_int64]
+    lib.wg_packed_state_floats.restype = C.c_int64
     lib.wg_step.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_void_p]
     lib.wg_reset.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     lib.wg_stats_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]

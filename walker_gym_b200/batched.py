@@ -69,6 +69,7 @@ class BatchedPhysicsEnv:
                  friction=100, rand_sigma=0.1, *, max_steps: int = 1000, time_step: float = 0.01, k_sub: int = 1,
                  auto_reset="template", obs_layout: str = "row", act_layout: str = "row", seed: int = 0,
                  env_offset: int = 0, graph_safe: bool = False, integrator: str = "run1",
+                 state_layout: str = "auto",
                  track_info: bool = False, track_stats: bool = True, track_contacts: bool = False,
                  keep_old_a: bool = False, initial_reset: bool = True):
         self.lib = _lib.load()
@@ -99,11 +100,30 @@ class BatchedPhysicsEnv:
         self.step_count = 0        # global step index: the Philox counter word of the in-kernel jitter
         dev, f32 = self.device, torch.float32
         tmpl = torch.tensor(list(self.topo.tmpl_pos[: 3 * self.N]), dtype=f32, device=dev)
-        self.pos = tmpl[:, None].repeat(1, E).contiguous()
-        self.vel = torch.zeros(3 * self.N, E, dtype=f32, device=dev)
         x0 = torch.tensor([np.float32(m.x) for m in creature.muscles], dtype=f32, device=dev).reshape(self.M)
-        self.mx = x0[:, None].repeat(1, E).contiguous() if self.M else torch.zeros(0, E, dtype=f32, device=dev)
-        self.steps = torch.zeros(E, dtype=torch.int32, device=dev)
+        # state layout: "soa" = separate [rows, E] tensors; "packed" = one [tiles, R4, 128, 4] tensor moved with
+        # 16-byte accesses (bodies with a specialised kernel only); "auto" picks packed when it is available
+        if state_layout not in ("auto", "soa", "packed"):
+            raise ValueError("state_layout must be 'auto', 'soa' or 'packed'")
+        can_pack = self.lib.wg_kernel_variant(C.byref(self.topo)) in (1, 2)
+        if state_layout == "packed" and not can_pack:
+            raise ValueError("state_layout='packed' needs a body with a specialised kernel (Balance / Box topology)")
+        self.state_layout = "packed" if (state_layout == "packed" or (state_layout == "auto" and can_pack)) else "soa"
+        self._R = 6 * self.N + self.M + 2
+        if self.state_layout == "packed":
+            n_floats = self.lib.wg_packed_state_floats(C.byref(self.topo), E)
+            self._T, self._R4 = (E + 127) // 128, (self._R + 3) // 4
+            assert n_floats == self._T * self._R4 * 512
+            self.state = torch.zeros(self._T, self._R4, 128, 4, dtype=f32, device=dev)
+            self._pos = self._vel = self._mx = self._steps = self._ep_ret = None
+            self.set_state(pos=tmpl[:, None].expand(3 * self.N, E), mx=x0[:, None].expand(self.M, E))
+        else:
+            self.state = None
+            self._pos = tmpl[:, None].repeat(1, E).contiguous()
+            self._vel = torch.zeros(3 * self.N, E, dtype=f32, device=dev)
+            self._mx = x0[:, None].repeat(1, E).contiguous() if self.M else torch.zeros(0, E, dtype=f32, device=dev)
+            self._steps = torch.zeros(E, dtype=torch.int32, device=dev)
+            self._ep_ret = torch.zeros(E, dtype=f32, device=dev) if track_stats else None
         self.obs = torch.zeros((E, self.obs_dim) if obs_layout == "row" else (self.obs_dim, E), dtype=f32, device=dev)
         self.reward = torch.zeros(E, dtype=f32, device=dev)
         self._done_u8 = torch.zeros(E, dtype=torch.uint8, device=dev)
@@ -113,7 +133,6 @@ class BatchedPhysicsEnv:
         self.centroid = torch.zeros(3, E, dtype=f32, device=dev) if track_info else None
         self.contact_pre = torch.zeros(E, dtype=torch.int32, device=dev) if track_contacts else None
         self.contact_post = torch.zeros(E, dtype=torch.int32, device=dev) if track_contacts else None
-        self.ep_ret = torch.zeros(E, dtype=f32, device=dev) if track_stats else None
         self.fin_stats = torch.zeros(4, E, dtype=f32, device=dev) if track_stats else None
         self._stats_out = torch.zeros(8, dtype=torch.float64, device=dev)
         # graph_safe: the Philox step index lives in a device scalar advanced by a device op, so a
@@ -131,14 +150,15 @@ class BatchedPhysicsEnv:
 
     def _bind(self) -> None:
         b = self._buf
-        b.pos, b.vel, b.old_a, b.mx, b.steps = map(self._p, (self.pos, self.vel, self.old_a, self.mx, self.steps))
-        if self.M == 0:
-            b.mx = self._p(self.steps)     # never dereferenced (M == 0); keeps validation simple
+        b.pos, b.vel, b.old_a, b.mx, b.steps = map(self._p, (self._pos, self._vel, self.old_a, self._mx, self._steps))
+        b.state_packed = self._p(self.state)
+        if self.M == 0 and self.state is None:
+            b.mx = self._p(self._steps)    # never dereferenced (M == 0); keeps validation simple
         b.obs, b.reward, b.done = self._p(self.obs), self._p(self.reward), self._p(self._done_u8)
         b.obs_layout = 0 if self.obs_layout == "row" else 1
         b.contact_pre, b.contact_post = self._p(self.contact_pre), self._p(self.contact_post)
         b.energy, b.centroid = self._p(self.energy), self._p(self.centroid)
-        b.ep_ret, b.fin_stats = self._p(self.ep_ret), self._p(self.fin_stats)
+        b.ep_ret, b.fin_stats = self._p(self._ep_ret), self._p(self.fin_stats)
         b.action, b.act_dim, b.noise = None, 0, None
         b.act_layout = 0 if self.act_layout == "row" else 1
         b.step_counter = self._p(self._counter)
@@ -152,12 +172,73 @@ class BatchedPhysicsEnv:
     def _stamp(self) -> None:
         self.params.step_index = 0 if self._counter is not None else (self.step_count & 0xFFFFFFFF)
 
+    # ---- state access (layout independent) --------------------------------------------------------
+    def _var(self, k: int) -> torch.Tensor:
+        """Packed layout: strided view [tiles, 128] of per-env scalar k."""
+        return self.state[:, k >> 2, :, k & 3]
+
+    def _gather(self, k0: int, n: int, dtype=torch.float32) -> torch.Tensor:
+        out = torch.stack([self._var(k0 + i).reshape(-1)[: self.num_envs] for i in range(n)]) if n else \
+            torch.zeros(0, self.num_envs, dtype=torch.float32, device=self.device)
+        return out.view(dtype) if dtype != torch.float32 else out
+
+    @property
+    def pos(self) -> torch.Tensor:
+        """[3N, E] positions, row n*3+c.  A live tensor in the soa layout, a snapshot copy in the packed one
+        (write through ``set_state``)."""
+        return self._pos if self.state is None else self._gather(0, 3 * self.N)
+
+    @property
+    def vel(self) -> torch.Tensor:
+        return self._vel if self.state is None else self._gather(3 * self.N, 3 * self.N)
+
+    @property
+    def mx(self) -> torch.Tensor:
+        return self._mx if self.state is None else self._gather(6 * self.N, self.M)
+
+    @property
+    def steps(self) -> torch.Tensor:
+        return self._steps if self.state is None else self._gather(6 * self.N + self.M, 1, torch.int32)[0]
+
+    @property
+    def ep_ret(self):
+        if self.state is None:
+            return self._ep_ret
+        return self._gather(6 * self.N + self.M + 1, 1)[0]
+
+    def set_state(self, pos=None, vel=None, mx=None, steps=None, ep_ret=None) -> None:
+        """Overwrite (parts of) the state of all envs from [rows, E] / [E] tensors, in either layout."""
+        def put(k0, t, rows):
+            if t is None:
+                return
+            t = torch.as_tensor(t, device=self.device)
+            t = t.reshape(rows, self.num_envs)
+            if t.dtype == torch.int32:
+                t = t.view(torch.float32)
+            pad = self._T * 128 - self.num_envs
+            for i in range(rows):
+                row = t[i].to(torch.float32) if t.dtype != torch.float32 else t[i]
+                if pad:
+                    row = torch.cat([row, row.new_zeros(pad)])
+                self._var(k0 + i).copy_(row.reshape(self._T, 128))
+        if self.state is None:
+            for dst, src in ((self._pos, pos), (self._vel, vel), (self._mx, mx), (self._steps, steps), (self._ep_ret, ep_ret)):
+                if src is not None and dst is not None:
+                    dst.copy_(torch.as_tensor(src, device=self.device).reshape(dst.shape))
+            return
+        put(0, pos, 3 * self.N)
+        put(3 * self.N, vel, 3 * self.N)
+        put(6 * self.N, mx, self.M)
+        if steps is not None:
+            put(6 * self.N + self.M, torch.as_tensor(steps, device=self.device).to(torch.int32), 1)
+        put(6 * self.N + self.M + 1, ep_ret, 1)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _check_f32(self, t: torch.Tensor, shape, what: str) -> torch.Tensor:
-        if t.device != self.pos.device or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
-            raise ValueError(f"{what} must be a contiguous float32 tensor of shape {tuple(shape)} on {self.pos.device}")
+        if t.device != self.obs.device or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{what} must be a contiguous float32 tensor of shape {tuple(shape)} on {self.obs.device}")
         return t
 
     @property
@@ -282,16 +363,19 @@ class BatchedPhysicsEnv:
     def state_dict(self) -> dict:
         d = {"pos": self.pos, "vel": self.vel, "mx": self.mx, "steps": self.steps, "obs": self.obs,
              "step_count": self.step_count}
-        for k in ("old_a", "ep_ret", "fin_stats"):
+        if self.ep_ret is not None:
+            d["ep_ret"] = self.ep_ret
+        for k in ("old_a", "fin_stats"):
             if getattr(self, k) is not None:
                 d[k] = getattr(self, k)
         return d
 
     def load_state_dict(self, d: dict) -> None:
+        self.set_state(**{k: d[k] for k in ("pos", "vel", "mx", "steps", "ep_ret") if k in d})
         for k, v in d.items():
             if k == "step_count":
                 self.step_count = int(v)
-            elif getattr(self, k, None) is not None:
+            elif k in ("obs", "old_a", "fin_stats") and getattr(self, k, None) is not None:
                 getattr(self, k).copy_(v)
 
     def save_state(self, path: str, env_index: int = 0) -> None:
@@ -322,9 +406,11 @@ class BatchedPhysicsEnv:
             raise ValueError(f"snapshot has {len(pts)} points, this body has {self.N}")
         pos = torch.tensor(np.stack([p.pos for p in pts]).reshape(-1), dtype=torch.float32, device=self.device)
         vel = torch.tensor(np.stack([p.v for p in pts]).reshape(-1), dtype=torch.float32, device=self.device)
+        cur_pos, cur_vel = self.pos.clone(), self.vel.clone()
         if env_index is None:
-            self.pos.copy_(pos[:, None].expand_as(self.pos))
-            self.vel.copy_(vel[:, None].expand_as(self.vel))
+            cur_pos.copy_(pos[:, None].expand_as(cur_pos))
+            cur_vel.copy_(vel[:, None].expand_as(cur_vel))
         else:
-            self.pos[:, env_index] = pos
-            self.vel[:, env_index] = vel
+            cur_pos[:, env_index] = pos
+            cur_vel[:, env_index] = vel
+        self.set_state(pos=cur_pos, vel=cur_vel)

@@ -52,7 +52,12 @@ static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* 
     if (p->k_sub < 1) return fail(WG_ERR_BAD_ARG, "k_sub must be >= 1%s");
     if (p->auto_reset < 0 || p->auto_reset > 2) return fail(WG_ERR_BAD_ARG, "auto_reset must be 0, 1 or 2%s");
     if (p->integrator < 0 || p->integrator > 1) return fail(WG_ERR_BAD_ARG, "integrator must be 0 (run1) or 1 (run2)%s");
-    if (!b->pos || !b->vel || !b->steps || (t->n_muscle > 0 && !b->mx))
+    if (b->state_packed) {
+        const int v = pick_variant(t);
+        if (v != TopoBalance::kId && v != TopoBox::kId)
+            return fail(WG_ERR_BAD_ARG, "the packed state layout needs a body with wg_kernel_variant() 1 or 2%s");
+        if (reinterpret_cast<uintptr_t>(b->state_packed) & 15u) return fail(WG_ERR_BAD_ARG, "state_packed must be 16-byte aligned%s");
+    } else if (!b->pos || !b->vel || !b->steps || (t->n_muscle > 0 && !b->mx))
         return fail(WG_ERR_BAD_ARG, "pos/vel/mx/steps must be set%s");
     if (b->obs_layout != 0 && b->obs_layout != 1) return fail(WG_ERR_BAD_ARG, "obs_layout must be 0 or 1%s");
     if (b->act_layout != 0 && b->act_layout != 1) return fail(WG_ERR_BAD_ARG, "act_layout must be 0 or 1%s");
@@ -95,6 +100,12 @@ int wg_kernel_variant(const wg_topology* topo) {
 
 int wg_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
 
+int64_t wg_packed_state_floats(const wg_topology* topo, int64_t n_env) {
+    if (!topo || n_env < 0) return fail(WG_ERR_BAD_ARG, "bad argument to wg_packed_state_floats%s");
+    const int64_t r4 = (6 * topo->n_mass + topo->n_muscle + 2 + 3) / 4;
+    return ((n_env + 127) / 128) * r4 * 512;
+}
+
 int wg_set_tuning(int key, int value) {
     if (key < 0 || key > 3) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
     if (key == WG_TUNE_PREFETCH && value != 0 && value != 2 && value != 4) return fail(WG_ERR_BAD_ARG, "PREFETCH must be 0, 2 or 4%s");
@@ -110,6 +121,9 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
     if (n_env == 0) return WG_OK;
     cudaStream_t s = (cudaStream_t)cuda_stream;
     // one env per thread measured fastest on B200 (80 registers, 24 warps/SM); EPT=2 kept as a knob
+    if (buf->state_packed)
+        return pick_variant(topo) == TopoBalance::kId ? launch_balance_packed(topo, prm, buf, n_env, s)
+                                                      : launch_box_packed(topo, prm, buf, n_env, s);
     const int ept = (tuning(WG_TUNE_EPT) >= 2 && vec_ok(buf, n_env, 2)) ? 2 : 1;
     // larger bodies: several lanes per env (mass partition); automatic choice by body size
     int parts = tuning(WG_TUNE_PART);

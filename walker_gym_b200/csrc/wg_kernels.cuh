@@ -30,6 +30,7 @@ struct StepArgs {
     uint32_t* contact_pre; uint32_t* contact_post; float* energy; float* centroid;
     float* ep_ret; float* fin_stats; const float* noise;
     const uint32_t* step_counter;
+    float* state_packed;
     int64_t E;
     int32_t act_dim, act_layout;
 };
@@ -44,6 +45,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
+
+// packed state layout [tile][k/4][128][4] (include/walker_gym_b200.h)
+__host__ __device__ __forceinline__ int64_t packed_index(int64_t e, int k, int r4) {
+    return (((e >> 7) * r4 + (k >> 2)) << 9) + ((e & 127) << 2) + (k & 3);
+}
 
 // Philox counter word of this launch: the by-value step index plus the optional device-side counter
 template <class Args>
@@ -479,21 +485,30 @@ reset_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A, int mode,
     if (mask && !mask[e]) return;
     RuntimeTopo topo{ N, S, M, A.bv.si, A.bv.sj };
     LocalStore st;
+    const int r4 = (6 * N + M + 2 + 3) / 4;
+    float* const sp = A.state_packed;
     for (int r = 0; r < 3 * N; r++) {
-        st.p_[r / 3][r % 3] = A.pos[(int64_t)r * E + e];
-        st.v_[r / 3][r % 3] = A.vel[(int64_t)r * E + e];
+        st.p_[r / 3][r % 3] = sp ? sp[packed_index(e, r, r4)] : A.pos[(int64_t)r * E + e];
+        st.v_[r / 3][r % 3] = sp ? sp[packed_index(e, 3 * N + r, r4)] : A.vel[(int64_t)r * E + e];
         st.a_[r / 3][r % 3] = A.old_a ? A.old_a[(int64_t)r * E + e] : 0.0f;
     }
-    for (int m = 0; m < M; m++) st.mx_[m] = A.mx[(int64_t)m * E + e];
+    for (int m = 0; m < M; m++) st.mx_[m] = sp ? sp[packed_index(e, 6 * N + m, r4)] : A.mx[(int64_t)m * E + e];
     apply_reset<IN3D>(topo, A.bv, A.ec, st, mode, A.noise, E, e, step_index_of(A));
-    A.steps[e] = 0;
-    if (A.ep_ret) A.ep_ret[e] = 0.0f;
+    if (sp) {
+        sp[packed_index(e, 6 * N + M, r4)] = __int_as_float(0);
+        sp[packed_index(e, 6 * N + M + 1, r4)] = 0.0f;
+    } else {
+        A.steps[e] = 0;
+        if (A.ep_ret) A.ep_ret[e] = 0.0f;
+    }
     for (int r = 0; r < 3 * N; r++) {
-        A.pos[(int64_t)r * E + e] = st.p_[r / 3][r % 3];
-        A.vel[(int64_t)r * E + e] = st.v_[r / 3][r % 3];
+        if (sp) { sp[packed_index(e, r, r4)] = st.p_[r / 3][r % 3]; sp[packed_index(e, 3 * N + r, r4)] = st.v_[r / 3][r % 3]; }
+        else { A.pos[(int64_t)r * E + e] = st.p_[r / 3][r % 3]; A.vel[(int64_t)r * E + e] = st.v_[r / 3][r % 3]; }
         if (A.old_a) A.old_a[(int64_t)r * E + e] = st.a_[r / 3][r % 3];
     }
-    for (int m = 0; m < M; m++) A.mx[(int64_t)m * E + e] = st.mx_[m];
+    for (int m = 0; m < M; m++) {
+        if (sp) sp[packed_index(e, 6 * N + m, r4)] = st.mx_[m]; else A.mx[(int64_t)m * E + e] = st.mx_[m];
+    }
     if (A.obs) {
         // jitter-only reset without an old_a buffer: the acceleration slots of the
         // observation still hold Point.old_a of the last step -- leave them alone.

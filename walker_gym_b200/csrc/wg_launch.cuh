@@ -8,6 +8,7 @@
 #include "wg_kernels.cuh"
 #include "wg_kernels_tma.cuh"
 #include "wg_kernels_part.cuh"
+#include "wg_kernels_packed.cuh"
 
 namespace wg {
 
@@ -32,6 +33,8 @@ WG_STATIC_TOPO(TopoInsect, 4, 13, 23, 8,
 
 // one entry point per translation unit (ept = envs per thread the caller verified as legal)
 int launch_balance(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
+int launch_balance_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
+int launch_box_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_box(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
 int launch_quad(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
 int launch_insect(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
@@ -86,7 +89,7 @@ inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_pa
     A.action = b->action; A.obs = b->obs; A.reward = b->reward; A.done = b->done;
     A.contact_pre = b->contact_pre; A.contact_post = b->contact_post; A.energy = b->energy; A.centroid = b->centroid;
     A.ep_ret = b->ep_ret; A.fin_stats = b->fin_stats; A.noise = b->noise;
-    A.step_counter = b->step_counter;
+    A.step_counter = b->step_counter; A.state_packed = b->state_packed;
     A.E = E; A.act_dim = b->action ? b->act_dim : 0; A.act_layout = b->act_layout;
 }
 
@@ -163,6 +166,35 @@ inline int launch_static_tma(const wg_topology* t, const wg_params* p, const wg_
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (tma) launch: %s", cudaGetErrorString(e));
     return WG_OK;
+}
+
+// ---- packed state layout: float4 state access --------------------------------------------------------
+template <class Topo, bool IN3D, int OBS, int MM>
+inline int launch_static_packed(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
+    StepArgs<Topo::N, Topo::S> A;
+    fill_args(A, t, p, b, E);
+    constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
+    constexpr bool bulk = (OBS == 1) && gcd_c(D, 32) <= 2;
+    const size_t smem = (OBS == 1 && b->obs) ? sizeof(float) * kBlock * (bulk ? D : (D | 1)) : 0;
+    auto kern = step_static_packed_kernel<Topo, IN3D, OBS, MM>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    kern<<<(unsigned)((E + kBlock - 1) / kBlock), kBlock, smem, s>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (packed) launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
+template <class Topo>
+inline int launch_packed_flags(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
+    const int mm = mass_mode(t);
+    const bool rm = b->obs_layout == 0;
+#define WG_PK(I3, OB) (mm == 0 ? launch_static_packed<Topo, I3, OB, 0>(t, p, b, E, s) : launch_static_packed<Topo, I3, OB, 1>(t, p, b, E, s))
+    if (p->in3d) return rm ? WG_PK(true, 1) : WG_PK(true, 0);
+    return rm ? WG_PK(false, 1) : WG_PK(false, 0);
+#undef WG_PK
 }
 
 // ---- per-thread cp.async prefetch variant: TPC tiles per CTA -----------------------------------------

@@ -31,7 +31,8 @@ class _DeviceBody:
     def __init__(self, creature: Creature, env_kwargs: dict, device):
         self.creature = creature
         self.core = BatchedPhysicsEnv(creature, 1, device, auto_reset=None, keep_old_a=True, track_info=True,
-                                      track_contacts=True, track_stats=False, initial_reset=False, **env_kwargs)
+                                      track_contacts=True, track_stats=False, initial_reset=False, state_layout="soa",
+                                      **env_kwargs)
         c = self.core
         self.noise = torch.zeros(3 * c.N, 1, dtype=torch.float32, device=c.device)
 
