@@ -108,11 +108,20 @@ __device__ __forceinline__ void forced2(float (&a)[3], const float (&f)[3], cons
         for (int c = 0; c < 3; c++) a[c] = (a[c] + f[c]) + g[c];
         return;
     }
+    if (MM == 1) {
+        // one straight-line path for every mass of the body: with m == 1 (r == 1) the sequence degenerates to
+        // q0 = x, rem = 0, q = x, so unit masses need no branch -- a few redundant FMAs are cheaper than the
+        // instruction-cache footprint of a second code variant per endpoint
+        const float m = bv.mass_f[n], r = bv.mass_r[n];
+#pragma unroll
+        for (int c = 0; c < 3; c++) a[c] = (a[c] + div_smallint(f[c], m, r)) + div_smallint(g[c], m, r);
+        return;
+    }
     const int kind = bv.mass_kind[n];
     if (kind == 0) {
 #pragma unroll
         for (int c = 0; c < 3; c++) a[c] = (a[c] + f[c]) + g[c];
-    } else if (MM == 1 || kind <= 2) {
+    } else if (kind <= 2) {
         const float m = bv.mass_f[n], r = bv.mass_r[n];
 #pragma unroll
         for (int c = 0; c < 3; c++) a[c] = (a[c] + div_smallint(f[c], m, r)) + div_smallint(g[c], m, r);
@@ -155,6 +164,20 @@ __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store
     }
 }
 
+// Rarely used variants, kept out of line so that they do not dilute the hot instruction stream.
+static __device__ __noinline__ float3 damp_cold(float3 a, float3 v, float ndampk, float m, float r, int kind) {
+    a.x = a.x + div_const(ndampk * v.x, m, r, kind);
+    a.y = a.y + div_const(ndampk * v.y, m, r, kind);
+    a.z = a.z + div_const(ndampk * v.z, m, r, kind);
+    return a;
+}
+static __device__ __noinline__ void run2_cold(float3& p, float3& v, float3 a, float dt, float dt2) {
+    p.x = p.x + (v.x * dt + (0.5f * a.x) * dt2);
+    p.y = p.y + (v.y * dt + (0.5f * a.y) * dt2);
+    p.z = p.z + (v.z * dt + (0.5f * a.z) * dt2);
+    v.x = v.x + a.x * dt; v.y = v.y + a.y * dt; v.z = v.z + a.z * dt;
+}
+
 // Environment forces on mass n (gravity, damping, ground contact: gym/optimized_env.py:146-175) followed by
 // the integrator (Point.run1 / run2).  Returns the force-phase contact flag.
 template <bool IN3D, int MM, class BV, class Store>
@@ -168,11 +191,10 @@ __device__ __forceinline__ bool point_step(const BV& bv, const EnvConst& ec, Sto
         ay = (float)((double)ay + bv.gm[n]);                 // forced([0, -g, 0])
         if (ec.dampk_is_zero) {                               // forced(-0 * v): +-0, or NaN for non-finite v
             ax = ax + ec.ndampk * vx; ay = ay + ec.ndampk * vy; az = az + ec.ndampk * vz;
-        } else {                                              // forced(-k * v): float32 force / m
-            const ConstDiv md{ bv.mass_f[n], bv.mass_r[n], bv.mass_kind[n] };
-            ax = ax + div_const(ec.ndampk * vx, md.m, md.r, md.kind);
-            ay = ay + div_const(ec.ndampk * vy, md.m, md.r, md.kind);
-            az = az + div_const(ec.ndampk * vz, md.m, md.r, md.kind);
+        } else {                                              // forced(-k * v): float32 force / m  (cold: dampk defaults to 0)
+            const float3 r = damp_cold(make_float3(ax, ay, az), make_float3(vx, vy, vz), ec.ndampk,
+                                       bv.mass_f[n], bv.mass_r[n], bv.mass_kind[n]);
+            ax = r.x; ay = r.y; az = r.z;
         }
         if (hit) {
             const double m = bv.mass_d[n], rd = bv.mass_rd[n];
@@ -192,11 +214,11 @@ __device__ __forceinline__ bool point_step(const BV& bv, const EnvConst& ec, Sto
         st.pos(n, 1) = st.pos(n, 1) + nvy * ec.dt;
         st.pos(n, 2) = st.pos(n, 2) + nvz * ec.dt;
     } else {
-        // Point.run2 (gym/optimized_engine.py:274-288): pos += v*t + (0.5*a)*t**2; then v += a*t
-        st.pos(n, 0) = st.pos(n, 0) + (vx * ec.dt + (0.5f * ax) * ec.dt2);
-        st.pos(n, 1) = st.pos(n, 1) + (vy * ec.dt + (0.5f * ay) * ec.dt2);
-        st.pos(n, 2) = st.pos(n, 2) + (vz * ec.dt + (0.5f * az) * ec.dt2);
-        st.vel(n, 0) = vx + ax * ec.dt; st.vel(n, 1) = vy + ay * ec.dt; st.vel(n, 2) = vz + az * ec.dt;
+        // Point.run2 (gym/optimized_engine.py:274-288): pos += v*t + (0.5*a)*t**2; then v += a*t  (cold path)
+        float3 p = make_float3(st.pos(n, 0), st.pos(n, 1), st.pos(n, 2)), v = make_float3(vx, vy, vz);
+        run2_cold(p, v, make_float3(ax, ay, az), ec.dt, ec.dt2);
+        st.pos(n, 0) = p.x; st.pos(n, 1) = p.y; st.pos(n, 2) = p.z;
+        st.vel(n, 0) = v.x; st.vel(n, 1) = v.y; st.vel(n, 2) = v.z;
     }
     st.acc(n, 0) = ax; st.acc(n, 1) = ay; st.acc(n, 2) = az;
     return hit;
