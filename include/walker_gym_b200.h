@@ -151,6 +151,7 @@ int wg_force_generic(int on);
 #define WG_TUNE_EPT 1
 #define WG_TUNE_PART 2
 #define WG_TUNE_PREFETCH 3   /* 0 = off; 2 / 4 = tiles per CTA of the per-thread cp.async prefetch variant */
+#define WG_TUNE_L2_PREFETCH 4 /* packed-state kernel: distance, in 128-env tiles, of the L2 bulk prefetch (0 = off; default 256) */
 int wg_set_tuning(int key, int value);
 
 /*

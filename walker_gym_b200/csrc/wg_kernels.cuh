@@ -32,6 +32,7 @@ struct StepArgs {
     const uint32_t* step_counter;
     float* state_packed;
     int64_t E;
+    int32_t pf_dist;          // packed kernel: L2 prefetch distance in tiles (0 = off)
     int32_t act_dim, act_layout;
 };
 

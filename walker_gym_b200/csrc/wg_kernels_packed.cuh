@@ -33,6 +33,20 @@ step_static_packed_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) 
     const bool valid = e < E;
     float4* const base = reinterpret_cast<float4*>(A.state_packed) + (int64_t)blockIdx.x * (R4 * kBlock) + tid;
 
+    // L2 prefetch: a tile is one contiguous block, so one thread can ask the copy engine to pull the tile that a
+    // CTA launched `pf_dist` blocks later will read (CTAs are dispatched in index order) from HBM into L2 with a
+    // single cp.async.bulk.prefetch; that CTA's loads then pay L2 instead of DRAM latency.
+    if (tid == 0 && A.pf_dist > 0) {
+        const int64_t pt = (int64_t)blockIdx.x + A.pf_dist;
+        if (pt * kBlock + kBlock <= E) {
+            const float* ps = A.state_packed + pt * (R4 * kBlock * 4);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ps), "r"((uint32_t)(R4 * kBlock * 16)) : "memory");
+            if (M > 0 && A.action && A.act_layout == 0 && A.act_dim == M && ((reinterpret_cast<uintptr_t>(A.action) & 15u) == 0))
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.action + pt * kBlock * M),
+                             "r"((uint32_t)(kBlock * M * 4)) : "memory");
+        }
+    }
+
     if (valid) {
         // ---- single HBM read of the state: R4 coalesced 16-byte loads at immediate offsets ----
         float v[R4 * 4];

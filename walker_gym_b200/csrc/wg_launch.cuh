@@ -90,6 +90,7 @@ inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_pa
     A.contact_pre = b->contact_pre; A.contact_post = b->contact_post; A.energy = b->energy; A.centroid = b->centroid;
     A.ep_ret = b->ep_ret; A.fin_stats = b->fin_stats; A.noise = b->noise;
     A.step_counter = b->step_counter; A.state_packed = b->state_packed;
+    A.pf_dist = tuning(WG_TUNE_L2_PREFETCH);
     A.E = E; A.act_dim = b->action ? b->act_dim : 0; A.act_layout = b->act_layout;
 }
 
