@@ -299,7 +299,7 @@ def run_ours(args):
                                    f", in3d=True, {E} envs per GPU, 1 kernel launch per env-step, K_sub={k_sub}, template "
                                    "auto-reset, reference semantics as written, U(-1,1) f32 actions from a 16-deep device ring",
                        "baseline_config": args.config,
-                       "envs_per_gpu": E, "global_envs": world * E, "obs": (f"row-major [E,{env.obs_dim}] materialised" if args.obs_layout == "row"
+                       "envs_per_gpu": E, "global_envs": world * E, "state_layout": env.state_layout, "obs": (f"row-major [E,{env.obs_dim}] materialised" if args.obs_layout == "row"
                                else f"feature-major [{env.obs_dim},E] materialised"),
                        "l2": f"state+obs+actions per step = {E * bytes_per_env_step / 1e6:.0f} MB > 126 MB L2 "
                              "(inputs larger than L2, no flush needed)",
@@ -307,7 +307,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if tr is None else tr * E, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_per_env_step,
-                         "kernel": ("wg::step_static_kernel<TopoBalance, in3d, OBS=row-major staged, EPT=1, MM=1>" if args.config == 3
+                         "kernel": (f"wg::step_static_packed_kernel<Topo{args.body.capitalize()}, in3d, row-major obs via TMA bulk store, "
+                                    "packed float4 state, L2 bulk prefetch>" if args.config == 3
                                     else "wg::step_part_kernel<in3d, P=4 lanes per env, row-major, MM=1>"),
                          "kernel_us": per_launch_s * 1e6},
             "e2e": e2e, "gpu_launches": K, "clocks": clocks,
