@@ -344,3 +344,55 @@ def test_packed_layout_rejected_for_bodies_without_a_specialised_kernel():
         BatchedPhysicsEnv("humanb", 64, "cuda:0", state_layout="packed")
     assert BatchedPhysicsEnv("humanb", 64, "cuda:0").state_layout == "soa"
     assert BatchedPhysicsEnv("Balance-v0", 64, "cuda:0").state_layout == "packed"
+
+
+def _random_spec(rng, N, S, M):
+    pts = [(float(rng.choice([1, 1, 2, 3, 5, 0.5, 0.25, 7.5])), tuple(float(v) for v in rng.uniform(-150, 150, 3)), bool(n == 5))
+           for n in range(N)]
+    pairs = [(i, j) for i in range(N) for j in range(i + 1, N)]
+    rng.shuffle(pairs)
+    mus = [(i, j, {"k": float(rng.choice([500, 1000, -700]))}) for i, j in pairs[:M]]
+    sks = [(j, i, {"dampk": float(rng.choice([5, 20]))}) for i, j in pairs[M:S]]
+    return {"points": pts, "muscles": mus, "skeletons": sks}
+
+
+@pytest.mark.parametrize("N,S,M,parts", [(32, 96, 10, -1), (32, 96, 10, 8), (32, 96, 10, 0), (9, 30, 5, 2), (1, 0, 0, -1),
+                                          (2, 1, 1, -1), (17, 16, 0, 4)])
+def test_maximum_and_minimum_body_sizes(N, S, M, parts):
+    """The ABI limits (32 masses, 96 springs) and the degenerate ends (a single free mass, no muscles)
+    on the generic and the mass-partitioned kernels, with float masses and a DingPoint."""
+    import ctypes as C
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv, Creature, DingPoint, Muscle, Point, Skeleton, _lib
+    rng = np.random.default_rng(N * 100 + S)
+    spec = _random_spec(rng, N, S, M)
+    Point.clear()
+    pts = [DingPoint(m, list(p)) if f else Point(m, list(p), [0, 0, 0]) for m, p, f in spec["points"]]
+    cr = Creature(pts, [Muscle(pts[i], pts[j], **kw) for i, j, kw in spec["muscles"]],
+                  [Skeleton(pts[i], pts[j], **kw) for i, j, kw in spec["skeletons"]])
+    lib = _lib.load()
+    old = lib.wg_set_tuning(_lib.TUNE_PART, parts)
+    try:
+        E = 300
+        env = BatchedPhysicsEnv(cr, E, "cuda:0", in3d=True, auto_reset="template", max_steps=5, k_sub=2, seed=3,
+                                keep_old_a=True, track_info=True, track_contacts=True, initial_reset=False)
+        body = wo.make_body(spec)
+        prm = wo.make_params(in3d=True, auto_reset=2, max_steps=5, k_sub=2, seed=3)
+        st = wo.init_state(body, E)
+        run_lockstep(env, body, prm, st, 9, rng, noise_reset=False)
+    finally:
+        lib.wg_set_tuning(_lib.TUNE_PART, old)
+        Point.clear()
+
+
+def test_empty_batch_is_a_no_op():
+    import ctypes as C
+    from walker_gym_b200 import _lib, create_box_creature, make_params
+    from walker_gym_b200.topology import topology_from_creature
+    lib = _lib.load()
+    topo, prm, buf = topology_from_creature(create_box_creature()), make_params(in3d=True), _lib.WgBuffers()
+    import torch
+    z = torch.zeros(16, device="cuda:0")
+    buf.pos = buf.vel = buf.mx = buf.steps = z.data_ptr()
+    assert lib.wg_step(C.byref(topo), C.byref(prm), C.byref(buf), 0, None) == 0
+    assert lib.wg_reset(C.byref(topo), C.byref(prm), C.byref(buf), 0, 1, None, None) == 0
