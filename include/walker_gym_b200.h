@@ -141,17 +141,16 @@ int wg_kernel_variant(const wg_topology* topo);
 /* Force the generic kernel (1) or restore automatic dispatch (0); returns the old value. */
 int wg_force_generic(int on);
 /* Kernel-selection knobs for experiments and tests; results never depend on them.
- *   WG_TUNE_TMA (0): 1 = use the persistent TMA-pipelined variant of the specialised kernels when
- *                    the buffers allow it (E % 4 == 0, 16-byte aligned); default 0.
- *   WG_TUNE_EPT (1): envs per thread of the non-TMA specialised kernel, 1 (default) or 2.
- *   WG_TUNE_PART (2): lanes per env of the mass-partitioned kernel used for larger bodies:
+ *   WG_TUNE_TMA (0): 1 = use the persistent TMA-pipelined variant of the specialised SoA kernels when the
+ *                    buffers allow it (E % 4 == 0, 16-byte aligned); default 0 (measured slower).
+ *   WG_TUNE_PART (1): lanes per env of the mass-partitioned kernel used for larger bodies:
  *                    -1 = automatic (default), 0 = never, 2 / 4 / 8 = force that many parts.
+ *   WG_TUNE_L2_PREFETCH (2): distance, in thread blocks, of the L2 prefetch issued by the packed-state and
+ *                    mass-partitioned kernels (0 = off; default 256).
  * Returns the previous value, or WG_ERR_BAD_ARG. */
 #define WG_TUNE_TMA 0
-#define WG_TUNE_EPT 1
-#define WG_TUNE_PART 2
-#define WG_TUNE_PREFETCH 3   /* 0 = off; 2 / 4 = tiles per CTA of the per-thread cp.async prefetch variant */
-#define WG_TUNE_L2_PREFETCH 4 /* packed-state kernel: distance, in 128-env tiles, of the L2 bulk prefetch (0 = off; default 256) */
+#define WG_TUNE_PART 1
+#define WG_TUNE_L2_PREFETCH 2
 int wg_set_tuning(int key, int value);
 
 /*

@@ -19,7 +19,6 @@ DEV = "cuda:0"
 obs_layout = 0          # module-level switches the tests flip
 force_generic = False
 use_tma = False
-ept = 1
 
 
 class Body:
@@ -98,13 +97,11 @@ def step(body, prm, st, action, *, want_info=True, ep_ret=None, fin_stats=None, 
     b.ep_ret, b.fin_stats, b.noise = _ptr(d_ep), _ptr(d_fin), _ptr(d_noise)
     old = lib.wg_force_generic(1 if force_generic else 0)
     old_tma = lib.wg_set_tuning(_lib.TUNE_TMA, 1 if use_tma else 0)
-    old_ept = lib.wg_set_tuning(_lib.TUNE_EPT, ept)
     try:
         rc = lib.wg_step(C.byref(body.topo), C.byref(prm), C.byref(b), E, _stream())
     finally:
         lib.wg_force_generic(old)
         lib.wg_set_tuning(_lib.TUNE_TMA, old_tma)
-        lib.wg_set_tuning(_lib.TUNE_EPT, old_ept)
     _lib.check(rc, "wg_step")
     torch.cuda.synchronize()
     _download(st, d)

@@ -12,9 +12,9 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture()
 def stepper():
     import cuda_stepper as cs
-    cs.obs_layout, cs.force_generic, cs.use_tma, cs.ept = 0, False, False, 1
+    cs.obs_layout, cs.force_generic, cs.use_tma = 0, False, False
     yield cs
-    cs.obs_layout, cs.force_generic, cs.use_tma, cs.ept = 0, False, False, 1
+    cs.obs_layout, cs.force_generic, cs.use_tma = 0, False, False
 
 
 @pytest.mark.parametrize("name", gu.trajectory_names())
@@ -43,10 +43,9 @@ def test_cuda_matches_reference_batch(stepper, name, generic):
 
 
 @pytest.mark.parametrize("name", gu.batch_names())
-@pytest.mark.parametrize("variant", ["tma", "ept2", "tma_feature"])
+@pytest.mark.parametrize("variant", ["tma", "tma_feature"])
 def test_cuda_kernel_variants_match_reference_batch(stepper, name, variant):
-    """The persistent TMA-pipelined kernel and the two-envs-per-thread kernel give the same bits."""
+    """The persistent TMA-pipelined kernel gives the same bits."""
     stepper.use_tma = variant.startswith("tma")
-    stepper.ept = 2 if variant == "ept2" else 1
     stepper.obs_layout = 1 if variant.endswith("feature") else 0
     assert replay_batch(gu.load(name), stepper) == []

@@ -305,24 +305,6 @@ def test_partition_off_uses_one_thread_per_env():
         lib.wg_set_tuning(_lib.TUNE_PART, old)
 
 
-@pytest.mark.parametrize("tpc", [2, 4])
-@pytest.mark.parametrize("E", [1, 130, 4096, 5000])
-@pytest.mark.parametrize("name,layout", [("balance_v0", "row"), ("box_v0", "feature")])
-def test_prefetch_kernel_matches_oracle(name, layout, E, tpc):
-    """Per-thread cp.async prefetch variant (WG_TUNE_PREFETCH): several tiles per CTA, ragged tails, auto-reset."""
-    from walker_gym_b200 import _lib
-    lib = _lib.load()
-    old = lib.wg_set_tuning(_lib.TUNE_PREFETCH, tpc)
-    try:
-        env, body, prm, st = make_pair(name, E, env_kw=dict(in3d=True), auto_reset="template", max_steps=6,
-                                       obs_layout=layout, track_stats=True, state_layout="soa")
-        ep = (np.zeros(E, np.float32), np.zeros((4, E), np.float32))
-        run_lockstep(env, body, prm, st, 14, np.random.default_rng(E + tpc), noise_reset=False, ep=ep)
-        assert gu.same(env.fin_stats.cpu().numpy(), ep[1])
-    finally:
-        lib.wg_set_tuning(_lib.TUNE_PREFETCH, old)
-
-
 @pytest.mark.parametrize("state_layout", ["soa", "packed"])
 @pytest.mark.parametrize("E", [1, 127, 128, 129, 1000, 4096])
 @pytest.mark.parametrize("name,in3d,layout", [("balance_v0", True, "row"), ("box_v0", True, "feature"),

@@ -55,7 +55,7 @@ class WgBuffers(C.Structure):
     ]
 
 
-TUNE_TMA, TUNE_EPT, TUNE_PART, TUNE_PREFETCH, TUNE_L2_PREFETCH = 0, 1, 2, 3, 4
+TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH = 0, 1, 2
 
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
            "wg_set_tuning", "wg_packed_state_floats",

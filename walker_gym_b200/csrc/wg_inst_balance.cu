@@ -2,7 +2,6 @@
 #include "wg_launch.cuh"
 namespace wg {
 int launch_balance(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int ept, cudaStream_t s) {
-    if (ept == 2) return launch_static_flags<TopoBalance, 2>(t, p, b, E, s);
     (void)ept;
     return launch_static_flags<TopoBalance, 1>(t, p, b, E, s);
 }

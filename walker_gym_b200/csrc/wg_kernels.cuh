@@ -145,7 +145,6 @@ __device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const E
 // OBS: 0 = feature-major [D][E] (stores coalesced straight from registers),
 //      1 = row-major [E][D] staged through a padded shared-memory tile, each warp streaming its
 //          own 32*EPT rows (one contiguous span of global memory) with only a __syncwarp,
-//      2 = row-major written directly as 8-byte pieces of each thread's own row (no shared memory).
 template <class Topo, bool IN3D, int OBS, int EPT, int MM>
 __global__ void __launch_bounds__(kBlock, (Topo::N <= 4 && EPT == 1) ? WG_MIN_BLOCKS : 1)
 step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
@@ -266,13 +265,6 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
                 if (OBS == 1) {
                     float* row = tile + (tid * EPT + j) * STRIDE;
                     get_obs<IN3D>(topo, A.bv.ndiv, st[j], [&](int k, float v) { row[k] = v; });
-                } else if (OBS == 2) {
-                    static_assert(OBS != 2 || D % 2 == 0, "direct row-major stores need an even obs dim");
-                    float2* row = reinterpret_cast<float2*>(A.obs + (e + j) * D);
-                    float hold = 0.0f;
-                    get_obs<IN3D>(topo, A.bv.ndiv, st[j], [&](int k, float v) {
-                        if (k & 1) row[k >> 1] = make_float2(hold, v); else hold = v;
-                    });
                 } else {
                     get_obs<IN3D>(topo, A.bv.ndiv, st[j], [&](int k, float v) { A.obs[(int64_t)k * E + e + j] = v; });
                 }

@@ -72,6 +72,18 @@ step_part_kernel(const __grid_constant__ PartArgs PA) {
     const uint32_t skip = A.bv.fixed_mask | ~PA.pt.own_mask[part];
     __syncthreads();                               // staged tables visible
 
+    // L2 prefetch for a block dispatched `pf_dist` blocks later: every row segment of that block is one
+    // 128-byte-class span, so each thread asks for one line (pos/vel rows, then muscle rows)
+    if (A.pf_dist > 0) {
+        const int64_t pe0 = ((int64_t)blockIdx.x + A.pf_dist) * EB;
+        if (pe0 + EB <= E) {
+            for (int r = tid; r < 6 * N + M; r += kBlock) {
+                const float* ptr = r < 3 * N ? A.pos + (int64_t)r * E + pe0
+                                 : r < 6 * N ? A.vel + (int64_t)(r - 3 * N) * E + pe0 : A.mx + (int64_t)(r - 6 * N) * E + pe0;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            }
+        }
+    }
     // ---- single HBM read: the block's EB envs of every state row, coalesced ----
     for (int idx = tid; idx < 6 * N * EB; idx += kBlock) {
         const int r = idx / EB, c = idx - r * EB;

@@ -234,125 +234,4 @@ step_static_tma_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
     if (OBS == 1 && A.obs && LY::OBS_BULK && lane == 0) bulk_wait_read0();   // smem must outlive the last bulk store
 }
 
-// =================================================================================================
-// K1-PF: per-thread asynchronous prefetch.  Each CTA owns TPC consecutive tiles of 128 envs.  A thread
-// needs only ITS env's 6N + M + 2 scalars (+ M actions), so the prefetch needs no cross-thread
-// synchronisation at all: right after tile t's inputs have been moved from the thread's private
-// shared-memory column into registers, the thread issues cp.async (LDGSTS) copies of tile t+1's
-// scalars into the same column and computes tile t while they are in flight; cp.async.wait_group
-// is the only wait.  The observation rows leave through the warp's shared-memory tile as in the
-// other variants.  Works for every E and alignment (4-byte copies).
-// =================================================================================================
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-#ifndef WG_PF_MIN_BLOCKS
-#define WG_PF_MIN_BLOCKS 6
-#endif
-
-template <class Topo, bool IN3D>
-struct PfLayout {
-    static constexpr int N = Topo::N, M = Topo::M;
-    static constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;
-    static constexpr int ROW_STEPS = 6 * N + M, ROW_EPRET = ROW_STEPS + 1, ROW_ACT = ROW_STEPS + 2;
-    static constexpr int ROWS = ROW_ACT + (M > 0 ? M : 1);          // one row per action component
-    static constexpr int DP = D | 1;                               // padded obs tile pitch
-    static constexpr size_t smem_bytes(bool obs_tile) { return sizeof(float) * (ROWS * kBlock + (obs_tile ? kBlock * DP : 0)); }
-};
-
-template <class Topo, bool IN3D, int OBS, int MM, int TPC>
-__global__ void __launch_bounds__(kBlock, WG_PF_MIN_BLOCKS)
-step_static_pf_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
-    using LY = PfLayout<Topo, IN3D>;
-    constexpr int N = Topo::N, M = Topo::M, D = LY::D, DP = LY::DP;
-    extern __shared__ __align__(16) float smem_f[];
-    float* const col = smem_f + threadIdx.x;                        // this thread's private column: col[row * kBlock]
-    float* const obs_tile = smem_f + LY::ROWS * kBlock;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t E = A.E;
-    const int64_t n_tiles = (E + kBlock - 1) / kBlock;
-    const bool act_staged = (M > 0) && A.action && A.act_dim == M;
-    float* const wtile = obs_tile + warp * 32 * DP;
-
-    auto prefetch = [&](int64_t tile) {
-        const int64_t e = tile * kBlock + tid;
-        if (tile < n_tiles && e < E) {
-#pragma unroll
-            for (int r = 0; r < 3 * N; r++) {
-                cp_async4(col + r * kBlock, A.pos + (int64_t)r * E + e);
-                cp_async4(col + (3 * N + r) * kBlock, A.vel + (int64_t)r * E + e);
-            }
-#pragma unroll
-            for (int m = 0; m < M; m++) cp_async4(col + (6 * N + m) * kBlock, A.mx + (int64_t)m * E + e);
-            cp_async4(col + LY::ROW_STEPS * kBlock, A.steps + e);
-            if (A.ep_ret) cp_async4(col + LY::ROW_EPRET * kBlock, A.ep_ret + e);
-            if (act_staged) {
-#pragma unroll
-                for (int m = 0; m < M; m++)
-                    cp_async4(col + (LY::ROW_ACT + m) * kBlock, A.act_layout ? A.action + (int64_t)m * E + e : A.action + e * M + m);
-            }
-        }
-        cp_async_commit();
-    };
-
-    const int64_t tile0 = (int64_t)blockIdx.x * TPC;
-    prefetch(tile0);
-#pragma unroll 1
-    for (int t = 0; t < TPC; t++) {
-        const int64_t tile = tile0 + t;
-        if (tile >= n_tiles) break;
-        const int64_t e0 = tile * kBlock;
-        const int64_t e = e0 + tid;
-        const bool valid = e < E;
-        cp_async_wait0();
-        RegStore<N, M> st;
-        int32_t stp = 0;
-        float epr = 0.0f;
-        float act[M > 0 ? M : 1];
-        if (valid) {
-#pragma unroll
-            for (int r = 0; r < 3 * N; r++) { st.p_[r / 3][r % 3] = col[r * kBlock]; st.v_[r / 3][r % 3] = col[(3 * N + r) * kBlock]; }
-#pragma unroll
-            for (int m = 0; m < M; m++) st.mx(m) = col[(6 * N + m) * kBlock];
-            stp = __float_as_int(col[LY::ROW_STEPS * kBlock]);
-            if (A.ep_ret) epr = col[LY::ROW_EPRET * kBlock];
-            if (act_staged) {
-#pragma unroll
-                for (int m = 0; m < M; m++) act[m] = col[(LY::ROW_ACT + m) * kBlock];
-            }
-        }
-        if (t + 1 < TPC) prefetch(tile + 1);         // in flight during the whole compute below
-        if (OBS == 1 && A.obs) __syncwarp();         // the warp finished streaming out the previous tile's rows
-        if (valid) env_compute_store<Topo, IN3D, OBS, MM, DP>(A, st, stp, epr, act, act_staged, e, lane, wtile);
-        if (OBS == 1 && A.obs) {
-            __syncwarp();
-            const int64_t ew = e0 + (int64_t)warp * 32;
-            const int64_t remw = E - ew;
-            if (remw > 0) {
-                const int nvw = remw < 32 ? (int)remw : 32;
-                const float* src = wtile + lane;
-                float* out = A.obs + ew * D + lane;
-                if (nvw == 32) {
-#pragma unroll
-                    for (int i = 0; i < D; i++) {      // idx = 32*i + lane -> row el, column idx - el*D
-                        const int base = (32 * i) / D, r0 = (32 * i) % D;
-                        const int q = lane + r0;
-                        const int el = base + (q >= D ? 1 : 0) + (q >= 2 * D ? 1 : 0);
-                        out[32 * i] = src[32 * i + el * (DP - D)];
-                    }
-                } else {
-                    const int total = nvw * D;
-                    for (int idx = lane; idx < total; idx += 32) {
-                        const int el = idx / D;
-                        out[idx - lane] = src[idx - lane + el * (DP - D)];
-                    }
-                }
-            }
-        }
-    }
-}
-
 }  // namespace wg

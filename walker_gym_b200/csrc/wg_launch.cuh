@@ -105,12 +105,6 @@ inline int mass_mode(const wg_topology* t) {
     return mode;
 }
 
-inline int obs_mode(const wg_buffers* b, int D) {
-    static const int direct = [] { const char* v = getenv("WG_OBS_DIRECT"); return v ? atoi(v) : 0; }();   // tuning knob
-    if (b->obs_layout == 1) return 0;
-    return (direct && D % 2 == 0) ? 2 : 1;
-}
-
 template <class Topo, bool IN3D, int OBS, int EPT, int MM>
 inline int launch_static(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
     StepArgs<Topo::N, Topo::S> A;
@@ -198,44 +192,14 @@ inline int launch_packed_flags(const wg_topology* t, const wg_params* p, const w
 #undef WG_PK
 }
 
-// ---- per-thread cp.async prefetch variant: TPC tiles per CTA -----------------------------------------
-template <class Topo, bool IN3D, int OBS, int MM, int TPC>
-inline int launch_static_pf(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
-    using LY = PfLayout<Topo, IN3D>;
-    StepArgs<Topo::N, Topo::S> A;
-    fill_args(A, t, p, b, E);
-    const size_t smem = LY::smem_bytes(OBS == 1 && b->obs);
-    auto kern = step_static_pf_kernel<Topo, IN3D, OBS, MM, TPC>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    }
-    const int64_t n_tiles = (E + kBlock - 1) / kBlock;
-    const unsigned grid = (unsigned)((n_tiles + TPC - 1) / TPC);
-    kern<<<grid, kBlock, smem, s>>>(A);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (prefetch) launch: %s", cudaGetErrorString(e));
-    return WG_OK;
-}
-
 template <class Topo, bool IN3D, int EPT, int MM>
 inline int launch_static_obs(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
-    constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
-    const int om = obs_mode(b, D);
+    const int om = b->obs_layout == 1 ? 0 : 1;       // OBS template value: 0 feature-major, 1 row-major
     if constexpr (EPT == 1 && Topo::N <= 4) {
-        const int pf = tuning(WG_TUNE_PREFETCH);
-        if (om != 2 && pf >= 2) {
-            if (pf >= 4) return om == 0 ? launch_static_pf<Topo, IN3D, 0, MM, 4>(t, p, b, E, s) : launch_static_pf<Topo, IN3D, 1, MM, 4>(t, p, b, E, s);
-            return om == 0 ? launch_static_pf<Topo, IN3D, 0, MM, 2>(t, p, b, E, s) : launch_static_pf<Topo, IN3D, 1, MM, 2>(t, p, b, E, s);
-        }
-        if (om != 2 && tma_ok(b, E))
+        if (tma_ok(b, E))
             return om == 0 ? launch_static_tma<Topo, IN3D, 0, MM>(t, p, b, E, s) : launch_static_tma<Topo, IN3D, 1, MM>(t, p, b, E, s);
     }
-    switch (om) {
-        case 0: return launch_static<Topo, IN3D, 0, EPT, MM>(t, p, b, E, s);
-        case 2: if constexpr (D % 2 == 0) return launch_static<Topo, IN3D, 2, EPT, MM>(t, p, b, E, s);
-        default: return launch_static<Topo, IN3D, 1, EPT, MM>(t, p, b, E, s);
-    }
+    return om == 0 ? launch_static<Topo, IN3D, 0, EPT, MM>(t, p, b, E, s) : launch_static<Topo, IN3D, 1, EPT, MM>(t, p, b, E, s);
 }
 
 // static kernels exist for mass modes 0 and 1; bodies with arbitrary masses use the generic kernel
