@@ -433,6 +433,115 @@ int wgo_reset(const wgo_body *b, const wgo_params *p, int64_t E, int mode,
     return 0;
 }
 
+/* =============================================================================================
+ * L2: the reference's *package* lineage -- Environment.update_physics of
+ * gym/optimized_walker/env.py:135-184 on top of gym/optimized_walker/core.py (Point.forced :81-83,
+ * anti_forced :85-91, resilience :93-121, run1 :184-200, DingPoint :259-275).  A different physics
+ * model from the gym-style env above: physically signed springs with optional one-sided ("string")
+ * behaviour, gravity as an acceleration (g*m/m), multiplicative velocity damping, quadratic drag,
+ * and a ground that clamps the position and reflects the velocity.  No observation/reward/done.
+ * ============================================================================================= */
+typedef struct {
+    int32_t n_point, n_spring;
+    double mass[WGO_MAX_MASS];
+    uint8_t ding[WGO_MAX_MASS];
+    int32_t si[WGO_MAX_SPRING], sj[WGO_MAX_SPRING];
+    float sx[WGO_MAX_SPRING];        /* rest length as float32 */
+    float sk[WGO_MAX_SPRING];        /* float32(k) */
+    uint8_t sstring[WGO_MAX_SPRING]; /* rope: no force while shorter than the rest length */
+} wgo_l2_system;
+
+typedef struct {
+    float gravity[3];      /* to_data(gravity): float32 */
+    float damping;         /* float32(damping) */
+    float drag_c;          /* float32(-0.5 * air_resistance)  (python product, then weak cast) */
+    float ground_level, restitution, friction, dt;
+    float min_dist;        /* float32(Config.r) = float32(16e-36) */
+    int32_t ground;
+} wgo_l2_params;
+
+static void l2_anti_forced(float a[3], const float self_pos[3], const float other_pos[3], float nfs,
+                           float m, int ding, float min_dist) {
+    float dir[3];                                                 /* core.py:87 */
+    for (int c = 0; c < 3; c++) dir[c] = other_pos[c] - self_pos[c];
+    float dist = np_norm3(dir);                                   /* :89 max(norm, Config.r) */
+    if (min_dist > dist) dist = min_dist;
+    if (ding) return;                                             /* DingPoint.forced: pass */
+    for (int c = 0; c < 3; c++) {
+        float f = (nfs * dir[c]) / dist;                          /* :90 -f_size * direction / distance */
+        a[c] = a[c] + f / m;                                      /* :83 */
+    }
+}
+
+int wgo_l2_step(const wgo_l2_system *sys, const wgo_l2_params *p, int64_t E, int32_t n_steps,
+                float *pos, float *vel, float *old_a) {
+    const int P = sys->n_point, S = sys->n_spring;
+    if (P > WGO_MAX_MASS || S > WGO_MAX_SPRING) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < E; e++) {
+        float ps[WGO_MAX_MASS][3], vs[WGO_MAX_MASS][3], as[WGO_MAX_MASS][3];
+        for (int n = 0; n < P; n++)
+            for (int c = 0; c < 3; c++) { ps[n][c] = pos[(int64_t)(n * 3 + c) * E + e]; vs[n][c] = vel[(int64_t)(n * 3 + c) * E + e]; }
+        for (int t = 0; t < n_steps; t++) {
+            for (int n = 0; n < P; n++) for (int c = 0; c < 3; c++) as[n][c] = 0.0f;          /* env.py:141-142 */
+            for (int n = 0; n < P; n++) {                                                    /* :145-146 gravity*m */
+                if (sys->ding[n]) continue;
+                float mf = (float)sys->mass[n];
+                for (int c = 0; c < 3; c++) as[n][c] = as[n][c] + (p->gravity[c] * mf) / mf;
+            }
+            for (int s = 0; s < S; s++) {                                                    /* :149-150 resilience */
+                int i = sys->si[s], j = sys->sj[s];
+                float d[3];
+                for (int c = 0; c < 3; c++) d[c] = ps[i][c] - ps[j][c];
+                float cur = np_norm3(d);                                                     /* core.py:102 */
+                float dx = cur - sys->sx[s];
+                float nfs = (dx < 0 && sys->sstring[s]) ? 0.0f : -((-dx) * sys->sk[s]);      /* :115-118, then -f_size */
+                l2_anti_forced(as[i], ps[i], ps[j], nfs, (float)sys->mass[i], sys->ding[i], p->min_dist);
+                l2_anti_forced(as[j], ps[j], ps[i], nfs, (float)sys->mass[j], sys->ding[j], p->min_dist);
+            }
+            for (int n = 0; n < P; n++) {
+                if (sys->ding[n]) continue;
+                for (int c = 0; c < 3; c++) vs[n][c] = vs[n][c] * p->damping;                  /* env.py:153-154 */
+            }
+            for (int n = 0; n < P; n++) {                                                    /* :157-161 drag */
+                if (sys->ding[n]) continue;
+                float speed = np_norm3(vs[n]);
+                float cs = p->drag_c * speed;
+                float mf = (float)sys->mass[n];
+                for (int c = 0; c < 3; c++) as[n][c] = as[n][c] + (cs * vs[n][c]) / mf;
+            }
+            for (int n = 0; n < P; n++)                                                      /* Point.run1 */
+                for (int c = 0; c < 3; c++) {
+                    float at = as[n][c] * p->dt;
+                    vs[n][c] = vs[n][c] + at;
+                    float vt = vs[n][c] * p->dt;
+                    ps[n][c] = ps[n][c] + vt;
+                }
+            if (p->ground)                                                                   /* :167-181 */
+                for (int n = 0; n < P; n++) {
+                    if (sys->ding[n]) continue;
+                    if (ps[n][1] <= p->ground_level) {
+                        ps[n][1] = p->ground_level;
+                        if (vs[n][1] < 0) {
+                            vs[n][1] = (-vs[n][1]) * p->restitution;
+                            vs[n][0] = vs[n][0] * p->friction;
+                            vs[n][2] = vs[n][2] * p->friction;
+                        }
+                    }
+                }
+        }
+        for (int n = 0; n < P; n++)
+            for (int c = 0; c < 3; c++) {
+                pos[(int64_t)(n * 3 + c) * E + e] = ps[n][c];
+                vel[(int64_t)(n * 3 + c) * E + e] = vs[n][c];
+                if (old_a) old_a[(int64_t)(n * 3 + c) * E + e] = as[n][c];
+            }
+    }
+    return 0;
+}
+int wgo_sizeof_l2_system(void) { return (int)sizeof(wgo_l2_system); }
+int wgo_sizeof_l2_params(void) { return (int)sizeof(wgo_l2_params); }
+
 #ifdef _OPENMP
 #include <omp.h>
 void wgo_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

@@ -215,3 +215,62 @@ BOX = {
     "muscles": [(0, 1, {}), (0, 2, {}), (3, 1, {}), (3, 2, {})],
     "skeletons": [(1, 2, {})],
 }
+
+
+# ---- L2 (package lineage): Environment.update_physics of gym/optimized_walker/env.py ------------------
+class L2System(C.Structure):
+    _fields_ = [("n_point", C.c_int32), ("n_spring", C.c_int32),
+                ("mass", C.c_double * MAX_MASS), ("ding", C.c_uint8 * MAX_MASS),
+                ("si", C.c_int32 * MAX_SPRING), ("sj", C.c_int32 * MAX_SPRING),
+                ("sx", C.c_float * MAX_SPRING), ("sk", C.c_float * MAX_SPRING), ("sstring", C.c_uint8 * MAX_SPRING)]
+
+
+class L2Params(C.Structure):
+    _fields_ = [("gravity", C.c_float * 3), ("damping", C.c_float), ("drag_c", C.c_float),
+                ("ground_level", C.c_float), ("restitution", C.c_float), ("friction", C.c_float), ("dt", C.c_float),
+                ("min_dist", C.c_float), ("ground", C.c_int32)]
+
+
+def make_l2_system(system) -> L2System:
+    """system: {"points": [(m, pos, vel, ding)], "springs": [(i, j, x_or_None, k, string)]}"""
+    s = L2System()
+    pts, sps = system["points"], system["springs"]
+    s.n_point, s.n_spring = len(pts), len(sps)
+    P = [np.array(p[1], dtype=np.float32) for p in pts]
+    for n, (m, pos, vel, ding) in enumerate(pts):
+        s.mass[n], s.ding[n] = float(m), 1 if ding else 0
+    for q, (i, j, x, k, string) in enumerate(sps):
+        s.si[q], s.sj[q] = i, j
+        if x is None:                                       # add_spring (env.py:105-107)
+            x = np.linalg.norm(P[i] - P[j]).astype(np.float32)
+        s.sx[q], s.sk[q], s.sstring[q] = np.float32(x), np.float32(k), 1 if string else 0
+    return s
+
+
+def make_l2_params(gravity=(0, -9.8, 0), damping=0.99, ground=True, ground_level=-50, ground_restitution=0.8,
+                   air_resistance=0.01, friction=0.5, time_step=0.01) -> L2Params:
+    p = L2Params()
+    g = np.array(gravity, dtype=np.float32)
+    for c in range(3):
+        p.gravity[c] = g[c]
+    p.damping, p.drag_c = np.float32(damping), np.float32(-0.5 * air_resistance)
+    p.ground_level, p.restitution = np.float32(ground_level), np.float32(ground_restitution)
+    p.friction, p.dt, p.min_dist, p.ground = np.float32(friction), np.float32(time_step), np.float32(16e-36), int(bool(ground))
+    return p
+
+
+def l2_init_state(system, E: int):
+    pos = np.array([p[1] for p in system["points"]], np.float32).reshape(-1)
+    vel = np.array([p[2] for p in system["points"]], np.float32).reshape(-1)
+    return dict(pos=np.repeat(pos[:, None], E, 1).copy(), vel=np.repeat(vel[:, None], E, 1).copy(),
+                old_a=np.zeros((pos.size, E), np.float32))
+
+
+def l2_step(sysm: L2System, prm: L2Params, st: dict, n_steps: int = 1):
+    l = lib()
+    assert l.wgo_sizeof_l2_system() == C.sizeof(L2System) and l.wgo_sizeof_l2_params() == C.sizeof(L2Params)
+    E = st["pos"].shape[1]
+    rc = l.wgo_l2_step(C.byref(sysm), C.byref(prm), C.c_int64(E), C.c_int32(n_steps),
+                       _ptr(st["pos"], C.c_float), _ptr(st["vel"], C.c_float), _ptr(st.get("old_a"), C.c_float))
+    if rc != 0:
+        raise RuntimeError(f"wgo_l2_step failed: {rc}")

@@ -189,7 +189,39 @@ def main():
     engine.Point.clear()
 
 
+# ---- L2: the package lineage's Environment.update_physics (gym/optimized_walker/env.py:135-184) ------
+L2_CHAIN = {   # a pinned rope-and-rod chain swinging into the ground: DingPoint, string springs, explicit rest length
+    "points": [(1.0, (0, 50, 0), (0, 0, 0), True), (2.0, (30, 40, 0), (1, 0, 0.5), False),
+               (0.5, (60, 10, 5), (0, -3, 0), False), (3, (10, -45, 0), (5, -20, 1), False)],
+    "springs": [(0, 1, None, 100, False), (1, 2, None, 250, True), (0, 2, 70.0, 50, True), (2, 3, None, 1000, False)],
+}
+L2_BOX = {     # a free box dropped on the ground: restitution + friction branch
+    "points": [(1, (-20, 0, 0), (3, 0, 0), False), (1, (20, 0, 0), (3, 0, 0), False),
+               (1, (20, 40, 0), (3, 1, 0), False), (1, (-20, 40, 0), (3, 1, 0), False)],
+    "springs": [(0, 1, None, 500, False), (1, 2, None, 500, False), (2, 3, None, 500, False), (3, 0, None, 500, False),
+                (0, 2, None, 300, False), (1, 3, None, 300, False)],
+}
+
+
+def l2_case(name, system, steps, env_kwargs):
+    import ref_harness_l2 as r2
+    out = r2.rollout(system, steps, env_kwargs=env_kwargs)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), pos=out["pos"], vel=out["vel"], old_a=out["old_a"],
+                        system=np.array(json.dumps(system)), env_kwargs=np.array(json.dumps(env_kwargs)))
+    print(f"{name}: steps={steps} nonfinite={int((~np.isfinite(out['pos'])).sum())} "
+          f"ground_hits={int((out['pos'][:, :, 1] <= env_kwargs.get('ground_level', -50)).sum())}")
+
+
+def main_l2():
+    l2_case("l2_chain_default", L2_CHAIN, 300, dict())
+    l2_case("l2_chain_custom", L2_CHAIN, 300, dict(ground_level=-20, gravity=(0.5, -30, 0.1), damping=0.95, air_resistance=0.2,
+                                                   friction=0.3, ground_restitution=0.6, time_step=0.02))
+    l2_case("l2_box_bounce", L2_BOX, 400, dict(ground_level=-10, gravity=(0, -98, 0)))
+    l2_case("l2_chain_noground", L2_CHAIN, 150, dict(ground=False))
+
+
 if __name__ == "__main__":
     import warnings
     warnings.filterwarnings("ignore", category=RuntimeWarning)
     main()
+    main_l2()

@@ -21,7 +21,21 @@ def golden_names(prefix=""):
 
 
 def trajectory_names():
-    return [n for n in golden_names() if not n.startswith(("batch_", "compat_"))]
+    return [n for n in golden_names() if not n.startswith(("batch_", "compat_", "l2_"))]
+
+
+def l2_names():
+    return golden_names("l2_")
+
+
+def load_l2(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    g = {k: z[k] for k in ("pos", "vel", "old_a")}
+    sysm = json.loads(str(z["system"]))
+    g["system"] = {"points": [(m, tuple(p), tuple(v), bool(d)) for m, p, v, d in sysm["points"]],
+                   "springs": [(i, j, x, k, bool(s)) for i, j, x, k, s in sysm["springs"]]}
+    g["env_kwargs"] = json.loads(str(z["env_kwargs"]))
+    return g
 
 
 def batch_names():

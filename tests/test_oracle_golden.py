@@ -109,3 +109,29 @@ def test_golden_cover_the_branches():
     assert not np.isfinite(gu.load("box3d_overflow")["pos"]).all()
     assert gu.load("balance3d_s0")["contact_pre"].any()
     assert gu.load("autoreset_jitter")["done"].sum() >= 3
+
+
+def replay_l2(g, stepper, chunk=1):
+    """Replay an L2 (package lineage) trajectory; `chunk` steps per call."""
+    sysm = stepper.make_l2_system(g["system"])
+    prm = stepper.make_l2_params(**g["env_kwargs"])
+    st = stepper.l2_init_state(g["system"], 1)
+    P = len(g["system"]["points"])
+    T = g["pos"].shape[0] - 1
+    t = 0
+    while t < T:
+        n = min(chunk, T - t)
+        stepper.l2_step(sysm, prm, st, n)
+        t += n
+        ok = (gu.same(st["pos"].reshape(P, 3), g["pos"][t]) and gu.same(st["vel"].reshape(P, 3), g["vel"][t])
+              and gu.same(st["old_a"].reshape(P, 3), g["old_a"][t]))
+        if not ok:
+            return f"step {t}"
+    return None
+
+
+@pytest.mark.parametrize("chunk", [1, 7])
+@pytest.mark.parametrize("name", gu.l2_names())
+def test_oracle_matches_reference_package_physics(name, chunk):
+    """L2: Environment.update_physics of gym/optimized_walker/env.py, bit for bit."""
+    assert replay_l2(gu.load_l2(name), wo, chunk) is None
