@@ -43,7 +43,9 @@ def parse():
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
-    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
+    ap.add_argument("--steps-per-launch", type=int, default=1, help="config 6: update_physics calls fused in one launch")
+    ap.add_argument("--pkg-body", default="box", help="config 6: body builder of gym/optimized_walker/walker.py")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5, 6],
                     help="BASELINE.json config: 3 = Balance-v0 throughput (headline, default), 4 = enlarged body "
                          "(4x masses/springs) with 8 substeps, 5 = PPO rollout collection (torch MLP policy + step kernel)")
     ap.add_argument("--body", default="balance", choices=["balance", "box"],
@@ -207,6 +209,8 @@ def run_ours(args):
         _lib.load().wg_force_generic(1)
     if args.config == 5:
         return run_rollout(args, rank, world, dev)
+    if args.config == 6:
+        return run_pkg(args, rank, world, dev)
     env_id = ENV_ID if args.body == "balance" else "Box-v0"
     body, k_sub = (env_id, 1) if args.config == 3 else ("quad_balance", 8)
 
@@ -319,6 +323,80 @@ def run_ours(args):
                                         "against 1485 bytes (SURVEY 7.5); the HBM fraction is reported for completeness")
         if not args.no_cpu_baseline and world == 1 and args.config == 3 and args.body == "balance":
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_pkg(args, rank, world, dev):
+    """Next-row workload: the package lineage's Environment.update_physics
+    (gym/optimized_walker/env.py:135-184) on one of its own bodies, 2^20 independent copies per GPU.
+    A step = one launch = --steps-per-launch updates of every env; value counts env-updates."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import walker_gym_b200.optimized_walker as ow
+    W, K, E, T = max(args.warmup, 3), args.steps, args.envs_per_gpu, args.steps_per_launch
+    env = ow.Environment(num_envs=E, device=str(dev), ground_level=-8.0)
+    getattr(ow, args.pkg_body)(env)
+    P, S = len(env._order), len(env.springs)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    env.vel.add_(torch.randn(env.vel.shape, device=dev, generator=g))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        env.update_physics(T)
+    barrier()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        env.update_physics(T)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    tmax = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        bytes_per_launch_env = 48 * P + 12 * P            # pos + vel read and written, old_a written
+        per_launch_s = ms * 1e-3 / K
+        achieved = E * bytes_per_launch_env / per_launch_s / 1e9
+        line = {"metric": "env-updates/sec (whole box)", "value": world * E * K * T / (ms * 1e-3), "unit": "env-updates/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"package lineage Environment.update_physics, body {args.pkg_body} (P={P} points, "
+                                       f"S={S} springs), {E} envs per GPU, {T} update(s) per launch, ground at -8, N(0,1) "
+                                       "initial velocities", "baseline_config": "next row f3",
+                           "l2": f"state per launch = {E * bytes_per_launch_env / 1e6:.0f} MB > 126 MB L2"},
+                "roofline": {"bound": "hbm" if T == 1 else "fp32 issue", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_env_launch": bytes_per_launch_env,
+                             "kernel": "wg::pkg_update_kernel", "kernel_us": per_launch_s * 1e6},
+                "e2e": None, "gpu_launches": K, "clocks": clocks}
+        if not args.no_cpu_baseline and world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import walker_oracle as wo
+            threads = wo.set_threads(len(os.sched_getaffinity(0)))
+            n = 1 << 14
+            system = {"points": [(float(p.m), tuple(map(float, p.pos)), (0.0, 0.0, 0.0), p.fixed) for p in env._order],
+                      "springs": [(env._order.index(a), env._order.index(b), float(x), float(k), bool(st))
+                                  for a, b, x, k, st in env.springs]}
+            so, po, st = wo.make_l2_system(system), wo.make_l2_params(ground_level=-8.0), wo.l2_init_state(system, n)
+            st["vel"] += np.random.default_rng(0).normal(0, 1, st["vel"].shape).astype(np.float32)
+            wo.l2_step(so, po, st, 20)
+            t0 = time.perf_counter()
+            wo.l2_step(so, po, st, 2000)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n * 2000 / dt, "unit": "env-updates/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n} envs x 2000 updates, oracle wgo_l2_step (OpenMP), {dt:.1f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

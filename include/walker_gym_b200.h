@@ -186,6 +186,50 @@ int wg_step_host(const wg_topology* topo, const wg_params* prm, const wg_buffers
                  int64_t n_env, const float* h_action, float* h_obs, float* h_reward,
                  uint8_t* h_done, void* cuda_stream);
 
+/* =====================================================================================
+ * The reference's *package* lineage (gym/optimized_walker/{core,env}.py): a second
+ * physics model behind the same boundary.  Environment.update_physics (env.py:135-184)
+ * has no action / observation / reward: it advances a point-and-spring system, so the
+ * call takes a step count and keeps the state on chip for all n_steps substeps
+ * (one HBM read and one HBM write of the state per launch).
+ * ===================================================================================== */
+
+/*
+ * One point-and-spring system shared by all envs.  Replaces Environment.points /
+ * ding_points / springs (gym/optimized_walker/env.py:39-41) as filled by add_point
+ * (:56-72), add_ding_point (:74-90) and add_spring (:92-111).  Springs are applied in
+ * list order (:149-150), which fixes the float32 accumulation order of every point.
+ */
+typedef struct wg_pkg_system {
+    int32_t n_point, n_spring;
+    double  mass[WG_MAX_MASS];          /* Point.m */
+    uint8_t fixed[WG_MAX_MASS];         /* 1 = DingPoint (core.py:259-275): forced() ignored, not damped, no ground */
+    int32_t si[WG_MAX_SPRING], sj[WG_MAX_SPRING];   /* point1, point2 */
+    float   srest[WG_MAX_SPRING];       /* x: rest length (float32, as add_spring stores it) */
+    float   sk[WG_MAX_SPRING];          /* k */
+    uint8_t sstring[WG_MAX_SPRING];     /* string=True: no force while shorter than x (core.py:115-118) */
+} wg_pkg_system;
+
+/* Environment constructor arguments (gym/optimized_walker/env.py:10-37), as float32 at the point of use. */
+typedef struct wg_pkg_params {
+    float   gravity[3];     /* to_data(gravity) */
+    float   damping;        /* v *= damping  (:153-154) */
+    float   drag_c;         /* float32(-0.5 * air_resistance): drag = drag_c * |v| * v  (:157-161) */
+    float   ground_level, restitution, friction;   /* (:167-181) */
+    float   dt;             /* time_step */
+    float   min_dist;       /* float32(Config.r): lower clamp of the spring length in anti_forced (core.py:89) */
+    int32_t ground;         /* 0 = no ground */
+} wg_pkg_params;
+
+/*
+ * n_steps x Environment.update_physics for n_env independent copies of the system.
+ * pos, vel: in/out, SoA [(n*3 + c) * n_env + e]; old_a: optional out (Point.old_a of
+ * the last step, same layout).  One kernel launch; asynchronous on cuda_stream.
+ */
+int wg_pkg_update_physics(const wg_pkg_system* sys, const wg_pkg_params* prm,
+                          float* pos, float* vel, float* old_a,
+                          int64_t n_env, int32_t n_steps, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

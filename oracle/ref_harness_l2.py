@@ -71,3 +71,40 @@ def rollout(system, steps, *, env_kwargs=None, ref_root: str = DEFAULT_REF):
     core.Point.r_points = {}
     return dict(pos=np.stack([f[0] for f in frames]), vel=np.stack([f[1] for f in frames]),
                 old_a=np.stack([f[2] for f in frames]), rest=rest)
+
+
+def body_rollout(name, steps, *, env_kwargs=None, ref_root: str = DEFAULT_REF):
+    """Build body ``name`` with the reference's own builder (gym/optimized_walker/walker.py:356-639) in a default
+    Environment, record its tables and ``steps`` update_physics calls (points in env.points + env.ding_points
+    creation order as registered in Point.points)."""
+    core, envmod = load(ref_root)
+    walker = sys.modules[_PKG + ".walker"]
+    core.Point.points = []
+    core.Point.r_points = {}
+    env = envmod.Environment(**dict(env_kwargs or {}))
+    creature = getattr(walker, name)(env)
+    pts = list(core.Point.points)                       # creation order
+    index = {id(p): n for n, p in enumerate(pts)}
+    rec = dict(mass=np.array([float(p.m) for p in pts]), ding=np.array([isinstance(p, core.DingPoint) for p in pts]),
+               pos0=np.array([p.pos for p in pts], np.float32),
+               si=np.array([index[id(s[0])] for s in env.springs], np.int32),
+               sj=np.array([index[id(s[1])] for s in env.springs], np.int32),
+               sx=np.array([np.float32(s[2]) for s in env.springs], np.float32),
+               sk=np.array([float(s[3]) for s in env.springs]), sstring=np.array([bool(s[4]) for s in env.springs]),
+               muscle_i=np.array([index[id(m.point1)] for m in creature.skeleton.muscles], np.int32),
+               muscle_j=np.array([index[id(m.point2)] for m in creature.skeleton.muscles], np.int32),
+               muscle_x=np.array([np.float32(m.x) for m in creature.skeleton.muscles], np.float32),
+               muscle_par=np.array([[m.amp, m.freq, m.phase, m.power] for m in creature.skeleton.muscles], np.float64).reshape(-1, 4))
+    frames_p, frames_v = [rec["pos0"].copy()], [np.array([p.v for p in pts], np.float32)]
+    states = []
+    for _ in range(steps):
+        creature.act(env.time_step)                      # muscles push; update_physics wipes it (env.py:141-142)
+        states.append([float(m.state) for m in creature.skeleton.muscles])
+        env.update_physics()
+        frames_p.append(np.array([p.pos for p in pts], np.float32))
+        frames_v.append(np.array([p.v for p in pts], np.float32))
+    rec["pos"], rec["vel"] = np.stack(frames_p), np.stack(frames_v)
+    rec["muscle_state"] = np.array(states, np.float64).reshape(steps, -1)
+    core.Point.points = []
+    core.Point.r_points = {}
+    return rec

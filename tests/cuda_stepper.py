@@ -135,3 +135,44 @@ def reset(body, prm, st, *, mode=1, mask=None, noise=None):
     _download(st, d)
     o = obs.cpu().numpy()
     return np.ascontiguousarray(o.T) if obs_layout == 1 else o
+
+
+# ---- package lineage (Environment.update_physics) through wg_pkg_update_physics -------------------------
+def make_l2_system(system):
+    import walker_oracle as wo
+    o = wo.make_l2_system(system)            # same host-side evaluation of rest lengths; copy into the ABI struct
+    s = _lib.WgPkgSystem()
+    s.n_point, s.n_spring = o.n_point, o.n_spring
+    for n in range(o.n_point):
+        s.mass[n], s.fixed[n] = o.mass[n], o.ding[n]
+    for q in range(o.n_spring):
+        s.si[q], s.sj[q], s.srest[q], s.sk[q], s.sstring[q] = o.si[q], o.sj[q], o.sx[q], o.sk[q], o.sstring[q]
+    return s
+
+
+def make_l2_params(**kw):
+    import walker_oracle as wo
+    o = wo.make_l2_params(**kw)
+    p = _lib.WgPkgParams()
+    for c in range(3):
+        p.gravity[c] = o.gravity[c]
+    p.damping, p.drag_c, p.ground_level, p.restitution = o.damping, o.drag_c, o.ground_level, o.restitution
+    p.friction, p.dt, p.min_dist, p.ground = o.friction, o.dt, o.min_dist, o.ground
+    return p
+
+
+def l2_init_state(system, E):
+    import walker_oracle as wo
+    return wo.l2_init_state(system, E)
+
+
+def l2_step(sysm, prm, st, n_steps=1):
+    lib = _lib.load()
+    E = st["pos"].shape[1]
+    d = {k: _dev(st[k]) for k in ("pos", "vel", "old_a")}
+    rc = lib.wg_pkg_update_physics(C.byref(sysm), C.byref(prm), _ptr(d["pos"]), _ptr(d["vel"]), _ptr(d["old_a"]),
+                                   E, n_steps, _stream())
+    _lib.check(rc, "wg_pkg_update_physics")
+    torch.cuda.synchronize()
+    for k in ("pos", "vel", "old_a"):
+        st[k][...] = d[k].cpu().numpy()

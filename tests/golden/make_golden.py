@@ -218,6 +218,52 @@ def main_l2():
                                                    friction=0.3, ground_restitution=0.6, time_step=0.02))
     l2_case("l2_box_bounce", L2_BOX, 400, dict(ground_level=-10, gravity=(0, -98, 0)))
     l2_case("l2_chain_noground", L2_CHAIN, 150, dict(ground=False))
+    l2_bodies()
+    l2_env_state()
+
+
+def l2_bodies():
+    """Every body builder of gym/optimized_walker/walker.py:356-639, built by the reference: the point and spring
+    tables (pins the transcription in walker_gym_b200/optimized_walker/walker.py) and a 120-step trajectory."""
+    import ref_harness_l2 as r2
+    out = {}
+    for name in ("test", "leg2", "box", "balance1", "balance2", "balance3", "humanb", "insect"):
+        rec = r2.body_rollout(name, 120)
+        for k, v in rec.items():
+            out[f"{name}__{k}"] = v
+        print(f"l2 body {name}: points={len(rec['mass'])} springs={len(rec['si'])} muscles={len(rec['muscle_x'])}")
+    np.savez_compressed(os.path.join(HERE, "l2_bodies.npz"), **out)
+
+
+def l2_env_state():
+    """An env_state.pkl written by the reference's own Environment.save_state (env.py:262-281), in a
+    subprocess that imports the package under its real name so the pickled class path is the reference's."""
+    import subprocess
+    import sys
+    dst = os.path.join(HERE, "env_state_ref.pkl")
+    code = (
+        "import sys, types\n"
+        "from unittest import mock\n"
+        "sys.modules['pygame'] = mock.MagicMock(name='pygame')\n"
+        "sys.path.insert(0, '/root/reference/gym')\n"
+        "import optimized_walker as ow\n"
+        "from optimized_walker.env import Environment\n"
+        "env = Environment(gravity=(0.5, -30, 0.1), damping=0.95, ground_level=-20, air_resistance=0.2,\n"
+        "                  friction=0.3, ground_restitution=0.6, time_step=0.02)\n"
+        "a = env.add_ding_point(1.0, [0, 50, 0], [0, 0, 0])\n"
+        "b = env.add_point(2.0, [30, 40, 0], [1, 0, 0.5])\n"
+        "c = env.add_point(0.5, [60, 10, 5], [0, -3, 0])\n"
+        "env.add_spring(a, b, None, 100, False)\n"
+        "env.add_spring(b, c, None, 250, True)\n"
+        "env.add_spring(a, c, 70.0, 50, True)\n"
+        "for _ in range(25): env.update_physics()\n"
+        "env.renderer = None; env.scene = None\n"
+        f"env.save_state({dst!r})\n"
+        "import numpy as np\n"
+        "for _ in range(40): env.update_physics()\n"
+        f"np.savez({dst[:-4] + '_after40.npz'!r}, pos=np.array([p.pos for p in (a, b, c)]), vel=np.array([p.v for p in (a, b, c)]))\n")
+    subprocess.run([sys.executable, "-c", code], check=True)
+    print("env_state_ref.pkl written by the reference:", os.path.getsize(dst), "bytes")
 
 
 if __name__ == "__main__":

@@ -21,11 +21,11 @@ def golden_names(prefix=""):
 
 
 def trajectory_names():
-    return [n for n in golden_names() if not n.startswith(("batch_", "compat_", "l2_"))]
+    return [n for n in golden_names() if not n.startswith(("batch_", "compat_", "l2_", "env_state_"))]
 
 
 def l2_names():
-    return golden_names("l2_")
+    return [n for n in golden_names("l2_") if n != "l2_bodies"]
 
 
 def load_l2(name):

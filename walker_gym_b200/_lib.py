@@ -55,11 +55,26 @@ class WgBuffers(C.Structure):
     ]
 
 
+class WgPkgSystem(C.Structure):
+    """``wg_pkg_system``: Environment.points / ding_points / springs (gym/optimized_walker/env.py:39-41)."""
+    _fields_ = [("n_point", C.c_int32), ("n_spring", C.c_int32),
+                ("mass", C.c_double * MAX_MASS), ("fixed", C.c_uint8 * MAX_MASS),
+                ("si", C.c_int32 * MAX_SPRING), ("sj", C.c_int32 * MAX_SPRING),
+                ("srest", C.c_float * MAX_SPRING), ("sk", C.c_float * MAX_SPRING), ("sstring", C.c_uint8 * MAX_SPRING)]
+
+
+class WgPkgParams(C.Structure):
+    """``wg_pkg_params``: Environment constructor arguments (gym/optimized_walker/env.py:10-37)."""
+    _fields_ = [("gravity", C.c_float * 3), ("damping", C.c_float), ("drag_c", C.c_float),
+                ("ground_level", C.c_float), ("restitution", C.c_float), ("friction", C.c_float), ("dt", C.c_float),
+                ("min_dist", C.c_float), ("ground", C.c_int32)]
+
+
 TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH = 0, 1, 2
 
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
            "wg_set_tuning", "wg_packed_state_floats",
-           "wg_step", "wg_reset", "wg_stats_reduce", "wg_step_host")
+           "wg_step", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics")
 
 _lib = None
 
@@ -98,8 +113,10 @@ def load():
     lib.wg_stats_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.wg_step_host.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wg_pkg_update_physics.argtypes = [P(WgPkgSystem), P(WgPkgParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int64, C.c_int32, C.c_void_p]
     for name in ("wg_obs_dim", "wg_kernel_variant", "wg_force_generic", "wg_step", "wg_reset",
-                 "wg_stats_reduce", "wg_step_host"):
+                 "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -64,6 +64,9 @@ static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* 
     return WG_OK;
 }
 
+int launch_pkg_update(const wg_pkg_system*, const wg_pkg_params*, float* pos, float* vel, float* old_a,
+                      int64_t E, int32_t n_steps, cudaStream_t);
+
 }  // namespace wg
 
 using namespace wg;
@@ -155,6 +158,21 @@ int wg_step_host(const wg_topology* topo, const wg_params* prm, const wg_buffers
     if (e == cudaSuccess && h_done && buf->done) e = cudaMemcpyAsync(h_done, buf->done, n_env, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "D2H results: %s", cudaGetErrorString(e));
     return WG_OK;
+}
+
+int wg_pkg_update_physics(const wg_pkg_system* sys, const wg_pkg_params* prm, float* pos, float* vel, float* old_a,
+                          int64_t n_env, int32_t n_steps, void* cuda_stream) {
+    if (!sys || !prm) return fail(WG_ERR_BAD_ARG, "null argument%s");
+    if (sys->n_point < 1 || sys->n_point > WG_MAX_MASS) return fail(WG_ERR_BAD_ARG, "n_point out of range [1, 32]%s");
+    if (sys->n_spring < 0 || sys->n_spring > WG_MAX_SPRING) return fail(WG_ERR_BAD_ARG, "n_spring out of range [0, 96]%s");
+    for (int s = 0; s < sys->n_spring; s++)
+        if (sys->si[s] < 0 || sys->si[s] >= sys->n_point || sys->sj[s] < 0 || sys->sj[s] >= sys->n_point)
+            return fail(WG_ERR_BAD_ARG, "spring endpoint out of range%s");
+    if (n_env < 0 || n_env > ((int64_t)1 << 31) - 1) return fail(WG_ERR_BAD_ARG, "n_env out of range%s");
+    if (n_steps < 0) return fail(WG_ERR_BAD_ARG, "n_steps < 0%s");
+    if (n_env == 0 || n_steps == 0) return WG_OK;
+    if (!pos || !vel) return fail(WG_ERR_BAD_ARG, "pos/vel must be set%s");
+    return launch_pkg_update(sys, prm, pos, vel, old_a, n_env, n_steps, (cudaStream_t)cuda_stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,125 @@
+// wg_pkg.cuh -- the reference's *package* lineage: Environment.update_physics of
+// gym/optimized_walker/env.py:135-184 over Point.forced / anti_forced / resilience / run1 of
+// gym/optimized_walker/core.py:81-121,184-200 (DingPoint :259-275), batched over independent copies
+// of one point-and-spring system.
+//
+// A different model from PhysicsEnv.step: physically signed springs with optional one-sided
+// ("string") behaviour, gravity as an acceleration ((g*m)/m), multiplicative velocity damping,
+// quadratic drag, and a ground that clamps the position and reflects the velocity; no action,
+// observation, reward or done.  Because nothing enters or leaves between steps, the kernel keeps the
+// state on chip for n_steps consecutive updates: ONE HBM read and ONE HBM write per launch.
+//
+// One thread owns one env and applies the springs strictly in list order, with the reference's
+// separately rounded float32 operations (-fmad=false), so the result is bit-identical to NumPy.
+#pragma once
+#include "wg_physics.cuh"
+
+namespace wg {
+
+struct PkgArgs {
+    float ga[kMaxMass * 3];         // 0.0f + (gravity * float32(m)) / float32(m): what `a` holds after the gravity pass
+    float mass_f[kMaxMass];         // float32(m): divisor of every float32 force
+    float mass_r[kMaxMass];         // RN(1 / float32(m))
+    int32_t mass_kind[kMaxMass];    // div_const kind
+    float srest[kMaxSpring], sk[kMaxSpring];
+    uint8_t si[kMaxSpring], sj[kMaxSpring];
+    uint32_t string_mask[kMaxSpring / 32];
+    uint32_t fixed_mask;            // DingPoint bits
+    float damping, drag_c, ground_level, restitution, friction, dt, min_dist;
+    int32_t ground, n_point, n_spring, n_steps;
+    float* pos; float* vel; float* old_a;
+    int64_t E;
+};
+
+// One spring: Point.resilience (core.py:93-121) = two anti_forced calls (:85-91) with the same f_size.
+//   d = p1 - p2; L = |d|; dx = L - x; f_size = -dx * k (0 for a slack string);
+//   p1.anti_forced(p2, f_size): dir = p2 - p1, a1 += ((-f_size * dir) / max(|dir|, r)) / m1
+//   p2.anti_forced(p1, f_size): dir = p1 - p2, a2 += ((-f_size * dir) / max(|dir|, r)) / m2
+// p2 - p1 == -(p1 - p2) exactly and every operation is sign-symmetric, so the force on p1 is the exact
+// negation of the force on p2 and the norm is evaluated once.
+template <class Store>
+__device__ __forceinline__ void pkg_spring(const PkgArgs& A, Store& st, int sp) {
+    const int i = A.si[sp], j = A.sj[sp];
+    const float d0 = st.pos(i, 0) - st.pos(j, 0), d1 = st.pos(i, 1) - st.pos(j, 1), d2 = st.pos(i, 2) - st.pos(j, 2);
+    const float L = np_norm3(d0, d1, d2);
+    const float dx = L - A.srest[sp];
+    const bool slack = (dx < 0.0f) && ((A.string_mask[sp >> 5] >> (sp & 31)) & 1u);
+    const float nfs = slack ? 0.0f : -((-dx) * A.sk[sp]);                 // -f_size
+    const float dist = (A.min_dist > L) ? A.min_dist : L;                  // python max(norm, Config.r)
+    float f0 = nfs * d0, f1 = nfs * d1, f2 = nfs * d2;                     // force on p2 (dir = d)
+    div3_len<true>(f0, f1, f2, dist);                                           // dist > 0 or NaN: always a division
+    if (!((A.fixed_mask >> i) & 1u)) {
+        const float m = A.mass_f[i], r = A.mass_r[i]; const int kd = A.mass_kind[i];
+        st.acc(i, 0) = st.acc(i, 0) + div_const(-f0, m, r, kd);
+        st.acc(i, 1) = st.acc(i, 1) + div_const(-f1, m, r, kd);
+        st.acc(i, 2) = st.acc(i, 2) + div_const(-f2, m, r, kd);
+    }
+    if (!((A.fixed_mask >> j) & 1u)) {
+        const float m = A.mass_f[j], r = A.mass_r[j]; const int kd = A.mass_kind[j];
+        st.acc(j, 0) = st.acc(j, 0) + div_const(f0, m, r, kd);
+        st.acc(j, 1) = st.acc(j, 1) + div_const(f1, m, r, kd);
+        st.acc(j, 2) = st.acc(j, 2) + div_const(f2, m, r, kd);
+    }
+}
+
+// Everything update_physics does to one point after the springs: damping (:153-154), quadratic drag
+// (:157-161), Point.run1 (core.py:184-200), ground (:167-181).  The passes of the reference are
+// per-point independent, so running them back to back for one point keeps its order of operations.
+template <class Store>
+__device__ __forceinline__ void pkg_point(const PkgArgs& A, Store& st, int n) {
+    float vx = st.vel(n, 0), vy = st.vel(n, 1), vz = st.vel(n, 2);
+    float ax = st.acc(n, 0), ay = st.acc(n, 1), az = st.acc(n, 2);
+    const bool fixed = (A.fixed_mask >> n) & 1u;
+    if (!fixed) {
+        vx = vx * A.damping; vy = vy * A.damping; vz = vz * A.damping;
+        const float cs = A.drag_c * np_norm3(vx, vy, vz);
+        const float m = A.mass_f[n], r = A.mass_r[n]; const int kd = A.mass_kind[n];
+        ax = ax + div_const(cs * vx, m, r, kd);
+        ay = ay + div_const(cs * vy, m, r, kd);
+        az = az + div_const(cs * vz, m, r, kd);
+        st.acc(n, 0) = ax; st.acc(n, 1) = ay; st.acc(n, 2) = az;
+    }
+    vx = vx + ax * A.dt; vy = vy + ay * A.dt; vz = vz + az * A.dt;         // run1: every point, DingPoints drift
+    float px = st.pos(n, 0) + vx * A.dt, py = st.pos(n, 1) + vy * A.dt, pz = st.pos(n, 2) + vz * A.dt;
+    if (!fixed && A.ground && py <= A.ground_level) {
+        py = A.ground_level;
+        if (vy < 0.0f) { vy = (-vy) * A.restitution; vx = vx * A.friction; vz = vz * A.friction; }
+    }
+    st.vel(n, 0) = vx; st.vel(n, 1) = vy; st.vel(n, 2) = vz;
+    st.pos(n, 0) = px; st.pos(n, 1) = py; st.pos(n, 2) = pz;
+}
+
+// Run-time topology; per-env state in a shared-memory tile [row][kBlock + 1] that stays resident for
+// all n_steps updates.  Loads and stores are coalesced SoA rows.
+__global__ void __launch_bounds__(kBlock)
+pkg_update_kernel(const __grid_constant__ PkgArgs A) {
+    extern __shared__ float smem[];
+    constexpr int PITCH = kBlock + 1;
+    const int P = A.n_point, S = A.n_spring;
+    const int tid = threadIdx.x;
+    const int64_t E = A.E;
+    const int64_t e = (int64_t)blockIdx.x * kBlock + tid;
+    if (e >= E) return;
+    SmemStore st{ smem + tid, PITCH, P };
+    for (int r = 0; r < 3 * P; r++) {
+        st.base[r * PITCH] = A.pos[(int64_t)r * E + e];
+        st.base[(3 * P + r) * PITCH] = A.vel[(int64_t)r * E + e];
+    }
+    for (int t = 0; t < A.n_steps; t++) {
+        for (int n = 0; n < P; n++) {                                      // zero (:141-142) + gravity (:145-146)
+            const bool fixed = (A.fixed_mask >> n) & 1u;
+            st.acc(n, 0) = fixed ? 0.0f : A.ga[n * 3 + 0];
+            st.acc(n, 1) = fixed ? 0.0f : A.ga[n * 3 + 1];
+            st.acc(n, 2) = fixed ? 0.0f : A.ga[n * 3 + 2];
+        }
+        for (int sp = 0; sp < S; sp++) pkg_spring(A, st, sp);               // (:149-150)
+        for (int n = 0; n < P; n++) pkg_point(A, st, n);
+    }
+    for (int r = 0; r < 3 * P; r++) {
+        A.pos[(int64_t)r * E + e] = st.base[r * PITCH];
+        A.vel[(int64_t)r * E + e] = st.base[(3 * P + r) * PITCH];
+        if (A.old_a) A.old_a[(int64_t)r * E + e] = st.base[(6 * P + r) * PITCH];
+    }
+}
+
+}  // namespace wg
