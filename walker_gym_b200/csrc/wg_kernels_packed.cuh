@@ -11,12 +11,18 @@
 
 namespace wg {
 
-#ifndef WG_PACKED_MIN_BLOCKS
-#define WG_PACKED_MIN_BLOCKS 6
+#ifndef WG_PACKED_BLOCK
+#define WG_PACKED_BLOCK 128
 #endif
+#ifndef WG_PACKED_MIN_BLOCKS
+#define WG_PACKED_MIN_BLOCKS (768 / WG_PACKED_BLOCK)
+#endif
+// threads per CTA of the packed kernel: a multiple of the 128-env tile (a CTA covers PB / 128 consecutive tiles)
+constexpr int kPackedBlock = WG_PACKED_BLOCK;
+static_assert(kPackedBlock % 128 == 0, "the packed layout is tiled by 128 envs");
 
 template <class Topo, bool IN3D, int OBS, int MM>
-__global__ void __launch_bounds__(kBlock, WG_PACKED_MIN_BLOCKS)
+__global__ void __launch_bounds__(kPackedBlock, WG_PACKED_MIN_BLOCKS)
 step_static_packed_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
     constexpr int N = Topo::N, M = Topo::M;
     constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;
@@ -28,16 +34,18 @@ step_static_packed_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) 
     const Topo topo;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t E = A.E;
-    const int64_t e0 = (int64_t)blockIdx.x * kBlock;
+    constexpr int kBlock = 128;                       // envs per state tile (shadows the CTA size of the SoA kernels)
+    const int64_t e0 = (int64_t)blockIdx.x * kPackedBlock;
     const int64_t e = e0 + tid;
     const bool valid = e < E;
-    float4* const base = reinterpret_cast<float4*>(A.state_packed) + (int64_t)blockIdx.x * (R4 * kBlock) + tid;
+    const int64_t tile_idx = (int64_t)blockIdx.x * (kPackedBlock / kBlock) + (tid >> 7);
+    float4* const base = reinterpret_cast<float4*>(A.state_packed) + tile_idx * (R4 * kBlock) + (tid & 127);
 
     // L2 prefetch: a tile is one contiguous block, so one thread can ask the copy engine to pull the tile that a
     // CTA launched `pf_dist` blocks later will read (CTAs are dispatched in index order) from HBM into L2 with a
     // single cp.async.bulk.prefetch; that CTA's loads then pay L2 instead of DRAM latency.
-    if (tid == 0 && A.pf_dist > 0) {
-        const int64_t pt = (int64_t)blockIdx.x + A.pf_dist;
+    if ((tid & 127) == 0 && A.pf_dist > 0) {
+        const int64_t pt = tile_idx + A.pf_dist;
         if (pt * kBlock + kBlock <= E) {
             const float* ps = A.state_packed + pt * (R4 * kBlock * 4);
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ps), "r"((uint32_t)(R4 * kBlock * 16)) : "memory");

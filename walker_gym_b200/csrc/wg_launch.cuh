@@ -170,13 +170,13 @@ inline int launch_static_packed(const wg_topology* t, const wg_params* p, const 
     fill_args(A, t, p, b, E);
     constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
     constexpr bool bulk = (OBS == 1) && gcd_c(D, 32) <= 2;
-    const size_t smem = (OBS == 1 && b->obs) ? sizeof(float) * kBlock * (bulk ? D : (D | 1)) : 0;
+    const size_t smem = (OBS == 1 && b->obs) ? sizeof(float) * kPackedBlock * (bulk ? D : (D | 1)) : 0;
     auto kern = step_static_packed_kernel<Topo, IN3D, OBS, MM>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<(unsigned)((E + kBlock - 1) / kBlock), kBlock, smem, s>>>(A);
+    kern<<<(unsigned)((E + kPackedBlock - 1) / kPackedBlock), kPackedBlock, smem, s>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (packed) launch: %s", cudaGetErrorString(e));
     return WG_OK;
