@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
+    ap.add_argument("--policy", default="fused-fp32", choices=["fused-fp32", "fused-tf32", "torch"],
+                    help="config 5: wg_policy_act (3xTF32 float32-grade / plain TF32 tensor-core MLP) or torch ops")
     ap.add_argument("--steps-per-launch", type=int, default=1, help="config 6: update_physics calls fused in one launch")
     ap.add_argument("--pkg-body", default="box", help="config 6: body builder of gym/optimized_walker/walker.py")
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5, 6],
@@ -415,7 +417,8 @@ def run_rollout(args, rank, world, dev):
     env = BatchedPhysicsEnv(ENV_ID, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
                             obs_layout="feature", act_layout="feature", graph_safe=True)
     pol = FeatureMajorMLP(env.obs_dim, env.M).to(dev)
-    col = RolloutCollector(env, pol, T)
+    fused = args.policy != "torch"
+    col = RolloutCollector(env, pol, T, fused=fused, precision="tf32" if args.policy == "fused-tf32" else "fp32")
     n_roll = max(1, args.steps // T)
     n_warm = max(3, args.warmup // T)
 
@@ -450,9 +453,13 @@ def run_rollout(args, rank, world, dev):
             "config": {"workload": f"PPO rollout collection (BASELINE config 5): torch MLP policy {env.obs_dim}->64->64->{env.M} "
                                    f"(tanh, gaussian head, value head) + fused step kernel, {ENV_ID} in3d, {E} envs per GPU, "
                                    f"T={T} steps per CUDA-graph replay, GAE on device, feature-major obs/actions",
+                       "policy": {"fused-fp32": "wg_policy_act: the torch module's weights evaluated by one CUDA kernel per step, "
+                                                "error-compensated 3xTF32 mma.sync (float32-grade, 1e-5 vs torch fp32)",
+                                  "fused-tf32": "wg_policy_act with plain TF32 products and tanh.approx",
+                                  "torch": "torch eager ops captured in the CUDA graph"}[args.policy],
                        "baseline_config": 5, "envs_per_gpu": E, "global_envs": world * E,
                        "parallelism": f"env-sharded x{world}; one NCCL all-reduce of 8 doubles (episode-return stats) per timed region"},
-            "gpu_launches": steps, "clocks": clocks,
+            "gpu_launches": n_roll * col.kernel_launches_per_rollout, "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "return_mean", "length_mean")},
         }
         print(json.dumps(line), flush=True)

@@ -230,6 +230,49 @@ int wg_pkg_update_physics(const wg_pkg_system* sys, const wg_pkg_params* prm,
                           float* pos, float* vel, float* old_a,
                           int64_t n_env, int32_t n_steps, void* cuda_stream);
 
+/* =====================================================================================
+ * The caller of the hot path (BASELINE config 5): PPO rollout collection around wg_step.
+ * The reference has no policy code; these entry points replace the per-step torch glue of
+ * a rollout loop (gym/performance_demo.py:241-262 is the reference's random-action loop)
+ * so that one env step costs two launches: wg_policy_act + wg_step.
+ * ===================================================================================== */
+
+/*
+ * A gaussian MLP policy with two tanh hidden layers of 64 units and a value head, weights in
+ * torch.nn.Linear layout (weight [out][in] row-major), all device pointers, float32.
+ */
+typedef struct wg_mlp_policy {
+    const float* w1; const float* b1;        /* [64][obs_dim], [64] */
+    const float* w2; const float* b2;        /* [64][64], [64] */
+    const float* w_mu; const float* b_mu;    /* [act_dim][64], [act_dim] */
+    const float* w_v; const float* b_v;      /* [1][64], [1] */
+    const float* log_std;                    /* [act_dim] */
+    int32_t obs_dim;                         /* 1..64 */
+    int32_t act_dim;                         /* 1..7 */
+    float   obs_scale, obs_clip;             /* x = clamp(nan_to_num(obs * obs_scale), +-obs_clip) */
+    int32_t precision;                       /* 0 = float32-grade (3xTF32 error-compensated MMA), 1 = plain TF32 */
+    int32_t reserved;
+} wg_mlp_policy;
+
+/*
+ * One policy evaluation for n_env envs, one kernel launch:
+ *   obs [obs_dim][n_env] (feature-major, what wg_step writes with obs_layout 1)
+ *   -> mean, value = MLP(obs); action = mean + exp(log_std) * eps, eps ~ N(0,1) from Philox keyed by
+ *      (seed, env_offset + env, step_index [+ *step_counter], action index); logp = log N(action; mean, std).
+ * action [act_dim][n_env] (act_layout 1) or [n_env][act_dim] (0); logp, value [n_env]; mean [act_dim][n_env].
+ * Any output may be NULL.  sample = 0 returns action = mean.
+ */
+int wg_policy_act(const wg_mlp_policy* pol, const float* obs, float* action, int32_t act_layout, float* logp,
+                  float* value, float* mean, int64_t n_env, int32_t sample, uint32_t seed_lo, uint32_t seed_hi,
+                  uint32_t step_index, const uint32_t* step_counter, uint32_t env_offset, void* cuda_stream);
+
+/*
+ * GAE(lambda) over a trajectory: rewards [T][n_env], values [T+1][n_env], dones uint8 [T][n_env] ->
+ * advantages, returns [T][n_env].  Rewards are sanitised first (NaN -> 0, clamp to +-reward_clip).
+ */
+int wg_gae(const float* rewards, const float* values, const uint8_t* dones, float* advantages, float* returns,
+           int32_t horizon, int64_t n_env, float gamma, float lam, float reward_clip, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

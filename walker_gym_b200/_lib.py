@@ -70,11 +70,20 @@ class WgPkgParams(C.Structure):
                 ("min_dist", C.c_float), ("ground", C.c_int32)]
 
 
+class WgMlpPolicy(C.Structure):
+    """``wg_mlp_policy``: device pointers to torch.nn.Linear weights of a D -> 64 -> 64 -> (M, 1) tanh MLP."""
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("w_mu", C.c_void_p), ("b_mu", C.c_void_p), ("w_v", C.c_void_p), ("b_v", C.c_void_p),
+                ("log_std", C.c_void_p), ("obs_dim", C.c_int32), ("act_dim", C.c_int32),
+                ("obs_scale", C.c_float), ("obs_clip", C.c_float), ("precision", C.c_int32), ("reserved", C.c_int32)]
+
+
 TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH = 0, 1, 2
 
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
            "wg_set_tuning", "wg_packed_state_floats",
-           "wg_step", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics")
+           "wg_step", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics",
+           "wg_policy_act", "wg_gae")
 
 _lib = None
 
@@ -115,8 +124,13 @@ def load():
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.wg_pkg_update_physics.argtypes = [P(WgPkgSystem), P(WgPkgParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int64, C.c_int32, C.c_void_p]
+    lib.wg_policy_act.argtypes = [P(WgMlpPolicy), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int64, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
+                                  C.c_void_p]
+    lib.wg_gae.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                           C.c_float, C.c_float, C.c_float, C.c_void_p]
     for name in ("wg_obs_dim", "wg_kernel_variant", "wg_force_generic", "wg_step", "wg_reset",
-                 "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics"):
+                 "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics", "wg_policy_act", "wg_gae"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -276,7 +276,7 @@ class BatchedPhysicsEnv:
         self._advance()
         return self.obs
 
-    def step(self, action: Optional[torch.Tensor], noise: Optional[torch.Tensor] = None):
+    def step(self, action: Optional[torch.Tensor], noise: Optional[torch.Tensor] = None, out=None):
         """``PhysicsEnv.step`` for every env, one kernel launch.
 
         ``action``: float32 [E, A] (or [A, E] with ``act_layout="feature"``); only the first
@@ -284,8 +284,18 @@ class BatchedPhysicsEnv:
         ``None`` applies no action.
         Returns ``(obs, reward, done, info)``: views of buffers that the next call overwrites.
         With auto-reset on, ``obs`` of a done env is its post-reset observation while
-        ``reward``/``done`` describe the step that ended the episode."""
+        ``reward``/``done`` describe the step that ended the episode.
+        ``out=(obs, reward, done)``: write this step's results straight into caller-owned tensors (e.g. slot t
+        of a trajectory buffer) instead of the env's own buffers; ``done`` is uint8/bool."""
         b = self._buf
+        res_obs, res_rew, res_done = self.obs, self.reward, self.done
+        if out is not None:
+            res_obs, res_rew, res_done = out
+            self._check_f32(res_obs, self.obs.shape, "out obs")
+            self._check_f32(res_rew, (self.num_envs,), "out reward")
+            if res_done.element_size() != 1 or res_done.numel() != self.num_envs or not res_done.is_contiguous():
+                raise ValueError("out done must be a contiguous 1-byte tensor of length num_envs")
+            b.obs, b.reward, b.done = res_obs.data_ptr(), res_rew.data_ptr(), res_done.data_ptr()
         if action is None:
             b.action, b.act_dim = None, 0
         else:
@@ -299,12 +309,14 @@ class BatchedPhysicsEnv:
         with torch.cuda.device(self.device):
             rc = self.lib.wg_step(C.byref(self.topo), C.byref(self.params), C.byref(b), self.num_envs, self._stream())
         b.noise = None
+        if out is not None:
+            b.obs, b.reward, b.done = self._p(self.obs), self._p(self.reward), self._p(self._done_u8)
         _lib.check(rc, "wg_step")
         self._advance()
         info = {}
         if self.energy is not None:
             info = {"steps": self.steps, "centroid_position": self.centroid, "total_energy": self.energy}
-        return self.obs, self.reward, self.done, info
+        return res_obs, res_rew, res_done, info
 
     def step_host(self, h_action: torch.Tensor, d_action: torch.Tensor, h_obs: Optional[torch.Tensor] = None,
                   h_reward: Optional[torch.Tensor] = None, h_done: Optional[torch.Tensor] = None) -> None:

@@ -6,8 +6,12 @@
 #include <cstdlib>
 
 #include "wg_launch.cuh"
+#include "wg_policy.cuh"
 
 namespace wg {
+int launch_policy(const PolicyArgs& A, int precision, cudaStream_t s);
+int launch_gae(const float* rewards, const float* values, const uint8_t* dones, float* adv, float* ret, int T, int64_t E,
+               float gamma, float lam, float clip, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_force_generic{0};
@@ -173,6 +177,37 @@ int wg_pkg_update_physics(const wg_pkg_system* sys, const wg_pkg_params* prm, fl
     if (n_env == 0 || n_steps == 0) return WG_OK;
     if (!pos || !vel) return fail(WG_ERR_BAD_ARG, "pos/vel must be set%s");
     return launch_pkg_update(sys, prm, pos, vel, old_a, n_env, n_steps, (cudaStream_t)cuda_stream);
+}
+
+int wg_policy_act(const wg_mlp_policy* pol, const float* obs, float* action, int32_t act_layout, float* logp,
+                  float* value, float* mean, int64_t n_env, int32_t sample, uint32_t seed_lo, uint32_t seed_hi,
+                  uint32_t step_index, const uint32_t* step_counter, uint32_t env_offset, void* cuda_stream) {
+    if (!pol || !obs) return fail(WG_ERR_BAD_ARG, "null argument%s");
+    if (!pol->w1 || !pol->b1 || !pol->w2 || !pol->b2 || !pol->w_mu || !pol->b_mu || !pol->w_v || !pol->b_v || !pol->log_std)
+        return fail(WG_ERR_BAD_ARG, "wg_mlp_policy: every weight pointer must be set%s");
+    if (pol->obs_dim < 1 || pol->obs_dim > 64) return fail(WG_ERR_BAD_ARG, "obs_dim out of range [1, 64]%s");
+    if (pol->act_dim < 1 || pol->act_dim > 7) return fail(WG_ERR_BAD_ARG, "act_dim out of range [1, 7]%s");
+    if (pol->precision != 0 && pol->precision != 1) return fail(WG_ERR_BAD_ARG, "precision must be 0 or 1%s");
+    if (act_layout != 0 && act_layout != 1) return fail(WG_ERR_BAD_ARG, "act_layout must be 0 or 1%s");
+    if (n_env < 0 || n_env > ((int64_t)1 << 31) - 1) return fail(WG_ERR_BAD_ARG, "n_env out of range%s");
+    if (n_env == 0) return WG_OK;
+    PolicyArgs A;
+    A.w1 = pol->w1; A.b1 = pol->b1; A.w2 = pol->w2; A.b2 = pol->b2; A.w_mu = pol->w_mu; A.b_mu = pol->b_mu;
+    A.w_v = pol->w_v; A.b_v = pol->b_v; A.log_std = pol->log_std;
+    A.obs = obs; A.action = action; A.logp = logp; A.value = value; A.mean = mean; A.step_counter = step_counter;
+    A.E = n_env; A.D = pol->obs_dim; A.M = pol->act_dim; A.act_layout = act_layout; A.sample = sample ? 1 : 0;
+    A.obs_scale = pol->obs_scale; A.obs_clip = pol->obs_clip;
+    A.seed_lo = seed_lo; A.seed_hi = seed_hi; A.step_index = step_index; A.env_offset = env_offset;
+    return launch_policy(A, pol->precision, (cudaStream_t)cuda_stream);
+}
+
+int wg_gae(const float* rewards, const float* values, const uint8_t* dones, float* advantages, float* returns,
+           int32_t horizon, int64_t n_env, float gamma, float lam, float reward_clip, void* cuda_stream) {
+    if (!rewards || !values || !dones || !advantages || !returns) return fail(WG_ERR_BAD_ARG, "null argument%s");
+    if (horizon < 0 || n_env < 0) return fail(WG_ERR_BAD_ARG, "horizon / n_env < 0%s");
+    if (horizon == 0 || n_env == 0) return WG_OK;
+    return launch_gae(rewards, values, dones, advantages, returns, horizon, n_env, gamma, lam, reward_clip,
+                      (cudaStream_t)cuda_stream);
 }
 
 }  // extern "C"

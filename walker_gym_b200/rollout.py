@@ -14,12 +14,76 @@ are reduced by the K3 kernel and all-reduced across ranks (NCCL), once per rollo
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 from typing import Dict, Optional
 
 import torch
 
+from . import _lib
 from .batched import BatchedPhysicsEnv
+
+
+class FusedPolicy:
+    """``FeatureMajorMLP`` evaluated by ``wg_policy_act``: one CUDA kernel per env step instead of ~25 torch
+    kernels.  Reads the module's parameters in place (no copies: an optimiser step is visible to the next call).
+    ``precision="fp32"`` uses error-compensated 3xTF32 tensor-core products (float32-grade), ``"tf32"`` plain TF32."""
+
+    def __init__(self, module: "FeatureMajorMLP", precision: str = "fp32"):
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        hidden, obs_dim = module.l1.weight.shape
+        act_dim = module.mu.weight.shape[0]
+        if hidden != 64 or tuple(module.l2.weight.shape) != (64, 64) or not 1 <= obs_dim <= 64 or not 1 <= act_dim <= 7:
+            raise ValueError("the fused policy kernel needs hidden == 64, obs_dim <= 64 and act_dim <= 7")
+        self.module, self.obs_dim, self.act_dim = module, int(obs_dim), int(act_dim)
+        self.lib = _lib.load()
+        self.precision = precision
+
+    def _struct(self) -> "_lib.WgMlpPolicy":
+        m, p = self.module, _lib.WgMlpPolicy()
+        tensors = dict(w1=m.l1.weight, b1=m.l1.bias, w2=m.l2.weight, b2=m.l2.bias, w_mu=m.mu.weight, b_mu=m.mu.bias,
+                       w_v=m.v.weight, b_v=m.v.bias, log_std=m.log_std)
+        for name, t in tensors.items():
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device.type != "cuda":
+                raise ValueError(f"policy parameter {name} must be a contiguous float32 CUDA tensor")
+            setattr(p, name, t.data_ptr())
+        p.obs_dim, p.act_dim = self.obs_dim, self.act_dim
+        p.obs_scale, p.obs_clip = float(m.obs_scale), float(m.obs_clip)
+        p.precision = 0 if self.precision == "fp32" else 1
+        return p
+
+    def act(self, obs_fm: torch.Tensor, *, action=None, logp=None, value=None, mean=None, sample: bool = True,
+            seed: int = 0, step_index: int = 0, step_counter: Optional[torch.Tensor] = None, env_offset: int = 0,
+            act_layout: str = "feature") -> None:
+        """obs_fm [D, E] -> any of action [M, E] (or [E, M] with act_layout="row"), logp [E], value [E], mean [M, E]."""
+        D, E = obs_fm.shape
+        if D != self.obs_dim or obs_fm.dtype != torch.float32 or not obs_fm.is_contiguous():
+            raise ValueError(f"obs must be a contiguous float32 [{self.obs_dim}, E] tensor")
+        for t, n in ((action, self.act_dim * E), (logp, E), (value, E), (mean, self.act_dim * E)):
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n):
+                raise ValueError("outputs must be contiguous float32 tensors of the documented shapes")
+        pol = self._struct()
+        ptr = lambda t: None if t is None else t.data_ptr()          # noqa: E731
+        with torch.cuda.device(obs_fm.device):
+            rc = self.lib.wg_policy_act(C.byref(pol), obs_fm.data_ptr(), ptr(action), 1 if act_layout == "feature" else 0,
+                                        ptr(logp), ptr(value), ptr(mean), E, 1 if sample else 0,
+                                        seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, step_index & 0xFFFFFFFF,
+                                        ptr(step_counter), env_offset & 0xFFFFFFFF,
+                                        C.c_void_p(torch.cuda.current_stream(obs_fm.device).cuda_stream))
+        _lib.check(rc, "wg_policy_act")
+
+
+def gae(rewards, values, dones, advantages, returns, gamma: float, lam: float, reward_clip: float) -> None:
+    """``wg_gae``: rewards [T, E], values [T+1, E], dones [T, E] (1-byte) -> advantages, returns [T, E]."""
+    T, E = rewards.shape
+    if values.shape != (T + 1, E) or dones.shape != (T, E) or dones.element_size() != 1:
+        raise ValueError("gae: shape mismatch")
+    with torch.cuda.device(rewards.device):
+        rc = _lib.load().wg_gae(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), advantages.data_ptr(),
+                                returns.data_ptr(), T, E, gamma, lam, reward_clip,
+                                C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream))
+    _lib.check(rc, "wg_gae")
 
 
 class FeatureMajorMLP(torch.nn.Module):
@@ -53,7 +117,8 @@ class RolloutCollector:
     obs [T+1, D, E], actions [T, M, E], logp/values/rewards [T(+1), E], dones [T, E]."""
 
     def __init__(self, env: BatchedPhysicsEnv, policy: torch.nn.Module, horizon: int, *, gamma: float = 0.99,
-                 lam: float = 0.95, use_cuda_graph: bool = True, reward_clip: float = 1e3):
+                 lam: float = 0.95, use_cuda_graph: bool = True, reward_clip: float = 1e3, fused: Optional[bool] = None,
+                 precision: str = "fp32", seed: int = 0):
         if env.obs_layout != "feature" or env.act_layout != "feature":
             raise ValueError("RolloutCollector needs obs_layout='feature' and act_layout='feature'")
         if use_cuda_graph and env._counter is None:
@@ -72,10 +137,34 @@ class RolloutCollector:
         self.returns = torch.zeros(self.T, E, **f32)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._use_graph = use_cuda_graph
-        self.kernel_launches_per_rollout = self.T          # step kernels; policy kernels are torch's
+        # fused: the policy runs in wg_policy_act and GAE in wg_gae (2 launches per env step); otherwise torch ops.
+        # In fused mode ``rewards`` holds the raw env rewards (wg_gae sanitises them on the fly).
+        can_fuse = isinstance(policy, FeatureMajorMLP) and policy.l1.weight.shape[0] == 64 and D <= 64 and 1 <= M <= 7
+        if fused and not can_fuse:
+            raise ValueError("fused=True needs a FeatureMajorMLP with hidden=64, obs_dim <= 64, 1 <= act_dim <= 7")
+        self.fused = can_fuse if fused is None else bool(fused)
+        self._fp = FusedPolicy(policy, precision) if self.fused else None
+        self.seed = int(seed)
+        self.kernel_launches_per_rollout = (2 * self.T + 2) if self.fused else self.T   # ours only; torch's not counted
+
+    @torch.no_grad()
+    def _rollout_fused(self) -> None:
+        env, fp = self.env, self._fp
+        dones_u8 = self.dones.view(torch.uint8)
+        kw = dict(seed=self.seed, step_counter=env._counter, env_offset=int(env.params.env_offset))
+        self.obs[0].copy_(env.obs)
+        for t in range(self.T):
+            fp.act(self.obs[t], action=self.actions[t], logp=self.logp[t], value=self.values[t], sample=True,
+                   step_index=0 if env._counter is not None else env.step_count, **kw)
+            env.step(self.actions[t], out=(self.obs[t + 1], self.rewards[t], dones_u8[t]))
+        fp.act(self.obs[self.T], value=self.values[self.T], sample=False, **kw)
+        env.obs.copy_(self.obs[self.T])                  # keep env.obs current for the next rollout / other callers
+        gae(self.rewards, self.values, dones_u8, self.advantages, self.returns, self.gamma, self.lam, self.reward_clip)
 
     @torch.no_grad()
     def _rollout(self) -> None:
+        if self.fused:
+            return self._rollout_fused()
         env, pol = self.env, self.policy
         self.obs[0].copy_(env.obs)
         for t in range(self.T):
