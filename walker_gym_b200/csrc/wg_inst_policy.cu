@@ -3,9 +3,13 @@
 #include "wg_policy.cuh"
 namespace wg {
 
+#ifndef WG_POLICY_MT
+#define WG_POLICY_MT 1
+#endif
 template <int KT1, bool SPLIT>
 static int launch_policy_t(const PolicyArgs& A, cudaStream_t s) {
-    auto kern = policy_act_kernel<KT1, SPLIT>;
+    constexpr int MT = WG_POLICY_MT;
+    auto kern = policy_act_kernel<KT1, SPLIT, MT>;
     const size_t smem = sizeof(uint32_t) * (size_t)PolicySmem<KT1>::words(SPLIT);
     static thread_local int cached_dev = -1, n_sm = 0;
     int dev = 0;
@@ -18,7 +22,7 @@ static int launch_policy_t(const PolicyArgs& A, cudaStream_t s) {
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const int64_t n_tiles = (A.E + kPolBlock - 1) / kPolBlock;
     const int64_t resident = (int64_t)n_sm * 2;                 // persistent: weights are staged once per CTA
-    kern<<<(unsigned)(n_tiles < resident ? n_tiles : resident), kPolBlock, smem, s>>>(A);
+    kern<<<(unsigned)(n_tiles < resident ? n_tiles : resident), 32 * (kPolBlock / (16 * MT)), smem, s>>>(A);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "policy kernel launch: %s", cudaGetErrorString(e));
     return WG_OK;

@@ -54,7 +54,8 @@ __device__ __forceinline__ void split4(const float (&x)[4], uint32_t (&hi)[4], u
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         hi[i] = to_tf32(x[i]);
-        lo[i] = SPLIT ? to_tf32(x[i] - __uint_as_float(hi[i])) : 0u;
+        // the low part is left as float32: the MMA reads only its TF32 bits (truncation), residual ~2^-22 |x|
+        lo[i] = SPLIT ? __float_as_uint(x[i] - __uint_as_float(hi[i])) : 0u;
     }
 }
 // c += A * B with A given as float32 values (split on the fly) and B as pre-split hi / lo planes
@@ -76,9 +77,8 @@ __device__ __forceinline__ float pol_tanh(float x) {
         asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
         return y;
     }
-    const float xc = fminf(fmaxf(x, -15.0f), 15.0f);
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xc * 2.8853900817779268f));     // exp(2x)
+    float e;                              // no clamp needed: exp -> inf gives 1 - 2/inf = 1, exp -> 0 gives 1 - 2 = -1
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));      // exp(2x)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
     return __fmaf_rn(-2.0f, r, 1.0f);
@@ -124,8 +124,11 @@ __device__ __forceinline__ float2 pol_normal2(uint32_t seed_lo, uint32_t seed_hi
     return make_float2(r * co, r * s);
 }
 
-template <int KT1, bool SPLIT>
-__global__ void __launch_bounds__(kPolBlock, 2)
+// MT = m-tiles (16 envs each) per warp.  A CTA always covers a tile of 128 envs: 128 / (16 * MT) warps.  MT = 1
+// (8 warps per CTA, ~120 registers, 16 warps per SM) overlaps tensor and ALU work better than MT = 2 (half the
+// fragment loads per MMA, but only 8 warps per SM): measured 1.6x faster.
+template <int KT1, bool SPLIT, int MT>
+__global__ void __launch_bounds__(32 * (kPolBlock / (16 * MT)), 2)
 policy_act_kernel(const __grid_constant__ PolicyArgs A) {
     using L = PolicySmem<KT1>;
     constexpr int KP1 = L::KP1, KP2 = L::KP2, NPL = SPLIT ? 2 : 1;
@@ -156,20 +159,20 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
     const uint32_t step = A.step_index + (A.step_counter ? __ldg(A.step_counter) : 0u);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t e0 = tile * kPolBlock + warp * 32;           // this warp: envs e0 .. e0+31 = 2 m-tiles of 16
+        const int64_t e0 = tile * kPolBlock + warp * (16 * MT);    // this warp: envs e0 .. e0 + 16*MT - 1
         if (e0 >= E) continue;
         // env rows of this thread's fragments: (mt, h) -> e0 + 16*mt + 8*h + g
-        int64_t er[2][2];
-        bool ev[2][2];
+        int64_t er[MT][2];
+        bool ev[MT][2];
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++)
+        for (int mt = 0; mt < MT; mt++)
 #pragma unroll
             for (int h = 0; h < 2; h++) { er[mt][h] = e0 + 16 * mt + 8 * h + g; ev[mt][h] = er[mt][h] < E; }
 
         // ---- layer 1: h1 = tanh(W1 x + b1); A fragments straight from the feature-major observation ----
-        float acc[2][8][4];
+        float acc[MT][8][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++)
+        for (int mt = 0; mt < MT; mt++)
 #pragma unroll
             for (int nt = 0; nt < 8; nt++)
 #pragma unroll
@@ -177,9 +180,9 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
 #pragma unroll
         for (int kk = 0; kk < KT1; kk++) {
             const int f0 = 8 * kk + 2 * t, f1 = f0 + 1;               // k-slot t <-> feature f0, slot t+4 <-> f1
-            uint32_t ahi[2][4], alo[2][4];
+            uint32_t ahi[MT][4], alo[MT][4];
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++) {
+            for (int mt = 0; mt < MT; mt++) {
                 float x[4];                                              // a0 (g, f0), a1 (g+8, f0), a2 (g, f1), a3 (g+8, f1)
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -196,15 +199,15 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
                 const int off = (8 * nt + g) * KP1 + 8 * kk + 2 * t;
                 const uint2 bhi = *reinterpret_cast<const uint2*>(W1 + off);
                 const uint2 blo = SPLIT ? *reinterpret_cast<const uint2*>(W1 + kPolH * KP1 + off) : make_uint2(0u, 0u);
-                mma3<SPLIT>(acc[0][nt], ahi[0], alo[0], bhi, blo);
-                mma3<SPLIT>(acc[1][nt], ahi[1], alo[1], bhi, blo);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) mma3<SPLIT>(acc[mt][nt], ahi[mt], alo[mt], bhi, blo);
             }
         }
         // bias + tanh, then split once into the A fragments of layer 2: accumulator (g,2t) (g,2t+1) (g+8,2t) (g+8,2t+1)
         // -> a0 a2 a1 a3 under the k-slot permutation
-        uint32_t h1hi[2][8][4], h1lo[2][8][4];
+        uint32_t h1hi[MT][8][4], h1lo[MT][8][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++)
+        for (int mt = 0; mt < MT; mt++)
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
                 const float bA = B1[8 * nt + 2 * t], bB = B1[8 * nt + 2 * t + 1];
@@ -213,36 +216,55 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
                 split4<SPLIT>(x, h1hi[mt][nt], h1lo[mt][nt]);
             }
 
-        // ---- layer 2 + heads: n-tile nt2 of h2 is k-tile nt2 of the heads, so h2 is consumed tile by tile ----
-        float hd[2][4] = { { 0.0f, 0.0f, 0.0f, 0.0f }, { 0.0f, 0.0f, 0.0f, 0.0f } };
+        // ---- layer 2 + heads: n-tile nt2 of h2 is k-tile nt2 of the heads, so h2 is consumed group by group.
+        // Four n-tiles x MT m-tiles are accumulated together: independent MMA chains keep the tensor pipe busy
+        // (one chain per accumulator would serialise on the MMA latency).
+        float hd[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) hd[mt][i] = 0.0f;
 #pragma unroll 1
-        for (int nt2 = 0; nt2 < 8; nt2++) {
-            float a2[2][4] = { { 0.0f, 0.0f, 0.0f, 0.0f }, { 0.0f, 0.0f, 0.0f, 0.0f } };
+        for (int grp = 0; grp < 2; grp++) {
+            float a2[4][MT][4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) a2[q][mt][i] = 0.0f;
 #pragma unroll
             for (int kk = 0; kk < 8; kk++) {
-                const int off = (8 * nt2 + g) * KP2 + 8 * kk + 2 * t;
-                const uint2 bhi = *reinterpret_cast<const uint2*>(W2 + off);
-                const uint2 blo = SPLIT ? *reinterpret_cast<const uint2*>(W2 + kPolH * KP2 + off) : make_uint2(0u, 0u);
-                mma3<SPLIT>(a2[0], h1hi[0][kk], h1lo[0][kk], bhi, blo);
-                mma3<SPLIT>(a2[1], h1hi[1][kk], h1lo[1][kk], bhi, blo);
-            }
-            const float bA = B2[8 * nt2 + 2 * t], bB = B2[8 * nt2 + 2 * t + 1];
-            const int off = g * KP2 + 8 * nt2 + 2 * t;
-            const uint2 bhi = *reinterpret_cast<const uint2*>(WH + off);
-            const uint2 blo = SPLIT ? *reinterpret_cast<const uint2*>(WH + 8 * KP2 + off) : make_uint2(0u, 0u);
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++) {
-                const float x[4] = { pol_tanh<SPLIT>(a2[mt][0] + bA), pol_tanh<SPLIT>(a2[mt][2] + bA),
-                                     pol_tanh<SPLIT>(a2[mt][1] + bB), pol_tanh<SPLIT>(a2[mt][3] + bB) };
-                uint32_t ahi[4], alo[4];
-                split4<SPLIT>(x, ahi, alo);
-                mma3<SPLIT>(hd[mt], ahi, alo, bhi, blo);
+                for (int q = 0; q < 4; q++) {
+                    const int off = (8 * (4 * grp + q) + g) * KP2 + 8 * kk + 2 * t;
+                    const uint2 bhi = *reinterpret_cast<const uint2*>(W2 + off);
+                    const uint2 blo = SPLIT ? *reinterpret_cast<const uint2*>(W2 + kPolH * KP2 + off) : make_uint2(0u, 0u);
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) mma3<SPLIT>(a2[q][mt], h1hi[mt][kk], h1lo[mt][kk], bhi, blo);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int nt2 = 4 * grp + q;
+                const float bA = B2[8 * nt2 + 2 * t], bB = B2[8 * nt2 + 2 * t + 1];
+                const int off = g * KP2 + 8 * nt2 + 2 * t;
+                const uint2 bhi = *reinterpret_cast<const uint2*>(WH + off);
+                const uint2 blo = SPLIT ? *reinterpret_cast<const uint2*>(WH + 8 * KP2 + off) : make_uint2(0u, 0u);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const float x[4] = { pol_tanh<SPLIT>(a2[q][mt][0] + bA), pol_tanh<SPLIT>(a2[q][mt][2] + bA),
+                                         pol_tanh<SPLIT>(a2[q][mt][1] + bB), pol_tanh<SPLIT>(a2[q][mt][3] + bB) };
+                    uint32_t ahi[4], alo[4];
+                    split4<SPLIT>(x, ahi, alo);
+                    mma3<SPLIT>(hd[mt], ahi, alo, bhi, blo);
+                }
             }
         }
 
         // ---- heads: this thread holds outputs n = 2t, 2t+1 of env rows (mt, h); n < M mean, n == M value ----
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++)
+        for (int mt = 0; mt < MT; mt++)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int64_t e = er[mt][h];
