@@ -414,10 +414,11 @@ def run_rollout(args, rank, world, dev):
     E = args.envs_per_gpu if args.envs_per_gpu != (1 << 20) else (1 << 18)
     T = 32
     torch.manual_seed(7 + rank)
-    env = BatchedPhysicsEnv(ENV_ID, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
-                            obs_layout="feature", act_layout="feature", graph_safe=True)
-    pol = FeatureMajorMLP(env.obs_dim, env.M).to(dev)
     fused = args.policy != "torch"
+    lay = "row" if (fused and args.obs_layout == "row") else "feature"
+    env = BatchedPhysicsEnv(ENV_ID, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
+                            obs_layout=lay, act_layout=lay, graph_safe=True)
+    pol = FeatureMajorMLP(env.obs_dim, env.M).to(dev)
     col = RolloutCollector(env, pol, T, fused=fused, precision="tf32" if args.policy == "fused-tf32" else "fp32")
     n_roll = max(1, args.steps // T)
     n_warm = max(3, args.warmup // T)
@@ -452,7 +453,7 @@ def run_rollout(args, rank, world, dev):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"PPO rollout collection (BASELINE config 5): torch MLP policy {env.obs_dim}->64->64->{env.M} "
                                    f"(tanh, gaussian head, value head) + fused step kernel, {ENV_ID} in3d, {E} envs per GPU, "
-                                   f"T={T} steps per CUDA-graph replay, GAE on device, feature-major obs/actions",
+                                   f"T={T} steps per CUDA-graph replay, GAE on device, {lay}-major obs/actions",
                        "policy": {"fused-fp32": "wg_policy_act: the torch module's weights evaluated by one CUDA kernel per step, "
                                                 "error-compensated 3xTF32 mma.sync (float32-grade, 1e-5 vs torch fp32)",
                                   "fused-tf32": "wg_policy_act with plain TF32 products and tanh.approx",

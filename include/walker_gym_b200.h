@@ -256,13 +256,13 @@ typedef struct wg_mlp_policy {
 
 /*
  * One policy evaluation for n_env envs, one kernel launch:
- *   obs [obs_dim][n_env] (feature-major, what wg_step writes with obs_layout 1)
+ *   obs [n_env][obs_dim] (obs_layout 0) or [obs_dim][n_env] (obs_layout 1), as wg_step writes it
  *   -> mean, value = MLP(obs); action = mean + exp(log_std) * eps, eps ~ N(0,1) from Philox keyed by
  *      (seed, env_offset + env, step_index [+ *step_counter], action index); logp = log N(action; mean, std).
  * action [act_dim][n_env] (act_layout 1) or [n_env][act_dim] (0); logp, value [n_env]; mean [act_dim][n_env].
  * Any output may be NULL.  sample = 0 returns action = mean.
  */
-int wg_policy_act(const wg_mlp_policy* pol, const float* obs, float* action, int32_t act_layout, float* logp,
+int wg_policy_act(const wg_mlp_policy* pol, const float* obs, int32_t obs_layout, float* action, int32_t act_layout, float* logp,
                   float* value, float* mean, int64_t n_env, int32_t sample, uint32_t seed_lo, uint32_t seed_hi,
                   uint32_t step_index, const uint32_t* step_counter, uint32_t env_offset, void* cuda_stream);
 

@@ -57,7 +57,10 @@ def test_policy_matches_torch_fp32(D, M, E, precision, tol):
     mean, value = torch.full((M, E), 7.0, device=DEV), torch.full((E,), 7.0, device=DEV)
     action, logp = torch.zeros(M, E, device=DEV), torch.zeros(E, device=DEV)
     FusedPolicy(pol, precision).act(obs, action=action, logp=logp, value=value, mean=mean, sample=False)
+    mean_r, value_r = torch.zeros_like(mean), torch.zeros_like(value)       # the same from row-major observations
+    FusedPolicy(pol, precision).act(obs.t().contiguous(), obs_layout="row", value=value_r, mean=mean_r, sample=False)
     torch.cuda.synchronize()
+    assert torch.equal(mean, mean_r) and torch.equal(value, value_r)
     assert torch.isfinite(mean).all() and torch.isfinite(value).all()
     assert (mean - mean_t).abs().max().item() < tol and (value - value_t).abs().max().item() < tol
     assert torch.equal(action, mean)                                    # sample=False
@@ -124,14 +127,15 @@ def test_gae_matches_torch():
     assert (ret.double() - (want + values[:T].double())).abs().max().item() < 1e-5 * scale
 
 
+@pytest.mark.parametrize("layout", ["feature", "row"])
 @pytest.mark.parametrize("graph", [False, True])
-def test_fused_rollout_collector(graph):
+def test_fused_rollout_collector(graph, layout):
     """The fused collector (2 launches per env step) produces a trajectory that is self-consistent and whose
     physics is the bit-exact step kernel: replaying its actions through a second env gives the same obs/reward/done."""
     from walker_gym_b200 import BatchedPhysicsEnv
     from walker_gym_b200.rollout import FeatureMajorMLP, RolloutCollector
     E, T = 2048, 8
-    kw = dict(in3d=True, auto_reset="template", seed=5, obs_layout="feature", act_layout="feature", graph_safe=True)
+    kw = dict(in3d=True, auto_reset="template", seed=5, obs_layout=layout, act_layout=layout, graph_safe=True)
     env = BatchedPhysicsEnv("Balance-v0", E, DEV, **kw)
     torch.manual_seed(1)
     pol = FeatureMajorMLP(env.obs_dim, env.M).to(DEV)
@@ -154,10 +158,11 @@ def test_fused_rollout_collector(graph):
             assert torch.equal(torch.nan_to_num(o), torch.nan_to_num(out["obs"][t + 1])), t
             assert torch.equal(torch.nan_to_num(r), torch.nan_to_num(out["rewards"][t])) and torch.equal(d, out["dones"][t])
     # self-consistency of the returned trajectory (both modes)
-    mean = torch.zeros_like(out["actions"][0])
+    mean = torch.zeros(env.M, E, device=DEV)
     from walker_gym_b200.rollout import FusedPolicy
-    FusedPolicy(pol).act(out["obs"][2].contiguous(), mean=mean, sample=False)
-    eps = (out["actions"][2] - mean) / pol.log_std.detach().exp()
+    FusedPolicy(pol).act(out["obs"][2].contiguous(), mean=mean, sample=False, obs_layout=layout)
+    act2 = out["actions"][2] if layout == "feature" else out["actions"][2].t()
+    eps = (act2 - mean) / pol.log_std.detach().exp()
     want = (-0.5 * eps * eps - pol.log_std.detach() - 0.5 * math.log(2 * math.pi)).sum(0)
     assert (out["logp"][2] - want).abs().max().item() < 1e-3
     assert (out["returns"] - (out["advantages"] + out["values"][:T])).abs().max().item() < 1e-3

@@ -179,7 +179,7 @@ int wg_pkg_update_physics(const wg_pkg_system* sys, const wg_pkg_params* prm, fl
     return launch_pkg_update(sys, prm, pos, vel, old_a, n_env, n_steps, (cudaStream_t)cuda_stream);
 }
 
-int wg_policy_act(const wg_mlp_policy* pol, const float* obs, float* action, int32_t act_layout, float* logp,
+int wg_policy_act(const wg_mlp_policy* pol, const float* obs, int32_t obs_layout, float* action, int32_t act_layout, float* logp,
                   float* value, float* mean, int64_t n_env, int32_t sample, uint32_t seed_lo, uint32_t seed_hi,
                   uint32_t step_index, const uint32_t* step_counter, uint32_t env_offset, void* cuda_stream) {
     if (!pol || !obs) return fail(WG_ERR_BAD_ARG, "null argument%s");
@@ -189,9 +189,11 @@ int wg_policy_act(const wg_mlp_policy* pol, const float* obs, float* action, int
     if (pol->act_dim < 1 || pol->act_dim > 7) return fail(WG_ERR_BAD_ARG, "act_dim out of range [1, 7]%s");
     if (pol->precision != 0 && pol->precision != 1) return fail(WG_ERR_BAD_ARG, "precision must be 0 or 1%s");
     if (act_layout != 0 && act_layout != 1) return fail(WG_ERR_BAD_ARG, "act_layout must be 0 or 1%s");
+    if (obs_layout != 0 && obs_layout != 1) return fail(WG_ERR_BAD_ARG, "obs_layout must be 0 or 1%s");
     if (n_env < 0 || n_env > ((int64_t)1 << 31) - 1) return fail(WG_ERR_BAD_ARG, "n_env out of range%s");
     if (n_env == 0) return WG_OK;
     PolicyArgs A;
+    A.obs_layout = obs_layout;
     A.w1 = pol->w1; A.b1 = pol->b1; A.w2 = pol->w2; A.b2 = pol->b2; A.w_mu = pol->w_mu; A.b_mu = pol->b_mu;
     A.w_v = pol->w_v; A.b_v = pol->b_v; A.log_std = pol->log_std;
     A.obs = obs; A.action = action; A.logp = logp; A.value = value; A.mean = mean; A.step_counter = step_counter;

@@ -26,7 +26,7 @@ struct PolicyArgs {
     const float* w_mu; const float* b_mu;    // [M][64], [M]
     const float* w_v; const float* b_v;      // [1][64], [1]
     const float* log_std;                    // [M]
-    const float* obs;                        // [D][E] feature-major
+    const float* obs;                        // [D][E] feature-major (obs_layout 1) or [E][D] row-major (obs_layout 0)
     float* action;                           // [M][E] (act_layout 1) or [E][M] (act_layout 0); optional
     float* logp;                             // [E], optional
     float* value;                            // [E], optional
@@ -34,6 +34,7 @@ struct PolicyArgs {
     const uint32_t* step_counter;            // optional device scalar added to step_index (CUDA-graph replays)
     int64_t E;
     int32_t D, M, act_layout, sample;        // sample 0: action = mean
+    int32_t obs_layout;
     float obs_scale, obs_clip;
     uint32_t seed_lo, seed_hi, step_index, env_offset;
 };
@@ -157,6 +158,7 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
     const int64_t E = A.E;
     const int64_t n_tiles = (E + kPolBlock - 1) / kPolBlock;
     const uint32_t step = A.step_index + (A.step_counter ? __ldg(A.step_counter) : 0u);
+    const bool row_vec = (D % 2 == 0) && ((reinterpret_cast<uintptr_t>(A.obs) & 7u) == 0);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t e0 = tile * kPolBlock + warp * (16 * MT);    // this warp: envs e0 .. e0 + 16*MT - 1
@@ -184,13 +186,25 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
                 float x[4];                                              // a0 (g, f0), a1 (g+8, f0), a2 (g, f1), a3 (g+8, f1)
+                if (A.obs_layout == 0 && row_vec) {
+                    // row-major observation rows: features f0, f0+1 of one env are one aligned 8-byte load
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float2 v = (f0 < D && ev[mt][h]) ? __ldg(reinterpret_cast<const float2*>(A.obs + er[mt][h] * D + f0))
+                                                               : make_float2(0.0f, 0.0f);
+                        x[h] = v.x; x[2 + h] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int f = (i & 2) ? f1 : f0, h = i & 1;
+                        x[i] = (f < D && ev[mt][h]) ? __ldg(A.obs + (A.obs_layout ? (int64_t)f * E + er[mt][h] : er[mt][h] * D + f)) : 0.0f;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int f = (i & 2) ? f1 : f0, h = i & 1;
-                    float v = (f < D && ev[mt][h]) ? __ldg(A.obs + (int64_t)f * E + er[mt][h]) : 0.0f;
-                    v = v * A.obs_scale;                                 // nan_to_num + clamp of the torch reference
-                    v = (v != v) ? 0.0f : fminf(fmaxf(v, -A.obs_clip), A.obs_clip);
-                    x[i] = v;
+                    float v = x[i] * A.obs_scale;                        // nan_to_num + clamp of the torch reference
+                    x[i] = (v != v) ? 0.0f : fminf(fmaxf(v, -A.obs_clip), A.obs_clip);
                 }
                 split4<SPLIT>(x, ahi[mt], alo[mt]);
             }

@@ -55,18 +55,20 @@ class FusedPolicy:
 
     def act(self, obs_fm: torch.Tensor, *, action=None, logp=None, value=None, mean=None, sample: bool = True,
             seed: int = 0, step_index: int = 0, step_counter: Optional[torch.Tensor] = None, env_offset: int = 0,
-            act_layout: str = "feature") -> None:
-        """obs_fm [D, E] -> any of action [M, E] (or [E, M] with act_layout="row"), logp [E], value [E], mean [M, E]."""
-        D, E = obs_fm.shape
+            act_layout: str = "feature", obs_layout: str = "feature") -> None:
+        """obs [D, E] (or [E, D] with obs_layout="row") -> any of action [M, E] (or [E, M] with act_layout="row"),
+        logp [E], value [E], mean [M, E]."""
+        D, E = obs_fm.shape if obs_layout == "feature" else obs_fm.shape[::-1]
         if D != self.obs_dim or obs_fm.dtype != torch.float32 or not obs_fm.is_contiguous():
-            raise ValueError(f"obs must be a contiguous float32 [{self.obs_dim}, E] tensor")
+            raise ValueError(f"obs must be a contiguous float32 [{self.obs_dim}, E] (feature) or [E, {self.obs_dim}] (row) tensor")
         for t, n in ((action, self.act_dim * E), (logp, E), (value, E), (mean, self.act_dim * E)):
             if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n):
                 raise ValueError("outputs must be contiguous float32 tensors of the documented shapes")
         pol = self._struct()
         ptr = lambda t: None if t is None else t.data_ptr()          # noqa: E731
         with torch.cuda.device(obs_fm.device):
-            rc = self.lib.wg_policy_act(C.byref(pol), obs_fm.data_ptr(), ptr(action), 1 if act_layout == "feature" else 0,
+            rc = self.lib.wg_policy_act(C.byref(pol), obs_fm.data_ptr(), 1 if obs_layout == "feature" else 0,
+                                        ptr(action), 1 if act_layout == "feature" else 0,
                                         ptr(logp), ptr(value), ptr(mean), E, 1 if sample else 0,
                                         seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, step_index & 0xFFFFFFFF,
                                         ptr(step_counter), env_offset & 0xFFFFFFFF,
@@ -112,23 +114,26 @@ class FeatureMajorMLP(torch.nn.Module):
 class RolloutCollector:
     """Collect ``horizon`` steps from a ``BatchedPhysicsEnv`` under a policy.
 
-    The env must be built with ``obs_layout="feature"``, ``act_layout="feature"`` and
-    ``graph_safe=True``.  ``collect()`` returns views of device buffers:
-    obs [T+1, D, E], actions [T, M, E], logp/values/rewards [T(+1), E], dones [T, E]."""
+    The env must be built with ``graph_safe=True`` for CUDA-graph rollouts.  The fused collector (default for a
+    ``FeatureMajorMLP``) takes either layout; row-major observations (``obs_layout="row"``, the step kernel's fastest
+    path) and row-major actions are the fastest combination.  The torch-op collector needs feature-major both.
+    ``collect()`` returns views of device buffers: obs [T+1, D, E] (or [T+1, E, D]), actions [T, M, E] (or [T, E, M]),
+    logp/values/rewards [T(+1), E], dones [T, E]."""
 
     def __init__(self, env: BatchedPhysicsEnv, policy: torch.nn.Module, horizon: int, *, gamma: float = 0.99,
                  lam: float = 0.95, use_cuda_graph: bool = True, reward_clip: float = 1e3, fused: Optional[bool] = None,
                  precision: str = "fp32", seed: int = 0):
-        if env.obs_layout != "feature" or env.act_layout != "feature":
-            raise ValueError("RolloutCollector needs obs_layout='feature' and act_layout='feature'")
+        row = env.obs_layout == "row" or env.act_layout == "row"
+        if row and fused is False:
+            raise ValueError("the torch-op collector needs obs_layout='feature' and act_layout='feature'")
         if use_cuda_graph and env._counter is None:
             raise ValueError("CUDA-graph rollouts need BatchedPhysicsEnv(graph_safe=True)")
         self.env, self.policy, self.T = env, policy, int(horizon)
         self.gamma, self.lam, self.reward_clip = gamma, lam, reward_clip
         E, D, M, dev = env.num_envs, env.obs_dim, env.M, env.device
         f32 = dict(dtype=torch.float32, device=dev)
-        self.obs = torch.zeros(self.T + 1, D, E, **f32)
-        self.actions = torch.zeros(self.T, M, E, **f32)
+        self.obs = torch.zeros((self.T + 1, D, E) if env.obs_layout == "feature" else (self.T + 1, E, D), **f32)
+        self.actions = torch.zeros((self.T, M, E) if env.act_layout == "feature" else (self.T, E, M), **f32)
         self.logp = torch.zeros(self.T, E, **f32)
         self.values = torch.zeros(self.T + 1, E, **f32)
         self.rewards = torch.zeros(self.T, E, **f32)
@@ -140,8 +145,8 @@ class RolloutCollector:
         # fused: the policy runs in wg_policy_act and GAE in wg_gae (2 launches per env step); otherwise torch ops.
         # In fused mode ``rewards`` holds the raw env rewards (wg_gae sanitises them on the fly).
         can_fuse = isinstance(policy, FeatureMajorMLP) and policy.l1.weight.shape[0] == 64 and D <= 64 and 1 <= M <= 7
-        if fused and not can_fuse:
-            raise ValueError("fused=True needs a FeatureMajorMLP with hidden=64, obs_dim <= 64, 1 <= act_dim <= 7")
+        if (fused or row) and not can_fuse:
+            raise ValueError("the fused collector needs a FeatureMajorMLP with hidden=64, obs_dim <= 64, 1 <= act_dim <= 7")
         self.fused = can_fuse if fused is None else bool(fused)
         self._fp = FusedPolicy(policy, precision) if self.fused else None
         self.seed = int(seed)
@@ -151,7 +156,8 @@ class RolloutCollector:
     def _rollout_fused(self) -> None:
         env, fp = self.env, self._fp
         dones_u8 = self.dones.view(torch.uint8)
-        kw = dict(seed=self.seed, step_counter=env._counter, env_offset=int(env.params.env_offset))
+        kw = dict(seed=self.seed, step_counter=env._counter, env_offset=int(env.params.env_offset),
+                  obs_layout=env.obs_layout, act_layout=env.act_layout)
         self.obs[0].copy_(env.obs)
         for t in range(self.T):
             fp.act(self.obs[t], action=self.actions[t], logp=self.logp[t], value=self.values[t], sample=True,
