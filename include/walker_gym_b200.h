@@ -226,6 +226,11 @@ typedef struct wg_pkg_params {
  * pos, vel: in/out, SoA [(n*3 + c) * n_env + e]; old_a: optional out (Point.old_a of
  * the last step, same layout).  One kernel launch; asynchronous on cuda_stream.
  */
+/* Which kernel wg_pkg_update_physics will launch: 0 = run-time topology (shared-memory state), > 0 = a
+ * register-resident specialisation for one of the reference's small bodies (leg2, balance1-3, test).
+ * wg_force_generic(1) forces 0.  Results never depend on it. */
+int wg_pkg_kernel_variant(const wg_pkg_system* sys);
+
 int wg_pkg_update_physics(const wg_pkg_system* sys, const wg_pkg_params* prm,
                           float* pos, float* vel, float* old_a,
                           int64_t n_env, int32_t n_steps, void* cuda_stream);

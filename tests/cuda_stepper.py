@@ -170,8 +170,12 @@ def l2_step(sysm, prm, st, n_steps=1):
     lib = _lib.load()
     E = st["pos"].shape[1]
     d = {k: _dev(st[k]) for k in ("pos", "vel", "old_a")}
-    rc = lib.wg_pkg_update_physics(C.byref(sysm), C.byref(prm), _ptr(d["pos"]), _ptr(d["vel"]), _ptr(d["old_a"]),
-                                   E, n_steps, _stream())
+    old = lib.wg_force_generic(1 if force_generic else 0)
+    try:
+        rc = lib.wg_pkg_update_physics(C.byref(sysm), C.byref(prm), _ptr(d["pos"]), _ptr(d["vel"]), _ptr(d["old_a"]),
+                                       E, n_steps, _stream())
+    finally:
+        lib.wg_force_generic(old)
     _lib.check(rc, "wg_pkg_update_physics")
     torch.cuda.synchronize()
     for k in ("pos", "vel", "old_a"):

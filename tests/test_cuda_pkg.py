@@ -16,7 +16,9 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture()
 def cs():
     import cuda_stepper
-    return cuda_stepper
+    cuda_stepper.force_generic = False
+    yield cuda_stepper
+    cuda_stepper.force_generic = False
 
 
 @pytest.mark.parametrize("chunk", [1, 7, 1000])
@@ -27,9 +29,44 @@ def test_cuda_matches_reference_package_physics(cs, name, chunk):
     assert replay_l2(gu.load_l2(name), cs, chunk) is None
 
 
+@pytest.mark.parametrize("generic", [False, True])
 @pytest.mark.parametrize("name", BODY_NAMES)
-def test_cuda_matches_reference_bodies(cs, name):
-    assert replay_body(body_record(name), cs, 6) is None
+def test_cuda_matches_reference_bodies(cs, name, generic):
+    """Every body the reference ships, through its register-resident specialisation (box, leg2, balance1-3, test)
+    and through the run-time-topology kernel."""
+    import ctypes as C
+    from walker_gym_b200 import _lib
+    cs.force_generic = generic
+    rec = body_record(name)
+    lib = _lib.load()
+    old = lib.wg_force_generic(1 if generic else 0)
+    variant = lib.wg_pkg_kernel_variant(C.byref(cs.make_l2_system(system_of(rec))))
+    lib.wg_force_generic(old)
+    assert (variant > 0) == (not generic and name in ("leg2", "balance1", "balance2", "balance3", "test"))
+    assert replay_body(rec, cs, 6) is None
+
+
+def test_cuda_static_and_generic_kernels_agree_on_perturbed_bodies(cs):
+    """The specialised leg2 kernel vs the generic kernel vs the oracle on 5000 perturbed envs, strings and a DingPoint."""
+    rng = np.random.default_rng(11)
+    system = system_of(body_record("leg2"))
+    system["points"][3] = system["points"][3][:3] + (True,)
+    system["points"][5] = (2.5,) + system["points"][5][1:]
+    system["springs"][4] = system["springs"][4][:4] + (True,)
+    E = 5000
+    st = wo.l2_init_state(system, E)
+    st["pos"] += rng.normal(0, 1.0, st["pos"].shape).astype(np.float32)
+    st["vel"] += rng.normal(0, 3.0, st["vel"].shape).astype(np.float32)
+    kw = dict(ground_level=-17, gravity=(0.0, -50.0, 1.0))
+    res = []
+    for generic in (False, True):
+        cs.force_generic = generic
+        s2 = {k: v.copy() for k, v in st.items()}
+        cs.l2_step(cs.make_l2_system(system), cs.make_l2_params(**kw), s2, 60)
+        res.append(s2)
+    wo.l2_step(wo.make_l2_system(system), wo.make_l2_params(**kw), st, 60)
+    for k in ("pos", "vel", "old_a"):
+        assert gu.same(res[0][k], st[k]) and gu.same(res[1][k], st[k]), k
 
 
 def random_system(rng, P, S, dings=True):

@@ -69,7 +69,8 @@ static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* 
 }
 
 int launch_pkg_update(const wg_pkg_system*, const wg_pkg_params*, float* pos, float* vel, float* old_a,
-                      int64_t E, int32_t n_steps, cudaStream_t);
+                      int64_t E, int32_t n_steps, bool force_generic, cudaStream_t);
+int pkg_variant(const wg_pkg_system*);
 
 }  // namespace wg
 
@@ -164,6 +165,11 @@ int wg_step_host(const wg_topology* topo, const wg_params* prm, const wg_buffers
     return WG_OK;
 }
 
+int wg_pkg_kernel_variant(const wg_pkg_system* sys) {
+    if (!sys) return fail(WG_ERR_BAD_ARG, "null system%s");
+    return g_force_generic.load() ? 0 : pkg_variant(sys);
+}
+
 int wg_pkg_update_physics(const wg_pkg_system* sys, const wg_pkg_params* prm, float* pos, float* vel, float* old_a,
                           int64_t n_env, int32_t n_steps, void* cuda_stream) {
     if (!sys || !prm) return fail(WG_ERR_BAD_ARG, "null argument%s");
@@ -176,7 +182,7 @@ int wg_pkg_update_physics(const wg_pkg_system* sys, const wg_pkg_params* prm, fl
     if (n_steps < 0) return fail(WG_ERR_BAD_ARG, "n_steps < 0%s");
     if (n_env == 0 || n_steps == 0) return WG_OK;
     if (!pos || !vel) return fail(WG_ERR_BAD_ARG, "pos/vel must be set%s");
-    return launch_pkg_update(sys, prm, pos, vel, old_a, n_env, n_steps, (cudaStream_t)cuda_stream);
+    return launch_pkg_update(sys, prm, pos, vel, old_a, n_env, n_steps, g_force_generic.load() != 0, (cudaStream_t)cuda_stream);
 }
 
 int wg_policy_act(const wg_mlp_policy* pol, const float* obs, int32_t obs_layout, float* action, int32_t act_layout, float* logp,

@@ -3,8 +3,42 @@
 #include "wg_pkg.cuh"
 namespace wg {
 
+// bodies of gym/optimized_walker/walker.py with a register-resident kernel: endpoints as (point1, point2) pairs
+// (box, 8 points / 12 springs, was measured slower register-resident -- 128 registers, 190 us vs 163 us per 2^20
+// envs -- so it and the larger bodies use the run-time-topology kernel)
+// leg2 (:368-393): body, two 3-point legs
+WG_STATIC_TOPO(PkgLeg2, 2, 7, 6, 0, 0,1, 1,2, 2,3, 0,4, 4,5, 5,6)
+// balance3 (:452-467): pivot + 3 bobs; balance2 / balance1 / test are chains of 3 / 2 / 2 points
+WG_STATIC_TOPO(PkgChain4, 3, 4, 3, 0, 0,1, 1,2, 2,3)
+WG_STATIC_TOPO(PkgChain3, 4, 3, 2, 0, 0,1, 1,2)
+WG_STATIC_TOPO(PkgChain2, 5, 2, 1, 0, 0,1)
+
+template <class Topo>
+static bool pkg_matches(const wg_pkg_system* sy) {
+    if (sy->n_point != Topo::N || sy->n_spring != Topo::S) return false;
+    for (int s = 0; s < Topo::S; s++)
+        if (sy->si[s] != Topo::si(s) || sy->sj[s] != Topo::sj(s)) return false;
+    return true;
+}
+
+int pkg_variant(const wg_pkg_system* sy) {
+    if (pkg_matches<PkgLeg2>(sy)) return PkgLeg2::kId;
+    if (pkg_matches<PkgChain4>(sy)) return PkgChain4::kId;
+    if (pkg_matches<PkgChain3>(sy)) return PkgChain3::kId;
+    if (pkg_matches<PkgChain2>(sy)) return PkgChain2::kId;
+    return 0;
+}
+
+template <class Topo>
+static int launch_pkg_static(const PkgArgs& A, cudaStream_t s) {
+    pkg_update_static_kernel<Topo><<<(unsigned)((A.E + kBlock - 1) / kBlock), kBlock, 0, s>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "update_physics kernel (static) launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
 int launch_pkg_update(const wg_pkg_system* sy, const wg_pkg_params* p, float* pos, float* vel, float* old_a,
-                      int64_t E, int32_t n_steps, cudaStream_t s) {
+                      int64_t E, int32_t n_steps, bool force_generic, cudaStream_t s) {
     static thread_local PkgArgs A;
     memset(&A, 0, sizeof(A));
     for (int n = 0; n < sy->n_point; n++) {
@@ -28,6 +62,13 @@ int launch_pkg_update(const wg_pkg_system* sy, const wg_pkg_params* p, float* po
     A.restitution = p->restitution; A.friction = p->friction; A.dt = p->dt; A.min_dist = p->min_dist;
     A.ground = p->ground; A.n_point = sy->n_point; A.n_spring = sy->n_spring; A.n_steps = n_steps;
     A.pos = pos; A.vel = vel; A.old_a = old_a; A.E = E;
+    switch (force_generic ? 0 : pkg_variant(sy)) {
+        case PkgLeg2::kId:   return launch_pkg_static<PkgLeg2>(A, s);
+        case PkgChain4::kId: return launch_pkg_static<PkgChain4>(A, s);
+        case PkgChain3::kId: return launch_pkg_static<PkgChain3>(A, s);
+        case PkgChain2::kId: return launch_pkg_static<PkgChain2>(A, s);
+        default: break;
+    }
     const size_t smem = sizeof(float) * (size_t)(9 * sy->n_point) * (kBlock + 1);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(pkg_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

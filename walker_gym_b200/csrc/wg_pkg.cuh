@@ -37,9 +37,15 @@ struct PkgArgs {
 //   p2.anti_forced(p1, f_size): dir = p1 - p2, a2 += ((-f_size * dir) / max(|dir|, r)) / m2
 // p2 - p1 == -(p1 - p2) exactly and every operation is sign-symmetric, so the force on p1 is the exact
 // negation of the force on p2 and the norm is evaluated once.
-template <class Store>
-__device__ __forceinline__ void pkg_spring(const PkgArgs& A, Store& st, int sp) {
-    const int i = A.si[sp], j = A.sj[sp];
+struct PkgRuntimeTopo {
+    const uint8_t* si_; const uint8_t* sj_;
+    __device__ __forceinline__ int si(int k) const { return si_[k]; }
+    __device__ __forceinline__ int sj(int k) const { return sj_[k]; }
+};
+
+template <class Topo, class Store>
+__device__ __forceinline__ void pkg_spring(const Topo& topo, const PkgArgs& A, Store& st, int sp) {
+    const int i = topo.si(sp), j = topo.sj(sp);
     const float d0 = st.pos(i, 0) - st.pos(j, 0), d1 = st.pos(i, 1) - st.pos(j, 1), d2 = st.pos(i, 2) - st.pos(j, 2);
     const float L = np_norm3(d0, d1, d2);
     const float dx = L - A.srest[sp];
@@ -101,6 +107,7 @@ pkg_update_kernel(const __grid_constant__ PkgArgs A) {
     const int64_t e = (int64_t)blockIdx.x * kBlock + tid;
     if (e >= E) return;
     SmemStore st{ smem + tid, PITCH, P };
+    const PkgRuntimeTopo topo{ A.si, A.sj };
     for (int r = 0; r < 3 * P; r++) {
         st.base[r * PITCH] = A.pos[(int64_t)r * E + e];
         st.base[(3 * P + r) * PITCH] = A.vel[(int64_t)r * E + e];
@@ -112,13 +119,49 @@ pkg_update_kernel(const __grid_constant__ PkgArgs A) {
             st.acc(n, 1) = fixed ? 0.0f : A.ga[n * 3 + 1];
             st.acc(n, 2) = fixed ? 0.0f : A.ga[n * 3 + 2];
         }
-        for (int sp = 0; sp < S; sp++) pkg_spring(A, st, sp);               // (:149-150)
+        for (int sp = 0; sp < S; sp++) pkg_spring(topo, A, st, sp);         // (:149-150)
         for (int n = 0; n < P; n++) pkg_point(A, st, n);
     }
     for (int r = 0; r < 3 * P; r++) {
         A.pos[(int64_t)r * E + e] = st.base[r * PITCH];
         A.vel[(int64_t)r * E + e] = st.base[(3 * P + r) * PITCH];
         if (A.old_a) A.old_a[(int64_t)r * E + e] = st.base[(6 * P + r) * PITCH];
+    }
+}
+
+// Register-resident specialisation for small bodies the reference ships (compile-time endpoints): every state
+// element has a static register, the n_steps loop runs without touching memory.
+template <class Topo>
+__global__ void __launch_bounds__(kBlock, Topo::N <= 4 ? 6 : 4)
+pkg_update_static_kernel(const __grid_constant__ PkgArgs A) {
+    constexpr int P = Topo::N, S = Topo::S;
+    const int64_t E = A.E;
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= E) return;
+    const Topo topo;
+    RegStore<P, 0> st;
+#pragma unroll
+    for (int r = 0; r < 3 * P; r++) {
+        st.p_[r / 3][r % 3] = A.pos[(int64_t)r * E + e];
+        st.v_[r / 3][r % 3] = A.vel[(int64_t)r * E + e];
+    }
+    for (int t = 0; t < A.n_steps; t++) {
+#pragma unroll
+        for (int n = 0; n < P; n++) {
+            const bool fixed = (A.fixed_mask >> n) & 1u;
+#pragma unroll
+            for (int c = 0; c < 3; c++) st.a_[n][c] = fixed ? 0.0f : A.ga[n * 3 + c];
+        }
+#pragma unroll
+        for (int sp = 0; sp < S; sp++) pkg_spring(topo, A, st, sp);
+#pragma unroll
+        for (int n = 0; n < P; n++) pkg_point(A, st, n);
+    }
+#pragma unroll
+    for (int r = 0; r < 3 * P; r++) {
+        A.pos[(int64_t)r * E + e] = st.p_[r / 3][r % 3];
+        A.vel[(int64_t)r * E + e] = st.v_[r / 3][r % 3];
+        if (A.old_a) A.old_a[(int64_t)r * E + e] = st.a_[r / 3][r % 3];
     }
 }
 
