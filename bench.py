@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
     ap.add_argument("--policy", default="fused-fp32", choices=["fused-fp32", "fused-tf32", "torch"],
                     help="config 5: wg_policy_act (3xTF32 float32-grade / plain TF32 tensor-core MLP) or torch ops")
+    ap.add_argument("--probe-stream", action="store_true",
+                    help="measure the HBM rate of a pure streaming kernel with the step kernel's read:write mix and exit")
     ap.add_argument("--steps-per-launch", type=int, default=1, help="config 6: update_physics calls fused in one launch")
     ap.add_argument("--pkg-body", default="box", help="config 6: body builder of gym/optimized_walker/walker.py")
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5, 6],
@@ -468,8 +470,33 @@ def run_rollout(args, rank, world, dev):
         dist.destroy_process_group()
 
 
+def probe_stream():
+    """HBM rate of pure streaming kernels (wg_stream_probe) at several read : write mixes, 2^20 threads."""
+    import torch
+    from walker_gym_b200 import _lib
+    lib, dev, n = _lib.load(), torch.device("cuda", 0), 1 << 20
+    src = torch.zeros(32 * n * 4, dtype=torch.float32, device=dev)
+    dst = torch.zeros(32 * n * 4, dtype=torch.float32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    out = {}
+    for name, (R, W) in {"copy 16:16": (16, 16), "balance 7.5:16.8 (120 B read, 269 B written per env)": (7, 17),
+                         "box 8:17.8": (8, 18), "read only 24:0": (24, 0), "write only 0:24": (0, 24)}.items():
+        for _ in range(5):
+            lib.wg_stream_probe(src.data_ptr(), dst.data_ptr(), n, R, W, stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(200):
+            lib.wg_stream_probe(src.data_ptr(), dst.data_ptr(), n, R, W, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = round(200 * n * 16 * (R + W) / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)
+    print(json.dumps({"probe": "wg_stream_probe, 2^20 threads x 16-byte vectors, GB/s", "hbm_peak_measured": hbm_peak()[0], **out}))
+
+
 def main():
     args = parse()
+    if args.probe_stream:
+        return probe_stream()
     if args.impl == "reference":
         run_reference(args)
     else:

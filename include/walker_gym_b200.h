@@ -278,6 +278,13 @@ int wg_policy_act(const wg_mlp_policy* pol, const float* obs, int32_t obs_layout
 int wg_gae(const float* rewards, const float* values, const uint8_t* dones, float* advantages, float* returns,
            int32_t horizon, int64_t n_env, float gamma, float lam, float reward_clip, void* cuda_stream);
 
+/*
+ * Measurement aid (bench.py --probe-stream): n_threads threads each read vec_reads and write vec_writes 16-byte
+ * vectors from / to coalesced planes src[k][n_threads], dst[k][n_threads] and do nothing else.  Gives the HBM rate
+ * that a kernel with the step kernel's read : write mix can reach on this GPU.
+ */
+int wg_stream_probe(const float* src, float* dst, int64_t n_threads, int32_t vec_reads, int32_t vec_writes, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,7 +83,7 @@ TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH = 0, 1, 2
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
            "wg_set_tuning", "wg_packed_state_floats",
            "wg_step", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics", "wg_pkg_kernel_variant",
-           "wg_policy_act", "wg_gae")
+           "wg_policy_act", "wg_gae", "wg_stream_probe")
 
 _lib = None
 
@@ -129,6 +129,8 @@ def load():
     lib.wg_policy_act.argtypes = [P(WgMlpPolicy), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
                                   C.c_void_p]
+    lib.wg_stream_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.wg_stream_probe.restype = C.c_int
     lib.wg_gae.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                            C.c_float, C.c_float, C.c_float, C.c_void_p]
     for name in ("wg_obs_dim", "wg_kernel_variant", "wg_force_generic", "wg_step", "wg_reset",

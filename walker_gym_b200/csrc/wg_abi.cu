@@ -10,6 +10,7 @@
 
 namespace wg {
 int launch_policy(const PolicyArgs& A, int precision, cudaStream_t s);
+int launch_stream_probe(const float* src, float* dst, int64_t n, int R, int W, cudaStream_t s);
 int launch_gae(const float* rewards, const float* values, const uint8_t* dones, float* adv, float* ret, int T, int64_t E,
                float gamma, float lam, float clip, cudaStream_t s);
 
@@ -207,6 +208,12 @@ int wg_policy_act(const wg_mlp_policy* pol, const float* obs, int32_t obs_layout
     A.obs_scale = pol->obs_scale; A.obs_clip = pol->obs_clip;
     A.seed_lo = seed_lo; A.seed_hi = seed_hi; A.step_index = step_index; A.env_offset = env_offset;
     return launch_policy(A, pol->precision, (cudaStream_t)cuda_stream);
+}
+
+int wg_stream_probe(const float* src, float* dst, int64_t n_threads, int32_t vec_reads, int32_t vec_writes, void* cuda_stream) {
+    if (!src || !dst || n_threads < 0 || vec_reads < 0 || vec_writes < 0) return fail(WG_ERR_BAD_ARG, "bad argument to wg_stream_probe%s");
+    if (n_threads == 0) return WG_OK;
+    return launch_stream_probe(src, dst, n_threads, vec_reads, vec_writes, (cudaStream_t)cuda_stream);
 }
 
 int wg_gae(const float* rewards, const float* values, const uint8_t* dones, float* advantages, float* returns,

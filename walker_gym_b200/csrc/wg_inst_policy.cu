@@ -38,6 +38,24 @@ int launch_policy(const PolicyArgs& A, int precision, cudaStream_t s) {
 #undef WG_POL
 }
 
+// Streaming probe: every thread reads R and writes W 16-byte vectors (coalesced planes), nothing else.  Measures the
+// HBM rate a kernel with the step kernel's read : write mix can reach at all (bench.py --probe-stream).
+__global__ void __launch_bounds__(128) stream_probe_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                                                           int64_t n, int R, int W) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < R; k++) { const float4 v = src[(int64_t)k * n + i]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    for (int k = 0; k < W; k++) { acc.x += 1.0f; dst[(int64_t)k * n + i] = acc; }
+}
+int launch_stream_probe(const float* src, float* dst, int64_t n, int R, int W, cudaStream_t s) {
+    stream_probe_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(reinterpret_cast<const float4*>(src),
+                                                                    reinterpret_cast<float4*>(dst), n, R, W);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "stream probe launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
 int launch_gae(const float* rewards, const float* values, const uint8_t* dones, float* adv, float* ret, int T, int64_t E,
                float gamma, float lam, float clip, cudaStream_t s) {
     gae_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(rewards, values, dones, adv, ret, T, E, gamma, lam, clip);
