@@ -378,3 +378,39 @@ def test_empty_batch_is_a_no_op():
     buf.pos = buf.vel = buf.mx = buf.steps = z.data_ptr()
     assert lib.wg_step(C.byref(topo), C.byref(prm), C.byref(buf), 0, None) == 0
     assert lib.wg_reset(C.byref(topo), C.byref(prm), C.byref(buf), 0, 1, None, None) == 0
+
+
+def test_huge_batch_64bit_indexing():
+    """2^26 + 3 Box-v0 envs in one launch: the observation buffer has more than 2^31 elements, so every index
+    that is not 64-bit would wrap.  The batch repeats a pattern of 4096 distinct envs (no auto-reset, so nothing
+    depends on the env id): the last full pattern -- beyond the 2^31-element mark -- and the ragged tail must equal
+    the first pattern bit for bit, and the first pattern must equal the oracle."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    Pn, E, T = 4096, (1 << 26) + 3, 3
+    reps = (E + Pn - 1) // Pn
+    env = BatchedPhysicsEnv("Box-v0", E, "cuda:0", in3d=True, auto_reset=None, track_stats=False, initial_reset=False)
+    assert env.state_layout == "packed" and env.obs.numel() > 2 ** 31
+    rng = np.random.default_rng(42)
+    body = wo.make_body(spec_of("box_v0"))
+    prm = wo.make_params(in3d=True, auto_reset=0)
+    st = wo.init_state(body, Pn)
+    st["pos"] += rng.normal(0, 1.0, st["pos"].shape).astype(np.float32)
+    st["vel"] += rng.normal(0, 1.0, st["vel"].shape).astype(np.float32)
+    tile = lambda a: torch.from_numpy(a).to("cuda:0").repeat(1, reps)[:, :E]          # noqa: E731
+    env.set_state(pos=tile(st["pos"]), vel=tile(st["vel"]))
+    acts = [rng.uniform(-1, 1, (Pn, 4)).astype(np.float32) for _ in range(T)]
+    for t in range(T):
+        a = torch.from_numpy(acts[t]).to("cuda:0").repeat(reps, 1)[:E].contiguous()
+        obs, rew, done, _ = env.step(a)
+        out = wo.step(body, prm, st, acts[t], want_info=False)
+    torch.cuda.synchronize()
+    first = obs[:Pn]
+    last_full = obs[(reps - 2) * Pn:(reps - 1) * Pn]
+    tail = obs[(reps - 1) * Pn:]
+    assert (reps - 2) * Pn * env.obs_dim > 2 ** 31
+    assert torch.equal(first.view(torch.int32), last_full.view(torch.int32))
+    assert torch.equal(first[: tail.shape[0]].view(torch.int32), tail.view(torch.int32)) and tail.shape[0] == E - (reps - 1) * Pn
+    assert torch.equal(rew[:Pn].view(torch.int32), rew[(reps - 2) * Pn:(reps - 1) * Pn].view(torch.int32))
+    assert gu.same(first.cpu().numpy(), out["obs"]) and gu.same(rew[:Pn].cpu().numpy(), out["reward"])
+    assert gu.same(env.pos[:, (reps - 2) * Pn:(reps - 1) * Pn].cpu().numpy(), st["pos"])
