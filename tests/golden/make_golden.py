@@ -189,6 +189,34 @@ def main():
     engine.Point.clear()
 
 
+def f64_case(name, body, T, seed, env_kwargs):
+    """The reference driven the way its own demo loop drives it (gym/performance_demo.py:241-262): float64 ndarray
+    actions.  Muscle.x then silently becomes float64 and the muscle spring term is evaluated in double:
+    this is NOT reproduced bit for bit (the device computes in float32 on float32 actions); the fixture pins the
+    tolerance protocol of SURVEY 7.2 instead -- teacher-forced single steps within 1e-5, flags exact."""
+    spec = body if isinstance(body, dict) else {"balance-v0": wo.BALANCE, "box-v0": wo.BOX}[body.lower()]
+    rng = np.random.default_rng(7000 + seed)
+    actions = rng.uniform(-1, 1, (T, n_muscles(body)))                       # float64
+    noise = (np.random.default_rng(8000 + seed).standard_normal(4096) * env_kwargs.get("rand_sigma", 0.1)).astype(np.float32)
+    out = rh.rollout(body, actions, env_kwargs=env_kwargs, seed=seed, noise=noise)
+    assert out["x"].dtype == np.float64 and not np.array_equal(out["x"], out["x"].astype(np.float32).astype(np.float64))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), pos=out["pos"], vel=out["vel"], old_a=out["old_a"],
+                        x=out["x"], obs=out["obs"], reward=out["reward"], done=out["done"], contact_pre=out["contact_pre"],
+                        steps=out["steps"].astype(np.int32), reset_noise=out["reset_noise"].astype(np.float32),
+                        actions=actions, spec=np.array(json.dumps(spec)), env_kwargs=np.array(json.dumps(env_kwargs)))
+    print(f"{name}: T={T} float64 actions, done={int(out['done'].sum())} contact={int(out['contact_pre'].sum())} "
+          f"nonfinite={int((~np.isfinite(out['pos'])).sum())}")
+
+
+def main_f64():
+    f64_case("f64act_balance3d", "Balance-v0", 100, 0, dict(in3d=True))
+    f64_case("f64act_box2d", "Box-v0", 100, 1, dict(in3d=False))
+    phys_box = json.loads(json.dumps(wo.BOX))
+    for grp in ("muscles", "skeletons"):
+        phys_box[grp] = [(i, j, {"k": -1000}) for i, j, _ in phys_box[grp]]
+    f64_case("f64act_box3d_physical_sign", phys_box, 100, 2, dict(in3d=True))
+
+
 # ---- L2: the package lineage's Environment.update_physics (gym/optimized_walker/env.py:135-184) ------
 L2_CHAIN = {   # a pinned rope-and-rod chain swinging into the ground: DingPoint, string springs, explicit rest length
     "points": [(1.0, (0, 50, 0), (0, 0, 0), True), (2.0, (30, 40, 0), (1, 0, 0.5), False),
@@ -270,4 +298,5 @@ if __name__ == "__main__":
     import warnings
     warnings.filterwarnings("ignore", category=RuntimeWarning)
     main()
+    main_f64()
     main_l2()

@@ -21,7 +21,11 @@ def golden_names(prefix=""):
 
 
 def trajectory_names():
-    return [n for n in golden_names() if not n.startswith(("batch_", "compat_", "l2_", "env_state_"))]
+    return [n for n in golden_names() if not n.startswith(("batch_", "compat_", "l2_", "env_state_", "f64act_"))]
+
+
+def f64_names():
+    return golden_names("f64act_")
 
 
 def l2_names():

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import golden_util as gu
-from test_oracle_golden import replay_batch, replay_trajectory
+from test_oracle_golden import replay_batch, replay_f64_free_running, replay_f64_teacher_forced, replay_trajectory
 
 pytestmark = pytest.mark.gpu
 
@@ -49,3 +49,16 @@ def test_cuda_kernel_variants_match_reference_batch(stepper, name, variant):
     stepper.use_tma = variant.startswith("tma")
     stepper.obs_layout = 1 if variant.endswith("feature") else 0
     assert replay_batch(gu.load(name), stepper) == []
+
+
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("name", gu.f64_names())
+def test_cuda_float64_actions_teacher_forced(stepper, name, generic):
+    """Reference driven with float64 ndarray actions (its own demo loop): single steps within 1e-5, flags exact."""
+    stepper.force_generic = generic
+    worst, worst_acc, flags = replay_f64_teacher_forced(gu.load(name), stepper)
+    assert flags == 0 and worst < 1e-5 and worst_acc < 1e-4, (worst, worst_acc, flags)
+
+
+def test_cuda_float64_actions_free_running_100_steps(stepper):
+    assert replay_f64_free_running(gu.load("f64act_box3d_physical_sign"), stepper, 100) < 1e-3

@@ -135,3 +135,69 @@ def replay_l2(g, stepper, chunk=1):
 def test_oracle_matches_reference_package_physics(name, chunk):
     """L2: Environment.update_physics of gym/optimized_walker/env.py, bit for bit."""
     assert replay_l2(gu.load_l2(name), wo, chunk) is None
+
+
+# ---- float64 actions: the tolerance protocol (SURVEY 7.2) ---------------------------------------------------------
+def rel_err(a, b):
+    """max |a - b| / max |b| over finite reference entries (the north_star's "relative" state error)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    fin = np.isfinite(b)
+    if not fin.any():
+        return 0.0
+    return float(np.abs(a[fin] - b[fin]).max() / max(np.abs(b[fin]).max(), 1e-30))
+
+
+def replay_f64_teacher_forced(g, stepper):
+    """The reference was driven with float64 ndarray actions, which silently turns Muscle.x and the muscle spring
+    term into float64; the library computes in float32 on float32(action).  Every step is re-seeded
+    from the reference's state (x rounded to float32) and advanced once: the float32 state (positions, velocities,
+    muscle lengths) and the reward within 1e-5 relative (north_star's single-step tolerance), the accelerations --
+    differences of large spring forces, and with them the observation that carries them -- within 1e-4, force-phase
+    contact and done flags exact.  Returns (worst state error, worst acceleration/observation error, flag mismatches)."""
+    spec, kw = g["spec"], g["env_kwargs"]
+    body = stepper.make_body(spec)
+    N = body.n_mass
+    prm = stepper.make_params(**kw)
+    st = stepper.init_state(body, 1)
+    worst, worst_acc, flags = 0.0, 0.0, 0
+    for t in range(len(g["actions"])):
+        st["pos"][:] = gu.soa(g["pos"][t])
+        st["vel"][:] = gu.soa(g["vel"][t])
+        st["mx"][:, 0] = g["x"][t].astype(np.float32)
+        st["steps"][:] = 0 if t == 0 else int(g["steps"][t - 1])
+        out = stepper.step(body, prm, st, g["actions"][t:t + 1].astype(np.float32))
+        if not np.isfinite(g["pos"][t + 1]).all():
+            break
+        worst = max(worst, rel_err(gu.aos(st["pos"], N)[0], g["pos"][t + 1]), rel_err(gu.aos(st["vel"], N)[0], g["vel"][t + 1]),
+                    rel_err(st["mx"][:, 0], g["x"][t + 1]), rel_err(out["reward"][0], g["reward"][t]))
+        worst_acc = max(worst_acc, rel_err(gu.aos(st["old_a"], N)[0], g["old_a"][t + 1]), rel_err(out["obs"][0], g["obs"][t + 1]))
+        flags += int(bool(out["done"][0]) != bool(g["done"][t]))
+        flags += int(not gu.same(gu.mask_bits(out["contact_pre"], N)[0], g["contact_pre"][t]))
+    return worst, worst_acc, flags
+
+
+def replay_f64_free_running(g, stepper, T):
+    """Free-running T steps on float32(action) against the reference's float64-action trajectory."""
+    body = stepper.make_body(g["spec"])
+    N = body.n_mass
+    prm = stepper.make_params(**g["env_kwargs"])
+    st = stepper.init_state(body, 1)
+    st["pos"][:] = gu.soa(g["pos"][0])
+    st["vel"][:] = gu.soa(g["vel"][0])
+    worst = 0.0
+    for t in range(T):
+        stepper.step(body, prm, st, g["actions"][t:t + 1].astype(np.float32))
+        worst = max(worst, rel_err(gu.aos(st["pos"], N)[0], g["pos"][t + 1]))
+    return worst
+
+
+@pytest.mark.parametrize("name", gu.f64_names())
+def test_oracle_float64_actions_teacher_forced(name):
+    worst, worst_acc, flags = replay_f64_teacher_forced(gu.load(name), wo)
+    assert flags == 0 and worst < 1e-5 and worst_acc < 1e-4, (worst, worst_acc, flags)
+
+
+def test_oracle_float64_actions_free_running_100_steps():
+    """With physically signed springs (stable dynamics) the 100-step free-running trajectory stays within the
+    north_star's 1e-3 even though the reference ran its muscles in float64."""
+    assert replay_f64_free_running(gu.load("f64act_box3d_physical_sign"), wo, 100) < 1e-3
