@@ -86,12 +86,16 @@ __device__ __forceinline__ float pol_tanh(float x) {
 }
 
 // shared-memory planes of one weight matrix [n_rows][KP] (tf32 bit patterns), hi then lo
-template <bool SPLIT>
+// PERM_KT > 0: the layer-1 input permutation -- physical column 8*kk + 2*t + j holds feature (2*PERM_KT)*t + 2*kk + j,
+// so that the features one thread feeds into its A fragments over all k-tiles are contiguous in an observation row.
+template <bool SPLIT, int PERM_KT = 0>
 __device__ __forceinline__ void fill_plane(uint32_t* dst, int n_rows, int KP, int n_valid_rows, int k_valid,
                                            const float* __restrict__ w, int ld, const float* __restrict__ w_last) {
     // rows < n_valid_rows come from w (leading dimension ld); row n_valid_rows (if w_last) from w_last; rest 0
     for (int idx = threadIdx.x; idx < n_rows * KP; idx += blockDim.x) {
-        const int n = idx / KP, k = idx - n * KP;
+        const int n = idx / KP;
+        int k = idx - n * KP;
+        if (PERM_KT > 0) k = k < 8 * PERM_KT ? (2 * PERM_KT) * ((k & 7) >> 1) + 2 * (k >> 3) + (k & 1) : k_valid;
         float v = 0.0f;
         if (k < k_valid) {
             if (n < n_valid_rows) v = w[n * ld + k];
@@ -142,7 +146,7 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
     float* const BH = B2 + kPolH;
     float* const LS = BH + 8;
     const int D = A.D, M = A.M;
-    fill_plane<SPLIT>(W1, kPolH, KP1, kPolH, D, A.w1, D, nullptr);
+    fill_plane<SPLIT, KT1>(W1, kPolH, KP1, kPolH, D, A.w1, D, nullptr);
     fill_plane<SPLIT>(W2, kPolH, KP2, kPolH, kPolH, A.w2, kPolH, nullptr);
     fill_plane<SPLIT>(WH, 8, KP2, M, kPolH, A.w_mu, kPolH, A.w_v);
     for (int i = threadIdx.x; i < kPolH; i += blockDim.x) { B1[i] = A.b1[i]; B2[i] = A.b2[i]; }
@@ -181,7 +185,9 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
                 for (int i = 0; i < 4; i++) acc[mt][nt][i] = 0.0f;
 #pragma unroll
         for (int kk = 0; kk < KT1; kk++) {
-            const int f0 = 8 * kk + 2 * t, f1 = f0 + 1;               // k-slot t <-> feature f0, slot t+4 <-> f1
+            // k-slot t <-> feature f0, slot t+4 <-> f1; over the k-tiles thread t covers features [2*KT1*t, 2*KT1*(t+1)):
+            // contiguous bytes of a row-major observation row, so every 32-byte sector a warp touches is fully used
+            const int f0 = 2 * KT1 * t + 2 * kk, f1 = f0 + 1;
             uint32_t ahi[MT][4], alo[MT][4];
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
