@@ -414,3 +414,44 @@ def test_huge_batch_64bit_indexing():
     assert torch.equal(rew[:Pn].view(torch.int32), rew[(reps - 2) * Pn:(reps - 1) * Pn].view(torch.int32))
     assert gu.same(first.cpu().numpy(), out["obs"]) and gu.same(rew[:Pn].cpu().numpy(), out["reward"])
     assert gu.same(env.pos[:, (reps - 2) * Pn:(reps - 1) * Pn].cpu().numpy(), st["pos"])
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fuzz_random_bodies_and_parameters(seed):
+    """Seeded fuzz: random topology (1..32 masses, up to 96 springs), float / integer / unit masses, a DingPoint,
+    signed k, random environment parameters (gravity, global damping, ground height/spring/damper/friction, dt),
+    2-D or 3-D, run1 / run2, 1..4 substeps, both observation layouts, jitter or template auto-reset, and whichever
+    kernel the dispatcher picks (generic or mass-partitioned) -- bit for bit against the oracle."""
+    from walker_gym_b200 import BatchedPhysicsEnv, Creature, DingPoint, Muscle, Point, Skeleton
+    rng = np.random.default_rng(1234 + seed)
+    N = int(rng.integers(1, 33))
+    S = int(rng.integers(0, min(96, N * (N - 1) // 2) + 1))
+    M = int(rng.integers(0, min(S, 12) + 1))
+    spec = _random_spec(rng, N, S, M)
+    if rng.random() < 0.5:                                     # integer-only masses: the exact small-integer division path
+        spec["points"] = [(float(rng.integers(1, 9)), p, f) for _, p, f in spec["points"]]
+    in3d = bool(rng.random() < 0.6)
+    env_kw = dict(in3d=in3d, g=float(rng.choice([100, 9.8, 0, 250.5])), dampk=float(rng.choice([0, 0, 0.5, 3])),
+                  ground_high=float(rng.choice([0, -20, 35.5])), ground_k=float(rng.choice([1000, 0, 321])),
+                  ground_damp=float(rng.choice([100, 0, 12.5])), friction=float(rng.choice([100, 0, 7])),
+                  rand_sigma=float(rng.choice([0.1, 1.0])), time_step=float(rng.choice([0.01, 0.003])))
+    k_sub = int(rng.integers(1, 5))
+    integrator = "run2" if rng.random() < 0.3 else "run1"
+    auto = str(rng.choice(["template", "jitter"]))
+    layout = str(rng.choice(["row", "feature"]))
+    Point.clear()
+    try:
+        pts = [DingPoint(m, list(p)) if f else Point(m, list(p), [0, 0, 0]) for m, p, f in spec["points"]]
+        cr = Creature(pts, [Muscle(pts[i], pts[j], **kw) for i, j, kw in spec["muscles"]],
+                      [Skeleton(pts[i], pts[j], **kw) for i, j, kw in spec["skeletons"]])
+        E = int(rng.integers(1, 700))
+        env = BatchedPhysicsEnv(cr, E, "cuda:0", auto_reset=auto, max_steps=4, k_sub=k_sub, seed=seed, obs_layout=layout,
+                                integrator=integrator, keep_old_a=True, track_info=True, track_contacts=True,
+                                initial_reset=False, **env_kw)
+        body = wo.make_body(spec)
+        prm = wo.make_params(auto_reset={"jitter": 1, "template": 2}[auto], max_steps=4, k_sub=k_sub, seed=seed,
+                             integrator=1 if integrator == "run2" else 0, **env_kw)
+        st = wo.init_state(body, E)
+        run_lockstep(env, body, prm, st, 10, rng, noise_reset=True)
+    finally:
+        Point.clear()
