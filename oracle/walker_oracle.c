@@ -176,9 +176,25 @@ void wgo_normal3(uint32_t seed_lo, uint32_t seed_hi, uint32_t env, uint32_t step
 
 /* ---- the step ----------------------------------------------------------------- */
 
+/* "x64" mode: the reference driven with float64 ndarray actions (its own demo loop,
+ * gym/performance_demo.py:241-262).  `self.x += a` (optimized_walker.py:33) then makes Muscle.x an np.float64, and
+ * NumPy's promotion rules evaluate the muscle's spring term in double: dx = float64(L) - x, f_size = -dx * k,
+ * force = f_size * direction (a float64 array), and Point.forced adds force / m to the float32 accumulator in
+ * double, rounding once (:48-59 + optimized_engine.py:104-106).  A muscle that regulation() clamped (:27-30) holds
+ * the limit object instead -- an np.float32 (or the python float the user passed) -- and is back on the float32
+ * path until the next action.  So every muscle carries its length as a double plus a "weak" bit. */
+typedef struct {
+    double sk_d[WGO_MAX_SPRING];                          /* float(k) */
+    double x0_d[WGO_MAX_SPRING];                          /* originx as the object the constructor kept */
+    double mlo_d[WGO_MAX_SPRING], mhi_d[WGO_MAX_SPRING];  /* originx * minl, originx * maxl as the objects max()/min() compare */
+} wgo_x64;
+
 typedef struct {
     float pos[WGO_MAX_MASS][3], vel[WGO_MAX_MASS][3], acc[WGO_MAX_MASS][3], old_a[WGO_MAX_MASS][3];
     float mx[WGO_MAX_SPRING];
+    double mx64[WGO_MAX_SPRING];      /* x64 mode only */
+    uint8_t mxw[WGO_MAX_SPRING];      /* x64 mode: 1 = float32-typed ("weak") length: float32 arithmetic */
+    const wgo_x64 *xb;                /* NULL = float32 mode */
 } env_state;
 
 /* Muscle.run / Skeleton.run (optimized_walker.py:45-67, 84-106): identical bodies. */
@@ -194,9 +210,19 @@ static void spring_run(const wgo_body *b, const wgo_params *p, env_state *s, int
                                                                   (SURVEY 0.4); physical sign == negative k */
     for (int c = 0; c < 3; c++) dir[c] = s->pos[j][c] - s->pos[i][c];   /* :52 */
     if (L > 0) for (int c = 0; c < 3; c++) dir[c] = dir[c] / L;         /* :53-54 */
+    if (s->xb && sp < b->n_muscle && !s->mxw[sp]) {
+        /* np.float64 length: dx, f_size and force in double; forced() adds force / m in double */
+        double dx64 = (double)L - s->mx64[sp];
+        double fs64 = (-dx64) * s->xb->sk_d[sp];
+        double F64[3], nF64[3];
+        for (int c = 0; c < 3; c++) { F64[c] = fs64 * (double)dir[c]; nF64[c] = -F64[c]; }
+        forced_list(s->acc[i], F64, b->mass[i], b->fixed[i]);
+        forced_list(s->acc[j], nF64, b->mass[j], b->fixed[j]);
+    } else {
     for (int c = 0; c < 3; c++) { F[c] = fs * dir[c]; nF[c] = -F[c]; }  /* :57 */
     forced_f32(s->acc[i], F, mi, b->fixed[i]);                          /* :58 */
     forced_f32(s->acc[j], nF, mj, b->fixed[j]);                         /* :59 */
+    }
     for (int c = 0; c < 3; c++) dv[c] = s->vel[i][c] - s->vel[j][c];    /* :62 */
     float dk = np_dot3(dv, dir);                                        /* :63 */
     float cdk = dk * b->sdamp[sp];                                      /* :64 (dk*dampk)*direction */
@@ -304,7 +330,10 @@ static void apply_reset(const wgo_body *b, const wgo_params *p, env_state *s, in
             for (int c = 0; c < 3; c++) {
                 s->pos[n][c] = b->tmpl_pos[n * 3 + c]; s->vel[n][c] = 0.0f; s->old_a[n][c] = 0.0f;
             }
-        for (int m = 0; m < b->n_muscle; m++) s->mx[m] = b->srest[m];
+        for (int m = 0; m < b->n_muscle; m++) {
+            s->mx[m] = b->srest[m];
+            if (s->xb) { s->mx64[m] = s->xb->x0_d[m]; s->mxw[m] = 1; }      /* a fresh Muscle: x = originx */
+        }
     }
     for (int n = 0; n < b->n_mass; n++) {
         float z[3];
@@ -327,14 +356,15 @@ static void apply_reset(const wgo_body *b, const wgo_params *p, env_state *s, in
  * Optional outputs may be NULL.  noise (if given) is the already-scaled jitter
  * [N*3][E] used by auto-reset instead of the Philox stream.
  */
-int wgo_step(const wgo_body *b, const wgo_params *p, int64_t E,
+static int step_impl(const wgo_body *b, const wgo_params *p, int64_t E,
              float *pos, float *vel, float *old_a, float *mx, int32_t *steps,
              const float *action, int32_t act_dim,
              float *obs, float *reward, uint8_t *done,
              uint32_t *contact_pre, uint32_t *contact_post,
              float *energy, float *centroid,
              float *ep_ret, float *fin_stats,
-             const float *noise) {
+             const float *noise,
+             const wgo_x64 *xb, double *mx64, uint8_t *mx_weak, const double *action64) {
     int N = b->n_mass, M = b->n_muscle;
     int D = wgo_obs_dim(b, p->in3d);
     if (N > WGO_MAX_MASS || b->n_spring > WGO_MAX_SPRING) return -1;
@@ -342,8 +372,20 @@ int wgo_step(const wgo_body *b, const wgo_params *p, int64_t E,
     for (int64_t e = 0; e < E; e++) {
         env_state s;
         load_env(b, &s, E, e, pos, vel, old_a, mx);
+        s.xb = xb;
         /* Creature.act: for i < min(M, len(a)): x += a; x = max(x, lo); x = min(x, hi) */
         int na = act_dim < M ? act_dim : M;
+        if (xb) {
+            for (int m = 0; m < M; m++) { s.mx64[m] = mx64[(int64_t)m * E + e]; s.mxw[m] = mx_weak[(int64_t)m * E + e]; }
+            for (int m = 0; m < na; m++) {
+                double x = s.mx64[m] + action64[e * act_dim + m];    /* anything + np.float64 -> np.float64 */
+                uint8_t weak = 0;
+                if (xb->mlo_d[m] > x) { x = xb->mlo_d[m]; weak = 1; }  /* max() returns the limit OBJECT: float32-typed */
+                if (xb->mhi_d[m] < x) { x = xb->mhi_d[m]; weak = 1; }
+                s.mx64[m] = x; s.mxw[m] = weak;
+            }
+            for (int m = 0; m < M; m++) s.mx[m] = (float)s.mx64[m];  /* float32 view: weak muscles, observation */
+        } else
         for (int m = 0; m < na; m++) {
             float x = s.mx[m] + action[e * act_dim + m];
             if (b->mlo[m] > x) x = b->mlo[m];       /* python max(x, lo): lo wins only if lo > x */
@@ -411,9 +453,38 @@ int wgo_step(const wgo_body *b, const wgo_params *p, int64_t E,
         steps[e] = st;
         if (obs) get_obs(b, p, &s, obs + e * D);
         store_env(b, &s, E, e, pos, vel, old_a, mx);
+        if (xb) for (int m = 0; m < M; m++) { mx64[(int64_t)m * E + e] = s.mx64[m]; mx_weak[(int64_t)m * E + e] = s.mxw[m]; }
     }
     return 0;
 }
+
+int wgo_step(const wgo_body *b, const wgo_params *p, int64_t E,
+             float *pos, float *vel, float *old_a, float *mx, int32_t *steps,
+             const float *action, int32_t act_dim,
+             float *obs, float *reward, uint8_t *done,
+             uint32_t *contact_pre, uint32_t *contact_post,
+             float *energy, float *centroid,
+             float *ep_ret, float *fin_stats,
+             const float *noise) {
+    return step_impl(b, p, E, pos, vel, old_a, mx, steps, action, act_dim, obs, reward, done, contact_pre, contact_post,
+                     energy, centroid, ep_ret, fin_stats, noise, NULL, NULL, NULL, NULL);
+}
+
+/* PhysicsEnv.step driven with float64 ndarray actions (x64 mode, see wgo_x64): mx64 [M][E] double and mx_weak [M][E]
+ * are the muscle lengths and their type bits (in/out); mx receives the float32 view. */
+int wgo_step_x64(const wgo_body *b, const wgo_x64 *xb, const wgo_params *p, int64_t E,
+                 float *pos, float *vel, float *old_a, float *mx, double *mx64, uint8_t *mx_weak, int32_t *steps,
+                 const double *action64, int32_t act_dim,
+                 float *obs, float *reward, uint8_t *done,
+                 uint32_t *contact_pre, uint32_t *contact_post,
+                 float *energy, float *centroid,
+                 float *ep_ret, float *fin_stats,
+                 const float *noise) {
+    if (!xb || !mx64 || !mx_weak || (act_dim > 0 && !action64)) return -1;
+    return step_impl(b, p, E, pos, vel, old_a, mx, steps, NULL, act_dim, obs, reward, done, contact_pre, contact_post,
+                     energy, centroid, ep_ret, fin_stats, noise, xb, mx64, mx_weak, action64);
+}
+int wgo_sizeof_x64(void) { return (int)sizeof(wgo_x64); }
 
 /* Explicit reset of the envs whose mask byte is non-zero (mask NULL = all). */
 int wgo_reset(const wgo_body *b, const wgo_params *p, int64_t E, int mode,
@@ -425,6 +496,7 @@ int wgo_reset(const wgo_body *b, const wgo_params *p, int64_t E, int mode,
         if (mask && !mask[e]) continue;
         env_state s;
         load_env(b, &s, E, e, pos, vel, old_a, mx);
+        s.xb = NULL;
         apply_reset(b, p, &s, mode, noise, E, e, p->step_index);
         steps[e] = 0;
         if (obs) get_obs(b, p, &s, obs + e * D);

@@ -52,6 +52,12 @@ class Params(C.Structure):
     ]
 
 
+class X64(C.Structure):
+    """``wgo_x64``: the double-typed objects the reference keeps once a float64 action made Muscle.x an np.float64."""
+    _fields_ = [("sk_d", C.c_double * MAX_SPRING), ("x0_d", C.c_double * MAX_SPRING),
+                ("mlo_d", C.c_double * MAX_SPRING), ("mhi_d", C.c_double * MAX_SPRING)]
+
+
 _lib = None
 
 
@@ -215,6 +221,55 @@ BOX = {
     "muscles": [(0, 1, {}), (0, 2, {}), (3, 1, {}), (3, 2, {})],
     "skeletons": [(1, 2, {})],
 }
+
+
+def make_x64(spec) -> X64:
+    """The python / NumPy objects the reference's Muscle keeps, as doubles: float(k); originx (np.float32 from
+    distant(), or the python float the user passed); originx * minl and originx * maxl as regulation() forms them."""
+    xb = X64()
+    P = [np.array(p[1], dtype=np.float32) for p in spec["points"]]
+    for s, (i, j, kw) in enumerate(list(spec["muscles"]) + list(spec["skeletons"])):
+        xb.sk_d[s] = float(kw.get("k", 1000))
+        x = kw.get("x")
+        if x is None:
+            x = np.linalg.norm(P[i] - P[j])                # np.float32
+        xb.x0_d[s] = float(x)
+        if s < len(spec["muscles"]):
+            xb.mlo_d[s] = float(x * kw.get("minl", 0.1))    # np.float32 * python float -> np.float32; python * python -> double
+            xb.mhi_d[s] = float(x * kw.get("maxl", 1.5))
+    return xb
+
+
+def init_x64(body: Body, xb: X64, E: int):
+    """mx64 [M, E] = originx, mx_weak [M, E] = 1 (a fresh Muscle holds the constructor's object)."""
+    M = body.n_muscle
+    x0 = np.array([xb.x0_d[m] for m in range(M)], np.float64)
+    return np.repeat(x0[:, None], E, 1).copy().reshape(M, E), np.ones((M, E), np.uint8)
+
+
+def step_x64(body: Body, xb: X64, prm: Params, st: dict, action64, *, want_info=True, noise=None):
+    """``PhysicsEnv.step`` with float64 actions [E, A]; ``st`` additionally holds ``mx64`` and ``mx_weak``."""
+    l = lib()
+    assert l.wgo_sizeof_x64() == C.sizeof(X64)
+    E = st["pos"].shape[1]
+    D = obs_dim(body, prm.in3d)
+    action64 = np.ascontiguousarray(action64, dtype=np.float64).reshape(E, -1)
+    out = dict(obs=np.zeros((E, D), np.float32), reward=np.zeros(E, np.float32), done=np.zeros(E, np.uint8),
+               contact_pre=np.zeros(E, np.uint32), contact_post=np.zeros(E, np.uint32))
+    if want_info:
+        out["energy"] = np.zeros(E, np.float32)
+        out["centroid"] = np.zeros((3, E), np.float32)
+    rc = l.wgo_step_x64(C.byref(body), C.byref(xb), C.byref(prm), C.c_int64(E),
+                        _ptr(st["pos"], C.c_float), _ptr(st["vel"], C.c_float), _ptr(st.get("old_a"), C.c_float),
+                        _ptr(st["mx"], C.c_float), _ptr(st["mx64"], C.c_double), _ptr(st["mx_weak"], C.c_uint8),
+                        _ptr(st["steps"], C.c_int32), _ptr(action64, C.c_double), C.c_int32(action64.shape[1]),
+                        _ptr(out["obs"], C.c_float), _ptr(out["reward"], C.c_float), _ptr(out["done"], C.c_uint8),
+                        _ptr(out["contact_pre"], C.c_uint32), _ptr(out["contact_post"], C.c_uint32),
+                        _ptr(out.get("energy"), C.c_float), _ptr(out.get("centroid"), C.c_float), None, None,
+                        _ptr(noise, C.c_float))
+    if rc != 0:
+        raise RuntimeError(f"wgo_step_x64 failed: {rc}")
+    return out
 
 
 # ---- L2 (package lineage): Environment.update_physics of gym/optimized_walker/env.py ------------------

@@ -189,21 +189,22 @@ def main():
     engine.Point.clear()
 
 
-def f64_case(name, body, T, seed, env_kwargs):
+def f64_case(name, body, T, seed, env_kwargs, scale=1.0, n_act=None, **kw):
     """The reference driven the way its own demo loop drives it (gym/performance_demo.py:241-262): float64 ndarray
     actions.  Muscle.x then silently becomes float64 and the muscle spring term is evaluated in double:
     this is NOT reproduced bit for bit (the device computes in float32 on float32 actions); the fixture pins the
     tolerance protocol of SURVEY 7.2 instead -- teacher-forced single steps within 1e-5, flags exact."""
     spec = body if isinstance(body, dict) else {"balance-v0": wo.BALANCE, "box-v0": wo.BOX}[body.lower()]
     rng = np.random.default_rng(7000 + seed)
-    actions = rng.uniform(-1, 1, (T, n_muscles(body)))                       # float64
+    actions = rng.uniform(-1, 1, (T, n_act or n_muscles(body))) * scale      # float64
     noise = (np.random.default_rng(8000 + seed).standard_normal(4096) * env_kwargs.get("rand_sigma", 0.1)).astype(np.float32)
-    out = rh.rollout(body, actions, env_kwargs=env_kwargs, seed=seed, noise=noise)
+    out = rh.rollout(body, actions, env_kwargs=env_kwargs, seed=seed, noise=noise, **kw)
     assert out["x"].dtype == np.float64 and not np.array_equal(out["x"], out["x"].astype(np.float32).astype(np.float64))
     np.savez_compressed(os.path.join(HERE, name + ".npz"), pos=out["pos"], vel=out["vel"], old_a=out["old_a"],
                         x=out["x"], obs=out["obs"], reward=out["reward"], done=out["done"], contact_pre=out["contact_pre"],
                         steps=out["steps"].astype(np.int32), reset_noise=out["reset_noise"].astype(np.float32),
-                        actions=actions, spec=np.array(json.dumps(spec)), env_kwargs=np.array(json.dumps(env_kwargs)))
+                        actions=actions, spec=np.array(json.dumps(spec)), env_kwargs=np.array(json.dumps(env_kwargs)),
+                        **{k: np.array(int(v)) for k, v in kw.items() if k in ("max_steps", "reset_on_done", "k_sub")})
     print(f"{name}: T={T} float64 actions, done={int(out['done'].sum())} contact={int(out['contact_pre'].sum())} "
           f"nonfinite={int((~np.isfinite(out['pos'])).sum())}")
 
@@ -215,6 +216,18 @@ def main_f64():
     for grp in ("muscles", "skeletons"):
         phys_box[grp] = [(i, j, {"k": -1000}) for i, j, _ in phys_box[grp]]
     f64_case("f64act_box3d_physical_sign", phys_box, 100, 2, dict(in3d=True))
+    # clamps on most steps (narrow limits, large actions), a python-float rest length, float masses, a DingPoint,
+    # fewer action columns than muscles, physically signed springs so the run stays finite
+    clampy = {"points": [(2.5, (-30, 40, 5), False), (0.7, (35, 60, -3), False), (7, (0, 5, 0), False),
+                         (1, (10, 90, 2), True), (3, (-60, 20, 0), False)],
+              "muscles": [(0, 2, {"k": -800, "dampk": 15, "minl": 0.9, "maxl": 1.05}),
+                          (1, 2, {"x": 70.3, "k": -1200.5, "dampk": 25, "minl": 0.95, "maxl": 1.1}),
+                          (4, 0, {"k": -300, "minl": 0.5, "maxl": 2.0}), (3, 1, {"k": -150})],
+              "skeletons": [(0, 1, {"k": -500}), (1, 3, {"k": -2000, "dampk": 5}), (4, 2, {"x": 61.5, "k": -900})]}
+    f64_case("f64act_clamps_custom3d", clampy, 150, 3, dict(in3d=True, g=30, ground_high=-10), scale=6.0, n_act=3)
+    # substeps and jitter auto-reset under float64 actions (as-written springs)
+    f64_case("f64act_autoreset_box3d", "Box-v0", 40, 4, dict(in3d=True), max_steps=6, reset_on_done=True, k_sub=1)
+    f64_case("f64act_substeps_balance2d", "Balance-v0", 30, 5, dict(in3d=False), k_sub=3)
 
 
 # ---- L2: the package lineage's Environment.update_physics (gym/optimized_walker/env.py:135-184) ------

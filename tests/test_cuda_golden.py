@@ -51,8 +51,11 @@ def test_cuda_kernel_variants_match_reference_batch(stepper, name, variant):
     assert replay_batch(gu.load(name), stepper) == []
 
 
+from test_oracle_golden import TOLERANCE_FIXTURES  # noqa: E402
+
+
 @pytest.mark.parametrize("generic", [False, True])
-@pytest.mark.parametrize("name", gu.f64_names())
+@pytest.mark.parametrize("name", TOLERANCE_FIXTURES)
 def test_cuda_float64_actions_teacher_forced(stepper, name, generic):
     """Reference driven with float64 ndarray actions (its own demo loop): single steps within 1e-5, flags exact."""
     stepper.force_generic = generic

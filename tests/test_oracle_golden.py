@@ -191,7 +191,10 @@ def replay_f64_free_running(g, stepper, T):
     return worst
 
 
-@pytest.mark.parametrize("name", gu.f64_names())
+TOLERANCE_FIXTURES = ["f64act_balance3d", "f64act_box2d", "f64act_box3d_physical_sign"]
+
+
+@pytest.mark.parametrize("name", TOLERANCE_FIXTURES)
 def test_oracle_float64_actions_teacher_forced(name):
     worst, worst_acc, flags = replay_f64_teacher_forced(gu.load(name), wo)
     assert flags == 0 and worst < 1e-5 and worst_acc < 1e-4, (worst, worst_acc, flags)
@@ -201,3 +204,71 @@ def test_oracle_float64_actions_free_running_100_steps():
     """With physically signed springs (stable dynamics) the 100-step free-running trajectory stays within the
     north_star's 1e-3 even though the reference ran its muscles in float64."""
     assert replay_f64_free_running(gu.load("f64act_box3d_physical_sign"), wo, 100) < 1e-3
+
+
+def replay_x64(g, stepper):
+    """Bit-exact replay of a float64-action trajectory in x64 mode (Muscle.x as double + type bit): positions,
+    velocities, accelerations, the float64 muscle lengths, observation (the reference's float64 observation rounded to
+    float32), reward, done, contact.  Returns the first mismatch or None."""
+    spec, kw = g["spec"], g["env_kwargs"]
+    body, xb = stepper.make_body(spec), stepper.make_x64(spec)
+    N = body.n_mass
+    in3d = bool(kw.get("in3d", False))
+    d = 3 if in3d else 2
+    prm_kw = dict(kw)
+    if g["max_steps"] is not None:
+        prm_kw["max_steps"] = g["max_steps"]
+    if g["k_sub"] is not None:
+        prm_kw["k_sub"] = g["k_sub"]
+    auto = 1 if g["reset_on_done"] else 0
+    prm = stepper.make_params(auto_reset=auto, **prm_kw)
+    st = stepper.init_state(body, 1)
+    st["mx64"], st["mx_weak"] = stepper.init_x64(body, xb, 1)
+    draws = g["reset_noise"].astype(np.float32)
+    cursor = 0
+
+    def next_noise():
+        nonlocal cursor
+        nz = np.zeros((N, 3), np.float32)
+        nz[:, :d] = draws[cursor:cursor + N * d].reshape(N, d)
+        cursor += N * d
+        return gu.soa(nz)
+
+    stepper.reset(body, prm, st, mode=1, noise=next_noise())
+    for t in range(len(g["actions"])):
+        nz = next_noise() if (auto and g["done"][t]) else (np.zeros((N * 3, 1), np.float32) if auto else None)
+        out = stepper.step_x64(body, xb, prm, st, g["actions"][t:t + 1], noise=nz)
+        checks = {
+            "pos": gu.same(gu.aos(st["pos"], N)[0], g["pos"][t + 1]),
+            "vel": gu.same(gu.aos(st["vel"], N)[0], g["vel"][t + 1]),
+            "old_a": gu.same(gu.aos(st["old_a"], N)[0], g["old_a"][t + 1]),
+            "x": gu.same(st["mx64"][:, 0], g["x"][t + 1]),
+            "obs": gu.same(out["obs"][0], g["obs"][t + 1].astype(np.float32)),
+            "reward": gu.same(out["reward"][0], np.float32(g["reward"][t])),
+            "done": bool(out["done"][0]) == bool(g["done"][t]),
+            "contact_pre": gu.same(gu.mask_bits(out["contact_pre"], N)[0], g["contact_pre"][t]),
+            "steps": int(st["steps"][0]) == int(g["steps"][t]),
+        }
+        bad = [k for k, ok in checks.items() if not ok]
+        if bad:
+            return f"step {t}: {bad}"
+    return None
+
+
+@pytest.mark.parametrize("name", gu.f64_names())
+def test_oracle_x64_mode_matches_reference_bit_for_bit(name):
+    """The reference driven with float64 ndarray actions -- its own demo loop -- reproduced exactly: NumPy promotes
+    the muscle spring term to double while Muscle.x is an np.float64 and drops back to float32 when regulation()
+    replaced it by a limit object."""
+    assert replay_x64(gu.load(name), wo) is None
+
+
+def test_x64_fixtures_exercise_the_type_switch():
+    g = gu.load("f64act_clamps_custom3d")
+    body, xb = wo.make_body(g["spec"]), wo.make_x64(g["spec"])
+    lo = np.array([xb.mlo_d[m] for m in range(body.n_muscle)])
+    hi = np.array([xb.mhi_d[m] for m in range(body.n_muscle)])
+    clamped = (g["x"][1:] == lo) | (g["x"][1:] == hi)
+    assert clamped[:, :3].any(axis=0).all() and (~clamped[:, :3]).any(axis=0).all()    # both types occur per acted muscle
+    assert (g["x"][1:, 3] == g["x"][0, 3]).all()                                       # the un-acted muscle never moves
+    assert gu.load("f64act_autoreset_box3d")["done"].sum() >= 3
