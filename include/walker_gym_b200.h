@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define WG_ABI_VERSION 1
+#define WG_ABI_VERSION 2
 #define WG_MAX_MASS 32
 #define WG_MAX_SPRING 96
 
@@ -117,7 +117,25 @@ typedef struct wg_buffers {
                                    that replays wg_step advance the Philox counter without new parameters */
     float*       state_packed;  /* in/out, optional: the packed state layout (see below).  When set, pos / vel /
                                    mx / steps / ep_ret are ignored (they live inside it) */
+    /* x64 mode only (wg_step_x64): */
+    double*      mx64;          /* in/out: muscle lengths as doubles, [m * E + e] */
+    uint8_t*     mx_weak;       /* in/out: 1 = the length is float32-typed (a fresh or just-clamped muscle), [m * E + e] */
+    const double* action64;     /* in: float64 actions, laid out like action */
 } wg_buffers;
+
+/*
+ * x64 mode: PhysicsEnv.step driven with float64 ndarray actions, which is what the reference's own demo loop does
+ * (gym/performance_demo.py:241-262: np.random.uniform).  `self.x += a` (gym/optimized_walker.py:33) then turns
+ * Muscle.x into an np.float64 and NumPy evaluates the muscle's spring term in double (dx, f_size, force, force / m
+ * added to the float32 accumulator in double); a muscle that regulation() clamped (:27-30) holds the limit object
+ * and is float32-typed until the next action.  These are the double-typed objects of that path, per spring:
+ */
+typedef struct wg_x64 {
+    double sk_d[WG_MAX_SPRING];     /* float(k) */
+    double x0_d[WG_MAX_SPRING];     /* originx: np.float32 distance, or the python float the user passed */
+    double mlo_d[WG_MAX_SPRING];    /* originx * minl as regulation() forms it (np.float32 or python float) */
+    double mhi_d[WG_MAX_SPRING];    /* originx * maxl */
+} wg_x64;
 
 /*
  * Packed state layout (only for bodies with a register-resident specialisation, wg_kernel_variant() in {1, 2}).
@@ -160,6 +178,15 @@ int wg_set_tuning(int key, int value);
  */
 int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf,
             int64_t n_env, void* cuda_stream);
+
+/*
+ * wg_step in x64 mode: buf->mx64 / mx_weak / action64 must be set (action is ignored; mx still receives the float32
+ * view of the lengths, which is what the float32 observation carries).  Bit-identical to the reference driven
+ * with float64 actions.  Runs the run-time-topology kernel (a compatibility path, not the throughput path).
+ * wg_reset does not touch mx64 / mx_weak: after a template reset the caller sets them to x0_d / 1.
+ */
+int wg_step_x64(const wg_topology* topo, const wg_x64* x64, const wg_params* prm, const wg_buffers* buf,
+                int64_t n_env, void* cuda_stream);
 
 /*
  * PhysicsEnv.reset (gym/optimized_env.py:53-68) for the envs whose mask byte is

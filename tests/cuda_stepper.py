@@ -180,3 +180,61 @@ def l2_step(sysm, prm, st, n_steps=1):
     torch.cuda.synchronize()
     for k in ("pos", "vel", "old_a"):
         st[k][...] = d[k].cpu().numpy()
+
+
+# ---- x64 mode (float64 actions) through wg_step_x64 ------------------------------------------------------------------
+def make_x64(spec):
+    import walker_oracle as wo
+    o = wo.make_x64(spec)
+    x = _lib.WgX64()
+    for k in range(_lib.MAX_SPRING):
+        x.sk_d[k], x.x0_d[k], x.mlo_d[k], x.mhi_d[k] = o.sk_d[k], o.x0_d[k], o.mlo_d[k], o.mhi_d[k]
+    return x
+
+
+def init_x64(body, xb, E):
+    M = body.n_muscle
+    x0 = np.array([xb.x0_d[m] for m in range(M)], np.float64)
+    return np.repeat(x0[:, None], E, 1).copy().reshape(M, E), np.ones((M, E), np.uint8)
+
+
+def step_x64(body, xb, prm, st, action64, *, want_info=True, noise=None):
+    lib = _lib.load()
+    E = st["pos"].shape[1]
+    D = obs_dim(body, prm.in3d)
+    d = _upload(st)
+    d64, dw = _dev(st["mx64"]), _dev(st["mx_weak"])
+    act = _dev(np.ascontiguousarray(action64, dtype=np.float64).reshape(E, -1))
+    f32 = dict(dtype=torch.float32, device=DEV)
+    out = dict(obs=torch.zeros((E, D) if obs_layout == 0 else (D, E), **f32), reward=torch.zeros(E, **f32),
+               done=torch.zeros(E, dtype=torch.uint8, device=DEV),
+               contact_pre=torch.zeros(E, dtype=torch.int32, device=DEV),
+               contact_post=torch.zeros(E, dtype=torch.int32, device=DEV))
+    if want_info:
+        out["energy"] = torch.zeros(E, **f32)
+        out["centroid"] = torch.zeros(3, E, **f32)
+    d_noise = _dev(noise)
+    b = _lib.WgBuffers()
+    b.pos, b.vel, b.old_a, b.mx, b.steps = (_ptr(d[k]) for k in ("pos", "vel", "old_a", "mx", "steps"))
+    if body.n_muscle == 0:
+        b.mx = b.steps
+        b.mx64, b.mx_weak = b.steps, b.steps
+    else:
+        b.mx64, b.mx_weak = _ptr(d64), _ptr(dw)
+    b.action64, b.act_dim, b.obs_layout = _ptr(act), act.shape[1], obs_layout
+    b.obs, b.reward, b.done = _ptr(out["obs"]), _ptr(out["reward"]), _ptr(out["done"])
+    b.contact_pre, b.contact_post = _ptr(out["contact_pre"]), _ptr(out["contact_post"])
+    b.energy, b.centroid, b.noise = _ptr(out.get("energy")), _ptr(out.get("centroid")), _ptr(d_noise)
+    rc = lib.wg_step_x64(C.byref(body.topo), C.byref(xb), C.byref(prm), C.byref(b), E, _stream())
+    _lib.check(rc, "wg_step_x64")
+    torch.cuda.synchronize()
+    _download(st, d)
+    if body.n_muscle:
+        st["mx64"][...] = d64.cpu().numpy()
+        st["mx_weak"][...] = dw.cpu().numpy()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    if obs_layout == 1:
+        res["obs"] = np.ascontiguousarray(res["obs"].T)
+    res["contact_pre"] = res["contact_pre"].astype(np.uint32)
+    res["contact_post"] = res["contact_post"].astype(np.uint32)
+    return res

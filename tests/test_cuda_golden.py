@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 import golden_util as gu
-from test_oracle_golden import replay_batch, replay_f64_free_running, replay_f64_teacher_forced, replay_trajectory
+from test_oracle_golden import (replay_batch, replay_f64_free_running, replay_f64_teacher_forced, replay_trajectory,
+                                replay_x64)
 
 pytestmark = pytest.mark.gpu
 
@@ -65,3 +66,13 @@ def test_cuda_float64_actions_teacher_forced(stepper, name, generic):
 
 def test_cuda_float64_actions_free_running_100_steps(stepper):
     assert replay_f64_free_running(gu.load("f64act_box3d_physical_sign"), stepper, 100) < 1e-3
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("name", gu.f64_names())
+def test_cuda_x64_mode_matches_reference_bit_for_bit(stepper, name, layout):
+    """wg_step_x64: the reference driven with float64 ndarray actions (its own demo loop), bit for bit -- float64
+    muscle lengths, the float32/float64 type switch at the limits, python-float rest lengths, partial actions,
+    auto-reset, substeps."""
+    stepper.obs_layout = layout
+    assert replay_x64(gu.load(name), stepper) is None

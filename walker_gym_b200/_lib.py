@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 MAX_MASS, MAX_SPRING = 32, 96
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WG_LIB_PATH", os.path.join(_HERE, "libwalkergym_b200.so"))   # override: tuning experiments
@@ -52,7 +52,14 @@ class WgBuffers(C.Structure):
         ("energy", C.c_void_p), ("centroid", C.c_void_p),
         ("ep_ret", C.c_void_p), ("fin_stats", C.c_void_p), ("noise", C.c_void_p),
         ("step_counter", C.c_void_p), ("state_packed", C.c_void_p),
+        ("mx64", C.c_void_p), ("mx_weak", C.c_void_p), ("action64", C.c_void_p),      # x64 mode (wg_step_x64)
     ]
+
+
+class WgX64(C.Structure):
+    """``wg_x64``: the double-typed objects of a Muscle once a float64 action made its length an np.float64."""
+    _fields_ = [("sk_d", C.c_double * MAX_SPRING), ("x0_d", C.c_double * MAX_SPRING),
+                ("mlo_d", C.c_double * MAX_SPRING), ("mhi_d", C.c_double * MAX_SPRING)]
 
 
 class WgPkgSystem(C.Structure):
@@ -82,7 +89,7 @@ TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH = 0, 1, 2
 
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
            "wg_set_tuning", "wg_packed_state_floats",
-           "wg_step", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics", "wg_pkg_kernel_variant",
+           "wg_step", "wg_step_x64", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics", "wg_pkg_kernel_variant",
            "wg_policy_act", "wg_gae", "wg_stream_probe")
 
 _lib = None
@@ -118,6 +125,8 @@ def load():
     lib.wg_packed_state_floats.argtypes = [P(WgTopology), C.c_int64]
     lib.wg_packed_state_floats.restype = C.c_int64
     lib.wg_step.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_void_p]
+    lib.wg_step_x64.argtypes = [P(WgTopology), P(WgX64), P(WgParams), P(WgBuffers), C.c_int64, C.c_void_p]
+    lib.wg_step_x64.restype = C.c_int
     lib.wg_reset.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     lib.wg_stats_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.wg_step_host.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64,

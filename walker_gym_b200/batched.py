@@ -69,7 +69,7 @@ class BatchedPhysicsEnv:
                  friction=100, rand_sigma=0.1, *, max_steps: int = 1000, time_step: float = 0.01, k_sub: int = 1,
                  auto_reset="template", obs_layout: str = "row", act_layout: str = "row", seed: int = 0,
                  env_offset: int = 0, graph_safe: bool = False, integrator: str = "run1",
-                 state_layout: str = "auto",
+                 state_layout: str = "auto", x64: bool = False,
                  track_info: bool = False, track_stats: bool = True, track_contacts: bool = False,
                  keep_old_a: bool = False, initial_reset: bool = True):
         self.lib = _lib.load()
@@ -105,6 +105,13 @@ class BatchedPhysicsEnv:
         # 16-byte accesses (bodies with a specialised kernel only); "auto" picks packed when it is available
         if state_layout not in ("auto", "soa", "packed"):
             raise ValueError("state_layout must be 'auto', 'soa' or 'packed'")
+        # x64: float64 actions with the reference's NumPy promotion semantics (wg_step_x64): muscle lengths are kept
+        # as doubles plus a type bit; a compatibility path on the run-time-topology kernel, SoA state only
+        self.x64 = bool(x64)
+        if self.x64 and state_layout == "packed":
+            raise ValueError("x64 mode uses state_layout='soa'")
+        if self.x64:
+            state_layout = "soa"
         can_pack = self.lib.wg_kernel_variant(C.byref(self.topo)) in (1, 2)
         if state_layout == "packed" and not can_pack:
             raise ValueError("state_layout='packed' needs a body with a specialised kernel (Balance / Box topology)")
@@ -138,6 +145,14 @@ class BatchedPhysicsEnv:
         # graph_safe: the Philox step index lives in a device scalar advanced by a device op, so a
         # captured CUDA graph that replays step() keeps drawing fresh reset jitter
         self._counter = torch.zeros(1, dtype=torch.int32, device=dev) if graph_safe else None
+        if self.x64:
+            from .topology import x64_from_creature
+            self._x64 = x64_from_creature(creature)
+            self._x0_d = torch.tensor([self._x64.x0_d[m] for m in range(self.M)], dtype=torch.float64, device=dev)
+            self.mx64 = self._x0_d[:, None].repeat(1, E).contiguous()
+            self.mx_weak = torch.ones(self.M, E, dtype=torch.uint8, device=dev)
+        else:
+            self._x64 = self.mx64 = self.mx_weak = None
         self._buf = WgBuffers()
         self._bind()
         if initial_reset:
@@ -162,6 +177,7 @@ class BatchedPhysicsEnv:
         b.action, b.act_dim, b.noise = None, 0, None
         b.act_layout = 0 if self.act_layout == "row" else 1
         b.step_counter = self._p(self._counter)
+        b.mx64, b.mx_weak, b.action64 = self._p(self.mx64), self._p(self.mx_weak), None
 
     def _advance(self) -> None:
         if self._counter is not None:
@@ -273,6 +289,10 @@ class BatchedPhysicsEnv:
                                    self.num_envs, m, mptr, self._stream())
         self._buf.noise = None
         _lib.check(rc, "wg_reset")
+        if self.x64 and m == 2:                 # a fresh creature: every Muscle holds its originx again
+            sel = slice(None) if mask is None else mask.view(torch.bool)
+            self.mx64[:, sel] = self._x0_d[:, None]
+            self.mx_weak[:, sel] = 1
         self._advance()
         return self.obs
 
@@ -302,16 +322,26 @@ class BatchedPhysicsEnv:
             env_axis = 0 if self.act_layout == "row" else 1
             if action.dim() != 2 or action.shape[env_axis] != self.num_envs:
                 raise ValueError(f"action must have shape [{self.num_envs}, A] (row) or [A, {self.num_envs}] (feature)")
-            self._check_f32(action, action.shape, "action")
-            b.action, b.act_dim = action.data_ptr(), int(action.shape[1 - env_axis])
+            if self.x64:
+                if action.dtype != torch.float64 or not action.is_contiguous() or action.device != self.obs.device:
+                    raise ValueError("x64 mode takes contiguous float64 actions on the env's device")
+                b.action, b.action64 = None, action.data_ptr()
+            else:
+                self._check_f32(action, action.shape, "action")
+                b.action = action.data_ptr()
+            b.act_dim = int(action.shape[1 - env_axis])
         b.noise = self._p(self._check_f32(noise, (3 * self.N, self.num_envs), "noise")) if noise is not None else None
         self._stamp()
         with torch.cuda.device(self.device):
-            rc = self.lib.wg_step(C.byref(self.topo), C.byref(self.params), C.byref(b), self.num_envs, self._stream())
+            if self.x64:
+                rc = self.lib.wg_step_x64(C.byref(self.topo), C.byref(self._x64), C.byref(self.params), C.byref(b),
+                                          self.num_envs, self._stream())
+            else:
+                rc = self.lib.wg_step(C.byref(self.topo), C.byref(self.params), C.byref(b), self.num_envs, self._stream())
         b.noise = None
         if out is not None:
             b.obs, b.reward, b.done = self._p(self.obs), self._p(self.reward), self._p(self._done_u8)
-        _lib.check(rc, "wg_step")
+        _lib.check(rc, "wg_step_x64" if self.x64 else "wg_step")
         self._advance()
         info = {}
         if self.energy is not None:

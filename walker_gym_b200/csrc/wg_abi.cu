@@ -69,6 +69,7 @@ static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* 
     return WG_OK;
 }
 
+int launch_generic_step_x64(const wg_topology*, const wg_x64*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_pkg_update(const wg_pkg_system*, const wg_pkg_params*, float* pos, float* vel, float* old_a,
                       int64_t E, int32_t n_steps, bool force_generic, cudaStream_t);
 int pkg_variant(const wg_pkg_system*);
@@ -129,6 +130,18 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
         case TopoInsect::kId:  return launch_insect(topo, prm, buf, n_env, 1, s);
         default:               return launch_generic_step(topo, prm, buf, n_env, s);
     }
+}
+
+int wg_step_x64(const wg_topology* topo, const wg_x64* x64, const wg_params* prm, const wg_buffers* buf, int64_t n_env,
+                void* cuda_stream) {
+    int rc = validate(topo, prm, buf, n_env);
+    if (rc != WG_OK) return rc;
+    if (!x64) return fail(WG_ERR_BAD_ARG, "null wg_x64%s");
+    if (buf->state_packed) return fail(WG_ERR_BAD_ARG, "x64 mode uses the SoA state layout%s");
+    if (topo->n_muscle > 0 && (!buf->mx64 || !buf->mx_weak)) return fail(WG_ERR_BAD_ARG, "mx64 / mx_weak must be set%s");
+    if (buf->act_dim > 0 && !buf->action64) return fail(WG_ERR_BAD_ARG, "action64 must be set when act_dim > 0%s");
+    if (n_env == 0) return WG_OK;
+    return launch_generic_step_x64(topo, x64, prm, buf, n_env, (cudaStream_t)cuda_stream);
 }
 
 int wg_reset(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf, int64_t n_env, int mode,

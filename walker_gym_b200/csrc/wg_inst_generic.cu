@@ -6,17 +6,47 @@ static size_t generic_smem(const wg_topology* t) {
 }
 
 template <bool IN3D, bool ROWMAJOR>
+static int launch_generic_x64(const wg_topology* t, const wg_x64* x, const wg_params* p, const wg_buffers* b, int64_t E,
+                              cudaStream_t s) {
+    static thread_local StepArgs<kMaxMass, kMaxSpring> A;
+    static thread_local X64Args XA;
+    fill_args(A, t, p, b, E);
+    for (int k = 0; k < t->n_spring; k++) {
+        XA.v.sk_d[k] = x->sk_d[k]; XA.v.x0_d[k] = x->x0_d[k]; XA.v.mlo_d[k] = x->mlo_d[k]; XA.v.mhi_d[k] = x->mhi_d[k];
+    }
+    XA.mx64 = b->mx64; XA.mx_weak = b->mx_weak; XA.action64 = b->action64;
+    A.act_dim = b->action64 ? b->act_dim : 0;
+    const size_t smem = generic_smem(t) + sizeof(float) * (size_t)(3 * t->n_muscle) * (kBlock + 1);
+    auto kern = step_generic_kernel<IN3D, ROWMAJOR, X64Args>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    kern<<<(unsigned)((E + kBlock - 1) / kBlock), kBlock, smem, s>>>(A, XA);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "generic step kernel (x64) launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
+int launch_generic_step_x64(const wg_topology* t, const wg_x64* x, const wg_params* p, const wg_buffers* b, int64_t E,
+                            cudaStream_t s) {
+    const bool rm = b->obs_layout == 0;
+    if (p->in3d) return rm ? launch_generic_x64<true, true>(t, x, p, b, E, s) : launch_generic_x64<true, false>(t, x, p, b, E, s);
+    return rm ? launch_generic_x64<false, true>(t, x, p, b, E, s) : launch_generic_x64<false, false>(t, x, p, b, E, s);
+}
+
+template <bool IN3D, bool ROWMAJOR>
 static int launch_generic(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
     StepArgs<kMaxMass, kMaxSpring> A;
     fill_args(A, t, p, b, E);
     const size_t smem = generic_smem(t);
-    auto kern = step_generic_kernel<IN3D, ROWMAJOR>;
+    auto kern = step_generic_kernel<IN3D, ROWMAJOR, NoX64>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
     const unsigned grid = (unsigned)((E + kBlock - 1) / kBlock);
-    kern<<<grid, kBlock, smem, s>>>(A);
+    kern<<<grid, kBlock, smem, s>>>(A, NoX64{});
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "generic step kernel launch: %s", cudaGetErrorString(e));
     return WG_OK;

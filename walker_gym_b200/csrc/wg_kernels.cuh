@@ -352,9 +352,19 @@ step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
 // K1, generic: run-time topology, per-env state in a shared-memory tile that stays
 // resident across the k_sub substeps; one thread per env.
 // =================================================================================
-template <bool IN3D, bool ROWMAJOR>
+// x64 mode (see wg_physics.cuh): the muscle lengths live as doubles plus a type bit; XArgs = X64Args adds their buffers,
+// the float64 actions and the double-typed tables, XArgs = NoX64 is the plain float32 kernel.
+struct NoX64 { static constexpr bool kOn = false; };
+struct X64Args {
+    static constexpr bool kOn = true;
+    X64Vals v;
+    double* mx64; uint8_t* mx_weak; const double* action64;
+};
+
+template <bool IN3D, bool ROWMAJOR, class XArgs = NoX64>
 __global__ void __launch_bounds__(kBlock)
-step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A) {
+step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A, const __grid_constant__ XArgs XA) {
+    constexpr bool X64 = XArgs::kOn;
     extern __shared__ float smem[];
     const int N = A.bv.n_mass, S = A.bv.n_spring, M = A.bv.n_muscle;
     constexpr int d = IN3D ? 3 : 2;
@@ -373,16 +383,50 @@ step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A) {
             st.base[r * PITCH] = A.pos[(int64_t)r * E + e];
             st.base[(3 * N + r) * PITCH] = A.vel[(int64_t)r * E + e];
         }
-        for (int m = 0; m < M; m++) st.mx(m) = A.mx[(int64_t)m * E + e];
         const int na = A.act_dim < M ? A.act_dim : M;
+        // x64 rows after the scratch rows: [0,M) low word, [M,2M) high word of the double length, [2M,3M) type bit
+        float* const xrow = st.base + (size_t)(11 * N + M + 3) * PITCH;
+        uint32_t cp = 0;
+        if constexpr (X64) {
+            for (int m = 0; m < M; m++) {
+                double x = XA.mx64[(int64_t)m * E + e];
+                uint32_t weak = XA.mx_weak[(int64_t)m * E + e];
+                if (m < na) {                                               // anything + np.float64 -> np.float64
+                    x = x + (A.act_layout ? XA.action64[(int64_t)m * E + e] : XA.action64[e * A.act_dim + m]);
+                    weak = 0;
+                    if (XA.v.mlo_d[m] > x) { x = XA.v.mlo_d[m]; weak = 1; }   // max() returns the limit object
+                    if (XA.v.mhi_d[m] < x) { x = XA.v.mhi_d[m]; weak = 1; }
+                }
+                xrow[m * PITCH] = __int_as_float(__double2loint(x));
+                xrow[(M + m) * PITCH] = __int_as_float(__double2hiint(x));
+                xrow[(2 * M + m) * PITCH] = __uint_as_float(weak);
+                st.mx(m) = (float)x;                                        // float32 view: weak muscles, observation
+            }
+            for (int k = 0; k < A.ec.k_sub; k++) {
+                for (int n = 0; n < N; n++) { st.acc(n, 0) = 0.0f; st.acc(n, 1) = 0.0f; st.acc(n, 2) = 0.0f; }
+                for (int sp = 0; sp < M; sp++) {
+                    if (__float_as_uint(xrow[(2 * M + sp) * PITCH]))
+                        spring_run<2>(topo, A.bv, st, sp, st.mx(sp), A.bv.fixed_mask);
+                    else
+                        spring_run_x64(topo, A.bv, st, sp,
+                                       __hiloint2double(__float_as_int(xrow[(M + sp) * PITCH]), __float_as_int(xrow[sp * PITCH])),
+                                       XA.v.sk_d[sp], A.bv.fixed_mask);
+                }
+                for (int sp = M; sp < S; sp++) spring_run<2>(topo, A.bv, st, sp, A.bv.srest[sp], A.bv.fixed_mask);
+                cp = 0;
+                for (int n = 0; n < N; n++)
+                    if (point_step<IN3D, 2>(A.bv, A.ec, st, n)) cp |= 1u << n;
+            }
+        } else {
+        for (int m = 0; m < M; m++) st.mx(m) = A.mx[(int64_t)m * E + e];
         for (int m = 0; m < na; m++) {
             float x = st.mx(m) + (A.act_layout ? A.action[(int64_t)m * E + e] : A.action[e * A.act_dim + m]);
             if (A.bv.mlo[m] > x) x = A.bv.mlo[m];
             if (A.bv.mhi[m] < x) x = A.bv.mhi[m];
             st.mx(m) = x;
         }
-        uint32_t cp = 0;
         for (int k = 0; k < A.ec.k_sub; k++) cp = run_physics<IN3D, 2>(topo, A.bv, A.ec, st);
+        }
         int32_t sn = A.steps[e] + 1;
         EpiOut o;
         epilogue<IN3D>(topo, A.bv, A.ec, st, sn, A.energy != nullptr, A.centroid != nullptr,
@@ -407,6 +451,14 @@ step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A) {
         if (o.done && A.ec.auto_reset) {
             apply_reset<IN3D>(topo, A.bv, A.ec, st, A.ec.auto_reset, A.noise, E, e, step_index_of(A));
             sn = 0;
+            if constexpr (X64) {
+                if (A.ec.auto_reset == 2)                                   // a fresh Muscle: x = originx
+                    for (int m = 0; m < M; m++) {
+                        xrow[m * PITCH] = __int_as_float(__double2loint(XA.v.x0_d[m]));
+                        xrow[(M + m) * PITCH] = __int_as_float(__double2hiint(XA.v.x0_d[m]));
+                        xrow[(2 * M + m) * PITCH] = __uint_as_float(1u);
+                    }
+            }
         }
         A.steps[e] = sn;
         for (int r = 0; r < 3 * N; r++) {
@@ -415,6 +467,12 @@ step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A) {
             if (A.old_a) A.old_a[(int64_t)r * E + e] = st.base[(6 * N + r) * PITCH];
         }
         for (int m = 0; m < M; m++) A.mx[(int64_t)m * E + e] = st.mx(m);
+        if constexpr (X64) {
+            for (int m = 0; m < M; m++) {
+                XA.mx64[(int64_t)m * E + e] = __hiloint2double(__float_as_int(xrow[(M + m) * PITCH]), __float_as_int(xrow[m * PITCH]));
+                XA.mx_weak[(int64_t)m * E + e] = (uint8_t)__float_as_uint(xrow[(2 * M + m) * PITCH]);
+            }
+        }
         if (A.obs) {
             if (ROWMAJOR) {
                 // centroid of getstat (sequential sum, then / N) for the cooperative copy-out below

@@ -164,6 +164,52 @@ __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store
     }
 }
 
+// ---- x64 mode -----------------------------------------------------------------------------------------------------
+// The reference driven with float64 ndarray actions (its own demo loop, gym/performance_demo.py:241-262):
+// `self.x += a` (optimized_walker.py:33) makes Muscle.x an np.float64 and NumPy then evaluates the muscle's spring
+// term in double -- dx = float64(L) - x, f_size = -dx * k, force = f_size * direction (a float64 array), and
+// Point.forced adds force / m to the float32 accumulator in double, rounding once (:48-59, optimized_engine.py:104-106).
+// A muscle that regulation() clamped (:27-30) holds the limit object (np.float32 / python float) and is on the float32
+// path until the next action.  Direction and damping stay float32 either way.
+struct X64Vals {
+    double sk_d[kMaxSpring];                          // float(k)
+    double x0_d[kMaxSpring];                          // originx, the object a fresh Muscle holds
+    double mlo_d[kMaxSpring], mhi_d[kMaxSpring];      // originx * minl, originx * maxl as max() / min() compare them
+};
+
+template <class Topo, class BV, class Store>
+__device__ __forceinline__ void spring_run_x64(const Topo& topo, const BV& bv, Store& st, int sp, double x, double k_d,
+                                               uint32_t skip_mask) {
+    const int i = topo.si(sp), j = topo.sj(sp);
+    const float pix = st.pos(i, 0), piy = st.pos(i, 1), piz = st.pos(i, 2);
+    const float pjx = st.pos(j, 0), pjy = st.pos(j, 1), pjz = st.pos(j, 2);
+    const float L = np_norm3(pix - pjx, piy - pjy, piz - pjz);
+    float d0 = pjx - pix, d1 = pjy - piy, d2 = pjz - piz;
+    div3_len(d0, d1, d2, L);
+    const double fs = (-((double)L - x)) * k_d;
+    const double F[3] = { fs * (double)d0, fs * (double)d1, fs * (double)d2 };
+    const float dk = np_dot3(st.vel(i, 0) - st.vel(j, 0), st.vel(i, 1) - st.vel(j, 1),
+                             st.vel(i, 2) - st.vel(j, 2), d0, d1, d2);
+    const float cd = dk * bv.sdamp[sp];
+    const float D[3] = { cd * d0, cd * d1, cd * d2 };
+    if (!((skip_mask >> i) & 1u)) {                                        // p1.forced(force); p1.forced(-damp)
+        const double m = bv.mass_d[i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float a = (float)((double)st.acc(i, c) + F[c] / m);
+            st.acc(i, c) = a + div_const(-D[c], bv.mass_f[i], bv.mass_r[i], bv.mass_kind[i]);
+        }
+    }
+    if (!((skip_mask >> j) & 1u)) {                                        // p2.forced(-force); p2.forced(damp)
+        const double m = bv.mass_d[j];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float a = (float)((double)st.acc(j, c) + (-F[c]) / m);
+            st.acc(j, c) = a + div_const(D[c], bv.mass_f[j], bv.mass_r[j], bv.mass_kind[j]);
+        }
+    }
+}
+
 // Rarely used variants, kept out of line so that they do not dilute the hot instruction stream.
 static __device__ __noinline__ float3 damp_cold(float3 a, float3 v, float ndampk, float m, float r, int kind) {
     a.x = a.x + div_const(ndampk * v.x, m, r, kind);

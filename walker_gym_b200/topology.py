@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._lib import MAX_MASS, MAX_SPRING, WgTopology
+from ._lib import MAX_MASS, MAX_SPRING, WgTopology, WgX64
 from .walker import Creature
 
 
@@ -44,6 +44,22 @@ def topology_from_creature(creature: Creature) -> WgTopology:
         else:
             t.srest[s] = np.float32(sp.x)
     return t
+
+
+def x64_from_creature(creature: Creature) -> WgX64:
+    """The double-typed objects the reference's ``Muscle`` keeps (x64 mode, ``wg_step_x64``): ``float(k)``; ``originx``
+    (the np.float32 distance, or the python float the user passed); ``originx * minl`` / ``originx * maxl`` exactly as
+    ``regulation`` forms them (np.float32 * python float -> np.float32; python * python -> double)."""
+    x = WgX64()
+    for s, sp in enumerate(list(creature.muscles) + list(creature.skeletons)):
+        x.sk_d[s] = float(sp.k)
+        if s < len(creature.muscles):
+            x.x0_d[s] = float(sp.originx)
+            x.mlo_d[s] = float(sp.originx * sp.minl)
+            x.mhi_d[s] = float(sp.originx * sp.maxl)
+        else:
+            x.x0_d[s] = float(sp.x)
+    return x
 
 
 def topology_from_spec(spec) -> WgTopology:
