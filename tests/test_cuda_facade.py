@@ -155,3 +155,59 @@ def test_step_host_end_to_end_buffers():
     torch.cuda.synchronize()
     assert gu.same(h_obs.numpy(), obs.cpu().numpy()) and gu.same(h_rew.numpy(), rew.cpu().numpy())
     assert gu.same(h_done.numpy().astype(bool), done.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["f64act_balance3d", "f64act_box2d"])
+def test_facade_float64_ndarray_actions_bit_exact(name):
+    """The reference's own usage -- env.step(np.random.uniform(...)), float64 ndarrays -- through the drop-in facade:
+    observation (float64, Muscle.x at double precision), reward, done and the Point / Muscle objects, bit for bit."""
+    import walker_gym_b200 as wg
+    g = gu.load(name)
+    env_id = "Balance-v0" if "balance" in name else "Box-v0"
+    kw = g["env_kwargs"]
+    draws = list(g["reset_noise"].astype(np.float64))
+    with mock.patch.object(np.random, "normal", lambda loc=0.0, scale=1.0, size=None: draws.pop(0)):
+        wg.Point.clear()
+        env = wg.make_env(env_id, **kw)
+    for t in range(60):
+        obs, rew, done, info = env.step(g["actions"][t])                 # float64 ndarray
+        assert obs.dtype == np.float64 and gu.same(obs, g["obs"][t + 1]), t
+        assert gu.same(np.float32(rew), np.float32(g["reward"][t])) and done == bool(g["done"][t])
+        assert gu.same(np.array([p.pos for p in env.creature.phys]), g["pos"][t + 1])
+        assert gu.same(np.array([float(m.x) for m in env.creature.muscles]), g["x"][t + 1])
+    assert all(isinstance(m.x, (np.float64, np.float32)) for m in env.creature.muscles)
+    assert any(isinstance(m.x, np.float64) for m in env.creature.muscles)
+    # python-float / float32 actions afterwards keep working (Muscle.x stays np.float64: still the x64 path)
+    env.step([0.1] * len(env.creature.muscles))
+    env.reset()
+    assert any(isinstance(m.x, np.float64) for m in env.creature.muscles)   # reset() does not touch Muscle.x
+
+
+def test_batched_x64_many_envs_matches_oracle():
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    import walker_oracle as wo
+    E, T = 3000, 25
+    env = BatchedPhysicsEnv("Box-v0", E, "cuda:0", in3d=True, auto_reset="template", max_steps=9, seed=3, x64=True,
+                            keep_old_a=True, initial_reset=False)
+    assert env.state_layout == "soa"
+    spec = wo.BOX
+    body, xb = wo.make_body(spec), wo.make_x64(spec)
+    prm = wo.make_params(in3d=True, auto_reset=2, max_steps=9, seed=3)
+    st = wo.init_state(body, E)
+    st["mx64"], st["mx_weak"] = wo.init_x64(body, xb, E)
+    prm.step_index = env.step_count
+    env.reset(mode="template")
+    wo.reset(body, prm, st, mode=2)
+    rng = np.random.default_rng(0)
+    for t in range(T):
+        a = rng.uniform(-40, 40, (E, 4))                                  # large: the limits clamp often
+        prm.step_index = env.step_count
+        obs, rew, done, _ = env.step(torch.from_numpy(a).cuda())
+        out = wo.step_x64(body, xb, prm, st, a, want_info=False)
+        assert gu.same(obs.cpu().numpy(), out["obs"]) and gu.same(done.cpu().numpy(), out["done"].astype(bool)), t
+        assert gu.same(env.mx64.cpu().numpy(), st["mx64"]) and gu.same(env.mx_weak.cpu().numpy(), st["mx_weak"]), t
+        assert gu.same(env.pos.cpu().numpy(), st["pos"]) and gu.same(env.vel.cpu().numpy(), st["vel"]), t
+    assert 0 < st["mx_weak"].mean() < 1 and int(out["done"].sum()) >= 0
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(E, 4, device="cuda:0"))                      # float32 actions are not x64 actions

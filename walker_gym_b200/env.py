@@ -35,9 +35,18 @@ class _DeviceBody:
                                       **env_kwargs)
         c = self.core
         self.noise = torch.zeros(3 * c.N, 1, dtype=torch.float32, device=c.device)
+        self._env_kwargs, self._device = dict(env_kwargs), device
+        self.core64 = None                  # x64 twin (float64 actions), built on first use
 
-    def upload(self, steps: int) -> None:
-        c, cr = self.core, self.creature
+    def x64_core(self) -> BatchedPhysicsEnv:
+        if self.core64 is None:
+            self.core64 = BatchedPhysicsEnv(self.creature, 1, self._device, auto_reset=None, keep_old_a=True, track_info=True,
+                                            track_contacts=True, track_stats=False, initial_reset=False, x64=True,
+                                            **self._env_kwargs)
+        return self.core64
+
+    def upload(self, steps: int, x64: bool = False) -> None:
+        c, cr = (self.x64_core() if x64 else self.core), self.creature
         host = np.concatenate([np.asarray(p.pos, _f32) for p in cr.phys] + [np.asarray(p.v, _f32) for p in cr.phys]
                               + [np.asarray(p.old_a, _f32) for p in cr.phys] + [_f32([m.x for m in cr.muscles])])
         dev = torch.from_numpy(host).to(c.device)
@@ -45,10 +54,13 @@ class _DeviceBody:
         c.pos[:, 0], c.vel[:, 0], c.old_a[:, 0] = dev[:n3], dev[n3:2 * n3], dev[2 * n3:3 * n3]
         if c.M:
             c.mx[:, 0] = dev[3 * n3:]
+            if x64:     # the Muscle objects are the state: their python type is the "weak" bit (np.float64 = strong)
+                c.mx64[:, 0] = torch.tensor([float(m.x) for m in cr.muscles], dtype=torch.float64)
+                c.mx_weak[:, 0] = torch.tensor([0 if isinstance(m.x, np.float64) else 1 for m in cr.muscles], dtype=torch.uint8)
         c.steps.fill_(int(steps))
 
-    def download(self, refresh_contact: bool) -> None:
-        c, cr = self.core, self.creature
+    def download(self, refresh_contact: bool, x64: bool = False, muscles: bool = True) -> None:
+        c, cr = (self.core64 if x64 else self.core), self.creature
         n3 = 3 * c.N
         host = torch.cat([c.pos[:, 0], c.vel[:, 0], c.old_a[:, 0], c.mx[:, 0]]).cpu().numpy()
         cpre = int(c.contact_pre.item()) if refresh_contact else 0
@@ -60,6 +72,16 @@ class _DeviceBody:
             if refresh_contact:             # colour / radius side effects (gym/optimized_env.py:155-156,174-175)
                 hit = (cpre >> n) & 1
                 p.color, p.r = ("red", 3) if hit else ("black", 1)
+        if not muscles:                     # reset() does not touch Muscle.x (value or type)
+            return
+        if x64 and c.M:
+            x64v, weak = c.mx64[:, 0].cpu().numpy(), c.mx_weak[:, 0].cpu().numpy()
+            for i, m in enumerate(cr.muscles):
+                v = float(x64v[i])
+                # strong = np.float64 (after `x += np.float64`); weak = the limit / constructor object: np.float32
+                # when representable, else the python float the user passed
+                m.x = np.float64(v) if not weak[i] else (_f32(v) if float(_f32(v)) == v else v)
+            return
         for i, m in enumerate(cr.muscles):
             m.x = _f32(host[3 * n3 + i])
 
@@ -93,8 +115,12 @@ class PhysicsEnv:
                         k_sub=1, auto_reset=0)
         self._body.core.params = p
 
-    def _obs_array(self) -> np.ndarray:
-        return self._body.core.obs[0].cpu().numpy().astype(np.float64)
+    def _obs_array(self, x64: bool = False) -> np.ndarray:
+        core = self._body.core64 if x64 else self._body.core
+        obs = core.obs[0].cpu().numpy().astype(np.float64)
+        if core.M:                          # the reference's observation carries Muscle.x at its own precision
+            obs[-core.M:] = [float(m.x) for m in self.creature.muscles]
+        return obs
 
     def reset(self) -> np.ndarray:
         """Jitter-only reset, exactly the reference's (gym/optimized_env.py:53-68):
@@ -111,20 +137,28 @@ class PhysicsEnv:
         body.upload(0)
         body.noise.copy_(torch.from_numpy(nz.reshape(-1, 1)))
         core.reset(noise=body.noise, mode="jitter")
-        body.download(refresh_contact=False)
+        body.download(refresh_contact=False, muscles=False)
         self.steps = 0
         return self._obs_array()
 
     def step(self, action) -> Tuple[np.ndarray, float, bool, Dict[str, Any]]:
         """One environment step (gym/optimized_env.py:70-92).  ``action`` drives the first
-        min(len(action), M) muscles; it is evaluated in float32 (the reference's own
-        arithmetic when given float32 actions)."""
-        body, core = self._body, self._body.core
-        act = np.asarray(action, dtype=_f32).reshape(1, -1)
+        min(len(action), M) muscles.  NumPy's promotion rules decide the arithmetic exactly as in the
+        reference: python floats and float32 arrays keep ``Muscle.x`` in float32; a float64 ndarray (what
+        ``np.random.uniform`` returns, gym/performance_demo.py:241-262) turns it into an np.float64 and the
+        muscle's spring term into double (x64 mode, ``wg_step_x64``) -- both are bit-identical to the reference."""
+        body = self._body
+        x64 = ((isinstance(action, np.ndarray) and action.dtype == np.float64)
+               or any(isinstance(v, np.float64) for v in np.asarray(action, dtype=object).reshape(-1))
+               or any(isinstance(m.x, np.float64) for m in self.creature.muscles))
+        core = body.x64_core() if x64 else body.core
         self._refresh_params()
-        body.upload(self.steps)
+        if x64:
+            core.params = body.core.params
+        body.upload(self.steps, x64)
+        act = np.asarray(action, dtype=np.float64 if x64 else _f32).reshape(1, -1)
         core.step(torch.from_numpy(act).to(core.device))
-        body.download(refresh_contact=True)
+        body.download(refresh_contact=True, x64=x64)
         self.steps += 1
         reward = _f32(core.reward.item())
         done = bool(core.done.item())
@@ -133,7 +167,7 @@ class PhysicsEnv:
         info = {"steps": self.steps,
                 "centroid_position": core.centroid[:, 0].cpu().numpy().tolist(),
                 "total_energy": _f32(core.energy.item())}
-        return self._obs_array(), reward, done, info
+        return self._obs_array(x64), reward, done, info
 
     def render(self, mode: str = "human") -> Optional[np.ndarray]:
         """Rendering (pygame) is outside the accelerated path; this is a no-op."""
