@@ -29,6 +29,25 @@ def test_cuda_matches_reference_package_physics(cs, name, chunk):
     assert replay_l2(gu.load_l2(name), cs, chunk) is None
 
 
+@pytest.mark.parametrize("parts", [2, 4, 8])
+@pytest.mark.parametrize("name", ["box", "humanb", "insect", "leg2"])
+def test_cuda_partitioned_kernel_matches_reference_bodies(cs, part_knob, name, parts):
+    """The reference-built trajectories through the point-partitioned kernel (static specialisations off)."""
+    from walker_gym_b200 import _lib
+    part_knob(parts)
+    rec = body_record(name)
+    if name == "leg2":                       # has a register-resident kernel: take it out of the way
+        rec = dict(rec)
+        rec["si"], rec["sj"] = rec["sj"].copy(), rec["si"].copy()      # same springs, endpoints swapped: no static match
+        system = system_of(rec)
+        st_o, st_c = wo.l2_init_state(system, 5), wo.l2_init_state(system, 5)
+        wo.l2_step(wo.make_l2_system(system), wo.make_l2_params(), st_o, 50)
+        cs.l2_step(cs.make_l2_system(system), cs.make_l2_params(), st_c, 50)
+        assert gu.same(st_c["pos"], st_o["pos"]) and gu.same(st_c["old_a"], st_o["old_a"])
+        return
+    assert replay_body(rec, cs, 6) is None
+
+
 @pytest.mark.parametrize("generic", [False, True])
 @pytest.mark.parametrize("name", BODY_NAMES)
 def test_cuda_matches_reference_bodies(cs, name, generic):
@@ -85,9 +104,24 @@ def random_system(rng, P, S, dings=True):
     return {"points": pts, "springs": sps}
 
 
+@pytest.fixture()
+def part_knob():
+    from walker_gym_b200 import _lib
+    lib = _lib.load()
+    saved = lib.wg_set_tuning(_lib.TUNE_PART, -1)
+
+    def set_parts(parts):
+        lib.wg_set_tuning(_lib.TUNE_PART, parts)
+    yield set_parts
+    lib.wg_set_tuning(_lib.TUNE_PART, saved)
+
+
+@pytest.mark.parametrize("parts", [-1, 0, 2, 4, 8])
 @pytest.mark.parametrize("seed,P,S", [(0, 1, 0), (1, 2, 1), (2, 5, 9), (3, 12, 30), (4, 32, 96), (5, 21, 20)])
-def test_cuda_matches_oracle_on_random_systems(cs, seed, P, S):
-    """Random topologies up to the ABI limits, perturbed per env, 3 x 40 steps, ragged env counts."""
+def test_cuda_matches_oracle_on_random_systems(cs, part_knob, seed, P, S, parts):
+    """Random topologies up to the ABI limits, perturbed per env, 3 x 40 steps, ragged env counts; one thread per env
+    (parts 0) and 2 / 4 / 8 lanes per env (crossing springs evaluated by both owners): the bits must not change."""
+    part_knob(parts)
     rng = np.random.default_rng(seed)
     system = random_system(rng, P, S)
     kw = dict(ground_level=-30, gravity=(0.3, -25.0, -0.2), damping=0.97, air_resistance=0.05, time_step=0.01)

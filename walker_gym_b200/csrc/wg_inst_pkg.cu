@@ -29,6 +29,56 @@ int pkg_variant(const wg_pkg_system* sy) {
     return 0;
 }
 
+// Breadth-first order of the spring graph (components one after another) cut into `parts` chunks of near-equal size.
+static void build_pkg_partition(const wg_pkg_system* sy, int parts, PkgPartTables& pt) {
+    const int N = sy->n_point, S = sy->n_spring;
+    int order[kMaxMass], n_order = 0, owner[kMaxMass];
+    bool seen[kMaxMass] = {};
+    for (int root = 0; root < N; root++) {
+        if (seen[root]) continue;
+        int head = n_order;
+        order[n_order++] = root; seen[root] = true;
+        while (head < n_order) {
+            const int u = order[head++];
+            for (int s = 0; s < S; s++) {
+                int v = -1;
+                if (sy->si[s] == u) v = sy->sj[s]; else if (sy->sj[s] == u) v = sy->si[s];
+                if (v >= 0 && !seen[v]) { seen[v] = true; order[n_order++] = v; }
+            }
+        }
+    }
+    memset(&pt, 0, sizeof(pt));
+    for (int q = 0; q < N; q++) owner[order[q]] = (int)(((int64_t)q * parts) / N);
+    for (int n = 0; n < N; n++) {
+        const int p = owner[n];
+        pt.point[p][pt.n_point[p]++] = (uint8_t)n;
+        pt.own_mask[p] |= 1u << n;
+    }
+    for (int s = 0; s < S; s++) {                       // ascending spring order = list order
+        const int pi = owner[sy->si[s]], pj = owner[sy->sj[s]];
+        pt.spring[pi][pt.n_spring[pi]++] = (uint8_t)s;
+        if (pj != pi) pt.spring[pj][pt.n_spring[pj]++] = (uint8_t)s;
+    }
+}
+
+template <int LP>
+static int launch_pkg_part(const PkgArgs& A, const wg_pkg_system* sy, cudaStream_t s) {
+    static thread_local PkgPartArgs PA;
+    PA.A = A;
+    build_pkg_partition(sy, LP, PA.pt);
+    constexpr int EB = kBlock / LP;
+    const size_t smem = sizeof(float) * (size_t)(9 * sy->n_point) * (EB + 1) + (size_t)LP * (kMaxSpring + kMaxMass);
+    auto kern = pkg_update_part_kernel<LP>;
+    if (smem > 40 * 1024) {          // plus ~2.5 KB of static shared memory (staged tables)
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    kern<<<(unsigned)((A.E + EB - 1) / EB), kBlock, smem, s>>>(PA);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "update_physics kernel (partitioned) launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
 template <class Topo>
 static int launch_pkg_static(const PkgArgs& A, cudaStream_t s) {
     pkg_update_static_kernel<Topo><<<(unsigned)((A.E + kBlock - 1) / kBlock), kBlock, 0, s>>>(A);
@@ -68,6 +118,17 @@ int launch_pkg_update(const wg_pkg_system* sy, const wg_pkg_params* p, float* po
         case PkgChain3::kId: return launch_pkg_static<PkgChain3>(A, s);
         case PkgChain2::kId: return launch_pkg_static<PkgChain2>(A, s);
         default: break;
+    }
+    // larger bodies: several lanes per env (WG_TUNE_PART: -1 automatic, 0 never, 2 / 4 / 8 forced)
+    int parts = tuning(WG_TUNE_PART);
+    // measured on the reference's bodies (2^20 envs, us per update): insect (21 points) 769 / 746 / 607 / 961 with
+    // 1 / 2 / 4 / 8 lanes per env, humanb (14) 410 / 402 / 459 / 874, box (8) 163 / 208 / 345 / 806
+    if (parts < 0) parts = sy->n_point >= 18 ? 4 : (sy->n_point >= 12 ? 2 : 0);
+    if (parts > sy->n_point) parts = 0;
+    if (!force_generic && parts >= 2) {
+        if (parts == 2) return launch_pkg_part<2>(A, sy, s);
+        if (parts == 4) return launch_pkg_part<4>(A, sy, s);
+        return launch_pkg_part<8>(A, sy, s);
     }
     const size_t smem = sizeof(float) * (size_t)(9 * sy->n_point) * (kBlock + 1);
     if (smem > 48 * 1024) {

@@ -44,7 +44,7 @@ struct PkgRuntimeTopo {
 };
 
 template <class Topo, class Store>
-__device__ __forceinline__ void pkg_spring(const Topo& topo, const PkgArgs& A, Store& st, int sp) {
+__device__ __forceinline__ void pkg_spring(const Topo& topo, const PkgArgs& A, Store& st, int sp, uint32_t skip_mask) {
     const int i = topo.si(sp), j = topo.sj(sp);
     const float d0 = st.pos(i, 0) - st.pos(j, 0), d1 = st.pos(i, 1) - st.pos(j, 1), d2 = st.pos(i, 2) - st.pos(j, 2);
     const float L = np_norm3(d0, d1, d2);
@@ -54,13 +54,15 @@ __device__ __forceinline__ void pkg_spring(const Topo& topo, const PkgArgs& A, S
     const float dist = (A.min_dist > L) ? A.min_dist : L;                  // python max(norm, Config.r)
     float f0 = nfs * d0, f1 = nfs * d1, f2 = nfs * d2;                     // force on p2 (dir = d)
     div3_len<true>(f0, f1, f2, dist);                                           // dist > 0 or NaN: always a division
-    if (!((A.fixed_mask >> i) & 1u)) {
+    // skip_mask: points whose accumulator this thread must not touch -- DingPoints (forced() is a no-op) and, in the
+    // partitioned kernel, points owned by another lane
+    if (!((skip_mask >> i) & 1u)) {
         const float m = A.mass_f[i], r = A.mass_r[i]; const int kd = A.mass_kind[i];
         st.acc(i, 0) = st.acc(i, 0) + div_const(-f0, m, r, kd);
         st.acc(i, 1) = st.acc(i, 1) + div_const(-f1, m, r, kd);
         st.acc(i, 2) = st.acc(i, 2) + div_const(-f2, m, r, kd);
     }
-    if (!((A.fixed_mask >> j) & 1u)) {
+    if (!((skip_mask >> j) & 1u)) {
         const float m = A.mass_f[j], r = A.mass_r[j]; const int kd = A.mass_kind[j];
         st.acc(j, 0) = st.acc(j, 0) + div_const(f0, m, r, kd);
         st.acc(j, 1) = st.acc(j, 1) + div_const(f1, m, r, kd);
@@ -119,13 +121,92 @@ pkg_update_kernel(const __grid_constant__ PkgArgs A) {
             st.acc(n, 1) = fixed ? 0.0f : A.ga[n * 3 + 1];
             st.acc(n, 2) = fixed ? 0.0f : A.ga[n * 3 + 2];
         }
-        for (int sp = 0; sp < S; sp++) pkg_spring(topo, A, st, sp);         // (:149-150)
+        for (int sp = 0; sp < S; sp++) pkg_spring(topo, A, st, sp, A.fixed_mask);  // (:149-150)
         for (int n = 0; n < P; n++) pkg_point(A, st, n);
     }
     for (int r = 0; r < 3 * P; r++) {
         A.pos[(int64_t)r * E + e] = st.base[r * PITCH];
         A.vel[(int64_t)r * E + e] = st.base[(3 * P + r) * PITCH];
         if (A.old_a) A.old_a[(int64_t)r * E + e] = st.base[(6 * P + r) * PITCH];
+    }
+}
+
+// Larger bodies: LP adjacent lanes share one env ("point partition", the scheme of wg_kernels_part.cuh).  With one
+// thread per env a 21-point body needs 756 bytes of shared-memory state per thread, which leaves an SM 9 warps; here
+// the points are split into LP parts, lane `part` evaluates -- in list order -- every spring that touches one of its
+// points and accumulates only into ITS points (a spring crossing two parts is evaluated by both owners: same inputs,
+// same operations, same bits), then damps / integrates / grounds its own points.  Per-point accumulation order is the
+// reference's, so the bits do not change, while an env exposes LP-fold parallelism and the SM holds LP times the warps.
+struct PkgPartTables {
+    uint8_t spring[8][kMaxSpring];    // springs touching part p, ascending (= list order)
+    uint8_t point[8][kMaxMass];       // points owned by part p
+    uint8_t n_spring[8], n_point[8];
+    uint32_t own_mask[8];
+};
+struct PkgPartArgs { PkgArgs A; PkgPartTables pt; };
+
+template <int LP>
+__global__ void __launch_bounds__(kBlock)
+pkg_update_part_kernel(const __grid_constant__ PkgPartArgs PA) {
+    extern __shared__ float smem[];
+    // lanes of one warp work on different springs and points: per-spring constants would be divergent constant-bank
+    // reads, so the tables are staged once per block in shared memory
+    __shared__ PkgArgs A;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&PA.A);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&A);
+        for (int i = threadIdx.x; i < (int)(sizeof(PkgArgs) / 4); i += kBlock) dst[i] = src[i];
+    }
+    constexpr int EB = kBlock / LP, PITCH = EB + 1;
+    const int P = PA.A.n_point;
+    const int tid = threadIdx.x, el = tid / LP, part = tid % LP;
+    const int64_t E = PA.A.E;
+    const int64_t e0 = (int64_t)blockIdx.x * EB;
+    const bool valid = e0 + el < E;
+    const int64_t rem = E - e0;
+    const int nvalid = rem < EB ? (int)rem : EB;
+    uint8_t* tab = reinterpret_cast<uint8_t*>(smem + 9 * P * PITCH);
+    uint8_t* my_springs = tab + part * kMaxSpring;
+    uint8_t* my_points = tab + LP * kMaxSpring + part * kMaxMass;
+    for (int i = tid; i < LP * kMaxSpring; i += kBlock) tab[i] = PA.pt.spring[i / kMaxSpring][i % kMaxSpring];
+    for (int i = tid; i < LP * kMaxMass; i += kBlock) tab[LP * kMaxSpring + i] = PA.pt.point[i / kMaxMass][i % kMaxMass];
+    const int n_my_springs = PA.pt.n_spring[part], n_my_points = PA.pt.n_point[part];
+    const uint32_t skip = PA.A.fixed_mask | ~PA.pt.own_mask[part];
+    // single HBM read: the block's EB envs of every state row, coalesced
+    for (int idx = tid; idx < 3 * P * EB; idx += kBlock) {
+        const int r = idx / EB, c = idx - r * EB;
+        if (c < nvalid) {
+            smem[r * PITCH + c] = PA.A.pos[(int64_t)r * E + e0 + c];
+            smem[(3 * P + r) * PITCH + c] = PA.A.vel[(int64_t)r * E + e0 + c];
+        }
+    }
+    __syncthreads();
+    SmemStore st{ smem + el, PITCH, P };
+    const PkgRuntimeTopo topo{ A.si, A.sj };
+    for (int t = 0; t < A.n_steps; t++) {
+        if (valid) {
+            for (int q = 0; q < n_my_points; q++) {
+                const int n = my_points[q];
+                const bool fixed = (A.fixed_mask >> n) & 1u;
+                st.acc(n, 0) = fixed ? 0.0f : A.ga[n * 3 + 0];
+                st.acc(n, 1) = fixed ? 0.0f : A.ga[n * 3 + 1];
+                st.acc(n, 2) = fixed ? 0.0f : A.ga[n * 3 + 2];
+            }
+            for (int q = 0; q < n_my_springs; q++) pkg_spring(topo, A, st, my_springs[q], skip);
+        }
+        __syncwarp();                              // every lane of the env has read the old positions
+        if (valid)
+            for (int q = 0; q < n_my_points; q++) pkg_point(A, st, my_points[q]);
+        __syncwarp();                              // new positions / velocities visible to the env's other lanes
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 3 * P * EB; idx += kBlock) {
+        const int r = idx / EB, c = idx - r * EB;
+        if (c < nvalid) {
+            PA.A.pos[(int64_t)r * E + e0 + c] = smem[r * PITCH + c];
+            PA.A.vel[(int64_t)r * E + e0 + c] = smem[(3 * P + r) * PITCH + c];
+            if (PA.A.old_a) PA.A.old_a[(int64_t)r * E + e0 + c] = smem[(6 * P + r) * PITCH + c];
+        }
     }
 }
 
@@ -153,7 +234,7 @@ pkg_update_static_kernel(const __grid_constant__ PkgArgs A) {
             for (int c = 0; c < 3; c++) st.a_[n][c] = fixed ? 0.0f : A.ga[n * 3 + c];
         }
 #pragma unroll
-        for (int sp = 0; sp < S; sp++) pkg_spring(topo, A, st, sp);
+        for (int sp = 0; sp < S; sp++) pkg_spring(topo, A, st, sp, A.fixed_mask);
 #pragma unroll
         for (int n = 0; n < P; n++) pkg_point(A, st, n);
     }
