@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5, 6],
                     help="BASELINE.json config: 3 = Balance-v0 throughput (headline, default), 4 = enlarged body "
                          "(4x masses/springs) with 8 substeps, 5 = PPO rollout collection (torch MLP policy + step kernel)")
-    ap.add_argument("--body", default="balance", choices=["balance", "box"],
+    ap.add_argument("--body", default="balance", choices=["balance", "box", "legacy_box", "test", "intrian", "hat", "humanb", "box4", "leg"],
                     help="config 3 body: Balance-v0 (headline) or Box-v0, both from gym/optimized_walker.py:176-224")
     ap.add_argument("--obs-layout", default="row", choices=["row", "feature"],
                     help="observation layout written by the kernel: row-major [E,D] (default) or feature-major [D,E]")
@@ -215,7 +215,7 @@ def run_ours(args):
         return run_rollout(args, rank, world, dev)
     if args.config == 6:
         return run_pkg(args, rank, world, dev)
-    env_id = ENV_ID if args.body == "balance" else "Box-v0"
+    env_id = {"balance": ENV_ID, "box": "Box-v0", "legacy_box": "box"}.get(args.body, args.body)
     body, k_sub = (env_id, 1) if args.config == 3 else ("quad_balance", 8)
 
     env = BatchedPhysicsEnv(body, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,

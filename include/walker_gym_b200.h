@@ -137,8 +137,12 @@ typedef struct wg_x64 {
     double mhi_d[WG_MAX_SPRING];    /* originx * maxl */
 } wg_x64;
 
+/* 1 if this body has a packed-state kernel (Balance / Box topologies and the smaller walker.py bodies: box, test,
+ * intrian, hat, humanb, box4 -- unit / power-of-two / small-integer masses, no DingPoints), else 0. */
+int wg_packed_available(const wg_topology* topo);
+
 /*
- * Packed state layout (only for bodies with a register-resident specialisation, wg_kernel_variant() in {1, 2}).
+ * Packed state layout (only for bodies with wg_packed_available() == 1).
  * The R = 6*n_mass + n_muscle + 2 per-env scalars k -- pos rows 0..3N-1 (n*3+c), vel rows 3N..6N-1, muscle
  * lengths 6N..6N+M-1, steps (int32 bits) 6N+M, ep_ret 6N+M+1 -- are stored as [tile][k/4][128 envs][4]:
  *     index(e, k) = ((e >> 7) * R4 + (k >> 2)) * 512 + (e & 127) * 4 + (k & 3),   R4 = ceil(R / 4)

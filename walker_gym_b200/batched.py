@@ -112,7 +112,7 @@ class BatchedPhysicsEnv:
             raise ValueError("x64 mode uses state_layout='soa'")
         if self.x64:
             state_layout = "soa"
-        can_pack = self.lib.wg_kernel_variant(C.byref(self.topo)) in (1, 2)
+        can_pack = self.lib.wg_packed_available(C.byref(self.topo)) == 1
         if state_layout == "packed" and not can_pack:
             raise ValueError("state_layout='packed' needs a body with a specialised kernel (Balance / Box topology)")
         self.state_layout = "packed" if (state_layout == "packed" or (state_layout == "auto" and can_pack)) else "soa"

@@ -41,8 +41,17 @@ static int pick_variant(const wg_topology* t) {
     if (topo_matches<TopoBox>(t)) return TopoBox::kId;
     if (topo_matches<TopoQuad>(t)) return TopoQuad::kId;
     if (topo_matches<TopoInsect>(t)) return TopoInsect::kId;
+    if (topo_matches<TopoLegacyBox>(t)) return TopoLegacyBox::kId;
+    if (topo_matches<TopoTest>(t)) return TopoTest::kId;
+    if (topo_matches<TopoIntrian>(t)) return TopoIntrian::kId;
+    if (topo_matches<TopoHat>(t)) return TopoHat::kId;
+    if (topo_matches<TopoHumanb>(t)) return TopoHumanb::kId;
+    if (topo_matches<TopoBox4>(t)) return TopoBox4::kId;
     return 0;
 }
+
+// bodies with a packed-state kernel
+static bool packed_variant(int v) { return v == TopoBalance::kId || v == TopoBox::kId || (v >= TopoLegacyBox::kId && v <= TopoBox4::kId); }
 
 static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E) {
     if (!t || !p || !b) return fail(WG_ERR_BAD_ARG, "null argument%s");
@@ -58,8 +67,8 @@ static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* 
     if (p->integrator < 0 || p->integrator > 1) return fail(WG_ERR_BAD_ARG, "integrator must be 0 (run1) or 1 (run2)%s");
     if (b->state_packed) {
         const int v = pick_variant(t);
-        if (v != TopoBalance::kId && v != TopoBox::kId)
-            return fail(WG_ERR_BAD_ARG, "the packed state layout needs a body with wg_kernel_variant() 1 or 2%s");
+        if (!packed_variant(v))
+            return fail(WG_ERR_BAD_ARG, "the packed state layout needs a body with wg_packed_available() == 1%s");
         if (reinterpret_cast<uintptr_t>(b->state_packed) & 15u) return fail(WG_ERR_BAD_ARG, "state_packed must be 16-byte aligned%s");
     } else if (!b->pos || !b->vel || !b->steps || (t->n_muscle > 0 && !b->mx))
         return fail(WG_ERR_BAD_ARG, "pos/vel/mx/steps must be set%s");
@@ -93,6 +102,11 @@ int wg_kernel_variant(const wg_topology* topo) {
     return pick_variant(topo);
 }
 
+int wg_packed_available(const wg_topology* topo) {
+    if (!topo) return fail(WG_ERR_BAD_ARG, "null topology%s");
+    return packed_variant(pick_variant(topo)) ? 1 : 0;
+}
+
 int wg_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
 
 int64_t wg_packed_state_floats(const wg_topology* topo, int64_t n_env) {
@@ -115,15 +129,24 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
     if (n_env == 0) return WG_OK;
     cudaStream_t s = (cudaStream_t)cuda_stream;
     // one env per thread: two envs per thread (128 registers, 16 warps/SM) measured 35 % slower
-    if (buf->state_packed)
-        return pick_variant(topo) == TopoBalance::kId ? launch_balance_packed(topo, prm, buf, n_env, s)
-                                                      : launch_box_packed(topo, prm, buf, n_env, s);
+    if (buf->state_packed) {
+        switch (pick_variant(topo)) {
+            case TopoBalance::kId:   return launch_balance_packed(topo, prm, buf, n_env, s);
+            case TopoBox::kId:       return launch_box_packed(topo, prm, buf, n_env, s);
+            case TopoLegacyBox::kId: return launch_legacy_box_packed(topo, prm, buf, n_env, s);
+            case TopoTest::kId:      return launch_test_packed(topo, prm, buf, n_env, s);
+            case TopoIntrian::kId:   return launch_intrian_packed(topo, prm, buf, n_env, s);
+            case TopoHat::kId:       return launch_hat_packed(topo, prm, buf, n_env, s);
+            case TopoHumanb::kId:    return launch_humanb_packed(topo, prm, buf, n_env, s);
+            default:                 return launch_box4_packed(topo, prm, buf, n_env, s);
+        }
+    }
     // larger bodies: several lanes per env (mass partition); automatic choice by body size
     int parts = tuning(WG_TUNE_PART);
     if (parts < 0) parts = topo->n_mass >= 12 ? 4 : (topo->n_mass >= 6 ? 2 : 0);
     if (parts > topo->n_mass) parts = 0;
     if (parts >= 2 && !g_force_generic.load()) return launch_part_step(topo, prm, buf, n_env, parts, s);
-    switch (pick_variant(topo)) {
+    switch (pick_variant(topo)) {      // SoA state: ids >= 5 have packed kernels only and take the generic kernel here
         case TopoBalance::kId: return launch_balance(topo, prm, buf, n_env, 1, s);
         case TopoBox::kId:     return launch_box(topo, prm, buf, n_env, 1, s);
         case TopoQuad::kId:    return launch_quad(topo, prm, buf, n_env, 1, s);

@@ -31,6 +31,21 @@ WG_STATIC_TOPO(TopoInsect, 4, 13, 23, 8,
                9,4, 9,5, 10,5, 10,6, 11,6, 11,7, 12,7, 12,8,
                0,1, 0,4, 0,5, 1,2, 1,5, 1,6, 2,3, 2,6, 2,7, 3,7, 3,8, 4,5, 5,6, 6,7, 7,8)
 
+// Smaller walker.py bodies (gym/walker.py:112-353; spring order = muscles then skeletons as the builders list them):
+// packed-state kernels only.
+WG_STATIC_TOPO(TopoLegacyBox, 5, 4, 5, 2, 0,2, 1,3, 0,1, 1,2, 2,3)                       // box (:160-171)
+WG_STATIC_TOPO(TopoTest, 6, 4, 6, 1, 1,2, 0,1, 0,3, 2,3, 0,2, 1,3)                       // test (:112-136)
+WG_STATIC_TOPO(TopoIntrian, 7, 3, 3, 3, 0,2, 1,2, 0,1)                                   // intrian (:225-234)
+WG_STATIC_TOPO(TopoHat, 8, 5, 7, 4, 1,3, 1,4, 2,3, 2,4, 0,1, 0,2, 1,2)                   // hat (:339-353)
+WG_STATIC_TOPO(TopoHumanb, 9, 6, 9, 4, 2,4, 2,5, 3,4, 3,5, 0,1, 0,2, 1,2, 1,3, 2,3)      // humanb (:236-253)
+WG_STATIC_TOPO(TopoBox4, 10, 6, 9, 8, 0,2, 0,3, 0,4, 0,5, 1,2, 1,3, 1,4, 1,5, 0,1)       // box4 (:295-312)
+int launch_legacy_box_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
+int launch_test_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
+int launch_intrian_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
+int launch_hat_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
+int launch_humanb_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
+int launch_box4_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
+
 // one entry point per translation unit (ept = envs per thread the caller verified as legal)
 int launch_balance(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int ept, cudaStream_t);
 int launch_balance_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
