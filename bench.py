@@ -47,12 +47,13 @@ def parse():
                     help="config 5: wg_policy_act (3xTF32 float32-grade / plain TF32 tensor-core MLP) or torch ops")
     ap.add_argument("--probe-stream", action="store_true",
                     help="measure the HBM rate of a pure streaming kernel with the step kernel's read:write mix and exit")
+    ap.add_argument("--k-sub", type=int, default=0, help="physics substeps per env step (0 = the config's default)")
     ap.add_argument("--steps-per-launch", type=int, default=1, help="config 6: update_physics calls fused in one launch")
     ap.add_argument("--pkg-body", default="box", help="config 6: body builder of gym/optimized_walker/walker.py")
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5, 6],
                     help="BASELINE.json config: 3 = Balance-v0 throughput (headline, default), 4 = enlarged body "
                          "(4x masses/springs) with 8 substeps, 5 = PPO rollout collection (torch MLP policy + step kernel)")
-    ap.add_argument("--body", default="balance", choices=["balance", "box", "legacy_box", "test", "intrian", "hat", "humanb", "box4", "leg"],
+    ap.add_argument("--body", default="balance", choices=["balance", "box", "legacy_box", "test", "intrian", "hat", "humanb", "box4", "leg", "leg2", "insect", "quad"],
                     help="config 3 body: Balance-v0 (headline) or Box-v0, both from gym/optimized_walker.py:176-224")
     ap.add_argument("--obs-layout", default="row", choices=["row", "feature"],
                     help="observation layout written by the kernel: row-major [E,D] (default) or feature-major [D,E]")
@@ -217,6 +218,10 @@ def run_ours(args):
         return run_pkg(args, rank, world, dev)
     env_id = {"balance": ENV_ID, "box": "Box-v0", "legacy_box": "box"}.get(args.body, args.body)
     body, k_sub = (env_id, 1) if args.config == 3 else ("quad_balance", 8)
+    if args.body == "quad":
+        body = "quad_balance"
+    if args.k_sub > 0:
+        k_sub = args.k_sub
 
     env = BatchedPhysicsEnv(body, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
                             track_stats=True, k_sub=k_sub, obs_layout=args.obs_layout)

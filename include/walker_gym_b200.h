@@ -165,8 +165,9 @@ int wg_force_generic(int on);
 /* Kernel-selection knobs for experiments and tests; results never depend on them.
  *   WG_TUNE_TMA (0): 1 = use the persistent TMA-pipelined variant of the specialised SoA kernels when the
  *                    buffers allow it (E % 4 == 0, 16-byte aligned); default 0 (measured slower).
- *   WG_TUNE_PART (1): lanes per env of the mass-partitioned kernel used for larger bodies:
- *                    -1 = automatic (default), 0 = never, 2 / 4 / 8 = force that many parts.
+ *   WG_TUNE_PART (1): lanes per env of the mass-partitioned kernels:
+ *                    -1 = automatic (default: wg_step uses 4 lanes for bodies of >= 16 masses stepped with >= 2
+ *                    substeps, wg_pkg_update_physics 2 / 4 lanes from 12 / 18 points), 0 = never, 2 / 4 / 8 = forced.
  *   WG_TUNE_L2_PREFETCH (2): distance, in thread blocks, of the L2 prefetch issued by the packed-state and
  *                    mass-partitioned kernels (0 = off; default 256).
  * Returns the previous value, or WG_ERR_BAD_ARG. */

@@ -143,7 +143,11 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
     }
     // larger bodies: several lanes per env (mass partition); automatic choice by body size
     int parts = tuning(WG_TUNE_PART);
-    if (parts < 0) parts = topo->n_mass >= 12 ? 4 : (topo->n_mass >= 6 ? 2 : 0);
+    // measured (2^20 envs, us per env-step, lanes per env 1 / 2 / 4): quad (N = 16) k_sub 1: 986 / 1516 / 988, k_sub 2:
+    // 1194 / 1752 / 1165, k_sub 8: 2493 / 3032 / 2284; insect (N = 13, static kernel) k_sub 1: 425 / 1237 / 1009,
+    // k_sub 8: 1510 / 2828 / 3477; leg (N = 8) k_sub 1: 391 / 589 / 659; leg2 (N = 7): 319 / 525 / 630.
+    // The partition only pays for the largest bodies once several substeps amortise its staging.
+    if (parts < 0) parts = (topo->n_mass >= 16 && prm->k_sub >= 2) ? 4 : 0;
     if (parts > topo->n_mass) parts = 0;
     if (parts >= 2 && !g_force_generic.load()) return launch_part_step(topo, prm, buf, n_env, parts, s);
     switch (pick_variant(topo)) {      // SoA state: ids >= 5 have packed kernels only and take the generic kernel here
