@@ -138,7 +138,7 @@ typedef struct wg_x64 {
 } wg_x64;
 
 /* 1 if this body has a packed-state kernel (Balance / Box topologies and the smaller walker.py bodies: box, test,
- * intrian, hat, humanb, box4 -- unit / power-of-two / small-integer masses, no DingPoints), else 0. */
+ * intrian, hat, humanb, box4, leg2, leg -- unit / power-of-two / small-integer masses, no DingPoints), else 0. */
 int wg_packed_available(const wg_topology* topo);
 
 /*

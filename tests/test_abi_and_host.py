@@ -91,11 +91,11 @@ def test_kernel_dispatch():
     from walker_gym_b200.topology import topology_from_creature
     lib = _lib.load()
     want = {"balance_v0": 1, "balance": 1, "balance3": 0, "balance2": 0, "box_v0": 2, "box2": 2, "quad_balance": 3,
-            "insect": 4, "box": 5, "test": 6, "intrian": 7, "hat": 8, "humanb": 9, "box4": 10, "leg": 0, "leg2": 0}
+            "insect": 4, "box": 5, "test": 6, "intrian": 7, "hat": 8, "humanb": 9, "box4": 10, "leg2": 11, "leg": 12, "balance3": 0}
     for name, variant in want.items():
         topo = topology_from_creature(make_creature(name))
         assert lib.wg_kernel_variant(C.byref(topo)) == variant, name
-        assert lib.wg_packed_available(C.byref(topo)) == (1 if variant in (1, 2, 5, 6, 7, 8, 9, 10) else 0), name
+        assert lib.wg_packed_available(C.byref(topo)) == (1 if variant in (1, 2, 5, 6, 7, 8, 9, 10, 11, 12) else 0), name
     old = lib.wg_force_generic(1)
     try:
         assert lib.wg_kernel_variant(C.byref(topology_from_creature(make_creature("box_v0")))) == 0

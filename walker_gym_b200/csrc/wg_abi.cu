@@ -47,11 +47,13 @@ static int pick_variant(const wg_topology* t) {
     if (topo_matches<TopoHat>(t)) return TopoHat::kId;
     if (topo_matches<TopoHumanb>(t)) return TopoHumanb::kId;
     if (topo_matches<TopoBox4>(t)) return TopoBox4::kId;
+    if (topo_matches<TopoLeg2>(t)) return TopoLeg2::kId;
+    if (topo_matches<TopoLeg>(t)) return TopoLeg::kId;
     return 0;
 }
 
 // bodies with a packed-state kernel
-static bool packed_variant(int v) { return v == TopoBalance::kId || v == TopoBox::kId || (v >= TopoLegacyBox::kId && v <= TopoBox4::kId); }
+static bool packed_variant(int v) { return v == TopoBalance::kId || v == TopoBox::kId || (v >= TopoLegacyBox::kId && v <= TopoLeg::kId); }
 
 static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E) {
     if (!t || !p || !b) return fail(WG_ERR_BAD_ARG, "null argument%s");
@@ -138,6 +140,8 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
             case TopoIntrian::kId:   return launch_intrian_packed(topo, prm, buf, n_env, s);
             case TopoHat::kId:       return launch_hat_packed(topo, prm, buf, n_env, s);
             case TopoHumanb::kId:    return launch_humanb_packed(topo, prm, buf, n_env, s);
+            case TopoLeg2::kId:      return launch_leg2_packed(topo, prm, buf, n_env, s);
+            case TopoLeg::kId:       return launch_leg_packed(topo, prm, buf, n_env, s);
             default:                 return launch_box4_packed(topo, prm, buf, n_env, s);
         }
     }

@@ -22,7 +22,7 @@ constexpr int kPackedBlock = WG_PACKED_BLOCK;
 static_assert(kPackedBlock % 128 == 0, "the packed layout is tiled by 128 envs");
 
 template <class Topo, bool IN3D, int OBS, int MM>
-__global__ void __launch_bounds__(kPackedBlock, Topo::N <= 4 ? WG_PACKED_MIN_BLOCKS : (512 / WG_PACKED_BLOCK))
+__global__ void __launch_bounds__(kPackedBlock, Topo::N <= 4 ? WG_PACKED_MIN_BLOCKS : (Topo::N <= 6 ? 512 : 384) / WG_PACKED_BLOCK)
 step_static_packed_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
     constexpr int N = Topo::N, M = Topo::M;
     constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;

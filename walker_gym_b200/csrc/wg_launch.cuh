@@ -39,6 +39,10 @@ WG_STATIC_TOPO(TopoIntrian, 7, 3, 3, 3, 0,2, 1,2, 0,1)                          
 WG_STATIC_TOPO(TopoHat, 8, 5, 7, 4, 1,3, 1,4, 2,3, 2,4, 0,1, 0,2, 1,2)                   // hat (:339-353)
 WG_STATIC_TOPO(TopoHumanb, 9, 6, 9, 4, 2,4, 2,5, 3,4, 3,5, 0,1, 0,2, 1,2, 1,3, 2,3)      // humanb (:236-253)
 WG_STATIC_TOPO(TopoBox4, 10, 6, 9, 8, 0,2, 0,3, 0,4, 0,5, 1,2, 1,3, 1,4, 1,5, 0,1)       // box4 (:295-312)
+WG_STATIC_TOPO(TopoLeg2, 11, 7, 11, 4, 1,3, 4,6, 0,2, 0,5, 0,1, 0,4, 1,4, 1,2, 2,3, 4,5, 5,6)              // leg2 (:138-158)
+WG_STATIC_TOPO(TopoLeg, 12, 8, 13, 3, 1,3, 2,4, 5,7, 0,1, 0,2, 1,2, 2,3, 3,4, 3,5, 4,5, 4,6, 5,6, 6,7)     // leg (:314-337)
+int launch_leg2_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
+int launch_leg_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_legacy_box_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_test_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_intrian_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
