@@ -311,7 +311,9 @@ def test_partition_off_uses_one_thread_per_env():
                                                ("balance", False, "row"), ("box2", False, "feature"),
                                                ("box", True, "row"), ("test", False, "row"), ("intrian", True, "feature"),
                                                ("hat", True, "row"), ("humanb", True, "row"), ("box4", False, "feature"),
-                                               ("leg2", True, "row"), ("leg", True, "feature")])
+                                               ("leg2", True, "row"), ("leg", True, "feature"),
+                                               ("balance2", True, "row"), ("balance3", True, "feature"),
+                                               ("balance3", False, "row")])
 def test_state_layouts_match_oracle(name, in3d, layout, E, state_layout):
     """Both state layouts -- separate SoA rows and the packed [tile][k/4][128][4] float4 layout -- against the
     oracle: full and ragged tiles, 2-D and 3-D, unit and integer masses, auto-reset with episode statistics."""
@@ -328,9 +330,8 @@ def test_packed_layout_rejected_for_bodies_without_a_specialised_kernel():
     with pytest.raises(ValueError):
         BatchedPhysicsEnv("insect", 64, "cuda:0", state_layout="packed")
     assert BatchedPhysicsEnv("insect", 64, "cuda:0").state_layout == "soa"
-    assert BatchedPhysicsEnv("balance3", 64, "cuda:0").state_layout == "soa"          # DingPoint: generic kernel
-    assert BatchedPhysicsEnv("balance2", 64, "cuda:0").state_layout == "soa"          # mass 0.1: generic kernel
-    for name in ("Balance-v0", "Box-v0", "box", "test", "intrian", "hat", "humanb", "box4", "leg", "leg2"):
+    for name in ("Balance-v0", "Box-v0", "box", "test", "intrian", "hat", "humanb", "box4", "leg", "leg2",
+                 "balance2", "balance3"):          # the last two: mass 0.1 / a DingPoint on the Balance spring graph
         assert BatchedPhysicsEnv(name, 64, "cuda:0").state_layout == "packed", name
 
 

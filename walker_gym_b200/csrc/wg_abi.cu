@@ -33,10 +33,8 @@ static bool topo_matches(const wg_topology* t) {
     return true;
 }
 
-static int pick_variant(const wg_topology* t) {
-    if (g_force_generic.load()) return 0;
-    if (mass_mode(t) == 2) return 0;       // arbitrary masses: only the generic kernel carries full IEEE division
-    for (int n = 0; n < t->n_mass; n++) if (t->fixed[n]) return 0;   // DingPoints: generic kernel only
+// topology id of the register-resident specialisation this body's spring graph matches (0 = none), whatever its masses
+static int topo_id(const wg_topology* t) {
     if (topo_matches<TopoBalance>(t)) return TopoBalance::kId;
     if (topo_matches<TopoBox>(t)) return TopoBox::kId;
     if (topo_matches<TopoQuad>(t)) return TopoQuad::kId;
@@ -51,9 +49,28 @@ static int pick_variant(const wg_topology* t) {
     if (topo_matches<TopoLeg>(t)) return TopoLeg::kId;
     return 0;
 }
+static bool general_masses(const wg_topology* t) {      // arbitrary masses or DingPoints: mass mode 2
+    if (mass_mode(t) == 2) return true;
+    for (int n = 0; n < t->n_mass; n++) if (t->fixed[n]) return true;
+    return false;
+}
+
+static int pick_variant(const wg_topology* t) {
+    if (g_force_generic.load()) return 0;
+    // only the Balance topology's packed kernel carries the general path (full IEEE division, DingPoint masks)
+    if (general_masses(t)) return 0;
+    return topo_id(t);
+}
 
 // bodies with a packed-state kernel
 static bool packed_variant(int v) { return v == TopoBalance::kId || v == TopoBox::kId || (v >= TopoLegacyBox::kId && v <= TopoLeg::kId); }
+// the kernel a packed-state call launches: like pick_variant, plus the Balance topology with general masses
+static int packed_pick(const wg_topology* t) {
+    if (g_force_generic.load()) return 0;
+    const int id = topo_id(t);
+    if (general_masses(t)) return id == TopoBalance::kId ? id : 0;
+    return packed_variant(id) ? id : 0;
+}
 
 static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E) {
     if (!t || !p || !b) return fail(WG_ERR_BAD_ARG, "null argument%s");
@@ -68,8 +85,7 @@ static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* 
     if (p->auto_reset < 0 || p->auto_reset > 2) return fail(WG_ERR_BAD_ARG, "auto_reset must be 0, 1 or 2%s");
     if (p->integrator < 0 || p->integrator > 1) return fail(WG_ERR_BAD_ARG, "integrator must be 0 (run1) or 1 (run2)%s");
     if (b->state_packed) {
-        const int v = pick_variant(t);
-        if (!packed_variant(v))
+        if (!packed_pick(t))
             return fail(WG_ERR_BAD_ARG, "the packed state layout needs a body with wg_packed_available() == 1%s");
         if (reinterpret_cast<uintptr_t>(b->state_packed) & 15u) return fail(WG_ERR_BAD_ARG, "state_packed must be 16-byte aligned%s");
     } else if (!b->pos || !b->vel || !b->steps || (t->n_muscle > 0 && !b->mx))
@@ -106,7 +122,7 @@ int wg_kernel_variant(const wg_topology* topo) {
 
 int wg_packed_available(const wg_topology* topo) {
     if (!topo) return fail(WG_ERR_BAD_ARG, "null topology%s");
-    return packed_variant(pick_variant(topo)) ? 1 : 0;
+    return packed_pick(topo) ? 1 : 0;
 }
 
 int wg_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
@@ -132,7 +148,7 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
     cudaStream_t s = (cudaStream_t)cuda_stream;
     // one env per thread: two envs per thread (128 registers, 16 warps/SM) measured 35 % slower
     if (buf->state_packed) {
-        switch (pick_variant(topo)) {
+        switch (packed_pick(topo)) {
             case TopoBalance::kId:   return launch_balance_packed(topo, prm, buf, n_env, s);
             case TopoBox::kId:       return launch_box_packed(topo, prm, buf, n_env, s);
             case TopoLegacyBox::kId: return launch_legacy_box_packed(topo, prm, buf, n_env, s);

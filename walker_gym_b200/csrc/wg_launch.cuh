@@ -201,10 +201,22 @@ inline int launch_static_packed(const wg_topology* t, const wg_params* p, const 
     return WG_OK;
 }
 
-template <class Topo>
+// GENERAL = true also instantiates mass mode 2 (arbitrary masses, DingPoints) for this topology
+template <class Topo, bool GENERAL = false>
 inline int launch_packed_flags(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
-    const int mm = mass_mode(t);
+    int mm = mass_mode(t);
+    for (int n = 0; n < t->n_mass; n++) if (t->fixed[n]) mm = 2;
     const bool rm = b->obs_layout == 0;
+    if (mm == 2) {
+        if constexpr (GENERAL) {
+#define WG_PK2(I3, OB) launch_static_packed<Topo, I3, OB, 2>(t, p, b, E, s)
+            if (p->in3d) return rm ? WG_PK2(true, 1) : WG_PK2(true, 0);
+            return rm ? WG_PK2(false, 1) : WG_PK2(false, 0);
+#undef WG_PK2
+        } else {
+            return fail(WG_ERR_BAD_ARG, "this body's packed kernel needs unit / power-of-two / small-integer masses and no DingPoints%s");
+        }
+    }
 #define WG_PK(I3, OB) (mm == 0 ? launch_static_packed<Topo, I3, OB, 0>(t, p, b, E, s) : launch_static_packed<Topo, I3, OB, 1>(t, p, b, E, s))
     if (p->in3d) return rm ? WG_PK(true, 1) : WG_PK(true, 0);
     return rm ? WG_PK(false, 1) : WG_PK(false, 0);
