@@ -137,8 +137,18 @@ typedef struct wg_x64 {
     double mhi_d[WG_MAX_SPRING];    /* originx * maxl */
 } wg_x64;
 
+/*
+ * Run-time specialisation.  A body with at most 8 masses and 16 springs that has no ahead-of-time kernel gets the
+ * packed-state step kernel compiled for ITS spring graph and masses class with NVRTC (about one second, once per
+ * process and (body, in3d, obs_layout) combination), so user-built creatures run the same register-resident code as
+ * the in-tree bodies.  wg_step compiles on first use; wg_jit_prepare does it eagerly and reports a compiler or
+ * loader failure (then use the SoA layout: the run-time-topology kernel needs no compiler).  Results are identical.
+ */
+int wg_jit_prepare(const wg_topology* topo, int in3d, int obs_layout);
+
 /* 1 if this body has a packed-state kernel (Balance / Box topologies and the smaller walker.py bodies: box, test,
- * intrian, hat, humanb, box4, leg2, leg -- unit / power-of-two / small-integer masses, no DingPoints), else 0. */
+ * intrian, hat, humanb, box4, leg2, leg -- unit / power-of-two / small-integer masses, no DingPoints), or can get one
+ * at run time (WG_TUNE_JIT on, NVRTC present, <= 8 masses, <= 16 springs), else 0. */
 int wg_packed_available(const wg_topology* topo);
 
 /*
@@ -174,6 +184,7 @@ int wg_force_generic(int on);
 #define WG_TUNE_TMA 0
 #define WG_TUNE_PART 1
 #define WG_TUNE_L2_PREFETCH 2
+#define WG_TUNE_JIT 3             /* 1 (default) = bodies without an ahead-of-time kernel get one compiled at run time */
 int wg_set_tuning(int key, int value);
 
 /*

@@ -462,3 +462,47 @@ def test_fuzz_random_bodies_and_parameters(seed):
         run_lockstep(env, body, prm, st, 10, rng, noise_reset=True)
     finally:
         Point.clear()
+
+
+def _custom_creature(masses, ding=()):
+    from walker_gym_b200 import Creature, DingPoint, Muscle, Point, Skeleton
+    Point.clear()
+    pos = [(-30, 40, 5), (35, 60, -3), (0, 5, 0), (10, 90, 2), (-60, 20, 0)]
+    pts = [DingPoint(m, list(p)) if n in ding else Point(m, list(p), [0, 0, 0]) for n, (m, p) in enumerate(zip(masses, pos))]
+    mus = [Muscle(pts[0], pts[2], k=800, dampk=15, minl=0.3, maxl=1.2), Muscle(pts[1], pts[2], k=1200, dampk=25), Muscle(pts[4], pts[0], k=-300)]
+    sks = [Skeleton(pts[0], pts[1], k=500), Skeleton(pts[1], pts[3], k=2000, dampk=5), Skeleton(pts[4], pts[2], x=61.5)]
+    spec = {"points": [(m, p, n in ding) for n, (m, p) in enumerate(zip(masses, pos))],
+            "muscles": [(0, 2, {"k": 800, "dampk": 15, "minl": 0.3, "maxl": 1.2}), (1, 2, {"k": 1200, "dampk": 25}), (4, 0, {"k": -300})],
+            "skeletons": [(0, 1, {"k": 500}), (1, 3, {"k": 2000, "dampk": 5}), (4, 2, {"x": 61.5})]}
+    return Creature(pts, mus, sks), spec
+
+
+@pytest.mark.parametrize("masses,ding,in3d,layout", [((1, 1, 1, 1, 1), (), True, "row"), ((2, 5, 1, 3, 4), (), False, "feature"),
+                                                      ((2.5, 0.1, 7, 1, 3), (3,), True, "row")])
+def test_runtime_specialised_kernel_for_user_bodies(masses, ding, in3d, layout):
+    """A user-built creature gets the packed-state kernel compiled for its spring graph at run time (NVRTC): unit,
+    integer and arbitrary masses with a DingPoint; bit for bit against the oracle, and switched off it falls back to
+    the run-time-topology kernel with the same bits."""
+    from walker_gym_b200 import BatchedPhysicsEnv, Point, _lib
+    lib = _lib.load()
+    try:
+        cr, spec = _custom_creature(masses, ding)
+        E = 700
+        kw = dict(in3d=in3d, auto_reset="template", max_steps=6, k_sub=2, seed=4, obs_layout=layout, keep_old_a=True,
+                  track_info=True, track_contacts=True, initial_reset=False)
+        env = BatchedPhysicsEnv(cr, E, "cuda:0", **kw)
+        assert env.state_layout == "packed" and env.kernel_variant == 0          # no ahead-of-time kernel: compiled now
+        body = wo.make_body(spec)
+        prm = wo.make_params(in3d=in3d, auto_reset=2, max_steps=6, k_sub=2, seed=4)
+        st = wo.init_state(body, E)
+        run_lockstep(env, body, prm, st, 14, np.random.default_rng(0), noise_reset=True)
+        old = lib.wg_set_tuning(_lib.TUNE_JIT, 0)
+        try:
+            env2 = BatchedPhysicsEnv(cr, E, "cuda:0", **kw)
+            assert env2.state_layout == "soa"
+            with pytest.raises(ValueError):
+                BatchedPhysicsEnv(cr, E, "cuda:0", state_layout="packed", **kw)
+        finally:
+            lib.wg_set_tuning(_lib.TUNE_JIT, old)
+    finally:
+        Point.clear()

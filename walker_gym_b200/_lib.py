@@ -85,10 +85,10 @@ class WgMlpPolicy(C.Structure):
                 ("obs_scale", C.c_float), ("obs_clip", C.c_float), ("precision", C.c_int32), ("reserved", C.c_int32)]
 
 
-TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH = 0, 1, 2
+TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH, TUNE_JIT = 0, 1, 2, 3
 
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
-           "wg_set_tuning", "wg_packed_state_floats", "wg_packed_available",
+           "wg_set_tuning", "wg_packed_state_floats", "wg_packed_available", "wg_jit_prepare",
            "wg_step", "wg_step_x64", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics", "wg_pkg_kernel_variant",
            "wg_policy_act", "wg_gae", "wg_stream_probe")
 
@@ -121,6 +121,8 @@ def load():
     lib.wg_kernel_variant.argtypes = [P(WgTopology)]
     lib.wg_packed_available.argtypes = [P(WgTopology)]
     lib.wg_packed_available.restype = C.c_int
+    lib.wg_jit_prepare.argtypes = [P(WgTopology), C.c_int, C.c_int]
+    lib.wg_jit_prepare.restype = C.c_int
     lib.wg_force_generic.argtypes = [C.c_int]
     lib.wg_set_tuning.argtypes = [C.c_int, C.c_int]
     lib.wg_set_tuning.restype = C.c_int

@@ -113,6 +113,14 @@ class BatchedPhysicsEnv:
         if self.x64:
             state_layout = "soa"
         can_pack = self.lib.wg_packed_available(C.byref(self.topo)) == 1
+        if can_pack and state_layout != "soa":
+            # bodies without an ahead-of-time kernel: compile one for this spring graph now (NVRTC, ~1 s); on failure
+            # keep the SoA layout and the run-time-topology kernel
+            rc = self.lib.wg_jit_prepare(C.byref(self.topo), int(self.in3d), 0 if obs_layout == "row" else 1)
+            if rc != 0:
+                if state_layout == "packed":
+                    _lib.check(rc, "wg_jit_prepare")
+                can_pack = False
         if state_layout == "packed" and not can_pack:
             raise ValueError("state_layout='packed' needs a body with a specialised kernel (Balance / Box topology)")
         self.state_layout = "packed" if (state_layout == "packed" or (state_layout == "auto" and can_pack)) else "soa"

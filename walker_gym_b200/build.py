@@ -62,7 +62,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log for _, log in results))
     if verbose:
         print("\n".join(log for _, log in results))
-    r = subprocess.run([nvcc, "-shared", "-o", OUT, *[o for o, _ in results]], capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", "-o", OUT, *[o for o, _ in results], "-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:

@@ -9,6 +9,10 @@
 #include "wg_policy.cuh"
 
 namespace wg {
+bool jit_eligible(const wg_topology*);
+bool jit_runtime_available();
+int jit_prepare(const wg_topology*, int in3d, int obs_layout, cudaKernel_t* kernel);
+int launch_jit_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_policy(const PolicyArgs& A, int precision, cudaStream_t s);
 int launch_stream_probe(const float* src, float* dst, int64_t n, int R, int W, cudaStream_t s);
 int launch_gae(const float* rewards, const float* values, const uint8_t* dones, float* adv, float* ret, int T, int64_t E,
@@ -17,7 +21,8 @@ int launch_gae(const float* rewards, const float* values, const uint8_t* dones, 
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_force_generic{0};
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
-static std::atomic<int> g_tune[3] = { {env_int("WG_TMA", 0)}, {env_int("WG_PART", -1)}, {env_int("WG_L2_PREFETCH", 256)} };
+static std::atomic<int> g_tune[4] = { {env_int("WG_TMA", 0)}, {env_int("WG_PART", -1)}, {env_int("WG_L2_PREFETCH", 256)},
+                                      {env_int("WG_JIT", 1)} };
 int tuning(int key) { return g_tune[key].load(std::memory_order_relaxed); }
 
 int fail(int code, const char* fmt, const char* a) {
@@ -65,11 +70,13 @@ static int pick_variant(const wg_topology* t) {
 // bodies with a packed-state kernel
 static bool packed_variant(int v) { return v == TopoBalance::kId || v == TopoBox::kId || (v >= TopoLegacyBox::kId && v <= TopoLeg::kId); }
 // the kernel a packed-state call launches: like pick_variant, plus the Balance topology with general masses
+constexpr int kJitId = 99;     // a kernel compiled at run time for this body's spring graph (wg_jit.cu)
 static int packed_pick(const wg_topology* t) {
     if (g_force_generic.load()) return 0;
     const int id = topo_id(t);
-    if (general_masses(t)) return id == TopoBalance::kId ? id : 0;
-    return packed_variant(id) ? id : 0;
+    if (general_masses(t)) { if (id == TopoBalance::kId) return id; }
+    else if (packed_variant(id)) return id;
+    return (tuning(WG_TUNE_JIT) && jit_eligible(t) && jit_runtime_available()) ? kJitId : 0;
 }
 
 static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E) {
@@ -125,6 +132,12 @@ int wg_packed_available(const wg_topology* topo) {
     return packed_pick(topo) ? 1 : 0;
 }
 
+int wg_jit_prepare(const wg_topology* topo, int in3d, int obs_layout) {
+    if (!topo) return fail(WG_ERR_BAD_ARG, "null topology%s");
+    if (packed_pick(topo) != kJitId) return WG_OK;            // an ahead-of-time kernel (or none): nothing to compile
+    return jit_prepare(topo, in3d, obs_layout, nullptr);
+}
+
 int wg_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
 
 int64_t wg_packed_state_floats(const wg_topology* topo, int64_t n_env) {
@@ -134,7 +147,7 @@ int64_t wg_packed_state_floats(const wg_topology* topo, int64_t n_env) {
 }
 
 int wg_set_tuning(int key, int value) {
-    if (key < 0 || key > 2) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
+    if (key < 0 || key > 3) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
     if (key == WG_TUNE_PART && value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
         return fail(WG_ERR_BAD_ARG, "PART must be -1, 0, 2, 4 or 8%s");
     if (key == WG_TUNE_L2_PREFETCH && (value < 0 || value > (1 << 20))) return fail(WG_ERR_BAD_ARG, "L2 prefetch distance out of range%s");
@@ -158,6 +171,7 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
             case TopoHumanb::kId:    return launch_humanb_packed(topo, prm, buf, n_env, s);
             case TopoLeg2::kId:      return launch_leg2_packed(topo, prm, buf, n_env, s);
             case TopoLeg::kId:       return launch_leg_packed(topo, prm, buf, n_env, s);
+            case kJitId:             return launch_jit_packed(topo, prm, buf, n_env, s);
             default:                 return launch_box4_packed(topo, prm, buf, n_env, s);
         }
     }

@@ -21,9 +21,11 @@ namespace wg {
 constexpr int kPackedBlock = WG_PACKED_BLOCK;
 static_assert(kPackedBlock % 128 == 0, "the packed layout is tiled by 128 envs");
 
-template <class Topo, bool IN3D, int OBS, int MM>
+// Args: StepArgs<Topo::N, Topo::S> for the ahead-of-time specialisations; the run-time compiled ones (wg_jit.cu) take
+// the full-size StepArgs<kMaxMass, kMaxSpring> the host can fill for any body.
+template <class Topo, bool IN3D, int OBS, int MM, class Args = StepArgs<Topo::N, Topo::S>>
 __global__ void __launch_bounds__(kPackedBlock, Topo::N <= 4 ? WG_PACKED_MIN_BLOCKS : (Topo::N <= 6 ? 512 : 384) / WG_PACKED_BLOCK)
-step_static_packed_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
+step_static_packed_kernel(const __grid_constant__ Args A) {
     constexpr int N = Topo::N, M = Topo::M;
     constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;
     constexpr int R = 6 * N + M + 2, R4 = (R + 3) / 4;
