@@ -4,8 +4,9 @@
 namespace wg {
 
 // bodies of gym/optimized_walker/walker.py with a register-resident kernel: endpoints as (point1, point2) pairs
-// (box, 8 points / 12 springs, was measured slower register-resident -- 128 registers, 190 us vs 163 us per 2^20
-// envs -- so it and the larger bodies use the run-time-topology kernel)
+// (box, 8 points / 12 springs, was measured slower register-resident -- 190 us at 128 registers / 4 CTAs per SM,
+// 202 us at 154 registers / 3 CTAs, vs 163 us per 2^20 envs -- so it and the larger bodies use the run-time-topology
+// kernel)
 // leg2 (:368-393): body, two 3-point legs
 WG_STATIC_TOPO(PkgLeg2, 2, 7, 6, 0, 0,1, 1,2, 2,3, 0,4, 4,5, 5,6)
 // balance3 (:452-467): pivot + 3 bobs; balance2 / balance1 / test are chains of 3 / 2 / 2 points
