@@ -19,6 +19,12 @@ int tuning(int key);      // current value of a WG_TUNE_* knob (wg_abi.cu)
 // endpoints listed as (p1, p2) pairs, muscles first then skeletons (Creature.run order)
 // Balance-v0: gym/optimized_walker.py:176-199 (also walker.py balance/balance2/balance3)
 WG_STATIC_TOPO(TopoBalance, 1, 4, 5, 2, 0,2, 1,2, 0,1, 0,3, 1,3)
+// Balance-v0 with the mass pattern of create_balance_creature ([k, k, 1, j]: point 2 has unit mass, points 0 and 1
+// share one): mass mode 3 skips the unit-mass divisions and shares the quotients of the (0,1) bone at compile time
+struct TopoBalanceV0 : TopoBalance {
+    __host__ __device__ static constexpr bool unit(int n) { return n == 2; }
+    __host__ __device__ static constexpr bool same(int i, int j) { return (i == 0 && j == 1) || (i == 1 && j == 0); }
+};
 // Box-v0: gym/optimized_walker.py:201-224 (== walker.py box2)
 WG_STATIC_TOPO(TopoBox, 2, 4, 5, 4, 0,1, 0,2, 3,1, 3,2, 1,2)
 // 4x Balance in one env (N=16, S=20, M=8): the enlarged morphology of BASELINE config 4.
@@ -215,6 +221,14 @@ inline int launch_packed_flags(const wg_topology* t, const wg_params* p, const w
 #undef WG_PK2
         } else {
             return fail(WG_ERR_BAD_ARG, "this body's packed kernel needs unit / power-of-two / small-integer masses and no DingPoints%s");
+        }
+    }
+    if constexpr (GENERAL) {          // the Balance spring graph: is it also Balance-v0's mass pattern?
+        if (mm == 1 && t->mass[2] == 1.0 && t->mass[0] == t->mass[1] && t->mass[0] != 1.0 && t->mass[3] != 1.0) {
+#define WG_PK3(I3, OB) launch_static_packed<TopoBalanceV0, I3, OB, 3>(t, p, b, E, s)
+            if (p->in3d) return rm ? WG_PK3(true, 1) : WG_PK3(true, 0);
+            return rm ? WG_PK3(false, 1) : WG_PK3(false, 0);
+#undef WG_PK3
         }
     }
 #define WG_PK(I3, OB) (mm == 0 ? launch_static_packed<Topo, I3, OB, 0>(t, p, b, E, s) : launch_static_packed<Topo, I3, OB, 1>(t, p, b, E, s))

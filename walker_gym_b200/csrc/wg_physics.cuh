@@ -108,7 +108,7 @@ __device__ __forceinline__ void forced2(float (&a)[3], const float (&f)[3], cons
         for (int c = 0; c < 3; c++) a[c] = (a[c] + f[c]) + g[c];
         return;
     }
-    if (MM == 1) {
+    if (MM == 1 || MM == 3) {           // (mode 3 is handled in spring_run; this instance is never reached)
         // one straight-line path for every mass of the body: with m == 1 (r == 1) the sequence degenerates to
         // q0 = x, rem = 0, q = x, so unit masses need no branch -- a few redundant FMAs are cheaper than the
         // instruction-cache footprint of a second code variant per endpoint
@@ -152,6 +152,28 @@ __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store
     // skip_mask: masses whose accumulator this thread must not touch -- DingPoints (forced() is a no-op)
     // and, in the mass-partitioned kernel, masses owned by another lane.  Compiled out (USE_SKIP false)
     // in the one-thread-per-env kernels for bodies without DingPoints.
+    if constexpr (MM == 3) {
+        // mass pattern known at compile time (Topo::unit / Topo::same, constant-folded after unrolling): a unit mass
+        // needs no division, and two endpoints of equal mass share the quotients -- (-F)/m == -(F/m) and
+        // D/m == -((-D)/m) exactly, so p2's increments are the negated increments of p1
+        const bool ui = Topo::unit(i), uj = Topo::unit(j);
+        float qF[3], qD[3];                                                 // F / m_i, (-D) / m_i
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            qF[c] = ui ? F[c] : div_smallint(F[c], bv.mass_f[i], bv.mass_r[i]);
+            qD[c] = ui ? nD[c] : div_smallint(nD[c], bv.mass_f[i], bv.mass_r[i]);
+            st.acc(i, c) = (st.acc(i, c) + qF[c]) + qD[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float pF, pD;                                                   // (-F) / m_j, D / m_j
+            if (Topo::same(i, j)) { pF = -qF[c]; pD = -qD[c]; }
+            else if (uj) { pF = nF[c]; pD = D[c]; }
+            else { pF = div_smallint(nF[c], bv.mass_f[j], bv.mass_r[j]); pD = div_smallint(D[c], bv.mass_f[j], bv.mass_r[j]); }
+            st.acc(j, c) = (st.acc(j, c) + pF) + pD;
+        }
+        return;
+    }
     if (!USE_SKIP || !((skip_mask >> i) & 1u)) {                            // p1.forced(force); p1.forced(-damp)
         float a[3] = { st.acc(i, 0), st.acc(i, 1), st.acc(i, 2) };
         forced2<MM>(a, F, nD, bv, i);
