@@ -320,8 +320,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if tr is None else tr * E, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_per_env_step,
-                         "kernel": (f"wg::step_static_packed_kernel<Topo{args.body.capitalize()}, in3d, row-major obs via TMA bulk store, "
-                                    "packed float4 state, L2 bulk prefetch>" if args.config == 3
+                         "kernel": (("wg::step_static_packed_kernel<TopoBalanceV0, in3d, row-major obs via TMA bulk store, packed "
+                                     "float4 state, L2 bulk prefetch, mass pattern [k,k,1,j] at compile time>" if args.body == "balance"
+                                     else f"wg::step_static_packed_kernel<{env.creature_name if hasattr(env, 'creature_name') else args.body}, "
+                                          f"in3d, {env.state_layout} state>") if args.config == 3
                                     else "wg::step_part_kernel<in3d, P=4 lanes per env, row-major, MM=1>"),
                          "kernel_us": per_launch_s * 1e6},
             "e2e": e2e, "gpu_launches": K, "clocks": clocks,
