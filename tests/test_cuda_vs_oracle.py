@@ -478,6 +478,7 @@ def _custom_creature(masses, ding=()):
 
 
 @pytest.mark.parametrize("masses,ding,in3d,layout", [((1, 1, 1, 1, 1), (), True, "row"), ((2, 5, 1, 3, 4), (), False, "feature"),
+                                                      ((2, 2, 1, 3, 2), (), True, "row"), ((2, 3, 1, 3, 1), (), True, "row"),
                                                       ((2.5, 0.1, 7, 1, 3), (3,), True, "row")])
 def test_runtime_specialised_kernel_for_user_bodies(masses, ding, in3d, layout):
     """A user-built creature gets the packed-state kernel compiled for its spring graph at run time (NVRTC): unit,

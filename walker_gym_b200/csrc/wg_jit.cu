@@ -64,7 +64,16 @@ std::map<std::string, JitKernel> g_cache;
 std::string key_of(const wg_topology* t, int in3d, int obs_rm, int mm) {
     std::string k = std::to_string(t->n_mass) + "," + std::to_string(t->n_spring) + "," + std::to_string(t->n_muscle) + ":";
     for (int s = 0; s < t->n_spring; s++) k += std::to_string(t->si[s]) + "-" + std::to_string(t->sj[s]) + ",";
-    return k + "|" + std::to_string(in3d) + std::to_string(obs_rm) + std::to_string(mm);
+    k += "|" + std::to_string(in3d) + std::to_string(obs_rm) + std::to_string(mm);
+    if (mm == 1) {                       // mass mode 3 bakes the mass pattern (which masses are 1 / equal) into the code
+        k += "|";
+        for (int n = 0; n < t->n_mass; n++) {
+            int c = 0;
+            if (t->mass[n] != 1.0) { c = n + 1; for (int q = 0; q < n; q++) if (t->mass[q] == t->mass[n]) { c = q + 1; break; } }
+            k += std::to_string(c) + ",";
+        }
+    }
+    return k;
 }
 
 JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm) {
@@ -74,9 +83,27 @@ JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm) {
     std::string src = "#include \"wg_kernels_packed.cuh\"\nnamespace wg { WG_STATIC_TOPO(TopoJit, 99, " + std::to_string(t->n_mass) + ", " +
                       std::to_string(t->n_spring) + ", " + std::to_string(t->n_muscle);
     for (int s = 0; s < t->n_spring; s++) src += ", " + std::to_string(t->si[s]) + "," + std::to_string(t->sj[s]);
-    src += ") }\n";
-    const std::string name = std::string("&wg::step_static_packed_kernel<wg::TopoJit, ") + (in3d ? "true" : "false") + ", " +
-                             std::to_string(obs_rm) + ", " + std::to_string(mm) + ", wg::StepArgs<wg::kMaxMass, wg::kMaxSpring>>";
+    src += ")\n";
+    // unit / small-integer masses: bake the mass pattern in as well (mass mode 3: unit masses need no division,
+    // endpoints of equal mass share their quotients); class ids, not values -- the values stay kernel arguments
+    std::string topo_name = "wg::TopoJit";
+    if (mm == 1) {
+        std::string cls;
+        // simple encoding: class[n] = index of the first mass equal to mass[n] (+1), 0 for unit masses
+        for (int n = 0; n < t->n_mass; n++) {
+            int c = 0;
+            if (t->mass[n] != 1.0) { c = n + 1; for (int q = 0; q < n; q++) if (t->mass[q] == t->mass[n]) { c = q + 1; break; } }
+            cls += (n ? ", " : "") + std::to_string(c);
+        }
+        src += "struct TopoJitP : TopoJit {\n"
+               "    __host__ __device__ static constexpr int cls(int n) { constexpr int c[" + std::to_string(t->n_mass) + "] = { " + cls + " }; return c[n]; }\n"
+               "    __host__ __device__ static constexpr bool unit(int n) { return cls(n) == 0; }\n"
+               "    __host__ __device__ static constexpr bool same(int i, int j) { return cls(i) != 0 && cls(i) == cls(j); }\n};\n";
+        topo_name = "wg::TopoJitP";
+    }
+    src += "}\n";
+    const std::string name = "&wg::step_static_packed_kernel<" + topo_name + ", " + (in3d ? "true" : "false") + ", " +
+                             std::to_string(obs_rm) + ", " + std::to_string(mm == 1 ? 3 : mm) + ", wg::StepArgs<wg::kMaxMass, wg::kMaxSpring>>";
     nvrtcProgram prog = nullptr;
     if (nv.CreateProgram(&prog, src.c_str(), "wg_jit.cu", 0, nullptr, nullptr) != 0) { out.rc = WG_ERR_CUDA; out.err = "nvrtcCreateProgram failed"; return out; }
     nv.AddNameExpression(prog, name.c_str());
