@@ -9,6 +9,8 @@
 #include "wg_policy.cuh"
 
 namespace wg {
+int balance_units(const wg_topology*);
+int launch_balance_units(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int R, cudaStream_t);
 bool jit_eligible(const wg_topology*);
 bool jit_runtime_available();
 int jit_prepare(const wg_topology*, int in3d, int obs_layout, cudaKernel_t* kernel);
@@ -174,6 +176,12 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
             case kJitId:             return launch_jit_packed(topo, prm, buf, n_env, s);
             default:                 return launch_box4_packed(topo, prm, buf, n_env, s);
         }
+    }
+    // bodies made of identical disconnected Balance units (config 4's enlarged morphology): one lane per unit, the
+    // unit's physics register-resident for all substeps (WG_TUNE_PART -1 = automatic; 0 / 2 / 4 / 8 select the older paths)
+    if (tuning(WG_TUNE_PART) < 0 && !g_force_generic.load()) {
+        const int R = balance_units(topo);
+        if (R) return launch_balance_units(topo, prm, buf, n_env, R, s);
     }
     // larger bodies: several lanes per env (mass partition); automatic choice by body size
     int parts = tuning(WG_TUNE_PART);

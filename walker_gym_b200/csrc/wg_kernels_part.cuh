@@ -51,6 +51,18 @@ step_part_kernel(const __grid_constant__ PartArgs PA) {
     constexpr int d = IN3D ? 3 : 2;
     const int N = A.bv.n_mass, S = A.bv.n_spring, M = A.bv.n_muscle;
     const int D = 3 * d * N + M;
+    __shared__ uint16_t obs_src[3 * 3 * kMaxMass + kMaxSpring], obs_cen[3 * 3 * kMaxMass + kMaxSpring];
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {                // Creature.getstat's entry order
+        int src, cen = 0;
+        if (k < 3 * d * N) {
+            const int n = k / (3 * d), rr = k - n * 3 * d, sec = rr / d, c = rr - sec * d;
+            src = sec * 3 * N + n * 3 + c;
+            if (sec == 0) cen = 9 * N + M + 2 * N + c;
+        } else {
+            src = 9 * N + (k - 3 * d * N);
+        }
+        obs_src[k] = (uint16_t)src; obs_cen[k] = (uint16_t)cen;
+    }
     const int ROWS = 11 * N + M + 3;               // pos, vel, acc, mx, ys, speeds, centroid
     RuntimeTopo topo{ N, S, M, bv.si, bv.sj };
     const int tid = threadIdx.x, lane = tid & 31;
@@ -85,10 +97,16 @@ step_part_kernel(const __grid_constant__ PartArgs PA) {
         }
     }
     // ---- single HBM read: the block's EB envs of every state row, coalesced ----
+    // cp.async (global -> shared without a register round trip): every thread has all of its elements in flight at
+    // once; the plain load-then-store loop serialised on DRAM latency (35 % of the kernel's stall samples at k_sub 1)
     for (int idx = tid; idx < 6 * N * EB; idx += kBlock) {
         const int r = idx / EB, c = idx - r * EB;
-        if (c < nvalid) smem[r * PITCH + c] = r < 3 * N ? A.pos[(int64_t)r * E + e0 + c] : A.vel[(int64_t)(r - 3 * N) * E + e0 + c];
+        if (c < nvalid) {
+            const float* src = r < 3 * N ? A.pos + (int64_t)r * E + e0 + c : A.vel + (int64_t)(r - 3 * N) * E + e0 + c;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem + r * PITCH + c)), "l"(src) : "memory");
+        }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     {   // Creature.act while loading the muscle lengths
         const int na = A.act_dim < M ? A.act_dim : M;
         for (int idx = tid; idx < M * EB; idx += kBlock) {
@@ -104,6 +122,7 @@ step_part_kernel(const __grid_constant__ PartArgs PA) {
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     uint32_t cpre = 0;
@@ -191,22 +210,231 @@ step_part_kernel(const __grid_constant__ PartArgs PA) {
     }
     if (ROWMAJOR && A.obs) {                        // whole warps stream observation rows out of the tile
         const int warp = tid >> 5;
+        // entry k of an observation row = tile row obs_src[k] (minus the centroid row obs_cen[k] for positions)
         for (int r = warp; r < nvalid; r += kBlock / 32) {
             const float* col = smem + r;
             float* out = A.obs + (e0 + r) * D;
             for (int k = lane; k < D; k += 32) {
-                float v;
-                if (k < 3 * d * N) {
-                    const int n = k / (3 * d), rr = k - n * 3 * d, sec = rr / d, c = rr - sec * d;
-                    v = col[(sec * 3 * N + n * 3 + c) * PITCH];
-                    if (sec == 0) v = v - col[(9 * N + M + 2 * N + c) * PITCH];
-                } else {
-                    v = col[(9 * N + (k - 3 * d * N)) * PITCH];
-                }
+                float v = col[obs_src[k] * PITCH];
+                const int cr = obs_cen[k];
+                if (cr) v = v - col[cr * PITCH];
                 out[k] = v;
             }
         }
     }
 }
+
+// =====================================================================================================================
+// Bodies made of P identical, disconnected units (BASELINE config 4's enlarged morphology is 4 Balance units; the
+// compat Environment steps a *list* of creatures the same way): lane u of an env owns unit u and runs the unit's
+// register-resident physics -- the code of the one-unit specialisation, UnitTopo's compile-time spring table, the
+// unit's constants in the constant bank -- for all k_sub substeps without touching memory; only the env-level tail
+// (reward / done over all masses in NumPy's summation order, auto-reset, observation) goes through the shared tile.
+// Global mass U::N*u + n is unit u's mass n; global spring U::M*u + s (s < U::M, the muscles) or
+// M + (U::S-U::M)*u + (s-U::M) (the bones) is its spring s: the order in which a mass accumulates its springs is the
+// reference's (all muscles, then all bones, each in list order), so the bits are those of every other kernel.
+// =====================================================================================================================
+template <class U, int UMM>
+struct UnitsArgs {
+    PartArgs P;                        // env-level tables (pt unused)
+    BodyVals<U::N, U::S> ubv;          // the unit's constants (identical for every unit: checked on the host)
+};
+
+// KB threads per CTA = KB / P envs: wide tiles, because a [row][E] row segment of only 32 envs is one 128-byte DRAM
+// access per row and block (measured: 1.2 ms of fixed cost per 2^20-env step at KB = 128 for N = 16)
+template <class U, bool IN3D, int P, bool ROWMAJOR, int MM, int KB>
+__global__ void __launch_bounds__(KB, 512 / KB)
+step_units_kernel(const __grid_constant__ UnitsArgs<U, MM> UA) {
+    const auto& PA = UA.P;
+    const auto& A = PA.A;
+    extern __shared__ float smem[];
+    // lanes of one warp work on different springs and masses: per-spring / per-mass constants would be
+    // divergent constant-bank reads (serialised per distinct address), so the tables are staged once per
+    // block in shared memory
+    __shared__ BodyVals<kMaxMass, kMaxSpring> bv;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&A.bv);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&bv);
+        for (int i = threadIdx.x; i < (int)(sizeof(bv) / 4); i += KB) dst[i] = src[i];
+    }
+    constexpr int EB = KB / P;                 // envs per block
+    constexpr int PITCH = EB + 1;
+    constexpr int d = IN3D ? 3 : 2;
+    const int N = A.bv.n_mass, S = A.bv.n_spring, M = A.bv.n_muscle;
+    const int D = 3 * d * N + M;
+    __shared__ uint16_t obs_src[3 * 3 * kMaxMass + kMaxSpring], obs_cen[3 * 3 * kMaxMass + kMaxSpring];
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {                // Creature.getstat's entry order
+        int src, cen = 0;
+        if (k < 3 * d * N) {
+            const int n = k / (3 * d), rr = k - n * 3 * d, sec = rr / d, c = rr - sec * d;
+            src = sec * 3 * N + n * 3 + c;
+            if (sec == 0) cen = 9 * N + M + 2 * N + c;
+        } else {
+            src = 9 * N + (k - 3 * d * N);
+        }
+        obs_src[k] = (uint16_t)src; obs_cen[k] = (uint16_t)cen;
+    }
+    const int ROWS = 11 * N + M + 3;               // pos, vel, acc, mx, ys, speeds, centroid
+    RuntimeTopo topo{ N, S, M, bv.si, bv.sj };
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int el = tid / P, part = tid % P;        // env within the block, lane's part
+    const int64_t E = A.E;
+    const int64_t e0 = (int64_t)blockIdx.x * EB;
+    const int64_t e = e0 + el;
+    const bool valid = e < E;
+    const int64_t rem = E - e0;
+    const int nvalid = rem < EB ? (int)rem : EB;
+    SmemStore st{ smem + el, PITCH, N };
+    // per-part tables in shared memory (lanes of a warp read different parts)
+    constexpr int n_my_masses = U::N;
+    const int m0 = U::N * part;                    // first global mass of this lane's unit
+    auto my_mass = [&](int q) { return m0 + q; };
+    __syncthreads();                               // staged tables visible
+
+    // L2 prefetch for a block dispatched `pf_dist` blocks later: every row segment of that block is one
+    // 128-byte-class span, so each thread asks for one line (pos/vel rows, then muscle rows)
+    if (A.pf_dist > 0) {
+        const int64_t pe0 = ((int64_t)blockIdx.x + A.pf_dist) * EB;
+        if (pe0 + EB <= E) {
+            for (int r = tid; r < 6 * N + M; r += KB) {
+                const float* ptr = r < 3 * N ? A.pos + (int64_t)r * E + pe0
+                                 : r < 6 * N ? A.vel + (int64_t)(r - 3 * N) * E + pe0 : A.mx + (int64_t)(r - 6 * N) * E + pe0;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            }
+        }
+    }
+    // ---- single HBM read: the block's EB envs of every state row, coalesced ----
+    // cp.async (global -> shared without a register round trip): every thread has all of its elements in flight at
+    // once; the plain load-then-store loop serialised on DRAM latency (35 % of the kernel's stall samples at k_sub 1)
+    for (int idx = tid; idx < 6 * N * EB; idx += KB) {
+        const int r = idx / EB, c = idx - r * EB;
+        if (c < nvalid) {
+            const float* src = r < 3 * N ? A.pos + (int64_t)r * E + e0 + c : A.vel + (int64_t)(r - 3 * N) * E + e0 + c;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem + r * PITCH + c)), "l"(src) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    {   // Creature.act while loading the muscle lengths
+        const int na = A.act_dim < M ? A.act_dim : M;
+        for (int idx = tid; idx < M * EB; idx += KB) {
+            const int m = idx / EB, c = idx - m * EB;
+            if (c < nvalid) {
+                float x = A.mx[(int64_t)m * E + e0 + c];
+                if (m < na) {
+                    x = x + (A.act_layout ? A.action[(int64_t)m * E + e0 + c] : A.action[(e0 + c) * A.act_dim + m]);
+                    if (bv.mlo[m] > x) x = bv.mlo[m];
+                    if (bv.mhi[m] < x) x = bv.mhi[m];
+                }
+                smem[(9 * N + m) * PITCH + c] = x;
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    uint32_t cpre = 0;
+    if (valid) {
+        // the unit's state into registers, k_sub substeps of the one-unit code, and back into the tile
+        RegStore<U::N, U::M> rs;
+#pragma unroll
+        for (int n = 0; n < U::N; n++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { rs.p_[n][c] = st.pos(m0 + n, c); rs.v_[n][c] = st.vel(m0 + n, c); rs.a_[n][c] = 0.0f; }
+#pragma unroll
+        for (int m = 0; m < U::M; m++) rs.mx(m) = st.mx(U::M * part + m);
+        const U utopo;
+        uint32_t cu = 0;
+        for (int k = 0; k < A.ec.k_sub; k++) cu = run_physics<IN3D, MM>(utopo, UA.ubv, A.ec, rs);
+        cpre = cu << m0;
+#pragma unroll
+        for (int n = 0; n < U::N; n++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { st.pos(m0 + n, c) = rs.p_[n][c]; st.vel(m0 + n, c) = rs.v_[n][c]; st.acc(m0 + n, c) = rs.a_[n][c]; }
+    }
+    __syncwarp();
+    // ---- reward / done / info: speeds in parallel, the reduction on the env's first lane ----
+    if (valid)
+        for (int q = 0; q < n_my_masses; q++) {
+            const int n = my_mass(q);
+            st.scratch(M, n) = st.pos(n, 1);
+            st.scratch(M, N + n) = np_norm3(st.vel(n, 0), st.vel(n, 1), st.vel(n, 2));
+        }
+#pragma unroll
+    for (int off = 1; off < P; off <<= 1) cpre |= __shfl_xor_sync(0xffffffffu, cpre, off);
+    __syncwarp();
+    int do_reset = 0;
+    if (valid && part == 0) {
+        const int32_t sn = A.steps[e] + 1;
+        EpiOut o;
+        epilogue_reduce(N, bv, A.ec, st, sn, A.energy != nullptr, A.centroid != nullptr,
+                        [&](int i) -> float& { return st.scratch(M, i); },
+                        [&](int i) -> float& { return st.scratch(M, N + i); }, o);
+        if (A.reward) A.reward[e] = o.reward;
+        if (A.done) A.done[e] = (uint8_t)o.done;
+        if (A.contact_pre) A.contact_pre[e] = cpre;
+        if (A.contact_post) A.contact_post[e] = o.cpost;
+        if (A.energy) A.energy[e] = o.energy;
+        if (A.centroid) { A.centroid[e] = o.cen[0]; A.centroid[E + e] = o.cen[1]; A.centroid[2 * E + e] = o.cen[2]; }
+        if (A.ep_ret) {
+            const float r = A.ep_ret[e] + o.reward;
+            if (o.done && A.fin_stats) {
+                A.fin_stats[0 * E + e] += r;
+                A.fin_stats[1 * E + e] += r * r;
+                A.fin_stats[2 * E + e] += (float)sn;
+                A.fin_stats[3 * E + e] += 1.0f;
+            }
+            A.ep_ret[e] = (o.done && A.ec.auto_reset) ? 0.0f : r;
+        }
+        do_reset = (o.done && A.ec.auto_reset) ? 1 : 0;
+        A.steps[e] = do_reset ? 0 : sn;
+        if (do_reset && A.ec.auto_reset == 2)
+            for (int m = 0; m < M; m++) st.mx(m) = bv.srest[m];
+    }
+    do_reset = __shfl_sync(0xffffffffu, do_reset, lane - part);
+    if (valid && do_reset) {                       // each lane resets its own masses (Philox keyed per mass)
+        const uint32_t si = step_index_of(A);
+        for (int q = 0; q < n_my_masses; q++) reset_mass<IN3D>(bv, A.ec, st, my_mass(q), A.ec.auto_reset, A.noise, E, e, si);
+    }
+    __syncwarp();
+    if (valid && part == 0 && A.obs && ROWMAJOR) {  // getstat centroid: sequential sum over the masses, then / N
+        float mid[3] = { 0.0f, 0.0f, 0.0f };
+        for (int n = 0; n < N; n++) { mid[0] = mid[0] + st.pos(n, 0); mid[1] = mid[1] + st.pos(n, 1); mid[2] = mid[2] + st.pos(n, 2); }
+        const ConstDiv nd = bv.ndiv;
+        st.scratch(M, 2 * N + 0) = div_const(mid[0], nd.m, nd.r, nd.kind);
+        st.scratch(M, 2 * N + 1) = div_const(mid[1], nd.m, nd.r, nd.kind);
+        st.scratch(M, 2 * N + 2) = div_const(mid[2], nd.m, nd.r, nd.kind);
+    }
+    if (valid && part == 0 && A.obs && !ROWMAJOR)
+        get_obs<IN3D>(topo, bv.ndiv, st, [&](int k, float v) { A.obs[(int64_t)k * E + e] = v; });
+    __syncthreads();
+    // ---- single HBM write of the state, coalesced ----
+    for (int idx = tid; idx < 3 * N * EB; idx += KB) {
+        const int r = idx / EB, c = idx - r * EB;
+        if (c < nvalid) {
+            A.pos[(int64_t)r * E + e0 + c] = smem[r * PITCH + c];
+            A.vel[(int64_t)r * E + e0 + c] = smem[(3 * N + r) * PITCH + c];
+            if (A.old_a) A.old_a[(int64_t)r * E + e0 + c] = smem[(6 * N + r) * PITCH + c];
+        }
+    }
+    for (int idx = tid; idx < M * EB; idx += KB) {
+        const int m = idx / EB, c = idx - m * EB;
+        if (c < nvalid) A.mx[(int64_t)m * E + e0 + c] = smem[(9 * N + m) * PITCH + c];
+    }
+    if (ROWMAJOR && A.obs) {                        // whole warps stream observation rows out of the tile
+        const int warp = tid >> 5;
+        // entry k of an observation row = tile row obs_src[k] (minus the centroid row obs_cen[k] for positions)
+        for (int r = warp; r < nvalid; r += KB / 32) {
+            const float* col = smem + r;
+            float* out = A.obs + (e0 + r) * D;
+            for (int k = lane; k < D; k += 32) {
+                float v = col[obs_src[k] * PITCH];
+                const int cr = obs_cen[k];
+                if (cr) v = v - col[cr * PITCH];
+                out[k] = v;
+            }
+        }
+    }
+}
+
 
 }  // namespace wg
