@@ -33,12 +33,13 @@ static int launch_units_t(const wg_topology* t, const wg_topology* ut, const wg_
     fill_args(tmp, ut, p, b, E);
     UA.ubv = tmp.bv;
 #ifndef WG_UNITS_BLOCK
-#define WG_UNITS_BLOCK 256
+#define WG_UNITS_BLOCK 128
 #endif
     constexpr int KB = WG_UNITS_BLOCK, EB = KB / R;
-    const size_t smem = sizeof(float) * (size_t)(11 * t->n_mass + t->n_muscle + 3) * (EB + 1);
+    constexpr int N = R * U::N, D = 3 * (IN3D ? 3 : 2) * N + R * U::M, SCR = 5 * N + 4;
+    const size_t smem = sizeof(float) * ((size_t)((EB * SCR + 31) / 32) * 32 + (ROWMAJOR ? (size_t)EB * D : 0));
     auto kern = step_units_kernel<U, IN3D, R, ROWMAJOR, MM, KB>;
-    if (smem > 32 * 1024) {
+    if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }

@@ -240,135 +240,89 @@ struct UnitsArgs {
     BodyVals<U::N, U::S> ubv;          // the unit's constants (identical for every unit: checked on the host)
 };
 
-// KB threads per CTA = KB / P envs: wide tiles, because a [row][E] row segment of only 32 envs is one 128-byte DRAM
-// access per row and block (measured: 1.2 ms of fixed cost per 2^20-env step at KB = 128 for N = 16)
+// positions of every mass of an env in the per-env scratch (the env-level tail reads them in NumPy's order)
+struct ScratchPos {
+    float* p;                                         // [3N] for this env
+    __device__ __forceinline__ float& pos(int n, int c) { return p[n * 3 + c]; }
+};
+// a unit's registers addressed by GLOBAL mass / muscle index (reset_mass and friends take global indices)
+template <class U>
+struct UnitView {
+    RegStore<U::N, U::M>& rs; int m0, g0;
+    __device__ __forceinline__ float& pos(int n, int c) { return rs.p_[n - m0][c]; }
+    __device__ __forceinline__ float& vel(int n, int c) { return rs.v_[n - m0][c]; }
+    __device__ __forceinline__ float& acc(int n, int c) { return rs.a_[n - m0][c]; }
+    __device__ __forceinline__ float& mx(int m) { return rs.mx_[m - g0]; }
+};
+
+// KB threads per CTA = KB / P envs.  Nothing of the state goes through shared memory: lane u loads unit u's rows
+// straight into registers (a warp request = P rows x 32/P consecutive envs: whole 32-byte sectors), steps it, and
+// stores it back; shared memory only carries the env-level scratch (heights, speeds, positions, centroid) and the
+// row-major observation tile, which leaves with one TMA bulk store per warp.
 template <class U, bool IN3D, int P, bool ROWMAJOR, int MM, int KB>
-__global__ void __launch_bounds__(KB, 512 / KB)
+__global__ void __launch_bounds__(KB, 768 / KB)
 step_units_kernel(const __grid_constant__ UnitsArgs<U, MM> UA) {
-    const auto& PA = UA.P;
-    const auto& A = PA.A;
-    extern __shared__ float smem[];
-    // lanes of one warp work on different springs and masses: per-spring / per-mass constants would be
-    // divergent constant-bank reads (serialised per distinct address), so the tables are staged once per
-    // block in shared memory
-    __shared__ BodyVals<kMaxMass, kMaxSpring> bv;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&A.bv);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&bv);
-        for (int i = threadIdx.x; i < (int)(sizeof(bv) / 4); i += KB) dst[i] = src[i];
-    }
-    constexpr int EB = KB / P;                 // envs per block
-    constexpr int PITCH = EB + 1;
-    constexpr int d = IN3D ? 3 : 2;
-    const int N = A.bv.n_mass, S = A.bv.n_spring, M = A.bv.n_muscle;
-    const int D = 3 * d * N + M;
-    __shared__ uint16_t obs_src[3 * 3 * kMaxMass + kMaxSpring], obs_cen[3 * 3 * kMaxMass + kMaxSpring];
-    for (int k = threadIdx.x; k < D; k += blockDim.x) {                // Creature.getstat's entry order
-        int src, cen = 0;
-        if (k < 3 * d * N) {
-            const int n = k / (3 * d), rr = k - n * 3 * d, sec = rr / d, c = rr - sec * d;
-            src = sec * 3 * N + n * 3 + c;
-            if (sec == 0) cen = 9 * N + M + 2 * N + c;
-        } else {
-            src = 9 * N + (k - 3 * d * N);
-        }
-        obs_src[k] = (uint16_t)src; obs_cen[k] = (uint16_t)cen;
-    }
-    const int ROWS = 11 * N + M + 3;               // pos, vel, acc, mx, ys, speeds, centroid
-    RuntimeTopo topo{ N, S, M, bv.si, bv.sj };
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int el = tid / P, part = tid % P;        // env within the block, lane's part
+    const auto& A = UA.P.A;
+    constexpr int N = P * U::N, M = P * U::M, d = IN3D ? 3 : 2, D = 3 * d * N + M;
+    constexpr int EB = KB / P, EW = 32 / P;           // envs per block / per warp
+    constexpr int SCR = 5 * N + 4;                    // per env: ys[N], speeds[N], pos[3N], centroid[3], pad
+    constexpr bool OBS_BULK = ROWMAJOR && ((EW * D * 4) % 16 == 0);
+    extern __shared__ __align__(128) float smem[];
+    float* const otile = smem + ((EB * SCR + 31) / 32) * 32;          // [EB][D], 128-byte aligned
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int el = tid / P, u = tid % P;
+    const int m0 = U::N * u, g0 = U::M * u;
     const int64_t E = A.E;
     const int64_t e0 = (int64_t)blockIdx.x * EB;
     const int64_t e = e0 + el;
     const bool valid = e < E;
-    const int64_t rem = E - e0;
-    const int nvalid = rem < EB ? (int)rem : EB;
-    SmemStore st{ smem + el, PITCH, N };
-    // per-part tables in shared memory (lanes of a warp read different parts)
-    constexpr int n_my_masses = U::N;
-    const int m0 = U::N * part;                    // first global mass of this lane's unit
-    auto my_mass = [&](int q) { return m0 + q; };
-    __syncthreads();                               // staged tables visible
-
-    // L2 prefetch for a block dispatched `pf_dist` blocks later: every row segment of that block is one
-    // 128-byte-class span, so each thread asks for one line (pos/vel rows, then muscle rows)
-    if (A.pf_dist > 0) {
-        const int64_t pe0 = ((int64_t)blockIdx.x + A.pf_dist) * EB;
-        if (pe0 + EB <= E) {
-            for (int r = tid; r < 6 * N + M; r += KB) {
-                const float* ptr = r < 3 * N ? A.pos + (int64_t)r * E + pe0
-                                 : r < 6 * N ? A.vel + (int64_t)(r - 3 * N) * E + pe0 : A.mx + (int64_t)(r - 6 * N) * E + pe0;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-            }
-        }
-    }
-    // ---- single HBM read: the block's EB envs of every state row, coalesced ----
-    // cp.async (global -> shared without a register round trip): every thread has all of its elements in flight at
-    // once; the plain load-then-store loop serialised on DRAM latency (35 % of the kernel's stall samples at k_sub 1)
-    for (int idx = tid; idx < 6 * N * EB; idx += KB) {
-        const int r = idx / EB, c = idx - r * EB;
-        if (c < nvalid) {
-            const float* src = r < 3 * N ? A.pos + (int64_t)r * E + e0 + c : A.vel + (int64_t)(r - 3 * N) * E + e0 + c;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem + r * PITCH + c)), "l"(src) : "memory");
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    {   // Creature.act while loading the muscle lengths
-        const int na = A.act_dim < M ? A.act_dim : M;
-        for (int idx = tid; idx < M * EB; idx += KB) {
-            const int m = idx / EB, c = idx - m * EB;
-            if (c < nvalid) {
-                float x = A.mx[(int64_t)m * E + e0 + c];
-                if (m < na) {
-                    x = x + (A.act_layout ? A.action[(int64_t)m * E + e0 + c] : A.action[(e0 + c) * A.act_dim + m]);
-                    if (bv.mlo[m] > x) x = bv.mlo[m];
-                    if (bv.mhi[m] < x) x = bv.mhi[m];
-                }
-                smem[(9 * N + m) * PITCH + c] = x;
-            }
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-
+    float* const scr = smem + el * SCR;
+    RegStore<U::N, U::M> rs;
     uint32_t cpre = 0;
     if (valid) {
-        // the unit's state into registers, k_sub substeps of the one-unit code, and back into the tile
-        RegStore<U::N, U::M> rs;
+        // ---- single HBM read: this lane's unit, coalesced per (row, 32/P envs) ----
 #pragma unroll
         for (int n = 0; n < U::N; n++)
 #pragma unroll
-            for (int c = 0; c < 3; c++) { rs.p_[n][c] = st.pos(m0 + n, c); rs.v_[n][c] = st.vel(m0 + n, c); rs.a_[n][c] = 0.0f; }
+            for (int c = 0; c < 3; c++) {
+                rs.p_[n][c] = A.pos[(int64_t)((m0 + n) * 3 + c) * E + e];
+                rs.v_[n][c] = A.vel[(int64_t)((m0 + n) * 3 + c) * E + e];
+                rs.a_[n][c] = 0.0f;
+            }
+        const int na = A.act_dim < M ? A.act_dim : M;
 #pragma unroll
-        for (int m = 0; m < U::M; m++) rs.mx(m) = st.mx(U::M * part + m);
+        for (int m = 0; m < U::M; m++) {                // Creature.act on this unit's muscles
+            float x = A.mx[(int64_t)(g0 + m) * E + e];
+            if (g0 + m < na) {
+                x = x + (A.act_layout ? A.action[(int64_t)(g0 + m) * E + e] : A.action[e * A.act_dim + g0 + m]);
+                if (UA.ubv.mlo[m] > x) x = UA.ubv.mlo[m];
+                if (UA.ubv.mhi[m] < x) x = UA.ubv.mhi[m];
+            }
+            rs.mx(m) = x;
+        }
         const U utopo;
         uint32_t cu = 0;
         for (int k = 0; k < A.ec.k_sub; k++) cu = run_physics<IN3D, MM>(utopo, UA.ubv, A.ec, rs);
         cpre = cu << m0;
+        // ---- env-level scratch: heights, speeds, positions ----
 #pragma unroll
-        for (int n = 0; n < U::N; n++)
+        for (int n = 0; n < U::N; n++) {
+            scr[m0 + n] = rs.p_[n][1];
+            scr[N + m0 + n] = np_norm3(rs.v_[n][0], rs.v_[n][1], rs.v_[n][2]);
 #pragma unroll
-            for (int c = 0; c < 3; c++) { st.pos(m0 + n, c) = rs.p_[n][c]; st.vel(m0 + n, c) = rs.v_[n][c]; st.acc(m0 + n, c) = rs.a_[n][c]; }
-    }
-    __syncwarp();
-    // ---- reward / done / info: speeds in parallel, the reduction on the env's first lane ----
-    if (valid)
-        for (int q = 0; q < n_my_masses; q++) {
-            const int n = my_mass(q);
-            st.scratch(M, n) = st.pos(n, 1);
-            st.scratch(M, N + n) = np_norm3(st.vel(n, 0), st.vel(n, 1), st.vel(n, 2));
+            for (int c = 0; c < 3; c++) scr[2 * N + (m0 + n) * 3 + c] = rs.p_[n][c];
         }
+    }
 #pragma unroll
     for (int off = 1; off < P; off <<= 1) cpre |= __shfl_xor_sync(0xffffffffu, cpre, off);
     __syncwarp();
     int do_reset = 0;
-    if (valid && part == 0) {
+    if (valid && u == 0) {                              // reward / done / info on the env's first lane
         const int32_t sn = A.steps[e] + 1;
         EpiOut o;
-        epilogue_reduce(N, bv, A.ec, st, sn, A.energy != nullptr, A.centroid != nullptr,
-                        [&](int i) -> float& { return st.scratch(M, i); },
-                        [&](int i) -> float& { return st.scratch(M, N + i); }, o);
+        ScratchPos sp{ scr + 2 * N };
+        epilogue_reduce(N, A.bv, A.ec, sp, sn, A.energy != nullptr, A.centroid != nullptr,
+                        [&](int i) -> float& { return scr[i]; }, [&](int i) -> float& { return scr[N + i]; }, o);
         if (A.reward) A.reward[e] = o.reward;
         if (A.done) A.done[e] = (uint8_t)o.done;
         if (A.contact_pre) A.contact_pre[e] = cpre;
@@ -387,54 +341,85 @@ step_units_kernel(const __grid_constant__ UnitsArgs<U, MM> UA) {
         }
         do_reset = (o.done && A.ec.auto_reset) ? 1 : 0;
         A.steps[e] = do_reset ? 0 : sn;
-        if (do_reset && A.ec.auto_reset == 2)
-            for (int m = 0; m < M; m++) st.mx(m) = bv.srest[m];
     }
-    do_reset = __shfl_sync(0xffffffffu, do_reset, lane - part);
-    if (valid && do_reset) {                       // each lane resets its own masses (Philox keyed per mass)
+    do_reset = __shfl_sync(0xffffffffu, do_reset, lane - u);
+    if (valid && do_reset) {                            // each lane resets its own unit (Philox keyed per global mass)
         const uint32_t si = step_index_of(A);
-        for (int q = 0; q < n_my_masses; q++) reset_mass<IN3D>(bv, A.ec, st, my_mass(q), A.ec.auto_reset, A.noise, E, e, si);
+        UnitView<U> view{ rs, m0, g0 };
+        if (A.ec.auto_reset == 2) {
+#pragma unroll
+            for (int m = 0; m < U::M; m++) rs.mx(m) = UA.ubv.srest[m];
+        }
+#pragma unroll
+        for (int n = 0; n < U::N; n++) reset_mass<IN3D>(A.bv, A.ec, view, m0 + n, A.ec.auto_reset, A.noise, E, e, si);
+#pragma unroll
+        for (int n = 0; n < U::N; n++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) scr[2 * N + (m0 + n) * 3 + c] = rs.p_[n][c];
     }
     __syncwarp();
-    if (valid && part == 0 && A.obs && ROWMAJOR) {  // getstat centroid: sequential sum over the masses, then / N
-        float mid[3] = { 0.0f, 0.0f, 0.0f };
-        for (int n = 0; n < N; n++) { mid[0] = mid[0] + st.pos(n, 0); mid[1] = mid[1] + st.pos(n, 1); mid[2] = mid[2] + st.pos(n, 2); }
-        const ConstDiv nd = bv.ndiv;
-        st.scratch(M, 2 * N + 0) = div_const(mid[0], nd.m, nd.r, nd.kind);
-        st.scratch(M, 2 * N + 1) = div_const(mid[1], nd.m, nd.r, nd.kind);
-        st.scratch(M, 2 * N + 2) = div_const(mid[2], nd.m, nd.r, nd.kind);
-    }
-    if (valid && part == 0 && A.obs && !ROWMAJOR)
-        get_obs<IN3D>(topo, bv.ndiv, st, [&](int k, float v) { A.obs[(int64_t)k * E + e] = v; });
-    __syncthreads();
-    // ---- single HBM write of the state, coalesced ----
-    for (int idx = tid; idx < 3 * N * EB; idx += KB) {
-        const int r = idx / EB, c = idx - r * EB;
-        if (c < nvalid) {
-            A.pos[(int64_t)r * E + e0 + c] = smem[r * PITCH + c];
-            A.vel[(int64_t)r * E + e0 + c] = smem[(3 * N + r) * PITCH + c];
-            if (A.old_a) A.old_a[(int64_t)r * E + e0 + c] = smem[(6 * N + r) * PITCH + c];
+    if (valid && A.obs) {
+        if (u == 0) {                                   // getstat centroid: sequential sum over all masses, then / N
+            float mid[3] = { 0.0f, 0.0f, 0.0f };
+#pragma unroll
+            for (int n = 0; n < N; n++) { mid[0] = mid[0] + scr[2 * N + n * 3]; mid[1] = mid[1] + scr[2 * N + n * 3 + 1]; mid[2] = mid[2] + scr[2 * N + n * 3 + 2]; }
+            const ConstDiv nd = A.bv.ndiv;
+            scr[5 * N + 0] = div_const(mid[0], nd.m, nd.r, nd.kind);
+            scr[5 * N + 1] = div_const(mid[1], nd.m, nd.r, nd.kind);
+            scr[5 * N + 2] = div_const(mid[2], nd.m, nd.r, nd.kind);
         }
     }
-    for (int idx = tid; idx < M * EB; idx += KB) {
-        const int m = idx / EB, c = idx - m * EB;
-        if (c < nvalid) A.mx[(int64_t)m * E + e0 + c] = smem[(9 * N + m) * PITCH + c];
+    __syncwarp();
+    if (valid && A.obs) {
+        // this lane's entries of the observation row: masses m0 .. m0+U::N-1 and muscles g0 .. g0+U::M-1
+        const float mid[3] = { scr[5 * N + 0], scr[5 * N + 1], scr[5 * N + 2] };
+        auto emit = [&](int k, float v) {
+            if (ROWMAJOR) { if (OBS_BULK) otile[el * D + k] = v; else A.obs[e * D + k] = v; }
+            else A.obs[(int64_t)k * E + e] = v;
+        };
+#pragma unroll
+        for (int n = 0; n < U::N; n++) {
+            const int k0 = (m0 + n) * 3 * d;
+#pragma unroll
+            for (int c = 0; c < d; c++) {
+                emit(k0 + c, rs.p_[n][c] - mid[c]);
+                emit(k0 + d + c, rs.v_[n][c]);
+                emit(k0 + 2 * d + c, rs.a_[n][c]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < U::M; m++) emit(3 * d * N + g0 + m, rs.mx(m));
     }
-    if (ROWMAJOR && A.obs) {                        // whole warps stream observation rows out of the tile
-        const int warp = tid >> 5;
-        // entry k of an observation row = tile row obs_src[k] (minus the centroid row obs_cen[k] for positions)
-        for (int r = warp; r < nvalid; r += KB / 32) {
-            const float* col = smem + r;
-            float* out = A.obs + (e0 + r) * D;
-            for (int k = lane; k < D; k += 32) {
-                float v = col[obs_src[k] * PITCH];
-                const int cr = obs_cen[k];
-                if (cr) v = v - col[cr * PITCH];
-                out[k] = v;
+    if (valid) {
+        // ---- single HBM write of the state ----
+#pragma unroll
+        for (int n = 0; n < U::N; n++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                A.pos[(int64_t)((m0 + n) * 3 + c) * E + e] = rs.p_[n][c];
+                A.vel[(int64_t)((m0 + n) * 3 + c) * E + e] = rs.v_[n][c];
+                if (A.old_a) A.old_a[(int64_t)((m0 + n) * 3 + c) * E + e] = rs.a_[n][c];
+            }
+#pragma unroll
+        for (int m = 0; m < U::M; m++) A.mx[(int64_t)(g0 + m) * E + e] = rs.mx(m);
+    }
+    if (OBS_BULK && A.obs) {
+        // the warp's EW observation rows are one contiguous span of global memory: one TMA bulk store
+        __syncwarp();
+        const int64_t ew = e0 + (int64_t)warp * EW;
+        const int64_t remw = E - ew;
+        if (remw > 0) {
+            float* wt = otile + warp * EW * D;
+            if (remw >= EW && ((reinterpret_cast<uintptr_t>(A.obs) & 15u) == 0) && ((ew * D * 4) % 16 == 0)) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { bulk_s2g(A.obs + ew * D, wt, (uint32_t)(EW * D * 4)); bulk_commit(); bulk_wait_read0(); }
+            } else {
+                const int nvw = remw < EW ? (int)remw : EW;
+                for (int idx = lane; idx < nvw * D; idx += 32) A.obs[ew * D + idx] = wt[idx];
             }
         }
     }
 }
-
 
 }  // namespace wg
