@@ -324,14 +324,15 @@ def run_ours(args):
                                      "float4 state, L2 bulk prefetch, mass pattern [k,k,1,j] at compile time>" if args.body == "balance"
                                      else f"wg::step_static_packed_kernel<{env.creature_name if hasattr(env, 'creature_name') else args.body}, "
                                           f"in3d, {env.state_layout} state>") if args.config == 3
-                                    else "wg::step_part_kernel<in3d, P=4 lanes per env, row-major, MM=1>"),
+                                    else "wg::step_units_kernel<TopoBalanceV0, in3d, P=4 lanes per env (one per Balance unit), row-major obs via TMA bulk store, MM=3>"),
                          "kernel_us": per_launch_s * 1e6},
             "e2e": e2e, "gpu_launches": K, "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "return_mean", "length_mean")},
         }
         if args.config == 4:
-            line["roofline"]["note"] = ("config 4 is fp32-issue bound, not HBM bound: ~8 substeps x 20 springs per env-step "
-                                        "against 1485 bytes (SURVEY 7.5); the HBM fraction is reported for completeness")
+            line["roofline"]["note"] = ("config 4 is fp32-issue bound, not HBM bound: 8 substeps x 20 springs per env-step "
+                                        "against 1485 bytes (SURVEY 7.5); the HBM fraction is reported for completeness; "
+                                        "with 1 substep the same body reaches 0.51")
         if not args.no_cpu_baseline and world == 1 and args.config == 3 and args.body == "balance":
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         print(json.dumps(line), flush=True)

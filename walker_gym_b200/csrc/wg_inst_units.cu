@@ -33,7 +33,7 @@ static int launch_units_t(const wg_topology* t, const wg_topology* ut, const wg_
     fill_args(tmp, ut, p, b, E);
     UA.ubv = tmp.bv;
 #ifndef WG_UNITS_BLOCK
-#define WG_UNITS_BLOCK 128
+#define WG_UNITS_BLOCK 256
 #endif
     constexpr int KB = WG_UNITS_BLOCK, EB = KB / R;
     constexpr int N = R * U::N, D = 3 * (IN3D ? 3 : 2) * N + R * U::M, SCR = 5 * N + 4;

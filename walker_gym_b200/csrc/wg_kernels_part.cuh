@@ -259,8 +259,11 @@ struct UnitView {
 // straight into registers (a warp request = P rows x 32/P consecutive envs: whole 32-byte sectors), steps it, and
 // stores it back; shared memory only carries the env-level scratch (heights, speeds, positions, centroid) and the
 // row-major observation tile, which leaves with one TMA bulk store per warp.
+#ifndef WG_UNITS_THREADS_PER_SM
+#define WG_UNITS_THREADS_PER_SM 768
+#endif
 template <class U, bool IN3D, int P, bool ROWMAJOR, int MM, int KB>
-__global__ void __launch_bounds__(KB, 768 / KB)
+__global__ void __launch_bounds__(KB, WG_UNITS_THREADS_PER_SM / KB)
 step_units_kernel(const __grid_constant__ UnitsArgs<U, MM> UA) {
     const auto& A = UA.P.A;
     constexpr int N = P * U::N, M = P * U::M, d = IN3D ? 3 : 2, D = 3 * d * N + M;
