@@ -372,6 +372,20 @@ step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A, co
     constexpr int PITCH = kBlock + 1;             // odd pitch: row-wise and column-wise access conflict-free
     RuntimeTopo topo{ N, S, M, A.bv.si, A.bv.sj };
     const int tid = threadIdx.x;
+    __shared__ uint16_t obs_src[3 * 3 * kMaxMass + kMaxSpring], obs_cen[3 * 3 * kMaxMass + kMaxSpring];
+    if (ROWMAJOR) {
+        for (int k = tid; k < D; k += kBlock) {                     // Creature.getstat's entry order
+            int src, cen = 0;
+            if (k < 3 * d * N) {
+                const int n = k / (3 * d), r = k - n * 3 * d, part = r / d, c = r - part * d;
+                src = part * 3 * N + n * 3 + c;
+                if (part == 0) cen = 9 * N + M + 2 * N + c;
+            } else {
+                src = 9 * N + (k - 3 * d * N);
+            }
+            obs_src[k] = (uint16_t)src; obs_cen[k] = (uint16_t)cen;
+        }
+    }
     const int64_t E = A.E;
     const int64_t e0 = (int64_t)blockIdx.x * kBlock;
     const int64_t e = e0 + tid;
@@ -495,18 +509,15 @@ step_generic_kernel(const __grid_constant__ StepArgs<kMaxMass, kMaxSpring> A, co
         const int64_t rem = E - e0;
         const int nvalid = rem < kBlock ? (int)rem : kBlock;
         const int warp = tid >> 5, lane = tid & 31;
+        // entry k of an observation row = tile row obs_src[k] (minus the centroid row obs_cen[k] for positions):
+        // a per-block lookup table instead of index arithmetic per element
         for (int el = warp; el < nvalid; el += kBlock / 32) {
             const float* col = smem + el;
             float* out = A.obs + (e0 + el) * D;
             for (int k = lane; k < D; k += 32) {
-                float v;
-                if (k < 3 * d * N) {
-                    const int n = k / (3 * d), r = k - n * 3 * d, part = r / d, c = r - part * d;
-                    v = col[(part * 3 * N + n * 3 + c) * PITCH];
-                    if (part == 0) v = v - col[(9 * N + M + 2 * N + c) * PITCH];
-                } else {
-                    v = col[(9 * N + (k - 3 * d * N)) * PITCH];
-                }
+                float v = col[obs_src[k] * PITCH];
+                const int cr = obs_cen[k];
+                if (cr) v = v - col[cr * PITCH];
                 out[k] = v;
             }
         }
