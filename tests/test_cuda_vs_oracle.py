@@ -507,3 +507,37 @@ def test_runtime_specialised_kernel_for_user_bodies(masses, ding, in3d, layout):
             lib.wg_set_tuning(_lib.TUNE_JIT, old)
     finally:
         Point.clear()
+
+
+def test_runtime_specialised_soa_kernel_for_mid_size_user_bodies():
+    """9..16 masses: no packed layout, but the SoA step kernel is compiled for the body's spring graph at run time
+    (NVRTC); bit for bit against the oracle, and against the run-time-topology kernel when the compiler is switched off."""
+    from walker_gym_b200 import BatchedPhysicsEnv, Creature, Muscle, Point, Skeleton, _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(77)
+    spec = _random_spec(rng, 11, 18, 5)
+    spec["points"] = [(float(rng.integers(1, 4)), p, False) for _, p, _ in spec["points"]]      # integer masses, no DingPoint
+    Point.clear()
+    try:
+        pts = [Point(m, list(p), [0, 0, 0]) for m, p, _ in spec["points"]]
+        cr = Creature(pts, [Muscle(pts[i], pts[j], **kw) for i, j, kw in spec["muscles"]],
+                      [Skeleton(pts[i], pts[j], **kw) for i, j, kw in spec["skeletons"]])
+        E = 900
+        kw = dict(in3d=True, auto_reset="template", max_steps=5, k_sub=2, seed=8, keep_old_a=True, track_info=True,
+                  track_contacts=True, initial_reset=False)
+        res = []
+        for jit in (1, 0):
+            old = lib.wg_set_tuning(_lib.TUNE_JIT, jit)
+            try:
+                env = BatchedPhysicsEnv(cr, E, "cuda:0", **kw)
+                assert env.state_layout == "soa"
+                body = wo.make_body(spec)
+                prm = wo.make_params(in3d=True, auto_reset=2, max_steps=5, k_sub=2, seed=8)
+                st = wo.init_state(body, E)
+                run_lockstep(env, body, prm, st, 12, np.random.default_rng(5), noise_reset=True)
+                res.append(env.pos.clone())
+            finally:
+                lib.wg_set_tuning(_lib.TUNE_JIT, old)
+        assert gu.same(res[0].cpu().numpy(), res[1].cpu().numpy())
+    finally:
+        Point.clear()

@@ -13,7 +13,9 @@ int balance_units(const wg_topology*);
 int launch_balance_units(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int R, cudaStream_t);
 bool jit_eligible(const wg_topology*);
 bool jit_runtime_available();
-int jit_prepare(const wg_topology*, int in3d, int obs_layout, cudaKernel_t* kernel);
+bool jit_eligible_soa(const wg_topology*);
+int jit_prepare(const wg_topology*, int in3d, int obs_layout, cudaKernel_t* kernel, bool packed);
+int launch_jit_soa(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_jit_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_policy(const PolicyArgs& A, int precision, cudaStream_t s);
 int launch_stream_probe(const float* src, float* dst, int64_t n, int R, int W, cudaStream_t s);
@@ -137,7 +139,7 @@ int wg_packed_available(const wg_topology* topo) {
 int wg_jit_prepare(const wg_topology* topo, int in3d, int obs_layout) {
     if (!topo) return fail(WG_ERR_BAD_ARG, "null topology%s");
     if (packed_pick(topo) != kJitId) return WG_OK;            // an ahead-of-time kernel (or none): nothing to compile
-    return jit_prepare(topo, in3d, obs_layout, nullptr);
+    return jit_prepare(topo, in3d, obs_layout, nullptr, true);
 }
 
 int wg_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
@@ -197,7 +199,13 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
         case TopoBox::kId:     return launch_box(topo, prm, buf, n_env, 1, s);
         case TopoQuad::kId:    return launch_quad(topo, prm, buf, n_env, 1, s);
         case TopoInsect::kId:  return launch_insect(topo, prm, buf, n_env, 1, s);
-        default:               return launch_generic_step(topo, prm, buf, n_env, s);
+        default:
+            // no ahead-of-time kernel: a kernel compiled for this spring graph at run time (up to 16 masses); if the
+            // run-time compiler is missing or fails, the run-time-topology kernel (same bits)
+            if (!g_force_generic.load() && tuning(WG_TUNE_JIT) && jit_eligible_soa(topo) && jit_runtime_available() &&
+                launch_jit_soa(topo, prm, buf, n_env, s) == WG_OK)
+                return WG_OK;
+            return launch_generic_step(topo, prm, buf, n_env, s);
     }
 }
 

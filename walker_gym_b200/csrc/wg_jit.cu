@@ -61,8 +61,8 @@ struct JitKernel { cudaKernel_t kernel = nullptr; int rc = WG_OK; std::string er
 std::mutex g_mu;
 std::map<std::string, JitKernel> g_cache;
 
-std::string key_of(const wg_topology* t, int in3d, int obs_rm, int mm) {
-    std::string k = std::to_string(t->n_mass) + "," + std::to_string(t->n_spring) + "," + std::to_string(t->n_muscle) + ":";
+std::string key_of(const wg_topology* t, int in3d, int obs_rm, int mm, bool packed) {
+    std::string k = std::string(packed ? "P" : "S") + std::to_string(t->n_mass) + "," + std::to_string(t->n_spring) + "," + std::to_string(t->n_muscle) + ":";
     for (int s = 0; s < t->n_spring; s++) k += std::to_string(t->si[s]) + "-" + std::to_string(t->sj[s]) + ",";
     k += "|" + std::to_string(in3d) + std::to_string(obs_rm) + std::to_string(mm);
     if (mm == 1) {                       // mass mode 3 bakes the mass pattern (which masses are 1 / equal) into the code
@@ -76,7 +76,7 @@ std::string key_of(const wg_topology* t, int in3d, int obs_rm, int mm) {
     return k;
 }
 
-JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm) {
+JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm, bool packed) {
     JitKernel out;
     Nvrtc& nv = nvrtc();
     if (!nv.ok) { out.rc = WG_ERR_UNSUPPORTED; out.err = "libnvrtc not available"; return out; }
@@ -102,8 +102,9 @@ JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm) {
         topo_name = "wg::TopoJitP";
     }
     src += "}\n";
-    const std::string name = "&wg::step_static_packed_kernel<" + topo_name + ", " + (in3d ? "true" : "false") + ", " +
-                             std::to_string(obs_rm) + ", " + std::to_string(mm == 1 ? 3 : mm) + ", wg::StepArgs<wg::kMaxMass, wg::kMaxSpring>>";
+    const std::string name = std::string(packed ? "&wg::step_static_packed_kernel<" : "&wg::step_static_kernel<") + topo_name + ", " +
+                             (in3d ? "true" : "false") + ", " + std::to_string(obs_rm) + (packed ? ", " : ", 1, ") +
+                             std::to_string(mm == 1 ? 3 : mm) + ", wg::StepArgs<wg::kMaxMass, wg::kMaxSpring>>";
     nvrtcProgram prog = nullptr;
     if (nv.CreateProgram(&prog, src.c_str(), "wg_jit.cu", 0, nullptr, nullptr) != 0) { out.rc = WG_ERR_CUDA; out.err = "nvrtcCreateProgram failed"; return out; }
     nv.AddNameExpression(prog, name.c_str());
@@ -134,8 +135,11 @@ JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm) {
 }
 }  // namespace
 
-// bodies the run-time specialisation accepts: small enough for a register-resident kernel
+// bodies the run-time specialisation accepts: small enough for a register-resident kernel (packed state: the
+// float4 layout pays up to 8 masses; SoA state: one thread per env holds up to 16 masses in registers, as the
+// ahead-of-time insect / quad kernels do)
 bool jit_eligible(const wg_topology* t) { return t->n_mass >= 1 && t->n_mass <= 8 && t->n_spring >= 1 && t->n_spring <= 16; }
+bool jit_eligible_soa(const wg_topology* t) { return t->n_mass >= 1 && t->n_mass <= 16 && t->n_spring >= 1 && t->n_spring <= 32; }
 bool jit_runtime_available() { return nvrtc().ok; }
 
 static int mode_of(const wg_topology* t) {
@@ -145,12 +149,12 @@ static int mode_of(const wg_topology* t) {
 }
 
 // compile (or fetch) the kernel for this body / variant; WG_OK or an error with the compiler log in the error string
-int jit_prepare(const wg_topology* t, int in3d, int obs_layout, cudaKernel_t* kernel) {
+int jit_prepare(const wg_topology* t, int in3d, int obs_layout, cudaKernel_t* kernel, bool packed) {
     const int obs_rm = obs_layout == 0 ? 1 : 0, mm = mode_of(t);
-    const std::string key = key_of(t, in3d ? 1 : 0, obs_rm, mm);
+    const std::string key = key_of(t, in3d ? 1 : 0, obs_rm, mm, packed);
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_cache.find(key);
-    if (it == g_cache.end()) it = g_cache.emplace(key, compile(t, in3d ? 1 : 0, obs_rm, mm)).first;
+    if (it == g_cache.end()) it = g_cache.emplace(key, compile(t, in3d ? 1 : 0, obs_rm, mm, packed)).first;
     if (it->second.rc != WG_OK) return fail(it->second.rc, "run-time specialisation failed: %s", it->second.err.c_str());
     if (kernel) *kernel = it->second.kernel;
     return WG_OK;
@@ -158,7 +162,7 @@ int jit_prepare(const wg_topology* t, int in3d, int obs_layout, cudaKernel_t* ke
 
 int launch_jit_packed(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
     cudaKernel_t kernel = nullptr;
-    int rc = jit_prepare(t, p->in3d, b->obs_layout, &kernel);
+    int rc = jit_prepare(t, p->in3d, b->obs_layout, &kernel, true);
     if (rc != WG_OK) return rc;
     static thread_local StepArgs<kMaxMass, kMaxSpring> A;
     fill_args(A, t, p, b, E);
@@ -174,6 +178,27 @@ int launch_jit_packed(const wg_topology* t, const wg_params* p, const wg_buffers
     cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3((unsigned)((E + kPackedBlock - 1) / kPackedBlock)), dim3(kPackedBlock),
                                      args, smem, s);
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (jit) launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
+// SoA state: step_static_kernel<TopoJit, ..., EPT = 1, ...> compiled for this body (up to 16 masses)
+int launch_jit_soa(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
+    cudaKernel_t kernel = nullptr;
+    int rc = jit_prepare(t, p->in3d, b->obs_layout, &kernel, false);
+    if (rc != WG_OK) return rc;
+    static thread_local StepArgs<kMaxMass, kMaxSpring> A;
+    fill_args(A, t, p, b, E);
+    const int D = 3 * (p->in3d ? 3 : 2) * t->n_mass + t->n_muscle;
+    const bool rm = b->obs_layout == 0;
+    const bool bulk = rm && gcd_c(D, 32) <= 2;                                 // mirrors launch_static
+    const size_t smem = (rm && b->obs) ? sizeof(float) * kBlock * (bulk ? D : (D | 1)) : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute (jit): %s", cudaGetErrorString(e));
+    }
+    void* args[] = { &A };
+    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3((unsigned)((E + kBlock - 1) / kBlock)), dim3(kBlock), args, smem, s);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(WG_ERR_CUDA, "step kernel (jit, SoA) launch: %s", cudaGetErrorString(e)); }
     return WG_OK;
 }
 

@@ -145,9 +145,11 @@ __device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const E
 // OBS: 0 = feature-major [D][E] (stores coalesced straight from registers),
 //      1 = row-major [E][D] staged through a padded shared-memory tile, each warp streaming its
 //          own 32*EPT rows (one contiguous span of global memory) with only a __syncwarp,
-template <class Topo, bool IN3D, int OBS, int EPT, int MM>
+// Args: StepArgs<Topo::N, Topo::S> for the ahead-of-time specialisations; the run-time compiled ones (wg_jit.cu) take
+// the full-size StepArgs<kMaxMass, kMaxSpring>.
+template <class Topo, bool IN3D, int OBS, int EPT, int MM, class Args = StepArgs<Topo::N, Topo::S>>
 __global__ void __launch_bounds__(kBlock, (Topo::N <= 4 && EPT == 1) ? WG_MIN_BLOCKS : 1)
-step_static_kernel(const __grid_constant__ StepArgs<Topo::N, Topo::S> A) {
+step_static_kernel(const __grid_constant__ Args A) {
     constexpr bool ROWMAJOR = (OBS == 1);
     constexpr int N = Topo::N, M = Topo::M;
     constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;
