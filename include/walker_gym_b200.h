@@ -143,14 +143,15 @@ typedef struct wg_x64 {
  * process and (body, in3d, obs_layout) combination), so user-built creatures run the same register-resident code as
  * the in-tree bodies.  wg_step compiles on first use; wg_jit_prepare does it eagerly and reports a compiler or
  * loader failure (then use the SoA layout: the run-time-topology kernel needs no compiler).  With the SoA layout,
- * bodies of up to 16 masses and 32 springs get the one-thread SoA kernel compiled the same way (2-14 s once), and
+ * bodies of up to 16 masses and 32 springs stepped in batches of >= 4096 envs get the one-thread SoA kernel compiled
+ * the same way (2-14 s once), and
  * fall back to the run-time-topology kernel silently if the compiler is missing.  Results are identical.
  */
 int wg_jit_prepare(const wg_topology* topo, int in3d, int obs_layout);
 
-/* 1 if this body has a packed-state kernel (Balance / Box topologies and the smaller walker.py bodies: box, test,
- * intrian, hat, humanb, box4, leg2, leg -- unit / power-of-two / small-integer masses, no DingPoints), or can get one
- * at run time (WG_TUNE_JIT on, NVRTC present, <= 8 masses, <= 16 springs), else 0. */
+/* 1 if this body has an ahead-of-time packed-state kernel (Balance / Box topologies and the smaller walker.py bodies: box, test,
+ * intrian, hat, humanb, box4, leg2, leg -- unit / power-of-two / small-integer masses, no DingPoints), 2 if it can get
+ * one at run time (WG_TUNE_JIT on, NVRTC present, <= 8 masses, <= 16 springs), else 0. */
 int wg_packed_available(const wg_topology* topo);
 
 /*

@@ -98,7 +98,7 @@ def test_kernel_dispatch():
         # balance2 (mass 0.1) and balance3 (DingPoint) share the Balance spring graph, whose packed kernel also
         # carries the general-mass path; their SoA route is the run-time-topology kernel (variant 0)
         packed = variant in (1, 2, 5, 6, 7, 8, 9, 10, 11, 12) or name in ("balance2", "balance3")
-        assert lib.wg_packed_available(C.byref(topo)) == (1 if packed else 0), name
+        assert (lib.wg_packed_available(C.byref(topo)) == 1) == packed, name
     old = lib.wg_force_generic(1)
     try:
         assert lib.wg_kernel_variant(C.byref(topology_from_creature(make_creature("box_v0")))) == 0

@@ -488,7 +488,7 @@ def test_runtime_specialised_kernel_for_user_bodies(masses, ding, in3d, layout):
     lib = _lib.load()
     try:
         cr, spec = _custom_creature(masses, ding)
-        E = 700
+        E = 4100
         kw = dict(in3d=in3d, auto_reset="template", max_steps=6, k_sub=2, seed=4, obs_layout=layout, keep_old_a=True,
                   track_info=True, track_contacts=True, initial_reset=False)
         env = BatchedPhysicsEnv(cr, E, "cuda:0", **kw)
@@ -522,7 +522,7 @@ def test_runtime_specialised_soa_kernel_for_mid_size_user_bodies():
         pts = [Point(m, list(p), [0, 0, 0]) for m, p, _ in spec["points"]]
         cr = Creature(pts, [Muscle(pts[i], pts[j], **kw) for i, j, kw in spec["muscles"]],
                       [Skeleton(pts[i], pts[j], **kw) for i, j, kw in spec["skeletons"]])
-        E = 900
+        E = 4200
         kw = dict(in3d=True, auto_reset="template", max_steps=5, k_sub=2, seed=8, keep_old_a=True, track_info=True,
                   track_contacts=True, initial_reset=False)
         res = []

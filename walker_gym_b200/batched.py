@@ -112,7 +112,8 @@ class BatchedPhysicsEnv:
             raise ValueError("x64 mode uses state_layout='soa'")
         if self.x64:
             state_layout = "soa"
-        can_pack = self.lib.wg_packed_available(C.byref(self.topo)) == 1
+        avail = self.lib.wg_packed_available(C.byref(self.topo))       # 1 ahead-of-time kernel, 2 compiled at run time
+        can_pack = avail == 1 or (avail == 2 and (E >= 4096 or state_layout == "packed"))   # small batches: not worth ~1 s
         if can_pack and state_layout != "soa":
             # bodies without an ahead-of-time kernel: compile one for this spring graph now (NVRTC, ~1 s); on failure
             # keep the SoA layout and the run-time-topology kernel

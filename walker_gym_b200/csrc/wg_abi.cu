@@ -133,7 +133,8 @@ int wg_kernel_variant(const wg_topology* topo) {
 
 int wg_packed_available(const wg_topology* topo) {
     if (!topo) return fail(WG_ERR_BAD_ARG, "null topology%s");
-    return packed_pick(topo) ? 1 : 0;
+    const int v = packed_pick(topo);
+    return v == kJitId ? 2 : (v ? 1 : 0);
 }
 
 int wg_jit_prepare(const wg_topology* topo, int in3d, int obs_layout) {
@@ -202,7 +203,8 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
         default:
             // no ahead-of-time kernel: a kernel compiled for this spring graph at run time (up to 16 masses); if the
             // run-time compiler is missing or fails, the run-time-topology kernel (same bits)
-            if (!g_force_generic.load() && tuning(WG_TUNE_JIT) && jit_eligible_soa(topo) && jit_runtime_available() &&
+            // (only for batches that amortise the seconds of compilation)
+            if (n_env >= 4096 && !g_force_generic.load() && tuning(WG_TUNE_JIT) && jit_eligible_soa(topo) && jit_runtime_available() &&
                 launch_jit_soa(topo, prm, buf, n_env, s) == WG_OK)
                 return WG_OK;
             return launch_generic_step(topo, prm, buf, n_env, s);
