@@ -275,19 +275,43 @@ def run_ours(args):
         t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * E * Ke / (float(t2.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": E * env.M * 4, "d2h_bytes_per_step": E * (env.obs_dim * 4 + 4 + 1),
-               "steps": Ke,
-               "what": "wg_step_host: pinned host actions in; observations, rewards and dones out to pinned host memory "
-                       "every step (the reference-facing call); PCIe-bound by the 152-byte observation rows"}
-        # the other usage mode: policy on the device -- observations stay in HBM, only reward/done go to the host
-        Kd = max(Ke, 50)
-        for _ in range(3):
-            env.step_host(h_act, d_act, None, h_rew, h_done)
+        sync_e2e = {"value": world * E * Ke / (float(t2.item()) * 1e-3), "unit": UNIT, "steps": Ke,
+                    "what": "wg_step_host: upload, kernel and download back to back on one stream"}
+        # the same traffic double-buffered (HostStepPipeline): step t+1's upload + kernel overlap step t's download
+        from walker_gym_b200 import HostStepPipeline
+        pipe = HostStepPipeline(env)
+        h_obs2, h_rew2, h_done2 = h_obs.clone().pin_memory(), h_rew.clone().pin_memory(), h_done.clone().pin_memory()
+        slots = ((h_obs, h_rew, h_done), (h_obs2, h_rew2, h_done2))
+        for i in range(4):
+            pipe.submit(h_act, *slots[i & 1])
+        pipe.drain()
         barrier()
         e0.record()
-        for _ in range(Kd):
-            env.step_host(h_act, d_act, None, h_rew, h_done)
+        for i in range(Ke):
+            pipe.submit(h_act, *slots[i & 1])
+        pipe.drain()
+        e1.record()
+        barrier()
+        t2p = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2p, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * E * Ke / (float(t2p.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": E * env.M * 4, "d2h_bytes_per_step": E * (env.obs_dim * 4 + 4 + 1),
+               "steps": Ke,
+               "what": "HostStepPipeline: every step uploads its pinned host actions and downloads observations, rewards "
+                       "and dones to pinned host memory; two streams and two result slots overlap step t+1's upload + "
+                       "kernel with step t's download; PCIe-bound by the 152-byte observation rows",
+               "synchronous": sync_e2e}
+        # the other usage mode: policy on the device -- observations stay in HBM, only reward/done go to the host
+        Kd = max(Ke, 50)
+        for i in range(4):
+            pipe.submit(h_act, None, *slots[i & 1][1:])
+        pipe.drain()
+        barrier()
+        e0.record()
+        for i in range(Kd):
+            pipe.submit(h_act, None, *slots[i & 1][1:])
+        pipe.drain()
         e1.record()
         barrier()
         t3 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -295,7 +319,7 @@ def run_ours(args):
             dist.all_reduce(t3, op=dist.ReduceOp.MAX)
         e2e["device_policy_mode"] = {"value": world * E * Kd / (float(t3.item()) * 1e-3), "unit": UNIT,
                                      "h2d_bytes_per_step": E * env.M * 4, "d2h_bytes_per_step": E * 5, "steps": Kd,
-                                     "what": "same call with h_obs = NULL: observations stay on the device"}
+                                     "what": "same pipeline with h_obs = None: observations stay on the device"}
 
     if rank == 0:
         peak, peak_src = hbm_peak()

@@ -211,3 +211,30 @@ def test_batched_x64_many_envs_matches_oracle():
     assert 0 < st["mx_weak"].mean() < 1 and int(out["done"].sum()) >= 0
     with pytest.raises(ValueError):
         env.step(torch.zeros(E, 4, device="cuda:0"))                      # float32 actions are not x64 actions
+
+
+def test_host_step_pipeline_matches_synchronous_host_steps():
+    """HostStepPipeline (double-buffered, two streams) delivers exactly what back-to-back step_host calls deliver."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv, HostStepPipeline
+    E, T = 5000, 7
+    kw = dict(in3d=True, auto_reset="template", max_steps=4, seed=2)
+    a, b = BatchedPhysicsEnv("Balance-v0", E, "cuda:0", **kw), BatchedPhysicsEnv("Balance-v0", E, "cuda:0", **kw)
+    g = torch.Generator().manual_seed(0)
+    acts = [(torch.rand(E, 2, generator=g) * 2 - 1).pin_memory() for _ in range(T)]
+    obs_a = [torch.empty(E, a.obs_dim).pin_memory() for _ in range(T)]
+    rew_a = [torch.empty(E).pin_memory() for _ in range(T)]
+    done_a = [torch.empty(E, dtype=torch.uint8).pin_memory() for _ in range(T)]
+    pipe = HostStepPipeline(a)
+    for t in range(T):
+        pipe.submit(acts[t], obs_a[t], rew_a[t], done_a[t])
+    pipe.drain()
+    torch.cuda.synchronize()
+    d_act = torch.empty(E, 2, device="cuda:0")
+    h_obs, h_rew, h_done = torch.empty(E, b.obs_dim).pin_memory(), torch.empty(E).pin_memory(), torch.empty(E, dtype=torch.uint8).pin_memory()
+    for t in range(T):
+        b.step_host(acts[t], d_act, h_obs, h_rew, h_done)
+        torch.cuda.synchronize()
+        assert gu.same(obs_a[t].numpy(), h_obs.numpy()) and gu.same(rew_a[t].numpy(), h_rew.numpy()), t
+        assert gu.same(done_a[t].numpy(), h_done.numpy()), t
+    assert gu.same(a.pos.cpu().numpy(), b.pos.cpu().numpy())

@@ -465,3 +465,57 @@ class BatchedPhysicsEnv:
             cur_pos[:, env_index] = pos
             cur_vel[:, env_index] = vel
         self.set_state(pos=cur_pos, vel=cur_vel)
+
+
+class HostStepPipeline:
+    """Double-buffered end-to-end stepping on HOST buffers: step t+1's action upload and kernel overlap step t's
+    result download (two CUDA streams, two sets of device result buffers), so sustained throughput is bounded by the
+    slower direction of the PCIe link instead of the sum of upload + kernel + download.
+
+        pipe = HostStepPipeline(env)
+        for t in range(T):
+            pipe.submit(h_action[t], h_obs[t], h_reward[t], h_done[t])     # pinned host tensors; any result may be None
+        pipe.drain()                                                        # all results are in the host tensors
+
+    Results of step t are complete once a later ``submit`` that reuses the same slot (t + 2) or ``drain`` returned."""
+
+    def __init__(self, env: BatchedPhysicsEnv):
+        if env.act_layout != "row" or env.x64:
+            raise ValueError("HostStepPipeline needs act_layout='row' and float32 actions")
+        self.env = env
+        dev = env.device
+        self.s_step, self.s_copy = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.d_act = None
+        self.obs = [torch.empty_like(env.obs) for _ in range(2)]
+        self.rew = [torch.empty_like(env.reward) for _ in range(2)]
+        self.done = [torch.empty_like(env._done_u8) for _ in range(2)]
+        self.ev_step = [torch.cuda.Event() for _ in range(2)]
+        self.ev_copy = [torch.cuda.Event() for _ in range(2)]
+        self.t = 0
+        self.s_step.wait_stream(torch.cuda.current_stream(dev))
+
+    def submit(self, h_action, h_obs=None, h_reward=None, h_done=None) -> None:
+        env, k = self.env, self.t & 1
+        if self.d_act is None or self.d_act[0].shape != h_action.shape:
+            self.d_act = [torch.empty(h_action.shape, dtype=torch.float32, device=env.device) for _ in range(2)]
+        with torch.cuda.stream(self.s_step):
+            if self.t >= 2:
+                self.s_step.wait_event(self.ev_copy[k])           # slot k's previous results have left the device
+            self.d_act[k].copy_(h_action, non_blocking=True)
+            env.step(self.d_act[k], out=(self.obs[k], self.rew[k], self.done[k]))
+            self.ev_step[k].record(self.s_step)
+        with torch.cuda.stream(self.s_copy):
+            self.s_copy.wait_event(self.ev_step[k])
+            if h_obs is not None:
+                h_obs.copy_(self.obs[k], non_blocking=True)
+            if h_reward is not None:
+                h_reward.copy_(self.rew[k], non_blocking=True)
+            if h_done is not None:
+                h_done.copy_(self.done[k].view(h_done.dtype) if h_done.dtype != torch.uint8 else self.done[k], non_blocking=True)
+            self.ev_copy[k].record(self.s_copy)
+        self.t += 1
+
+    def drain(self) -> None:
+        cur = torch.cuda.current_stream(self.env.device)
+        cur.wait_stream(self.s_step)
+        cur.wait_stream(self.s_copy)
