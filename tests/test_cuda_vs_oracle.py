@@ -541,3 +541,34 @@ def test_runtime_specialised_soa_kernel_for_mid_size_user_bodies():
         assert gu.same(res[0].cpu().numpy(), res[1].cpu().numpy())
     finally:
         Point.clear()
+
+
+@pytest.mark.parametrize("R,masses,in3d,layout,auto", [(2, (5, 5, 1, 3), True, "row", "template"), (8, (5, 5, 1, 3), False, "feature", "jitter"),
+                                                       (4, (1, 1, 1, 1), False, "row", "template"), (4, (2, 3, 4, 5), True, "feature", "jitter"),
+                                                       (8, (5, 5, 1, 3), True, "row", "template")])
+def test_units_kernel_for_bodies_of_identical_disconnected_units(R, masses, in3d, layout, auto):
+    """R Balance units in one env (R = 2, 4, 8), one lane per unit: the Balance-v0 mass pattern (mode 3), unit masses
+    and other integer masses; 2-D and 3-D, both observation layouts, both auto-reset modes, substeps, ragged batches."""
+    from walker_gym_b200 import BODIES, BatchedPhysicsEnv, Creature, Muscle, Point, Skeleton
+    base = BODIES["balance_v0"]
+    pts_s, mus_s, sks_s = [], [], []
+    for u in range(R):
+        off = 150.0 * (u - (R - 1) / 2)
+        pts_s += [(float(masses[n]), (p[0] + off, p[1], p[2]), False) for n, (_, p) in enumerate(base["points"])]
+        mus_s += [(4 * u + i, 4 * u + j, {}) for i, j, _ in base["muscles"]]
+    for u in range(R):
+        sks_s += [(4 * u + i, 4 * u + j, {}) for i, j, _ in base["skeletons"]]
+    spec = {"points": pts_s, "muscles": mus_s, "skeletons": sks_s}
+    Point.clear()
+    try:
+        pts = [Point(m, list(p), [0, 0, 0]) for m, p, _ in pts_s]
+        cr = Creature(pts, [Muscle(pts[i], pts[j]) for i, j, _ in mus_s], [Skeleton(pts[i], pts[j]) for i, j, _ in sks_s])
+        E = 1003
+        env = BatchedPhysicsEnv(cr, E, "cuda:0", in3d=in3d, auto_reset=auto, max_steps=6, k_sub=3, seed=R, obs_layout=layout,
+                                keep_old_a=True, track_info=True, track_contacts=True, initial_reset=False)
+        body = wo.make_body(spec)
+        prm = wo.make_params(in3d=in3d, auto_reset={"jitter": 1, "template": 2}[auto], max_steps=6, k_sub=3, seed=R)
+        st = wo.init_state(body, E)
+        run_lockstep(env, body, prm, st, 14, np.random.default_rng(R), noise_reset=True)
+    finally:
+        Point.clear()
