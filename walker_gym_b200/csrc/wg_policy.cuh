@@ -244,7 +244,7 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
         for (int mt = 0; mt < MT; mt++)
 #pragma unroll
             for (int i = 0; i < 4; i++) hd[mt][i] = 0.0f;
-#pragma unroll 1
+#pragma unroll
         for (int grp = 0; grp < 2; grp++) {
             float a2[4][MT][4];
 #pragma unroll
