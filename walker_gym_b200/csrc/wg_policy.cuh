@@ -102,8 +102,27 @@ __device__ __forceinline__ void fill_plane(uint32_t* dst, int n_rows, int KP, in
             else if (n == n_valid_rows && w_last) v = w_last[k];
         }
         const uint32_t hi = to_tf32(v);
-        dst[idx] = hi;
-        if (SPLIT) dst[n_rows * KP + idx] = to_tf32(v - __uint_as_float(hi));
+        if (SPLIT) {
+            // hi and lo of a column pair share one 16-byte vector {hi(k), hi(k+1), lo(k), lo(k+1)}: one LDS.128 per
+            // B fragment instead of two LDS.64 (row pitch 2*KP words == 16 mod 32: conflict-free quarter-warps)
+            const int kc = idx - n * KP;
+            uint32_t* q = dst + ((size_t)n * KP + (kc & ~1)) * 2 + (kc & 1);
+            q[0] = hi;
+            q[2] = to_tf32(v - __uint_as_float(hi));
+        } else {
+            dst[idx] = hi;
+        }
+    }
+}
+// B fragment (b0, b1) of columns k, k+1 of row n: hi and lo planes
+template <bool SPLIT>
+__device__ __forceinline__ void load_b(const uint32_t* W, int n, int KP, int k, uint2& bhi, uint2& blo) {
+    if (SPLIT) {
+        const uint4 b = *reinterpret_cast<const uint4*>(W + ((size_t)n * KP + k) * 2);
+        bhi = make_uint2(b.x, b.y); blo = make_uint2(b.z, b.w);
+    } else {
+        bhi = *reinterpret_cast<const uint2*>(W + (size_t)n * KP + k);
+        blo = make_uint2(0u, 0u);
     }
 }
 
@@ -216,9 +235,8 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
             }
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
-                const int off = (8 * nt + g) * KP1 + 8 * kk + 2 * t;
-                const uint2 bhi = *reinterpret_cast<const uint2*>(W1 + off);
-                const uint2 blo = SPLIT ? *reinterpret_cast<const uint2*>(W1 + kPolH * KP1 + off) : make_uint2(0u, 0u);
+                uint2 bhi, blo;
+                load_b<SPLIT>(W1, 8 * nt + g, KP1, 8 * kk + 2 * t, bhi, blo);
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) mma3<SPLIT>(acc[mt][nt], ahi[mt], alo[mt], bhi, blo);
             }
@@ -257,9 +275,8 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
             for (int kk = 0; kk < 8; kk++) {
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const int off = (8 * (4 * grp + q) + g) * KP2 + 8 * kk + 2 * t;
-                    const uint2 bhi = *reinterpret_cast<const uint2*>(W2 + off);
-                    const uint2 blo = SPLIT ? *reinterpret_cast<const uint2*>(W2 + kPolH * KP2 + off) : make_uint2(0u, 0u);
+                    uint2 bhi, blo;
+                    load_b<SPLIT>(W2, 8 * (4 * grp + q) + g, KP2, 8 * kk + 2 * t, bhi, blo);
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) mma3<SPLIT>(a2[q][mt], h1hi[mt][kk], h1lo[mt][kk], bhi, blo);
                 }
@@ -268,9 +285,8 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
             for (int q = 0; q < 4; q++) {
                 const int nt2 = 4 * grp + q;
                 const float bA = B2[8 * nt2 + 2 * t], bB = B2[8 * nt2 + 2 * t + 1];
-                const int off = g * KP2 + 8 * nt2 + 2 * t;
-                const uint2 bhi = *reinterpret_cast<const uint2*>(WH + off);
-                const uint2 blo = SPLIT ? *reinterpret_cast<const uint2*>(WH + 8 * KP2 + off) : make_uint2(0u, 0u);
+                uint2 bhi, blo;
+                load_b<SPLIT>(WH, g, KP2, 8 * nt2 + 2 * t, bhi, blo);
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
                     const float x[4] = { pol_tanh<SPLIT>(a2[q][mt][0] + bA), pol_tanh<SPLIT>(a2[q][mt][2] + bA),
@@ -282,6 +298,22 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
             }
         }
 
+        // ---- gaussian noise: the tile needs one Philox + Box-Muller evaluation per (env row, action pair); spread them
+        // over all lanes (evaluation q = pair * 16*MT + row on lane q % 32) instead of leaving them to the few lanes that
+        // own an action pair, then hand each owner its pair with two shuffles ----
+        constexpr int ROWS = 16 * MT, JMAX = (ROWS * 4 + 31) / 32;
+        const int n_eval = A.sample ? ROWS * ((M + 1) / 2) : 0;
+        float2 zq[JMAX];
+#pragma unroll
+        for (int j = 0; j < JMAX; j++) {
+            zq[j] = make_float2(0.0f, 0.0f);
+            if (32 * j < n_eval) {                                            // warp-uniform
+                const int q = 32 * j + lane;
+                const int64_t eq = e0 + q % ROWS;
+                if (q < n_eval && eq < E)
+                    zq[j] = pol_normal2(A.seed_lo, A.seed_hi, A.env_offset + (uint32_t)eq, step, (uint32_t)(q / ROWS));
+            }
+        }
         // ---- heads: this thread holds outputs n = 2t, 2t+1 of env rows (mt, h); n < M mean, n == M value ----
 #pragma unroll
         for (int mt = 0; mt < MT; mt++)
@@ -291,8 +323,15 @@ policy_act_kernel(const __grid_constant__ PolicyArgs A) {
                 float lp = 0.0f;
                 float out[2] = { hd[mt][2 * h + 0] + BH[2 * t], hd[mt][2 * h + 1] + BH[2 * t + 1] };
                 float2 z = make_float2(0.0f, 0.0f);
-                if (A.sample && 2 * t < M && ev[mt][h])
-                    z = pol_normal2(A.seed_lo, A.seed_hi, A.env_offset + (uint32_t)e, step, (uint32_t)t);
+                const int qo = ROWS * t + 16 * mt + 8 * h + g;                // this thread's evaluation (pair t, its env row)
+#pragma unroll
+                for (int j = 0; j < JMAX; j++) {
+                    if (32 * j < n_eval) {                                    // warp-uniform
+                        const float zx = __shfl_sync(0xffffffffu, zq[j].x, qo & 31);
+                        const float zy = __shfl_sync(0xffffffffu, zq[j].y, qo & 31);
+                        if ((qo >> 5) == j) z = make_float2(zx, zy);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
                     const int n = 2 * t + j;
