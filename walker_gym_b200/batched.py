@@ -162,6 +162,7 @@ class BatchedPhysicsEnv:
             self.mx_weak = torch.ones(self.M, E, dtype=torch.uint8, device=dev)
         else:
             self._x64 = self.mx64 = self.mx_weak = None
+        self._step_offset, self._defer_advance = 0, False
         self._buf = WgBuffers()
         self._bind()
         if initial_reset:
@@ -190,12 +191,31 @@ class BatchedPhysicsEnv:
 
     def _advance(self) -> None:
         if self._counter is not None:
-            self._counter.add_(1)
+            if not self._defer_advance:
+                self._counter.add_(1)
         else:
             self.step_count += 1
 
     def _stamp(self) -> None:
-        self.params.step_index = 0 if self._counter is not None else (self.step_count & 0xFFFFFFFF)
+        self.params.step_index = (self._step_offset if self._counter is not None else self.step_count) & 0xFFFFFFFF
+
+    def deferred_steps(self, n: int):
+        """Context manager for a block of ``n`` steps in graph-safe mode: the caller sets ``_step_offset`` to the step's
+        position in the block before each step, the device counter is advanced once by ``n`` at the end instead of by
+        one tiny kernel per step.  The Philox indices are the ones per-step advancing would have produced."""
+        env = self
+
+        class _Block:
+            def __enter__(self_inner):
+                env._defer_advance = env._counter is not None
+                return env
+
+            def __exit__(self_inner, *exc):
+                if env._defer_advance:
+                    env._defer_advance, env._step_offset = False, 0
+                    env._counter.add_(n)
+                return False
+        return _Block()
 
     # ---- state access (layout independent) --------------------------------------------------------
     def _var(self, k: int) -> torch.Tensor:

@@ -159,10 +159,12 @@ class RolloutCollector:
         kw = dict(seed=self.seed, step_counter=env._counter, env_offset=int(env.params.env_offset),
                   obs_layout=env.obs_layout, act_layout=env.act_layout)
         self.obs[0].copy_(env.obs)
-        for t in range(self.T):
-            fp.act(self.obs[t], action=self.actions[t], logp=self.logp[t], value=self.values[t], sample=True,
-                   step_index=0 if env._counter is not None else env.step_count, **kw)
-            env.step(self.actions[t], out=(self.obs[t + 1], self.rewards[t], dones_u8[t]))
+        with env.deferred_steps(self.T):             # graph-safe mode: one counter update per rollout, not per step
+            for t in range(self.T):
+                env._step_offset = t
+                fp.act(self.obs[t], action=self.actions[t], logp=self.logp[t], value=self.values[t], sample=True,
+                       step_index=t if env._counter is not None else env.step_count, **kw)
+                env.step(self.actions[t], out=(self.obs[t + 1], self.rewards[t], dones_u8[t]))
         fp.act(self.obs[self.T], value=self.values[self.T], sample=False, **kw)
         env.obs.copy_(self.obs[self.T])                  # keep env.obs current for the next rollout / other callers
         gae(self.rewards, self.values, dones_u8, self.advantages, self.returns, self.gamma, self.lam, self.reward_clip)
