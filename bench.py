@@ -148,6 +148,18 @@ def cpu_run(n_env: int, steps: int, warmup: int, seed: int = 0):
     wo.reset(body, prm, st, mode=2)
     rng = np.random.default_rng(seed)
     ring = [rng.uniform(-1, 1, (n_env, N_MUSCLE)).astype(np.float32) for _ in range(8)]
+    # OpenMP pool spin-up on a scratch state (untimed): the first ~20 parallel regions of a fresh pool run 10-25x
+    # slower than steady state (thread creation, scheduler spreading the threads over the cores); without this a
+    # short --steps run would under-report the CPU arm.  Bounded at 3 s; the timed trajectory is not touched.
+    scratch = wo.init_state(body, n_env)
+    scratch.pop("old_a")
+    wo.reset(body, prm, scratch, mode=2)
+    t_spin = time.perf_counter()
+    for _ in range(60):
+        wo.step(body, prm, scratch, ring[0], want_info=False)
+        if time.perf_counter() - t_spin > 3.0:
+            break
+    del scratch
     for t in range(warmup):
         prm.step_index = t + 1
         wo.step(body, prm, st, ring[t % 8], want_info=False)
