@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--probe-stream", action="store_true",
                     help="measure the HBM rate of a pure streaming kernel with the step kernel's read:write mix and exit")
     ap.add_argument("--k-sub", type=int, default=0, help="physics substeps per env step (0 = the config's default)")
-    ap.add_argument("--steps-per-launch", type=int, default=1, help="config 6: update_physics calls fused in one launch")
+    ap.add_argument("--steps-per-launch", type=int, default=1, help="config 6: update_physics calls fused in one launch; config 3: env-steps per launch (wg_step_multi)")
     ap.add_argument("--pkg-body", default="box", help="config 6: body builder of gym/optimized_walker/walker.py")
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5, 6],
                     help="BASELINE.json config: 3 = Balance-v0 throughput (headline, default), 4 = enlarged body "
@@ -228,6 +228,8 @@ def run_ours(args):
         return run_rollout(args, rank, world, dev)
     if args.config == 6:
         return run_pkg(args, rank, world, dev)
+    if args.config == 3 and args.steps_per_launch > 1:
+        return run_multi(args, rank, world, dev)
     env_id = {"balance": ENV_ID, "box": "Box-v0", "legacy_box": "box"}.get(args.body, args.body)
     body, k_sub = (env_id, 1) if args.config == 3 else ("quad_balance", 8)
     if args.body == "quad":
@@ -371,6 +373,68 @@ def run_ours(args):
                                         "with 1 substep the same body reaches 0.51")
         if not args.no_cpu_baseline and world == 1 and args.config == 3 and args.body == "balance":
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_multi(args, rank, world, dev):
+    """Next-row workload: T env-steps per launch (wg_step_multi / BatchedPhysicsEnv.step_many) for
+    actions known up front.  A bench step = one launch = --steps-per-launch env-steps of every env; value counts
+    env-steps.  The state is read and written once per launch, so the kernel is bound by the instruction rate of
+    the bit-exact arithmetic, not by HBM: the HBM fraction is reported for completeness."""
+    import torch
+    import torch.distributed as dist
+    from walker_gym_b200 import BatchedPhysicsEnv
+    W, K, E, T = max(args.warmup, 3), args.steps, args.envs_per_gpu, args.steps_per_launch
+    env_id = {"balance": ENV_ID, "box": "Box-v0"}[args.body]
+    env = BatchedPhysicsEnv(env_id, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
+                            track_stats=True, k_sub=args.k_sub or 1, state_layout="packed")
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    ring = [(torch.rand(T, E, env.M, device=dev, generator=g) * 2 - 1) for _ in range(4)]
+    out = (torch.empty(T, E, device=dev), torch.empty(T, E, dtype=torch.uint8, device=dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for t in range(W):
+        env.step_many(ring[t % 4], out=out)
+    barrier()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for t in range(K):
+        env.step_many(ring[t % 4], out=out)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    tmax = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    stats = env.episode_stats(all_reduce=True)
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        bytes_per_launch_env = 48 * env.N + 8 * env.M + 8 + 36 * env.N + 4 * env.M + T * (4 * env.M + 5)
+        per_launch_s = ms * 1e-3 / K
+        achieved = E * bytes_per_launch_env / per_launch_s / 1e9
+        line = {"metric": METRIC, "value": world * E * K * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{env_id}, in3d=True, {E} envs per GPU, {T} env-steps per launch (wg_step_multi: actions "
+                                       f"[T,E,M] known up front, per-step reward / done, observation after the last step), "
+                                       "template auto-reset, U(-1,1) f32 actions from a 4-deep device ring of blocks",
+                           "baseline_config": "next row f2", "envs_per_gpu": E, "global_envs": world * E,
+                           "steps_per_launch": T, "us_per_env_step": per_launch_s * 1e6 / T,
+                           "l2": f"state+obs+actions per launch = {E * bytes_per_launch_env / 1e6:.0f} MB > 126 MB L2"},
+                "roofline": {"bound": "fp32 issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_launch": bytes_per_launch_env,
+                             "kernel": "wg::step_multi_packed_kernel", "kernel_us": per_launch_s * 1e6},
+                "e2e": None, "gpu_launches": K, "clocks": clocks,
+                "episode_stats": {k: stats[k] for k in ("episodes", "return_mean", "length_mean")}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -199,7 +199,24 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
             int64_t n_env, void* cuda_stream);
 
 /*
- * wg_step in x64 mode: buf->mx64 / mx_weak / action64 must be set (action is ignored; mx still receives the float32
+ * n_steps consecutive PhysicsEnv.step calls (gym/optimized_env.py:70-92) in ONE launch, for callers that know
+ * the next n_steps actions up front (scripted gaits / open-loop controllers as in gym/main.py's action tables,
+ * action repeat, replay of a recorded action sequence).  The state stays in registers between the steps, so an
+ * env-step costs its arithmetic plus 4 * n_muscle + 5 bytes of HBM traffic instead of the whole state.
+ * Bit-identical to n_steps wg_step calls with prm->step_index advanced by one per call (an auto-reset at step t
+ * of the block draws its jitter with Philox index step_index + t).
+ *   buf->state_packed  required (packed layout); Balance / Box spring graphs with unit / power-of-two /
+ *                      small-integer masses (WG_ERR_UNSUPPORTED otherwise)
+ *   buf->action        [n_steps][n_env][n_muscle] float32 (act_layout 0, act_dim == n_muscle), or null
+ *   buf->reward        [n_steps][n_env] float32, optional;  buf->done  [n_steps][n_env] uint8, optional
+ *   buf->obs           [n_env][obs_dim] row-major observation after the LAST step (obs_layout 0), optional
+ *   buf->old_a / contact_pre / contact_post / energy / centroid must be null.
+ */
+int wg_step_multi(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf,
+                  int64_t n_env, int32_t n_steps, void* cuda_stream);
+
+/*
+ * wg_step in x64 mode:buf->mx64 / mx_weak / action64 must be set (action is ignored; mx still receives the float32
  * view of the lengths, which is what the float32 observation carries).  Bit-identical to the reference driven
  * with float64 actions.  Runs the run-time-topology kernel (a compatibility path, not the throughput path).
  * wg_reset does not touch mx64 / mx_weak: after a template reset the caller sets them to x0_d / 1.

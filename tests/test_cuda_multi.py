@@ -1,0 +1,115 @@
+"""GPU: wg_step_multi (T env-steps per launch, BatchedPhysicsEnv.step_many) against the C oracle stepped T times
+on the same seeded inputs, and against T single wg_step launches.  Equality is exact (float32 bit patterns): every
+step of the block is the single-step kernel's device code with the state kept in registers."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import walker_oracle as wo
+from test_cuda_vs_oracle import spec_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pair(name, E, *, in3d, auto_reset, max_steps, seed, k_sub=1):
+    from walker_gym_b200 import BatchedPhysicsEnv
+    env = BatchedPhysicsEnv(name, E, DEV, in3d=in3d, auto_reset=auto_reset, max_steps=max_steps, seed=seed, k_sub=k_sub,
+                            state_layout="packed", track_stats=True, initial_reset=False)
+    body = wo.make_body(spec_of(name))
+    ar = {None: 0, "jitter": 1, "template": 2}[auto_reset]
+    prm = wo.make_params(max_steps=max_steps, k_sub=k_sub, auto_reset=ar, seed=seed, in3d=in3d)
+    return env, body, prm, wo.init_state(body, E)
+
+
+@pytest.mark.parametrize("name", ["balance_v0", "box_v0", "balance", "box2"])
+@pytest.mark.parametrize("in3d", [True, False])
+@pytest.mark.parametrize("auto_reset", ["template", "jitter", None])
+def test_step_many_matches_oracle(name, in3d, auto_reset):
+    """Blocks of 1, 7 and 12 steps with episodes ending (max_steps = 5) and being reset inside a block: per-step
+    rewards and dones, the observation after each block, the state and the episode statistics equal the oracle's."""
+    import torch
+    E = 4096 + 37                                   # a partial last tile and a partial last warp
+    env, body, prm, st = _pair(name, E, in3d=in3d, auto_reset=auto_reset, max_steps=5, seed=11)
+    rng = np.random.default_rng(3)
+    nz = (rng.standard_normal((3 * env.N, E)) * 0.1).astype(np.float32)
+    env.reset(noise=torch.from_numpy(nz).cuda(), mode="jitter")
+    wo.reset(body, prm, st, mode=1, noise=nz)
+    ep = (np.zeros(E, np.float32), np.zeros((4, E), np.float32))
+    for T in (1, 7, 12):
+        acts = rng.uniform(-1, 1, (T, E, env.M)).astype(np.float32)
+        first = env.step_count
+        obs, rew, done = env.step_many(torch.from_numpy(acts).cuda())
+        assert env.step_count == first + T
+        for t in range(T):
+            prm.step_index = first + t
+            out = wo.step(body, prm, st, acts[t], ep_ret=ep[0], fin_stats=ep[1])
+            assert gu.same(rew[t].cpu().numpy(), out["reward"]), f"reward @ block {T} step {t}"
+            assert gu.same(done[t].cpu().numpy(), out["done"].astype(bool)), f"done @ block {T} step {t}"
+        assert gu.same(obs.cpu().numpy(), out["obs"]), f"obs after block {T}"
+        assert gu.same(env.pos.cpu().numpy(), st["pos"]) and gu.same(env.vel.cpu().numpy(), st["vel"])
+        assert gu.same(env.mx.cpu().numpy(), st["mx"]) and gu.same(env.steps.cpu().numpy(), st["steps"])
+    assert gu.same(env.fin_stats.cpu().numpy(), ep[1])
+    if auto_reset:
+        assert ep[1][3].sum() > 0                   # episodes did end inside the blocks
+
+
+def test_step_many_equals_single_steps_at_full_size():
+    """BASELINE config 3 size (2^20 envs): one 16-step launch == 16 wg_step launches, graph-safe device counter
+    included; a block without actions equals steps without actions."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    E, T = 1 << 20, 16
+    kw = dict(in3d=True, auto_reset="template", max_steps=6, seed=5, state_layout="packed")
+    a = BatchedPhysicsEnv("Balance-v0", E, DEV, graph_safe=True, **kw)
+    b = BatchedPhysicsEnv("Balance-v0", E, DEV, **kw)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    acts = torch.rand(T, E, 2, device=DEV, generator=g) * 2 - 1
+    obs, rew, done = a.step_many(acts)
+    for t in range(T):
+        o, r, d, _ = b.step(acts[t])
+        assert torch.equal(r.view(torch.int32), rew[t].view(torch.int32)) or gu.same(r.cpu().numpy(), rew[t].cpu().numpy()), t
+        assert torch.equal(d, done[t]), t
+    assert gu.same(obs.cpu().numpy(), o.cpu().numpy())
+    assert torch.equal(a.state.view(torch.int32), b.state.view(torch.int32)) or gu.same(a.state.cpu().numpy(), b.state.cpu().numpy())
+    assert int(a._counter.item()) == b.step_count == T + 1
+    obs, rew, done = a.step_many(None, n_steps=3)
+    for t in range(3):
+        o, r, d, _ = b.step(None)
+        assert gu.same(r.cpu().numpy(), rew[t].cpu().numpy()) and torch.equal(d, done[t])
+    assert gu.same(obs.cpu().numpy(), o.cpu().numpy())
+
+
+def test_step_many_substeps_and_out_buffers():
+    """k_sub = 4 inside a block; results written into caller-owned trajectory slots."""
+    import torch
+    E, T = 1000, 9
+    env, body, prm, st = _pair("box_v0", E, in3d=True, auto_reset="template", max_steps=4, seed=2, k_sub=4)
+    rng = np.random.default_rng(8)
+    acts = rng.uniform(-1, 1, (T, E, env.M)).astype(np.float32)
+    rew = torch.full((T, E), 7.0, device=DEV)
+    done = torch.zeros(T, E, dtype=torch.uint8, device=DEV)
+    first = env.step_count
+    obs, r2, d2 = env.step_many(torch.from_numpy(acts).cuda(), out=(rew, done))
+    assert r2 is rew and d2 is done
+    for t in range(T):
+        prm.step_index = first + t
+        out = wo.step(body, prm, st, acts[t])
+        assert gu.same(rew[t].cpu().numpy(), out["reward"]) and gu.same(done[t].cpu().numpy().astype(bool), out["done"].astype(bool)), t
+    assert gu.same(obs.cpu().numpy(), out["obs"])
+
+
+def test_step_many_rejects_what_it_cannot_do():
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    soa = BatchedPhysicsEnv("Balance-v0", 256, DEV, state_layout="soa")
+    with pytest.raises(ValueError):
+        soa.step_many(torch.zeros(2, 256, 2, device=DEV))
+    env = BatchedPhysicsEnv("Balance-v0", 256, DEV, state_layout="packed")
+    with pytest.raises(ValueError):
+        env.step_many(torch.zeros(2, 255, 2, device=DEV))
+    with pytest.raises(ValueError):
+        env.step_many(None)
+    humanb = BatchedPhysicsEnv("humanb", 256, DEV, state_layout="packed")          # no T-steps kernel for this graph
+    with pytest.raises(RuntimeError):
+        humanb.step_many(torch.zeros(2, 256, humanb.M, device=DEV))

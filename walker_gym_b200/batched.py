@@ -377,6 +377,57 @@ class BatchedPhysicsEnv:
             info = {"steps": self.steps, "centroid_position": self.centroid, "total_energy": self.energy}
         return res_obs, res_rew, res_done, info
 
+    def step_many(self, actions: Optional[torch.Tensor], n_steps: Optional[int] = None, out=None):
+        """``n_steps`` consecutive ``PhysicsEnv.step`` calls in ONE launch (``wg_step_multi``) for actions known up
+        front: scripted gaits / open-loop controllers (the action tables of gym/main.py), action repeat, replays.
+
+        ``actions``: float32 [T, E, M] (``None``: T = ``n_steps`` steps without an action).  Returns
+        ``(obs, rewards [T, E], dones [T, E])``: ``obs`` is the observation after the last step (the env's own
+        buffer), rewards / dones are per step.  Bit-identical to T ``step`` calls; needs ``state_layout="packed"``,
+        row-major observations and actions, a Balance / Box body, and no per-step info buffers.
+        ``out=(rewards, dones)``: caller-owned result tensors (dones 1 byte per element)."""
+        if self.state is None or self.x64 or self.obs_layout != "row" or self.act_layout != "row":
+            raise ValueError("step_many needs state_layout='packed', obs_layout='row', act_layout='row' and float32 actions")
+        E = self.num_envs
+        if actions is not None:
+            if actions.dim() != 3 or actions.shape[1] != E or actions.shape[2] != self.M:
+                raise ValueError(f"actions must have shape [T, {E}, {self.M}]")
+            self._check_f32(actions, actions.shape, "actions")
+            T = int(actions.shape[0])
+            if n_steps is not None and int(n_steps) != T:
+                raise ValueError("n_steps disagrees with actions.shape[0]")
+        elif n_steps is None:
+            raise ValueError("n_steps is required when actions is None")
+        else:
+            T = int(n_steps)
+        if T < 1:
+            raise ValueError("step_many needs at least one step")
+        if out is None:
+            rew = torch.empty(T, E, dtype=torch.float32, device=self.obs.device)
+            done = torch.empty(T, E, dtype=torch.bool, device=self.obs.device)
+        else:
+            rew, done = out
+            self._check_f32(rew, (T, E), "out rewards")
+            if done.element_size() != 1 or tuple(done.shape) != (T, E) or not done.is_contiguous():
+                raise ValueError("out dones must be a contiguous 1-byte tensor of shape [T, E]")
+        b = self._buf
+        saved = (b.old_a, b.contact_pre, b.contact_post, b.energy, b.centroid)
+        b.old_a = b.contact_pre = b.contact_post = b.energy = b.centroid = None
+        b.action, b.act_dim, b.noise = self._p(actions), (self.M if actions is not None else 0), None
+        b.reward, b.done = rew.data_ptr(), done.data_ptr()
+        self._stamp()
+        with torch.cuda.device(self.device):
+            rc = self.lib.wg_step_multi(C.byref(self.topo), C.byref(self.params), C.byref(b), E, T, self._stream())
+        b.old_a, b.contact_pre, b.contact_post, b.energy, b.centroid = saved
+        b.reward, b.done = self._p(self.reward), self._p(self._done_u8)
+        _lib.check(rc, "wg_step_multi")
+        if self._counter is not None:
+            if not self._defer_advance:
+                self._counter.add_(T)
+        else:
+            self.step_count += T
+        return self.obs, rew, done
+
     def step_host(self, h_action: torch.Tensor, d_action: torch.Tensor, h_obs: Optional[torch.Tensor] = None,
                   h_reward: Optional[torch.Tensor] = None, h_done: Optional[torch.Tensor] = None) -> None:
         """End-to-end step on HOST buffers (``wg_step_host``): copies the pinned host

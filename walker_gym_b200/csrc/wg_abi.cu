@@ -107,6 +107,8 @@ static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* 
     return WG_OK;
 }
 
+int launch_balance_multi(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int n_steps, cudaStream_t);
+int launch_box_multi(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int n_steps, cudaStream_t);
 int launch_generic_step_x64(const wg_topology*, const wg_x64*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_pkg_update(const wg_pkg_system*, const wg_pkg_params*, float* pos, float* vel, float* old_a,
                       int64_t E, int32_t n_steps, bool force_generic, cudaStream_t);
@@ -208,6 +210,27 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
                 launch_jit_soa(topo, prm, buf, n_env, s) == WG_OK)
                 return WG_OK;
             return launch_generic_step(topo, prm, buf, n_env, s);
+    }
+}
+
+int wg_step_multi(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf, int64_t n_env, int32_t n_steps,
+                  void* cuda_stream) {
+    int rc = validate(topo, prm, buf, n_env);
+    if (rc != WG_OK) return rc;
+    if (n_steps < 1 || n_steps > 65536) return fail(WG_ERR_BAD_ARG, "n_steps out of range [1, 65536]%s");
+    if (!buf->state_packed) return fail(WG_ERR_BAD_ARG, "wg_step_multi needs the packed state layout%s");
+    if (general_masses(topo)) return fail(WG_ERR_UNSUPPORTED, "wg_step_multi: unit / power-of-two / small-integer masses and no DingPoints%s");
+    if (buf->obs && buf->obs_layout != 0) return fail(WG_ERR_BAD_ARG, "wg_step_multi writes row-major observations%s");
+    if (buf->action && (buf->act_layout != 0 || buf->act_dim != topo->n_muscle))
+        return fail(WG_ERR_BAD_ARG, "wg_step_multi reads actions as [n_steps][n_env][n_muscle]%s");
+    if (buf->old_a || buf->contact_pre || buf->contact_post || buf->energy || buf->centroid)
+        return fail(WG_ERR_BAD_ARG, "wg_step_multi has no per-step info outputs (old_a / contact / energy / centroid must be null)%s");
+    if (n_env == 0) return WG_OK;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    switch (g_force_generic.load() ? 0 : topo_id(topo)) {
+        case TopoBalance::kId: return launch_balance_multi(topo, prm, buf, n_env, n_steps, s);
+        case TopoBox::kId:     return launch_box_multi(topo, prm, buf, n_env, n_steps, s);
+        default:               return fail(WG_ERR_UNSUPPORTED, "wg_step_multi: only the Balance and Box spring graphs have a T-steps-per-launch kernel%s");
     }
 }
 
