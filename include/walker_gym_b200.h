@@ -200,7 +200,7 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
 
 /*
  * n_steps consecutive PhysicsEnv.step calls (gym/optimized_env.py:70-92) in ONE launch, for callers that know
- * the next n_steps actions up front (scripted gaits / open-loop controllers as in gym/main.py's action tables,
+ * the next n_steps actions up front (scripted gaits / open-loop controllers like the phase table sketched at gym/walker.py:356-366,
  * action repeat, replay of a recorded action sequence).  The state stays in registers between the steps, so an
  * env-step costs its arithmetic plus 4 * n_muscle + 5 bytes of HBM traffic instead of the whole state.
  * Bit-identical to n_steps wg_step calls with prm->step_index advanced by one per call (an auto-reset at step t

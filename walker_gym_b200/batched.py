@@ -379,7 +379,7 @@ class BatchedPhysicsEnv:
 
     def step_many(self, actions: Optional[torch.Tensor], n_steps: Optional[int] = None, out=None):
         """``n_steps`` consecutive ``PhysicsEnv.step`` calls in ONE launch (``wg_step_multi``) for actions known up
-        front: scripted gaits / open-loop controllers (the action tables of gym/main.py), action repeat, replays.
+        front: scripted gaits / open-loop controllers (the phase-table gait sketched at gym/walker.py:356-366), action repeat, replays.
 
         ``actions``: float32 [T, E, M] (``None``: T = ``n_steps`` steps without an action).  Returns
         ``(obs, rewards [T, E], dones [T, E])``: ``obs`` is the observation after the last step (the env's own

@@ -14,9 +14,15 @@
 
 namespace wg {
 
+// resident CTAs per SM the compiler must allow (small bodies): the kernel is instruction bound, so this trades
+// registers per thread against warps per scheduler
+#ifndef WG_MULTI_MIN_BLOCKS
+#define WG_MULTI_MIN_BLOCKS WG_PACKED_MIN_BLOCKS
+#endif
+
 // action: [T][E][M] row-major; reward: [T][E]; done: [T][E]; obs: [E][D] row-major, after the last step.
 template <class Topo, bool IN3D, int MM, class Args = StepArgs<Topo::N, Topo::S>>
-__global__ void __launch_bounds__(kPackedBlock, Topo::N <= 4 ? WG_PACKED_MIN_BLOCKS : (Topo::N <= 6 ? 512 : 384) / WG_PACKED_BLOCK)
+__global__ void __launch_bounds__(kPackedBlock, WG_MULTI_MIN_BLOCKS)
 step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps) {
     constexpr int N = Topo::N, M = Topo::M;
     constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;
