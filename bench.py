@@ -387,7 +387,7 @@ def run_multi(args, rank, world, dev):
     import torch.distributed as dist
     from walker_gym_b200 import BatchedPhysicsEnv
     W, K, E, T = max(args.warmup, 3), args.steps, args.envs_per_gpu, args.steps_per_launch
-    env_id = {"balance": ENV_ID, "box": "Box-v0"}[args.body]
+    env_id = {"balance": ENV_ID, "box": "Box-v0", "legacy_box": "box"}.get(args.body, args.body)
     env = BatchedPhysicsEnv(env_id, E, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * E,
                             track_stats=True, k_sub=args.k_sub or 1, state_layout="packed")
     g = torch.Generator(device=dev).manual_seed(100 + rank)

@@ -205,15 +205,18 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
  * env-step costs its arithmetic plus 4 * n_muscle + 5 bytes of HBM traffic instead of the whole state.
  * Bit-identical to n_steps wg_step calls with prm->step_index advanced by one per call (an auto-reset at step t
  * of the block draws its jitter with Philox index step_index + t).
- *   buf->state_packed  required (packed layout); Balance / Box spring graphs with unit / power-of-two /
- *                      small-integer masses (WG_ERR_UNSUPPORTED otherwise)
- *   buf->action        [n_steps][n_env][n_muscle] float32 (act_layout 0, act_dim == n_muscle), or null
+ *   buf->state_packed  required (packed layout); every body with an ahead-of-time packed kernel (the Balance / Box
+ *                      graphs and walker.py's box, test, intrian, hat, humanb, box4, leg2, leg) with unit /
+ *                      power-of-two / small-integer masses (WG_ERR_UNSUPPORTED otherwise)
+ *   buf->action        [n_action_steps][n_env][n_muscle] float32 (act_layout 0, act_dim == n_muscle), or null;
+ *                      n_action_steps == n_steps: one action block per step; n_action_steps == 1: the same block is
+ *                      applied at every step (action repeat / frame skip: Creature.act runs n_steps times with it)
  *   buf->reward        [n_steps][n_env] float32, optional;  buf->done  [n_steps][n_env] uint8, optional
  *   buf->obs           [n_env][obs_dim] row-major observation after the LAST step (obs_layout 0), optional
  *   buf->old_a / contact_pre / contact_post / energy / centroid must be null.
  */
 int wg_step_multi(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf,
-                  int64_t n_env, int32_t n_steps, void* cuda_stream);
+                  int64_t n_env, int32_t n_steps, int32_t n_action_steps, void* cuda_stream);
 
 /*
  * wg_step in x64 mode:buf->mx64 / mx_weak / action64 must be set (action is ignored; mx still receives the float32

@@ -110,6 +110,51 @@ def test_step_many_rejects_what_it_cannot_do():
         env.step_many(torch.zeros(2, 255, 2, device=DEV))
     with pytest.raises(ValueError):
         env.step_many(None)
-    humanb = BatchedPhysicsEnv("humanb", 256, DEV, state_layout="packed")          # no T-steps kernel for this graph
+    with pytest.raises(ValueError):
+        env.step_many(torch.zeros(256, 2, device=DEV))                             # action repeat needs n_steps
+    b2 = BatchedPhysicsEnv("balance2", 256, DEV, state_layout="packed")            # a 0.1 mass: general division
     with pytest.raises(RuntimeError):
-        humanb.step_many(torch.zeros(2, 256, humanb.M, device=DEV))
+        b2.step_many(torch.zeros(2, 256, b2.M, device=DEV))
+
+
+@pytest.mark.parametrize("name", ["box", "test", "intrian", "hat", "humanb", "box4", "leg2", "leg"])
+@pytest.mark.parametrize("in3d", [True, False])
+def test_step_many_every_packed_walker_py_body(name, in3d):
+    """Every body with an ahead-of-time packed kernel has the T-steps-per-launch kernel (gym/walker.py tables)."""
+    import torch
+    E = 300
+    env, body, prm, st = _pair(name, E, in3d=in3d, auto_reset="template", max_steps=4, seed=21)
+    rng = np.random.default_rng(5)
+    nz = (rng.standard_normal((3 * env.N, E)) * 0.1).astype(np.float32)
+    env.reset(noise=torch.from_numpy(nz).cuda(), mode="jitter")
+    wo.reset(body, prm, st, mode=1, noise=nz)
+    for T in (5, 3):
+        acts = rng.uniform(-1, 1, (T, E, env.M)).astype(np.float32)
+        first = env.step_count
+        obs, rew, done = env.step_many(torch.from_numpy(acts).cuda())
+        for t in range(T):
+            prm.step_index = first + t
+            out = wo.step(body, prm, st, acts[t])
+            assert gu.same(rew[t].cpu().numpy(), out["reward"]), f"reward @ block {T} step {t}"
+            assert gu.same(done[t].cpu().numpy(), out["done"].astype(bool)), f"done @ block {T} step {t}"
+        assert gu.same(obs.cpu().numpy(), out["obs"]), f"obs after block {T}"
+        assert gu.same(env.pos.cpu().numpy(), st["pos"]) and gu.same(env.vel.cpu().numpy(), st["vel"])
+        assert gu.same(env.mx.cpu().numpy(), st["mx"]) and gu.same(env.steps.cpu().numpy(), st["steps"])
+
+
+@pytest.mark.parametrize("name", ["balance_v0", "box_v0"])
+def test_step_many_action_repeat(name):
+    """One [E, M] action block applied at every step of the block (frame skip) == the oracle stepped T times with it."""
+    import torch
+    E, T = 2000, 6
+    env, body, prm, st = _pair(name, E, in3d=True, auto_reset="jitter", max_steps=4, seed=3)
+    rng = np.random.default_rng(6)
+    act = rng.uniform(-0.2, 0.2, (E, env.M)).astype(np.float32)
+    first = env.step_count
+    obs, rew, done = env.step_many(torch.from_numpy(act).cuda(), n_steps=T)
+    assert tuple(rew.shape) == (T, E)
+    for t in range(T):
+        prm.step_index = first + t
+        out = wo.step(body, prm, st, act)
+        assert gu.same(rew[t].cpu().numpy(), out["reward"]) and gu.same(done[t].cpu().numpy(), out["done"].astype(bool)), t
+    assert gu.same(obs.cpu().numpy(), out["obs"]) and gu.same(env.mx.cpu().numpy(), st["mx"])

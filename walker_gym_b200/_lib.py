@@ -129,7 +129,7 @@ def load():
     lib.wg_packed_state_floats.argtypes = [P(WgTopology), C.c_int64]
     lib.wg_packed_state_floats.restype = C.c_int64
     lib.wg_step.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_void_p]
-    lib.wg_step_multi.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_int32, C.c_void_p]
+    lib.wg_step_multi.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.wg_step_multi.restype = C.c_int
     lib.wg_step_x64.argtypes = [P(WgTopology), P(WgX64), P(WgParams), P(WgBuffers), C.c_int64, C.c_void_p]
     lib.wg_step_x64.restype = C.c_int

@@ -381,25 +381,34 @@ class BatchedPhysicsEnv:
         """``n_steps`` consecutive ``PhysicsEnv.step`` calls in ONE launch (``wg_step_multi``) for actions known up
         front: scripted gaits / open-loop controllers (the phase-table gait sketched at gym/walker.py:356-366), action repeat, replays.
 
-        ``actions``: float32 [T, E, M] (``None``: T = ``n_steps`` steps without an action).  Returns
-        ``(obs, rewards [T, E], dones [T, E])``: ``obs`` is the observation after the last step (the env's own
+        ``actions``: float32 [T, E, M]; or [E, M] with ``n_steps`` = T: the same action at every step (action repeat /
+        frame skip: ``Creature.act`` runs T times with it); or ``None`` with ``n_steps``: T steps without an action.
+        Returns ``(obs, rewards [T, E], dones [T, E])``: ``obs`` is the observation after the last step (the env's own
         buffer), rewards / dones are per step.  Bit-identical to T ``step`` calls; needs ``state_layout="packed"``,
-        row-major observations and actions, a Balance / Box body, and no per-step info buffers.
+        row-major observations and actions, a body with an ahead-of-time packed kernel, and no per-step info buffers.
         ``out=(rewards, dones)``: caller-owned result tensors (dones 1 byte per element)."""
         if self.state is None or self.x64 or self.obs_layout != "row" or self.act_layout != "row":
             raise ValueError("step_many needs state_layout='packed', obs_layout='row', act_layout='row' and float32 actions")
         E = self.num_envs
-        if actions is not None:
+        n_act = 1
+        if actions is not None and actions.dim() == 2:
+            if n_steps is None:
+                raise ValueError("n_steps is required with a single [E, M] action block (action repeat)")
+            if actions.shape[0] != E or actions.shape[1] != self.M:
+                raise ValueError(f"actions must have shape [{E}, {self.M}] or [T, {E}, {self.M}]")
+            self._check_f32(actions, actions.shape, "actions")
+            T = int(n_steps)
+        elif actions is not None:
             if actions.dim() != 3 or actions.shape[1] != E or actions.shape[2] != self.M:
                 raise ValueError(f"actions must have shape [T, {E}, {self.M}]")
             self._check_f32(actions, actions.shape, "actions")
-            T = int(actions.shape[0])
+            T = n_act = int(actions.shape[0])
             if n_steps is not None and int(n_steps) != T:
                 raise ValueError("n_steps disagrees with actions.shape[0]")
         elif n_steps is None:
             raise ValueError("n_steps is required when actions is None")
         else:
-            T = int(n_steps)
+            T = n_act = int(n_steps)
         if T < 1:
             raise ValueError("step_many needs at least one step")
         if out is None:
@@ -417,7 +426,7 @@ class BatchedPhysicsEnv:
         b.reward, b.done = rew.data_ptr(), done.data_ptr()
         self._stamp()
         with torch.cuda.device(self.device):
-            rc = self.lib.wg_step_multi(C.byref(self.topo), C.byref(self.params), C.byref(b), E, T, self._stream())
+            rc = self.lib.wg_step_multi(C.byref(self.topo), C.byref(self.params), C.byref(b), E, T, n_act, self._stream())
         b.old_a, b.contact_pre, b.contact_post, b.energy, b.centroid = saved
         b.reward, b.done = self._p(self.reward), self._p(self._done_u8)
         _lib.check(rc, "wg_step_multi")

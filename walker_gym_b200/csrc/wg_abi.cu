@@ -107,8 +107,10 @@ static int validate(const wg_topology* t, const wg_params* p, const wg_buffers* 
     return WG_OK;
 }
 
-int launch_balance_multi(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int n_steps, cudaStream_t);
-int launch_box_multi(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int n_steps, cudaStream_t);
+#define WG_MULTI_DECL(name) int launch_##name##_multi(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int n_steps, int64_t act_stride, cudaStream_t)
+WG_MULTI_DECL(balance); WG_MULTI_DECL(box); WG_MULTI_DECL(legacy_box); WG_MULTI_DECL(test); WG_MULTI_DECL(intrian);
+WG_MULTI_DECL(hat); WG_MULTI_DECL(humanb); WG_MULTI_DECL(box4); WG_MULTI_DECL(leg2); WG_MULTI_DECL(leg);
+#undef WG_MULTI_DECL
 int launch_generic_step_x64(const wg_topology*, const wg_x64*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_pkg_update(const wg_pkg_system*, const wg_pkg_params*, float* pos, float* vel, float* old_a,
                       int64_t E, int32_t n_steps, bool force_generic, cudaStream_t);
@@ -214,23 +216,28 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
 }
 
 int wg_step_multi(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf, int64_t n_env, int32_t n_steps,
-                  void* cuda_stream) {
+                  int32_t n_action_steps, void* cuda_stream) {
     int rc = validate(topo, prm, buf, n_env);
     if (rc != WG_OK) return rc;
     if (n_steps < 1 || n_steps > 65536) return fail(WG_ERR_BAD_ARG, "n_steps out of range [1, 65536]%s");
+    if (n_action_steps != n_steps && n_action_steps != 1) return fail(WG_ERR_BAD_ARG, "n_action_steps must be n_steps or 1 (action repeat)%s");
     if (!buf->state_packed) return fail(WG_ERR_BAD_ARG, "wg_step_multi needs the packed state layout%s");
     if (general_masses(topo)) return fail(WG_ERR_UNSUPPORTED, "wg_step_multi: unit / power-of-two / small-integer masses and no DingPoints%s");
     if (buf->obs && buf->obs_layout != 0) return fail(WG_ERR_BAD_ARG, "wg_step_multi writes row-major observations%s");
     if (buf->action && (buf->act_layout != 0 || buf->act_dim != topo->n_muscle))
-        return fail(WG_ERR_BAD_ARG, "wg_step_multi reads actions as [n_steps][n_env][n_muscle]%s");
+        return fail(WG_ERR_BAD_ARG, "wg_step_multi reads actions as [n_action_steps][n_env][n_muscle]%s");
     if (buf->old_a || buf->contact_pre || buf->contact_post || buf->energy || buf->centroid)
         return fail(WG_ERR_BAD_ARG, "wg_step_multi has no per-step info outputs (old_a / contact / energy / centroid must be null)%s");
     if (n_env == 0) return WG_OK;
     cudaStream_t s = (cudaStream_t)cuda_stream;
+    const int64_t as = n_action_steps == 1 ? 0 : n_env * (int64_t)topo->n_muscle;
     switch (g_force_generic.load() ? 0 : topo_id(topo)) {
-        case TopoBalance::kId: return launch_balance_multi(topo, prm, buf, n_env, n_steps, s);
-        case TopoBox::kId:     return launch_box_multi(topo, prm, buf, n_env, n_steps, s);
-        default:               return fail(WG_ERR_UNSUPPORTED, "wg_step_multi: only the Balance and Box spring graphs have a T-steps-per-launch kernel%s");
+#define WG_MULTI_CASE(T, name) case T::kId: return launch_##name##_multi(topo, prm, buf, n_env, n_steps, as, s)
+        WG_MULTI_CASE(TopoBalance, balance); WG_MULTI_CASE(TopoBox, box); WG_MULTI_CASE(TopoLegacyBox, legacy_box);
+        WG_MULTI_CASE(TopoTest, test); WG_MULTI_CASE(TopoIntrian, intrian); WG_MULTI_CASE(TopoHat, hat);
+        WG_MULTI_CASE(TopoHumanb, humanb); WG_MULTI_CASE(TopoBox4, box4); WG_MULTI_CASE(TopoLeg2, leg2); WG_MULTI_CASE(TopoLeg, leg);
+#undef WG_MULTI_CASE
+        default: return fail(WG_ERR_UNSUPPORTED, "wg_step_multi: only bodies with an ahead-of-time packed kernel have a T-steps-per-launch kernel%s");
     }
 }
 

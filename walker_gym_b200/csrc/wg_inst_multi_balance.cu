@@ -2,15 +2,10 @@
 #include "wg_launch.cuh"
 #include "wg_kernels_multi.cuh"
 namespace wg {
-int launch_balance_multi(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int n_steps, cudaStream_t s) {
-    const int mm = mass_mode(t);
-    if (mm == 1 && t->mass[2] == 1.0 && t->mass[0] == t->mass[1] && t->mass[0] != 1.0 && t->mass[3] != 1.0)   // Balance-v0
-        return p->in3d ? launch_multi_packed<TopoBalanceV0, true, 3>(t, p, b, E, n_steps, s)
-                       : launch_multi_packed<TopoBalanceV0, false, 3>(t, p, b, E, n_steps, s);
-    if (mm == 0)
-        return p->in3d ? launch_multi_packed<TopoBalance, true, 0>(t, p, b, E, n_steps, s)
-                       : launch_multi_packed<TopoBalance, false, 0>(t, p, b, E, n_steps, s);
-    return p->in3d ? launch_multi_packed<TopoBalance, true, 1>(t, p, b, E, n_steps, s)
-                   : launch_multi_packed<TopoBalance, false, 1>(t, p, b, E, n_steps, s);
+int launch_balance_multi(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int n_steps, int64_t as, cudaStream_t s) {
+    if (mass_mode(t) == 1 && t->mass[2] == 1.0 && t->mass[0] == t->mass[1] && t->mass[0] != 1.0 && t->mass[3] != 1.0)   // Balance-v0
+        return p->in3d ? launch_multi_packed<TopoBalanceV0, true, 3>(t, p, b, E, n_steps, as, s)
+                       : launch_multi_packed<TopoBalanceV0, false, 3>(t, p, b, E, n_steps, as, s);
+    return launch_multi_flags<TopoBalance>(t, p, b, E, n_steps, as, s);
 }
 }  // namespace wg

@@ -20,10 +20,11 @@ namespace wg {
 #define WG_MULTI_MIN_BLOCKS WG_PACKED_MIN_BLOCKS
 #endif
 
-// action: [T][E][M] row-major; reward: [T][E]; done: [T][E]; obs: [E][D] row-major, after the last step.
+// action: [T][E][M] row-major (act_stride = E * M), or one [E][M] block applied at every step (act_stride = 0:
+// action repeat); reward: [T][E]; done: [T][E]; obs: [E][D] row-major, after the last step.
 template <class Topo, bool IN3D, int MM, class Args = StepArgs<Topo::N, Topo::S>>
-__global__ void __launch_bounds__(kPackedBlock, WG_MULTI_MIN_BLOCKS)
-step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps) {
+__global__ void __launch_bounds__(kPackedBlock, Topo::N <= 4 ? WG_MULTI_MIN_BLOCKS : (Topo::N <= 6 ? 512 : 384) / WG_PACKED_BLOCK)
+step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, const int64_t act_stride) {
     constexpr int N = Topo::N, M = Topo::M;
     constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;
     constexpr int R = 6 * N + M + 2, R4 = (R + 3) / 4;
@@ -57,7 +58,6 @@ step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps) {
         float epr = v[K_EPRET];
         const uint32_t si0 = step_index_of(A);
         const float* ap = A.action ? A.action + e * M : nullptr;
-        const int64_t act_stride = E * M;
 
         // the first step's actions; inside the loop step t + 1's are requested before step t's physics
         float act[M > 0 ? M : 1];
@@ -145,7 +145,8 @@ step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps) {
 }
 
 template <class Topo, bool IN3D, int MM>
-inline int launch_multi_packed(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int n_steps, cudaStream_t s) {
+inline int launch_multi_packed(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int n_steps,
+                               int64_t act_stride, cudaStream_t s) {
     StepArgs<Topo::N, Topo::S> A;
     fill_args(A, t, p, b, E);
     constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
@@ -156,10 +157,21 @@ inline int launch_multi_packed(const wg_topology* t, const wg_params* p, const w
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<(unsigned)((E + kPackedBlock - 1) / kPackedBlock), kPackedBlock, smem, s>>>(A, n_steps);
+    kern<<<(unsigned)((E + kPackedBlock - 1) / kPackedBlock), kPackedBlock, smem, s>>>(A, n_steps, act_stride);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (multi) launch: %s", cudaGetErrorString(e));
     return WG_OK;
+}
+
+// unit masses (mode 0) or unit / power-of-two / small-integer masses (mode 1); 2-D and 3-D
+template <class Topo>
+inline int launch_multi_flags(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int n_steps,
+                              int64_t act_stride, cudaStream_t s) {
+    if (mass_mode(t) == 0)
+        return p->in3d ? launch_multi_packed<Topo, true, 0>(t, p, b, E, n_steps, act_stride, s)
+                       : launch_multi_packed<Topo, false, 0>(t, p, b, E, n_steps, act_stride, s);
+    return p->in3d ? launch_multi_packed<Topo, true, 1>(t, p, b, E, n_steps, act_stride, s)
+                   : launch_multi_packed<Topo, false, 1>(t, p, b, E, n_steps, act_stride, s);
 }
 
 }  // namespace wg
