@@ -416,6 +416,67 @@ def run_multi(args, rank, world, dev):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
     stats = env.episode_stats(all_reduce=True)
+
+    # ---- end to end through the host-buffer C-ABI call (wg_step_multi_host): pinned host actions [T,E,M] in,
+    # last observation + per-step rewards / dones out, every launch ----
+    e2e = None
+    if not args.no_e2e:
+        def tmax_of(ms_):
+            t_ = torch.tensor([ms_], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_.item())
+        Ke = max(3, args.e2e_steps // 2)
+        h_act = torch.empty(T, E, env.M).uniform_(-1, 1).pin_memory()
+        h_obs = torch.empty(E, env.obs_dim).pin_memory()
+        slots = [(torch.empty(T, E, env.M, device=dev), (torch.empty(T, E, device=dev), torch.empty(T, E, dtype=torch.uint8, device=dev)),
+                  torch.empty(T, E).pin_memory(), torch.empty(T, E, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        d_act, d_out, h_rew, h_done = slots[0]
+        for _ in range(2):
+            env.step_many_host(h_act, d_act, h_obs, h_rew, h_done, out=d_out)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(Ke):
+            env.step_many_host(h_act, d_act, h_obs, h_rew, h_done, out=d_out)
+        e1.record()
+        barrier()
+        ms_sync = tmax_of(e0.elapsed_time(e1))
+        h2d, d2h = T * E * env.M * 4, E * env.obs_dim * 4 + T * E * 5
+        e2e = {"value": world * E * T * Ke / (ms_sync * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": Ke, "what": f"wg_step_multi_host: one bench step = one {T}-env-step launch; uploads the pinned host action "
+                                    "block, downloads the last observation and the per-step rewards / dones, back to back on one stream"}
+        # open-loop mode: observations stay in HBM; two streams and two staging slots overlap launch i+1's upload and
+        # kernel with launch i's download (the kernels serialise on an event: they share the env state)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        kdone = [torch.cuda.Event() for _ in range(2)]
+
+        def submit(i):
+            st_, (da, do, hr, hd) = streams[i & 1], slots[i & 1]
+            with torch.cuda.stream(st_):
+                da.copy_(h_act, non_blocking=True)
+                if i > 0:
+                    st_.wait_event(kdone[(i - 1) & 1])
+                env.step_many(da, out=do)
+                kdone[i & 1].record(st_)
+                hr.copy_(do[0], non_blocking=True)
+                hd.copy_(do[1], non_blocking=True)
+        barrier()
+        for st_ in streams:
+            st_.wait_stream(torch.cuda.current_stream(dev))
+        for i in range(2):
+            submit(i)
+        barrier()
+        Kp = 2 * Ke
+        t0 = time.perf_counter()
+        for i in range(Kp):
+            submit(i)
+        barrier()
+        ms_pipe = tmax_of((time.perf_counter() - t0) * 1e3)
+        e2e["open_loop_mode"] = {"value": world * E * T * Kp / (ms_pipe * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                 "d2h_bytes_per_step": T * E * 5, "steps": Kp,
+                                 "what": "step_many on two streams with pinned-host copies around it: observations stay on the "
+                                         "device, rewards / dones come back every launch; timed host-side across a full drain"}
     if rank == 0:
         peak, peak_src = hbm_peak()
         bytes_per_launch_env = 48 * env.N + 8 * env.M + 8 + 36 * env.N + 4 * env.M + T * (4 * env.M + 5)
@@ -433,7 +494,7 @@ def run_multi(args, rank, world, dev):
                 "roofline": {"bound": "fp32 issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_launch": bytes_per_launch_env,
                              "kernel": "wg::step_multi_packed_kernel", "kernel_us": per_launch_s * 1e6},
-                "e2e": None, "gpu_launches": K, "clocks": clocks,
+                "e2e": e2e, "gpu_launches": K, "clocks": clocks,
                 "episode_stats": {k: stats[k] for k in ("episodes", "return_mean", "length_mean")}}
         print(json.dumps(line), flush=True)
     if world > 1:

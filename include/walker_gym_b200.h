@@ -252,6 +252,16 @@ int wg_step_host(const wg_topology* topo, const wg_params* prm, const wg_buffers
                  int64_t n_env, const float* h_action, float* h_obs, float* h_reward,
                  uint8_t* h_done, void* cuda_stream);
 
+/*
+ * The same for wg_step_multi: copies n_action_steps * n_env * n_muscle actions from (pinned) host memory into
+ * buf->action, runs the n_steps-step launch, and copies the last observation [n_env][obs_dim], the per-step rewards
+ * [n_steps][n_env] and dones back to the host pointers (any may be NULL), all on cuda_stream.  Per env-step the
+ * PCIe traffic is 4 * n_muscle bytes up and 5 + 4 * obs_dim / n_steps bytes down.
+ */
+int wg_step_multi_host(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf, int64_t n_env,
+                       int32_t n_steps, int32_t n_action_steps, const float* h_action, float* h_obs,
+                       float* h_reward, uint8_t* h_done, void* cuda_stream);
+
 /* =====================================================================================
  * The reference's *package* lineage (gym/optimized_walker/{core,env}.py): a second
  * physics model behind the same boundary.  Environment.update_physics (env.py:135-184)

@@ -158,3 +158,29 @@ def test_step_many_action_repeat(name):
         out = wo.step(body, prm, st, act)
         assert gu.same(rew[t].cpu().numpy(), out["reward"]) and gu.same(done[t].cpu().numpy(), out["done"].astype(bool)), t
     assert gu.same(obs.cpu().numpy(), out["obs"]) and gu.same(env.mx.cpu().numpy(), st["mx"])
+
+
+def test_step_many_host_buffers():
+    """wg_step_multi_host: pinned host actions in, last observation + per-step rewards / dones out == the device call."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    E, T = 5000, 6
+    kw = dict(in3d=True, auto_reset="template", max_steps=4, seed=8, state_layout="packed")
+    a = BatchedPhysicsEnv("Box-v0", E, DEV, **kw)
+    b = BatchedPhysicsEnv("Box-v0", E, DEV, **kw)
+    h_act = torch.empty(T, E, 4).uniform_(-1, 1).pin_memory()
+    d_act = torch.empty(T, E, 4, device=DEV)
+    h_obs = torch.empty(E, a.obs_dim).pin_memory()
+    h_rew = torch.empty(T, E).pin_memory()
+    h_done = torch.empty(T, E, dtype=torch.uint8).pin_memory()
+    a.step_many_host(h_act, d_act, h_obs, h_rew, h_done)
+    obs, rew, done = b.step_many(h_act.to(DEV))
+    torch.cuda.synchronize()
+    assert gu.same(h_obs.numpy(), obs.cpu().numpy()) and gu.same(h_rew.numpy(), rew.cpu().numpy())
+    assert gu.same(h_done.numpy().astype(bool), done.cpu().numpy())
+    # action repeat through host buffers
+    h_one, d_one = h_act[0].contiguous().pin_memory(), torch.empty(E, 4, device=DEV)
+    a.step_many_host(h_one, d_one, h_obs, h_rew[:3], h_done[:3], n_steps=3)
+    obs, rew, done = b.step_many(h_one.to(DEV), n_steps=3)
+    torch.cuda.synchronize()
+    assert gu.same(h_obs.numpy(), obs.cpu().numpy()) and gu.same(h_rew[:3].numpy(), rew.cpu().numpy())

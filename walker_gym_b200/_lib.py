@@ -89,7 +89,7 @@ TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH, TUNE_JIT = 0, 1, 2, 3
 
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
            "wg_set_tuning", "wg_packed_state_floats", "wg_packed_available", "wg_jit_prepare",
-           "wg_step", "wg_step_multi", "wg_step_x64", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_pkg_update_physics", "wg_pkg_kernel_variant",
+           "wg_step", "wg_step_multi", "wg_step_x64", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_step_multi_host", "wg_pkg_update_physics", "wg_pkg_kernel_variant",
            "wg_policy_act", "wg_gae", "wg_stream_probe")
 
 _lib = None
@@ -131,6 +131,9 @@ def load():
     lib.wg_step.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_void_p]
     lib.wg_step_multi.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.wg_step_multi.restype = C.c_int
+    lib.wg_step_multi_host.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wg_step_multi_host.restype = C.c_int
     lib.wg_step_x64.argtypes = [P(WgTopology), P(WgX64), P(WgParams), P(WgBuffers), C.c_int64, C.c_void_p]
     lib.wg_step_x64.restype = C.c_int
     lib.wg_reset.argtypes = [P(WgTopology), P(WgParams), P(WgBuffers), C.c_int64, C.c_int, C.c_void_p, C.c_void_p]

@@ -377,7 +377,7 @@ class BatchedPhysicsEnv:
             info = {"steps": self.steps, "centroid_position": self.centroid, "total_energy": self.energy}
         return res_obs, res_rew, res_done, info
 
-    def step_many(self, actions: Optional[torch.Tensor], n_steps: Optional[int] = None, out=None):
+    def step_many(self, actions: Optional[torch.Tensor], n_steps: Optional[int] = None, out=None, _host=None):
         """``n_steps`` consecutive ``PhysicsEnv.step`` calls in ONE launch (``wg_step_multi``) for actions known up
         front: scripted gaits / open-loop controllers (the phase-table gait sketched at gym/walker.py:356-366), action repeat, replays.
 
@@ -426,16 +426,37 @@ class BatchedPhysicsEnv:
         b.reward, b.done = rew.data_ptr(), done.data_ptr()
         self._stamp()
         with torch.cuda.device(self.device):
-            rc = self.lib.wg_step_multi(C.byref(self.topo), C.byref(self.params), C.byref(b), E, T, n_act, self._stream())
+            if _host is None:
+                rc = self.lib.wg_step_multi(C.byref(self.topo), C.byref(self.params), C.byref(b), E, T, n_act, self._stream())
+            else:
+                rc = self.lib.wg_step_multi_host(C.byref(self.topo), C.byref(self.params), C.byref(b), E, T, n_act,
+                                                 *[self._p(t) for t in _host], self._stream())
         b.old_a, b.contact_pre, b.contact_post, b.energy, b.centroid = saved
         b.reward, b.done = self._p(self.reward), self._p(self._done_u8)
-        _lib.check(rc, "wg_step_multi")
+        _lib.check(rc, "wg_step_multi" if _host is None else "wg_step_multi_host")
         if self._counter is not None:
             if not self._defer_advance:
                 self._counter.add_(T)
         else:
             self.step_count += T
         return self.obs, rew, done
+
+    def step_many_host(self, h_actions: torch.Tensor, d_actions: torch.Tensor, h_obs: Optional[torch.Tensor] = None,
+                       h_rewards: Optional[torch.Tensor] = None, h_dones: Optional[torch.Tensor] = None,
+                       n_steps: Optional[int] = None, out=None):
+        """End-to-end ``step_many`` on HOST buffers (``wg_step_multi_host``): copies the pinned host ``h_actions``
+        ([T, E, M], or [E, M] with ``n_steps`` for action repeat) into the device staging tensor ``d_actions`` of the
+        same shape, runs the T-step launch and copies the last observation, the [T, E] rewards and dones back into the
+        pinned host tensors, all asynchronously on the current stream.  ``out``: device (rewards, dones) staging."""
+        if h_actions.device.type != "cpu" or h_actions.dtype != torch.float32 or not h_actions.is_contiguous() \
+                or tuple(h_actions.shape) != tuple(d_actions.shape):
+            raise ValueError("h_actions must be a contiguous float32 host tensor with d_actions' shape")
+        T = int(n_steps) if h_actions.dim() == 2 and n_steps is not None else int(h_actions.shape[0])
+        for t, name, n, size in ((h_obs, "h_obs", self.obs.numel(), 4), (h_rewards, "h_rewards", T * self.num_envs, 4),
+                                 (h_dones, "h_dones", T * self.num_envs, 1)):
+            if t is not None and (t.device.type != "cpu" or not t.is_contiguous() or t.numel() != n or t.element_size() != size):
+                raise ValueError(f"{name} must be a contiguous host tensor of {n} elements of {size} byte(s)")
+        return self.step_many(d_actions, n_steps=n_steps, out=out, _host=(h_actions, h_obs, h_rewards, h_dones))
 
     def step_host(self, h_action: torch.Tensor, d_action: torch.Tensor, h_obs: Optional[torch.Tensor] = None,
                   h_reward: Optional[torch.Tensor] = None, h_done: Optional[torch.Tensor] = None) -> None:

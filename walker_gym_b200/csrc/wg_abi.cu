@@ -288,6 +288,30 @@ int wg_step_host(const wg_topology* topo, const wg_params* prm, const wg_buffers
     return WG_OK;
 }
 
+int wg_step_multi_host(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf, int64_t n_env, int32_t n_steps,
+                       int32_t n_action_steps, const float* h_action, float* h_obs, float* h_reward, uint8_t* h_done,
+                       void* cuda_stream) {
+    int rc = validate(topo, prm, buf, n_env);
+    if (rc != WG_OK) return rc;
+    if (n_steps < 1 || (n_action_steps != n_steps && n_action_steps != 1)) return fail(WG_ERR_BAD_ARG, "bad n_steps / n_action_steps%s");
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    cudaError_t e = cudaSuccess;
+    if (h_action) {
+        if (!buf->action) return fail(WG_ERR_BAD_ARG, "wg_step_multi_host: device action buffer missing%s");
+        e = cudaMemcpyAsync((void*)buf->action, h_action, sizeof(float) * n_action_steps * n_env * buf->act_dim, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return fail(WG_ERR_CUDA, "H2D actions: %s", cudaGetErrorString(e));
+    }
+    rc = wg_step_multi(topo, prm, buf, n_env, n_steps, n_action_steps, cuda_stream);
+    if (rc != WG_OK) return rc;
+    const int D = wg_obs_dim(topo, prm->in3d);
+    if (h_obs && buf->obs) e = cudaMemcpyAsync(h_obs, buf->obs, sizeof(float) * n_env * D, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && h_reward && buf->reward)
+        e = cudaMemcpyAsync(h_reward, buf->reward, sizeof(float) * n_steps * n_env, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && h_done && buf->done) e = cudaMemcpyAsync(h_done, buf->done, (size_t)n_steps * n_env, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "D2H results: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
 int wg_pkg_kernel_variant(const wg_pkg_system* sys) {
     if (!sys) return fail(WG_ERR_BAD_ARG, "null system%s");
     return g_force_generic.load() ? 0 : pkg_variant(sys);
