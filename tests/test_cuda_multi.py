@@ -184,3 +184,36 @@ def test_step_many_host_buffers():
     obs, rew, done = b.step_many(h_one.to(DEV), n_steps=3)
     torch.cuda.synchronize()
     assert gu.same(h_obs.numpy(), obs.cpu().numpy()) and gu.same(h_rew[:3].numpy(), rew.cpu().numpy())
+
+
+@pytest.mark.parametrize("masses,in3d", [((1, 1, 1, 1, 1), True), ((2, 5, 1, 3, 4), False), ((2, 2, 1, 3, 2), True)])
+def test_step_many_runtime_specialised_user_body(masses, in3d):
+    """A user-built creature (no ahead-of-time kernel) gets the T-steps-per-launch kernel compiled for its spring graph
+    at run time (NVRTC), like its single-step kernel: bit for bit against the oracle stepped T times."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv, Point
+    from test_cuda_vs_oracle import _custom_creature
+    try:
+        cr, spec = _custom_creature(masses)
+        E = 4100
+        env = BatchedPhysicsEnv(cr, E, DEV, in3d=in3d, auto_reset="template", max_steps=5, k_sub=2, seed=4, initial_reset=False)
+        assert env.state_layout == "packed" and env.kernel_variant == 0
+        body = wo.make_body(spec)
+        prm = wo.make_params(in3d=in3d, auto_reset=2, max_steps=5, k_sub=2, seed=4)
+        st = wo.init_state(body, E)
+        rng = np.random.default_rng(9)
+        nz = (rng.standard_normal((3 * env.N, E)) * 0.1).astype(np.float32)
+        env.reset(noise=torch.from_numpy(nz).cuda(), mode="jitter")
+        wo.reset(body, prm, st, mode=1, noise=nz)
+        for T in (8, 3):
+            acts = rng.uniform(-1, 1, (T, E, env.M)).astype(np.float32)
+            first = env.step_count
+            obs, rew, done = env.step_many(torch.from_numpy(acts).cuda())
+            for t in range(T):
+                prm.step_index = first + t
+                out = wo.step(body, prm, st, acts[t])
+                assert gu.same(rew[t].cpu().numpy(), out["reward"]) and gu.same(done[t].cpu().numpy(), out["done"].astype(bool)), (T, t)
+            assert gu.same(obs.cpu().numpy(), out["obs"])
+            assert gu.same(env.pos.cpu().numpy(), st["pos"]) and gu.same(env.vel.cpu().numpy(), st["vel"])
+    finally:
+        Point.clear()

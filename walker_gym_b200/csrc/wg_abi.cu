@@ -14,7 +14,8 @@ int launch_balance_units(const wg_topology*, const wg_params*, const wg_buffers*
 bool jit_eligible(const wg_topology*);
 bool jit_runtime_available();
 bool jit_eligible_soa(const wg_topology*);
-int jit_prepare(const wg_topology*, int in3d, int obs_layout, cudaKernel_t* kernel, bool packed);
+int jit_prepare(const wg_topology*, int in3d, int obs_layout, cudaKernel_t* kernel, int kind);      // kind: 0 SoA, 1 packed, 2 T-steps-per-launch
+int launch_jit_multi(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int n_steps, int64_t act_stride, cudaStream_t);
 int launch_jit_soa(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_jit_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_policy(const PolicyArgs& A, int precision, cudaStream_t s);
@@ -144,7 +145,7 @@ int wg_packed_available(const wg_topology* topo) {
 int wg_jit_prepare(const wg_topology* topo, int in3d, int obs_layout) {
     if (!topo) return fail(WG_ERR_BAD_ARG, "null topology%s");
     if (packed_pick(topo) != kJitId) return WG_OK;            // an ahead-of-time kernel (or none): nothing to compile
-    return jit_prepare(topo, in3d, obs_layout, nullptr, true);
+    return jit_prepare(topo, in3d, obs_layout, nullptr, 1);
 }
 
 int wg_force_generic(int on) { return g_force_generic.exchange(on ? 1 : 0); }
@@ -237,7 +238,9 @@ int wg_step_multi(const wg_topology* topo, const wg_params* prm, const wg_buffer
         WG_MULTI_CASE(TopoTest, test); WG_MULTI_CASE(TopoIntrian, intrian); WG_MULTI_CASE(TopoHat, hat);
         WG_MULTI_CASE(TopoHumanb, humanb); WG_MULTI_CASE(TopoBox4, box4); WG_MULTI_CASE(TopoLeg2, leg2); WG_MULTI_CASE(TopoLeg, leg);
 #undef WG_MULTI_CASE
-        default: return fail(WG_ERR_UNSUPPORTED, "wg_step_multi: only bodies with an ahead-of-time packed kernel have a T-steps-per-launch kernel%s");
+        default:
+            if (packed_pick(topo) == kJitId) return launch_jit_multi(topo, prm, buf, n_env, n_steps, as, s);    // compiled at run time
+            return fail(WG_ERR_UNSUPPORTED, "wg_step_multi: this body has no packed-state kernel%s");
     }
 }
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "wg_launch.cuh"
+#include "wg_kernels_multi.cuh"
 
 namespace wg {
 
@@ -61,8 +62,8 @@ struct JitKernel { cudaKernel_t kernel = nullptr; int rc = WG_OK; std::string er
 std::mutex g_mu;
 std::map<std::string, JitKernel> g_cache;
 
-std::string key_of(const wg_topology* t, int in3d, int obs_rm, int mm, bool packed) {
-    std::string k = std::string(packed ? "P" : "S") + std::to_string(t->n_mass) + "," + std::to_string(t->n_spring) + "," + std::to_string(t->n_muscle) + ":";
+std::string key_of(const wg_topology* t, int in3d, int obs_rm, int mm, int kind) {      // kind: 0 SoA, 1 packed, 2 packed T-steps-per-launch
+    std::string k = std::string(kind == 2 ? "M" : kind ? "P" : "S") + std::to_string(t->n_mass) + "," + std::to_string(t->n_spring) + "," + std::to_string(t->n_muscle) + ":";
     for (int s = 0; s < t->n_spring; s++) k += std::to_string(t->si[s]) + "-" + std::to_string(t->sj[s]) + ",";
     k += "|" + std::to_string(in3d) + std::to_string(obs_rm) + std::to_string(mm);
     if (mm == 1) {                       // mass mode 3 bakes the mass pattern (which masses are 1 / equal) into the code
@@ -76,11 +77,12 @@ std::string key_of(const wg_topology* t, int in3d, int obs_rm, int mm, bool pack
     return k;
 }
 
-JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm, bool packed) {
+JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm, int kind) {
+    const bool packed = kind != 0;
     JitKernel out;
     Nvrtc& nv = nvrtc();
     if (!nv.ok) { out.rc = WG_ERR_UNSUPPORTED; out.err = "libnvrtc not available"; return out; }
-    std::string src = "#include \"wg_kernels_packed.cuh\"\nnamespace wg { WG_STATIC_TOPO(TopoJit, 99, " + std::to_string(t->n_mass) + ", " +
+    std::string src = std::string(kind == 2 ? "#include \"wg_kernels_multi.cuh\"\n" : "#include \"wg_kernels_packed.cuh\"\n") + "namespace wg { WG_STATIC_TOPO(TopoJit, 99, " + std::to_string(t->n_mass) + ", " +
                       std::to_string(t->n_spring) + ", " + std::to_string(t->n_muscle);
     for (int s = 0; s < t->n_spring; s++) src += ", " + std::to_string(t->si[s]) + "," + std::to_string(t->sj[s]);
     src += ")\n";
@@ -102,9 +104,11 @@ JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm, bool packe
         topo_name = "wg::TopoJitP";
     }
     src += "}\n";
-    const std::string name = std::string(packed ? "&wg::step_static_packed_kernel<" : "&wg::step_static_kernel<") + topo_name + ", " +
-                             (in3d ? "true" : "false") + ", " + std::to_string(obs_rm) + (packed ? ", " : ", 1, ") +
-                             std::to_string(mm == 1 ? 3 : mm) + ", wg::StepArgs<wg::kMaxMass, wg::kMaxSpring>>";
+    const std::string mm_s = std::to_string(mm == 1 ? 3 : mm), i3 = in3d ? "true" : "false";
+    const std::string name = kind == 2
+        ? "&wg::step_multi_packed_kernel<" + topo_name + ", " + i3 + ", " + mm_s + ", wg::StepArgs<wg::kMaxMass, wg::kMaxSpring>>"
+        : std::string(packed ? "&wg::step_static_packed_kernel<" : "&wg::step_static_kernel<") + topo_name + ", " + i3 + ", " +
+          std::to_string(obs_rm) + (packed ? ", " : ", 1, ") + mm_s + ", wg::StepArgs<wg::kMaxMass, wg::kMaxSpring>>";
     nvrtcProgram prog = nullptr;
     if (nv.CreateProgram(&prog, src.c_str(), "wg_jit.cu", 0, nullptr, nullptr) != 0) { out.rc = WG_ERR_CUDA; out.err = "nvrtcCreateProgram failed"; return out; }
     nv.AddNameExpression(prog, name.c_str());
@@ -149,12 +153,12 @@ static int mode_of(const wg_topology* t) {
 }
 
 // compile (or fetch) the kernel for this body / variant; WG_OK or an error with the compiler log in the error string
-int jit_prepare(const wg_topology* t, int in3d, int obs_layout, cudaKernel_t* kernel, bool packed) {
+int jit_prepare(const wg_topology* t, int in3d, int obs_layout, cudaKernel_t* kernel, int kind) {
     const int obs_rm = obs_layout == 0 ? 1 : 0, mm = mode_of(t);
-    const std::string key = key_of(t, in3d ? 1 : 0, obs_rm, mm, packed);
+    const std::string key = key_of(t, in3d ? 1 : 0, obs_rm, mm, kind);
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_cache.find(key);
-    if (it == g_cache.end()) it = g_cache.emplace(key, compile(t, in3d ? 1 : 0, obs_rm, mm, packed)).first;
+    if (it == g_cache.end()) it = g_cache.emplace(key, compile(t, in3d ? 1 : 0, obs_rm, mm, kind)).first;
     if (it->second.rc != WG_OK) return fail(it->second.rc, "run-time specialisation failed: %s", it->second.err.c_str());
     if (kernel) *kernel = it->second.kernel;
     return WG_OK;
@@ -178,6 +182,27 @@ int launch_jit_packed(const wg_topology* t, const wg_params* p, const wg_buffers
     cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3((unsigned)((E + kPackedBlock - 1) / kPackedBlock)), dim3(kPackedBlock),
                                      args, smem, s);
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (jit) launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
+// T env-steps per launch (wg_step_multi) for a body without an ahead-of-time kernel
+int launch_jit_multi(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int n_steps, int64_t act_stride,
+                     cudaStream_t s) {
+    cudaKernel_t kernel = nullptr;
+    int rc = jit_prepare(t, p->in3d, 0, &kernel, 2);
+    if (rc != WG_OK) return rc;
+    static thread_local StepArgs<kMaxMass, kMaxSpring> A;
+    fill_args(A, t, p, b, E);
+    const int D = 3 * (p->in3d ? 3 : 2) * t->n_mass + t->n_muscle;
+    const size_t smem = b->obs ? sizeof(float) * kPackedBlock * (gcd_c(D, 32) <= 2 ? D : (D | 1)) : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute (jit): %s", cudaGetErrorString(e));
+    }
+    void* args[] = { &A, &n_steps, &act_stride };
+    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3((unsigned)((E + kPackedBlock - 1) / kPackedBlock)), dim3(kPackedBlock),
+                                     args, smem, s);
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (jit, multi) launch: %s", cudaGetErrorString(e));
     return WG_OK;
 }
 

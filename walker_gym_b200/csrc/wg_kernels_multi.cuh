@@ -144,6 +144,7 @@ step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, cons
     }
 }
 
+#ifndef __CUDACC_RTC__          // host-side launch helpers (not part of a run-time compiled translation unit)
 template <class Topo, bool IN3D, int MM>
 inline int launch_multi_packed(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int n_steps,
                                int64_t act_stride, cudaStream_t s) {
@@ -173,5 +174,6 @@ inline int launch_multi_flags(const wg_topology* t, const wg_params* p, const wg
     return p->in3d ? launch_multi_packed<Topo, true, 1>(t, p, b, E, n_steps, act_stride, s)
                    : launch_multi_packed<Topo, false, 1>(t, p, b, E, n_steps, act_stride, s);
 }
+#endif
 
 }  // namespace wg
