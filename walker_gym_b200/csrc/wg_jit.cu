@@ -194,13 +194,13 @@ int launch_jit_multi(const wg_topology* t, const wg_params* p, const wg_buffers*
     static thread_local StepArgs<kMaxMass, kMaxSpring> A;
     fill_args(A, t, p, b, E);
     const int D = 3 * (p->in3d ? 3 : 2) * t->n_mass + t->n_muscle;
-    const size_t smem = b->obs ? sizeof(float) * kPackedBlock * (gcd_c(D, 32) <= 2 ? D : (D | 1)) : 0;
+    const size_t smem = b->obs ? sizeof(float) * kMultiBlock * (gcd_c(D, 32) <= 2 ? D : (D | 1)) : 0;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute (jit): %s", cudaGetErrorString(e));
     }
     void* args[] = { &A, &n_steps, &act_stride };
-    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3((unsigned)((E + kPackedBlock - 1) / kPackedBlock)), dim3(kPackedBlock),
+    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3((unsigned)((E + kMultiBlock - 1) / kMultiBlock)), dim3(kMultiBlock),
                                      args, smem, s);
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (jit, multi) launch: %s", cudaGetErrorString(e));
     return WG_OK;

@@ -20,10 +20,25 @@ namespace wg {
 #define WG_MULTI_MIN_BLOCKS WG_PACKED_MIN_BLOCKS
 #endif
 
+// threads per CTA (a multiple of the 128-env tile) and, optionally, a per-scheduler named barrier at the top of every
+// step that keeps the warps sharing an instruction cache in phase (experiment knobs)
+#ifndef WG_MULTI_BLOCK
+#define WG_MULTI_BLOCK 128
+#endif
+#ifndef WG_MULTI_SYNC
+#define WG_MULTI_SYNC 0
+#endif
+constexpr int kMultiBlock = WG_MULTI_BLOCK;
+static_assert(kMultiBlock % 128 == 0, "the packed layout is tiled by 128 envs");
+constexpr int multi_min_blocks(int n_mass) {
+    const int threads = n_mass <= 4 ? WG_MULTI_MIN_BLOCKS * 128 : (n_mass <= 6 ? 512 : 384);
+    return threads / kMultiBlock > 0 ? threads / kMultiBlock : 1;
+}
+
 // action: [T][E][M] row-major (act_stride = E * M), or one [E][M] block applied at every step (act_stride = 0:
 // action repeat); reward: [T][E]; done: [T][E]; obs: [E][D] row-major, after the last step.
 template <class Topo, bool IN3D, int MM, class Args = StepArgs<Topo::N, Topo::S>>
-__global__ void __launch_bounds__(kPackedBlock, Topo::N <= 4 ? WG_MULTI_MIN_BLOCKS : (Topo::N <= 6 ? 512 : 384) / WG_PACKED_BLOCK)
+__global__ void __launch_bounds__(kMultiBlock, multi_min_blocks(Topo::N))
 step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, const int64_t act_stride) {
     constexpr int N = Topo::N, M = Topo::M;
     constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;
@@ -36,10 +51,10 @@ step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t E = A.E;
     constexpr int kBlock = 128;
-    const int64_t e0 = (int64_t)blockIdx.x * kPackedBlock;
+    const int64_t e0 = (int64_t)blockIdx.x * kMultiBlock;
     const int64_t e = e0 + tid;
     const bool valid = e < E;
-    const int64_t tile_idx = (int64_t)blockIdx.x * (kPackedBlock / kBlock) + (tid >> 7);
+    const int64_t tile_idx = (int64_t)blockIdx.x * (kMultiBlock / kBlock) + (tid >> 7);
     float4* const base = reinterpret_cast<float4*>(A.state_packed) + tile_idx * (R4 * kBlock) + (tid & 127);
 
     if (valid) {
@@ -66,6 +81,10 @@ step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, cons
 
 #pragma unroll 1
         for (int t = 0; t < n_steps; t++) {
+#if WG_MULTI_SYNC
+            if (e0 + kMultiBlock <= E)      // whole CTA valid: the warps of one scheduler start every step together
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(kMultiBlock / 4) : "memory");
+#endif
             // ---- Creature.act ----
             if (ap) {
 #pragma unroll
@@ -152,13 +171,13 @@ inline int launch_multi_packed(const wg_topology* t, const wg_params* p, const w
     fill_args(A, t, p, b, E);
     constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
     constexpr bool bulk = gcd_c(D, 32) <= 2;
-    const size_t smem = b->obs ? sizeof(float) * kPackedBlock * (bulk ? D : (D | 1)) : 0;
+    const size_t smem = b->obs ? sizeof(float) * kMultiBlock * (bulk ? D : (D | 1)) : 0;
     auto kern = step_multi_packed_kernel<Topo, IN3D, MM>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<(unsigned)((E + kPackedBlock - 1) / kPackedBlock), kPackedBlock, smem, s>>>(A, n_steps, act_stride);
+    kern<<<(unsigned)((E + kMultiBlock - 1) / kMultiBlock), kMultiBlock, smem, s>>>(A, n_steps, act_stride);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (multi) launch: %s", cudaGetErrorString(e));
     return WG_OK;
