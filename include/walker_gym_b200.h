@@ -206,9 +206,9 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
  * Bit-identical to n_steps wg_step calls with prm->step_index advanced by one per call (an auto-reset at step t
  * of the block draws its jitter with Philox index step_index + t).
  *   buf->state_packed  required (packed layout); every body with an ahead-of-time packed kernel (the Balance / Box
- *                      graphs and walker.py's box, test, intrian, hat, humanb, box4, leg2, leg) with unit /
- *                      power-of-two / small-integer masses, and bodies whose packed kernel is compiled at run time
- *                      (wg_packed_available() == 2); WG_ERR_UNSUPPORTED otherwise
+ *                      graphs and walker.py's box, test, intrian, hat, humanb, box4, leg2, leg) and every body whose
+ *                      packed kernel is compiled at run time (wg_packed_available() != 0), i.e. whatever wg_step
+ *                      accepts on the packed layout
  *   buf->action        [n_action_steps][n_env][n_muscle] float32 (act_layout 0, act_dim == n_muscle), or null;
  *                      n_action_steps == n_steps: one action block per step; n_action_steps == 1: the same block is
  *                      applied at every step (action repeat / frame skip: Creature.act runs n_steps times with it)

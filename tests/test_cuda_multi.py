@@ -112,15 +112,15 @@ def test_step_many_rejects_what_it_cannot_do():
         env.step_many(None)
     with pytest.raises(ValueError):
         env.step_many(torch.zeros(256, 2, device=DEV))                             # action repeat needs n_steps
-    b2 = BatchedPhysicsEnv("balance2", 256, DEV, state_layout="packed")            # a 0.1 mass: general division
-    with pytest.raises(RuntimeError):
-        b2.step_many(torch.zeros(2, 256, b2.M, device=DEV))
+    with pytest.raises(ValueError):
+        env.step_many(torch.zeros(2, 256, 2, device=DEV), n_steps=3)               # n_steps disagrees with the block
 
 
-@pytest.mark.parametrize("name", ["box", "test", "intrian", "hat", "humanb", "box4", "leg2", "leg"])
+@pytest.mark.parametrize("name", ["box", "test", "intrian", "hat", "humanb", "box4", "leg2", "leg", "balance2", "balance3"])
 @pytest.mark.parametrize("in3d", [True, False])
 def test_step_many_every_packed_walker_py_body(name, in3d):
-    """Every body with an ahead-of-time packed kernel has the T-steps-per-launch kernel (gym/walker.py tables)."""
+    """Every body with an ahead-of-time packed kernel has the T-steps-per-launch kernel (gym/walker.py tables),
+    balance2 (a 0.1 mass: full IEEE division) and balance3 (a DingPoint) included."""
     import torch
     E = 300
     env, body, prm, st = _pair(name, E, in3d=in3d, auto_reset="template", max_steps=4, seed=21)
@@ -186,15 +186,16 @@ def test_step_many_host_buffers():
     assert gu.same(h_obs.numpy(), obs.cpu().numpy()) and gu.same(h_rew[:3].numpy(), rew.cpu().numpy())
 
 
-@pytest.mark.parametrize("masses,in3d", [((1, 1, 1, 1, 1), True), ((2, 5, 1, 3, 4), False), ((2, 2, 1, 3, 2), True)])
-def test_step_many_runtime_specialised_user_body(masses, in3d):
+@pytest.mark.parametrize("masses,in3d,ding", [((1, 1, 1, 1, 1), True, ()), ((2, 5, 1, 3, 4), False, ()), ((2, 2, 1, 3, 2), True, ()),
+                                               ((2.5, 0.1, 7, 1, 3), True, (3,))])
+def test_step_many_runtime_specialised_user_body(masses, in3d, ding):
     """A user-built creature (no ahead-of-time kernel) gets the T-steps-per-launch kernel compiled for its spring graph
     at run time (NVRTC), like its single-step kernel: bit for bit against the oracle stepped T times."""
     import torch
     from walker_gym_b200 import BatchedPhysicsEnv, Point
     from test_cuda_vs_oracle import _custom_creature
     try:
-        cr, spec = _custom_creature(masses)
+        cr, spec = _custom_creature(masses, ding)
         E = 4100
         env = BatchedPhysicsEnv(cr, E, DEV, in3d=in3d, auto_reset="template", max_steps=5, k_sub=2, seed=4, initial_reset=False)
         assert env.state_layout == "packed" and env.kernel_variant == 0

@@ -223,7 +223,6 @@ int wg_step_multi(const wg_topology* topo, const wg_params* prm, const wg_buffer
     if (n_steps < 1 || n_steps > 65536) return fail(WG_ERR_BAD_ARG, "n_steps out of range [1, 65536]%s");
     if (n_action_steps != n_steps && n_action_steps != 1) return fail(WG_ERR_BAD_ARG, "n_action_steps must be n_steps or 1 (action repeat)%s");
     if (!buf->state_packed) return fail(WG_ERR_BAD_ARG, "wg_step_multi needs the packed state layout%s");
-    if (general_masses(topo)) return fail(WG_ERR_UNSUPPORTED, "wg_step_multi: unit / power-of-two / small-integer masses and no DingPoints%s");
     if (buf->obs && buf->obs_layout != 0) return fail(WG_ERR_BAD_ARG, "wg_step_multi writes row-major observations%s");
     if (buf->action && (buf->act_layout != 0 || buf->act_dim != topo->n_muscle))
         return fail(WG_ERR_BAD_ARG, "wg_step_multi reads actions as [n_action_steps][n_env][n_muscle]%s");
@@ -232,15 +231,17 @@ int wg_step_multi(const wg_topology* topo, const wg_params* prm, const wg_buffer
     if (n_env == 0) return WG_OK;
     cudaStream_t s = (cudaStream_t)cuda_stream;
     const int64_t as = n_action_steps == 1 ? 0 : n_env * (int64_t)topo->n_muscle;
-    switch (g_force_generic.load() ? 0 : topo_id(topo)) {
+    // the kernel family wg_step would pick for this body on the packed layout: an ahead-of-time instance (the Balance
+    // graph also with arbitrary masses / DingPoints) or one compiled at run time for the body's spring graph
+    const int pick = packed_pick(topo);
+    if (pick == kJitId) return launch_jit_multi(topo, prm, buf, n_env, n_steps, as, s);
+    switch (pick) {
 #define WG_MULTI_CASE(T, name) case T::kId: return launch_##name##_multi(topo, prm, buf, n_env, n_steps, as, s)
         WG_MULTI_CASE(TopoBalance, balance); WG_MULTI_CASE(TopoBox, box); WG_MULTI_CASE(TopoLegacyBox, legacy_box);
         WG_MULTI_CASE(TopoTest, test); WG_MULTI_CASE(TopoIntrian, intrian); WG_MULTI_CASE(TopoHat, hat);
         WG_MULTI_CASE(TopoHumanb, humanb); WG_MULTI_CASE(TopoBox4, box4); WG_MULTI_CASE(TopoLeg2, leg2); WG_MULTI_CASE(TopoLeg, leg);
 #undef WG_MULTI_CASE
-        default:
-            if (packed_pick(topo) == kJitId) return launch_jit_multi(topo, prm, buf, n_env, n_steps, as, s);    // compiled at run time
-            return fail(WG_ERR_UNSUPPORTED, "wg_step_multi: this body has no packed-state kernel%s");
+        default: return fail(WG_ERR_UNSUPPORTED, "wg_step_multi: this body has no packed-state kernel%s");
     }
 }
 
