@@ -30,7 +30,7 @@ namespace wg {
 #endif
 constexpr int kMultiBlock = WG_MULTI_BLOCK;
 static_assert(kMultiBlock % 128 == 0, "the packed layout is tiled by 128 envs");
-constexpr int multi_min_blocks(int n_mass) {
+__host__ __device__ constexpr int multi_min_blocks(int n_mass) {
     const int threads = n_mass <= 4 ? WG_MULTI_MIN_BLOCKS * 128 : (n_mass <= 6 ? 512 : 384);
     return threads / kMultiBlock > 0 ? threads / kMultiBlock : 1;
 }
