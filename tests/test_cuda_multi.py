@@ -218,3 +218,26 @@ def test_step_many_runtime_specialised_user_body(masses, in3d, ding):
             assert gu.same(env.pos.cpu().numpy(), st["pos"]) and gu.same(env.vel.cpu().numpy(), st["vel"])
     finally:
         Point.clear()
+
+
+def test_step_many_sharding_is_invisible():
+    """SURVEY 8e for the T-steps launch: shard k of the batch (env_offset) equals the same envs stepped in one piece,
+    resets inside the block included (Philox keyed by the global env id and step index + t)."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    E, T = 8192, 24
+    kw = dict(in3d=True, auto_reset="template", max_steps=7, seed=123, track_stats=True, state_layout="packed")
+    whole = BatchedPhysicsEnv("balance_v0", E, DEV, **kw)
+    halves = [BatchedPhysicsEnv("balance_v0", E // 2, DEV, env_offset=k * E // 2, **kw) for k in range(2)]
+    g = torch.Generator(device=DEV).manual_seed(0)
+    acts = torch.rand(T, E, 2, device=DEV, generator=g) * 2 - 1
+    obs, rew, done = whole.step_many(acts)
+    parts = [h.step_many(acts[:, k * E // 2:(k + 1) * E // 2].contiguous()) for k, h in enumerate(halves)]
+    assert gu.same(obs.cpu().numpy(), torch.cat([p[0] for p in parts], 0).cpu().numpy())
+    assert gu.same(rew.cpu().numpy(), torch.cat([p[1] for p in parts], 1).cpu().numpy())
+    assert torch.equal(done, torch.cat([p[2] for p in parts], 1))
+    for name in ("pos", "vel", "mx", "fin_stats"):
+        cat = torch.cat([getattr(h, name) for h in halves], dim=1)
+        assert gu.same(getattr(whole, name).cpu().numpy(), cat.cpu().numpy()), name
+    a, b0, b1 = whole.episode_stats(), halves[0].episode_stats(), halves[1].episode_stats()
+    assert a["episodes"] == b0["episodes"] + b1["episodes"] > 0
