@@ -446,37 +446,30 @@ def run_multi(args, rank, world, dev):
         e2e = {"value": world * E * T * Ke / (ms_sync * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": Ke, "what": f"wg_step_multi_host: one bench step = one {T}-env-step launch; uploads the pinned host action "
                                     "block, downloads the last observation and the per-step rewards / dones, back to back on one stream"}
-        # open-loop mode: observations stay in HBM; two streams and two staging slots overlap launch i+1's upload and
-        # kernel with launch i's download (the kernels serialise on an event: they share the env state)
-        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-        kdone = [torch.cuda.Event() for _ in range(2)]
+        # open-loop mode: observations stay in HBM; HostStepPipeline.submit_many overlaps block i+1's upload and kernel
+        # with block i's download (two streams, two staging slots; the kernels serialise: they share the env state)
+        from walker_gym_b200 import HostStepPipeline
+        pipe = HostStepPipeline(env)
+        hres = [(slots[i][2], slots[i][3]) for i in range(2)]
 
         def submit(i):
-            st_, (da, do, hr, hd) = streams[i & 1], slots[i & 1]
-            with torch.cuda.stream(st_):
-                da.copy_(h_act, non_blocking=True)
-                if i > 0:
-                    st_.wait_event(kdone[(i - 1) & 1])
-                env.step_many(da, out=do)
-                kdone[i & 1].record(st_)
-                hr.copy_(do[0], non_blocking=True)
-                hd.copy_(do[1], non_blocking=True)
-        barrier()
-        for st_ in streams:
-            st_.wait_stream(torch.cuda.current_stream(dev))
+            pipe.submit_many(h_act, *hres[i & 1])
         for i in range(2):
             submit(i)
+        pipe.drain()
         barrier()
         Kp = 2 * Ke
         t0 = time.perf_counter()
         for i in range(Kp):
             submit(i)
+        pipe.drain()
         barrier()
         ms_pipe = tmax_of((time.perf_counter() - t0) * 1e3)
         e2e["open_loop_mode"] = {"value": world * E * T * Kp / (ms_pipe * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                                  "d2h_bytes_per_step": T * E * 5, "steps": Kp,
-                                 "what": "step_many on two streams with pinned-host copies around it: observations stay on the "
-                                         "device, rewards / dones come back every launch; timed host-side across a full drain"}
+                                 "what": "HostStepPipeline.submit_many (step_many on two streams with pinned-host copies around "
+                                         "it): observations stay on the device, rewards / dones come back every launch; "
+                                         "timed host-side across a full drain"}
     if rank == 0:
         peak, peak_src = hbm_peak()
         bytes_per_launch_env = 48 * env.N + 8 * env.M + 8 + 36 * env.N + 4 * env.M + T * (4 * env.M + 5)

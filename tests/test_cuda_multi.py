@@ -241,3 +241,28 @@ def test_step_many_sharding_is_invisible():
         assert gu.same(getattr(whole, name).cpu().numpy(), cat.cpu().numpy()), name
     a, b0, b1 = whole.episode_stats(), halves[0].episode_stats(), halves[1].episode_stats()
     assert a["episodes"] == b0["episodes"] + b1["episodes"] > 0
+
+
+def test_host_pipeline_submit_many():
+    """HostStepPipeline.submit_many: double-buffered T-step launches on pinned host buffers == step_many block by block."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv, HostStepPipeline
+    E, T, B = 3000, 5, 4
+    kw = dict(in3d=True, auto_reset="template", max_steps=4, seed=8, state_layout="packed")
+    a = BatchedPhysicsEnv("Balance-v0", E, DEV, **kw)
+    b = BatchedPhysicsEnv("Balance-v0", E, DEV, **kw)
+    pipe = HostStepPipeline(a)
+    h_act = [torch.empty(T, E, 2).uniform_(-1, 1).pin_memory() for _ in range(B)]
+    h_rew = [torch.empty(T, E).pin_memory() for _ in range(B)]
+    h_done = [torch.empty(T, E, dtype=torch.uint8).pin_memory() for _ in range(B)]
+    h_obs = [torch.empty(E, a.obs_dim).pin_memory() for _ in range(B)]
+    for i in range(B):
+        pipe.submit_many(h_act[i], h_rew[i], h_done[i], h_obs[i] if i % 2 == 0 else None)
+    pipe.drain()
+    torch.cuda.synchronize()
+    for i in range(B):
+        obs, rew, done = b.step_many(h_act[i].to(DEV))
+        assert gu.same(h_rew[i].numpy(), rew.cpu().numpy()) and gu.same(h_done[i].numpy().astype(bool), done.cpu().numpy()), i
+        if i % 2 == 0:
+            assert gu.same(h_obs[i].numpy(), obs.cpu().numpy()), i
+    assert gu.same(a.state.cpu().numpy(), b.state.cpu().numpy())

@@ -593,6 +593,7 @@ class HostStepPipeline:
         self.ev_step = [torch.cuda.Event() for _ in range(2)]
         self.ev_copy = [torch.cuda.Event() for _ in range(2)]
         self.t = 0
+        self._many_key, self.m_act, self.m_rew, self.m_done, self._obs_copy = None, None, None, None, None
         self.s_step.wait_stream(torch.cuda.current_stream(dev))
 
     def submit(self, h_action, h_obs=None, h_reward=None, h_done=None) -> None:
@@ -613,6 +614,44 @@ class HostStepPipeline:
                 h_reward.copy_(self.rew[k], non_blocking=True)
             if h_done is not None:
                 h_done.copy_(self.done[k].view(h_done.dtype) if h_done.dtype != torch.uint8 else self.done[k], non_blocking=True)
+            self.ev_copy[k].record(self.s_copy)
+        self.t += 1
+
+    def submit_many(self, h_actions, h_rewards=None, h_dones=None, h_obs=None, n_steps=None) -> None:
+        """The same pipeline for T-step launches (``step_many``): pinned host ``h_actions`` [T, E, M] (or [E, M] with
+        ``n_steps``: action repeat) up, per-step ``h_rewards`` / ``h_dones`` [T, E] and, optionally, the observation
+        after the last step down.  Block i+1's upload and kernel overlap block i's download; asking for ``h_obs``
+        makes the next kernel wait for that copy (the env has one observation buffer)."""
+        env, k = self.env, self.t & 1
+        T = int(n_steps) if h_actions.dim() == 2 else int(h_actions.shape[0])
+        key = (tuple(h_actions.shape), T)
+        if self._many_key != key:
+            self.drain()
+            torch.cuda.current_stream(env.device).synchronize()
+            dev, E = env.device, env.num_envs
+            self.m_act = [torch.empty(h_actions.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+            self.m_rew = [torch.empty(T, E, dtype=torch.float32, device=dev) for _ in range(2)]
+            self.m_done = [torch.empty(T, E, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self._many_key = key
+        with torch.cuda.stream(self.s_step):
+            if self.t >= 2:
+                self.s_step.wait_event(self.ev_copy[k])           # slot k's previous results have left the device
+            self.m_act[k].copy_(h_actions, non_blocking=True)
+            if self._obs_copy is not None:
+                self.s_step.wait_event(self._obs_copy)            # the previous block's observation has left the device
+                self._obs_copy = None
+            env.step_many(self.m_act[k], n_steps=n_steps, out=(self.m_rew[k], self.m_done[k]))
+            self.ev_step[k].record(self.s_step)
+        with torch.cuda.stream(self.s_copy):
+            self.s_copy.wait_event(self.ev_step[k])
+            if h_obs is not None:
+                h_obs.copy_(env.obs, non_blocking=True)
+                self._obs_copy = torch.cuda.Event()
+                self._obs_copy.record(self.s_copy)
+            if h_rewards is not None:
+                h_rewards.copy_(self.m_rew[k], non_blocking=True)
+            if h_dones is not None:
+                h_dones.copy_(self.m_done[k].view(h_dones.dtype) if h_dones.dtype != torch.uint8 else self.m_done[k], non_blocking=True)
             self.ev_copy[k].record(self.s_copy)
         self.t += 1
 
