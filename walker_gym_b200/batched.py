@@ -594,6 +594,7 @@ class HostStepPipeline:
         self.ev_copy = [torch.cuda.Event() for _ in range(2)]
         self.t = 0
         self._many_key, self.m_act, self.m_rew, self.m_done, self._obs_copy = None, None, None, None, None
+        self.s_up, self.ev_up = torch.cuda.Stream(device=dev), [torch.cuda.Event() for _ in range(2)]     # submit_many uploads
         self.s_step.wait_stream(torch.cuda.current_stream(dev))
 
     def submit(self, h_action, h_obs=None, h_reward=None, h_done=None) -> None:
@@ -633,10 +634,17 @@ class HostStepPipeline:
             self.m_rew = [torch.empty(T, E, dtype=torch.float32, device=dev) for _ in range(2)]
             self.m_done = [torch.empty(T, E, dtype=torch.uint8, device=dev) for _ in range(2)]
             self._many_key = key
+        with torch.cuda.stream(self.s_up):                       # the upload also overlaps the previous block's kernel
+            if self.t >= 2:
+                self.s_up.wait_event(self.ev_step[k])             # the kernel that read slot k's actions has finished
+            else:
+                self.s_up.wait_stream(torch.cuda.current_stream(env.device))
+            self.m_act[k].copy_(h_actions, non_blocking=True)
+            self.ev_up[k].record(self.s_up)
         with torch.cuda.stream(self.s_step):
             if self.t >= 2:
                 self.s_step.wait_event(self.ev_copy[k])           # slot k's previous results have left the device
-            self.m_act[k].copy_(h_actions, non_blocking=True)
+            self.s_step.wait_event(self.ev_up[k])
             if self._obs_copy is not None:
                 self.s_step.wait_event(self._obs_copy)            # the previous block's observation has left the device
                 self._obs_copy = None
@@ -657,5 +665,6 @@ class HostStepPipeline:
 
     def drain(self) -> None:
         cur = torch.cuda.current_stream(self.env.device)
+        cur.wait_stream(self.s_up)
         cur.wait_stream(self.s_step)
         cur.wait_stream(self.s_copy)
