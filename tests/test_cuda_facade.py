@@ -228,8 +228,12 @@ def test_host_step_pipeline_matches_synchronous_host_steps():
     pipe = HostStepPipeline(a)
     for t in range(T):
         pipe.submit(acts[t], obs_a[t], rew_a[t], done_a[t])
-    pipe.drain()
+    pipe.drain()                    # blocks the host: the results are in the host tensors now (no synchronize needed)
+    snap = [(o.clone(), r.clone(), d.clone()) for o, r, d in zip(obs_a, rew_a, done_a)]
     torch.cuda.synchronize()
+    for t in range(T):              # ... and nothing was still in flight when drain() returned
+        assert torch.equal(snap[t][0].view(torch.int32), obs_a[t].view(torch.int32)) and torch.equal(snap[t][1].view(torch.int32), rew_a[t].view(torch.int32))
+        assert torch.equal(snap[t][2], done_a[t])
     d_act = torch.empty(E, 2, device="cuda:0")
     h_obs, h_rew, h_done = torch.empty(E, b.obs_dim).pin_memory(), torch.empty(E).pin_memory(), torch.empty(E, dtype=torch.uint8).pin_memory()
     for t in range(T):
@@ -238,3 +242,10 @@ def test_host_step_pipeline_matches_synchronous_host_steps():
         assert gu.same(obs_a[t].numpy(), h_obs.numpy()) and gu.same(rew_a[t].numpy(), h_rew.numpy()), t
         assert gu.same(done_a[t].numpy(), h_done.numpy()), t
     assert gu.same(a.pos.cpu().numpy(), b.pos.cpu().numpy())
+    # work queued on the caller's stream between drains is ordered before the next submit (reset here)
+    a.reset(mode="template"); b.reset(mode="template")
+    pipe.submit(acts[0], obs_a[0], rew_a[0], done_a[0])
+    pipe.wait_slot(1)
+    b.step_host(acts[0], d_act, h_obs, h_rew, h_done)
+    torch.cuda.synchronize()
+    assert gu.same(obs_a[0].numpy(), h_obs.numpy()) and gu.same(rew_a[0].numpy(), h_rew.numpy())

@@ -258,8 +258,7 @@ def test_host_pipeline_submit_many():
     h_obs = [torch.empty(E, a.obs_dim).pin_memory() for _ in range(B)]
     for i in range(B):
         pipe.submit_many(h_act[i], h_rew[i], h_done[i], h_obs[i] if i % 2 == 0 else None)
-    pipe.drain()
-    torch.cuda.synchronize()
+    pipe.drain()                    # blocks the host until the results are in the host tensors
     for i in range(B):
         obs, rew, done = b.step_many(h_act[i].to(DEV))
         assert gu.same(h_rew[i].numpy(), rew.cpu().numpy()) and gu.same(h_done[i].numpy().astype(bool), done.cpu().numpy()), i

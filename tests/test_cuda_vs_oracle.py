@@ -10,6 +10,7 @@ import golden_util as gu
 import walker_oracle as wo
 
 pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
 
 
 def spec_of(name):
@@ -240,19 +241,15 @@ def test_rollout_collector_cuda_graph_and_eager():
                                 obs_layout="feature", act_layout="feature", graph_safe=True)
         pol = FeatureMajorMLP(env.obs_dim, env.M).to("cuda:0")
         col = RolloutCollector(env, pol, T, use_cuda_graph=use_graph)
-        if use_graph:
-            # the capture warm-up consumes one rollout: replay from the same state by rebuilding the env state
-            sd = {k: v.clone() if torch.is_tensor(v) else v for k, v in env.state_dict().items()}
-            ctr = env._counter.clone()
-            col.collect()
-            env.load_state_dict(sd); env._counter.copy_(ctr); env.fin_stats.zero_(); env.set_state(ep_ret=torch.zeros(E))
-            torch.cuda.manual_seed(0)
+        # the capture warm-up of the first graph collect() runs on a snapshot that is restored (env state, device step
+        # counter, finished-episode accumulators): the first collect() is one rollout from the initial state
         batch = col.collect()
         torch.cuda.synchronize()
         outs.append({k: v.clone() for k, v in batch.items()})
         stats = col.episode_stats(all_reduce=False)
         assert batch["obs"].shape == (T + 1, env.obs_dim, E) and batch["actions"].shape == (T, env.M, E)
         assert stats["episodes"] == E and torch.isfinite(batch["advantages"]).all()
+        assert int(env._counter.item()) == T + 1            # reset + exactly one rollout, graph or not
     assert torch.equal(outs[0]["dones"], outs[1]["dones"]) and int(outs[0]["dones"].sum()) == E
     assert torch.equal(outs[0]["obs"][0], outs[1]["obs"][0])
     for o in outs:
@@ -572,3 +569,67 @@ def test_units_kernel_for_bodies_of_identical_disconnected_units(R, masses, in3d
         run_lockstep(env, body, prm, st, 14, np.random.default_rng(R), noise_reset=True)
     finally:
         Point.clear()
+
+
+@pytest.mark.parametrize("mode", ["graph_safe_packed", "graph_safe_soa", "x64"])
+def test_state_dict_round_trip_is_a_complete_snapshot(mode):
+    """state_dict() is a snapshot (copies) that carries the device step counter of graph_safe envs and the float64
+    muscle state of x64 envs: restore + replay reproduces the same trajectory bit for bit, auto-reset jitter included."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    E, T = 3000, 9
+    x64 = mode == "x64"
+    kw = dict(in3d=True, auto_reset="template", max_steps=4, seed=21)
+    if x64:
+        env = BatchedPhysicsEnv("Box-v0", E, DEV, x64=True, **kw)
+    else:
+        env = BatchedPhysicsEnv("Balance-v0", E, DEV, graph_safe=True,
+                                state_layout="packed" if mode.endswith("packed") else "soa", **kw)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    dt = torch.float64 if x64 else torch.float32
+    acts = [(torch.rand(E, env.M, device=DEV, generator=g, dtype=dt) * (60 if x64 else 2) - (30 if x64 else 1)) for _ in range(2 * T)]
+    for t in range(T):
+        env.step(acts[t])
+    sd = env.state_dict()
+    before = {k: v.clone() for k, v in sd.items() if torch.is_tensor(v)}
+
+    def run():
+        out = []
+        for t in range(T, 2 * T):
+            obs, rew, done, _ = env.step(acts[t])
+            out.append((obs.clone(), rew.clone(), done.clone()))
+        return out, env.pos.clone(), env.vel.clone(), env.mx.clone()
+    first = run()
+    for k, v in before.items():                              # a snapshot: stepping did not change the dict's tensors
+        assert torch.equal(sd[k].view(torch.uint8), v.view(torch.uint8)), k
+    env.load_state_dict(sd)
+    second = run()
+    for (o1, r1, d1), (o2, r2, d2) in zip(first[0], second[0]):
+        assert gu.same(o1.cpu().numpy(), o2.cpu().numpy()) and gu.same(r1.cpu().numpy(), r2.cpu().numpy())
+        assert torch.equal(d1, d2)
+    for a, b in zip(first[1:], second[1:]):
+        assert gu.same(a.cpu().numpy(), b.cpu().numpy())
+    if x64:
+        assert "mx64" in sd and "mx_weak" in sd and 0 < float(sd["mx_weak"].float().mean()) < 1
+    else:
+        assert int(sd["counter"].item()) == T + 1
+
+
+def test_rejected_step_leaves_the_bound_buffers_alone():
+    """step(out=...) validates action / noise before it rebinds the result pointers: after a ValueError the next plain
+    step() writes the env's own buffers."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv
+    E = 513
+    env = BatchedPhysicsEnv("Box-v0", E, DEV, in3d=True, seed=1)
+    ref = BatchedPhysicsEnv("Box-v0", E, DEV, in3d=True, seed=1)
+    out = (torch.full((E, env.obs_dim), 7.0, device=DEV), torch.full((E,), 7.0, device=DEV), torch.zeros(E, dtype=torch.uint8, device=DEV))
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(E + 1, env.M, device=DEV), out=out)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(E, env.M, device=DEV), noise=torch.zeros(3, device=DEV), out=out)
+    a = torch.rand(E, env.M, device=DEV) * 2 - 1
+    obs, rew, done, _ = env.step(a)
+    obs_r, rew_r, done_r, _ = ref.step(a)
+    assert obs.data_ptr() == env.obs.data_ptr() and gu.same(obs.cpu().numpy(), obs_r.cpu().numpy())
+    assert gu.same(rew.cpu().numpy(), rew_r.cpu().numpy()) and float(out[0].min()) == 7.0 and float(out[1].min()) == 7.0

@@ -270,6 +270,12 @@ class BatchedPhysicsEnv:
             for dst, src in ((self._pos, pos), (self._vel, vel), (self._mx, mx), (self._steps, steps), (self._ep_ret, ep_ret)):
                 if src is not None and dst is not None:
                     dst.copy_(torch.as_tensor(src, device=self.device).reshape(dst.shape))
+            if self.x64 and mx is not None:
+                # x64 mode steps from the double muscle lengths: a float32 length is a float32-typed ("weak") muscle,
+                # a float64 tensor is taken as np.float64 lengths (gym/optimized_walker.py:33)
+                src = torch.as_tensor(mx, device=self.device).reshape(self.mx64.shape)
+                self.mx64.copy_(src.to(torch.float64))
+                self.mx_weak.fill_(0 if src.dtype == torch.float64 else 1)
             return
         put(0, pos, 3 * self.N)
         put(3 * self.N, vel, 3 * self.N)
@@ -338,37 +344,41 @@ class BatchedPhysicsEnv:
         of a trajectory buffer) instead of the env's own buffers; ``done`` is uint8/bool."""
         b = self._buf
         res_obs, res_rew, res_done = self.obs, self.reward, self.done
+        # validate everything before touching the bound buffers: a rejected call must leave the env as it was
         if out is not None:
             res_obs, res_rew, res_done = out
             self._check_f32(res_obs, self.obs.shape, "out obs")
             self._check_f32(res_rew, (self.num_envs,), "out reward")
-            if res_done.element_size() != 1 or res_done.numel() != self.num_envs or not res_done.is_contiguous():
-                raise ValueError("out done must be a contiguous 1-byte tensor of length num_envs")
-            b.obs, b.reward, b.done = res_obs.data_ptr(), res_rew.data_ptr(), res_done.data_ptr()
-        if action is None:
-            b.action, b.act_dim = None, 0
-        else:
+            if res_done.element_size() != 1 or res_done.numel() != self.num_envs or not res_done.is_contiguous() \
+                    or res_done.device != self.obs.device:
+                raise ValueError("out done must be a contiguous 1-byte tensor of length num_envs on the env's device")
+        act_ptr, act64_ptr, act_dim = None, None, 0
+        if action is not None:
             env_axis = 0 if self.act_layout == "row" else 1
             if action.dim() != 2 or action.shape[env_axis] != self.num_envs:
                 raise ValueError(f"action must have shape [{self.num_envs}, A] (row) or [A, {self.num_envs}] (feature)")
             if self.x64:
                 if action.dtype != torch.float64 or not action.is_contiguous() or action.device != self.obs.device:
                     raise ValueError("x64 mode takes contiguous float64 actions on the env's device")
-                b.action, b.action64 = None, action.data_ptr()
+                act64_ptr = action.data_ptr()
             else:
                 self._check_f32(action, action.shape, "action")
-                b.action = action.data_ptr()
-            b.act_dim = int(action.shape[1 - env_axis])
-        b.noise = self._p(self._check_f32(noise, (3 * self.N, self.num_envs), "noise")) if noise is not None else None
-        self._stamp()
-        with torch.cuda.device(self.device):
-            if self.x64:
-                rc = self.lib.wg_step_x64(C.byref(self.topo), C.byref(self._x64), C.byref(self.params), C.byref(b),
-                                          self.num_envs, self._stream())
-            else:
-                rc = self.lib.wg_step(C.byref(self.topo), C.byref(self.params), C.byref(b), self.num_envs, self._stream())
-        b.noise = None
+                act_ptr = action.data_ptr()
+            act_dim = int(action.shape[1 - env_axis])
+        noise_ptr = self._p(self._check_f32(noise, (3 * self.N, self.num_envs), "noise")) if noise is not None else None
+        b.action, b.action64, b.act_dim, b.noise = act_ptr, act64_ptr, act_dim, noise_ptr
         if out is not None:
+            b.obs, b.reward, b.done = res_obs.data_ptr(), res_rew.data_ptr(), res_done.data_ptr()
+        self._stamp()
+        try:
+            with torch.cuda.device(self.device):
+                if self.x64:
+                    rc = self.lib.wg_step_x64(C.byref(self.topo), C.byref(self._x64), C.byref(self.params), C.byref(b),
+                                              self.num_envs, self._stream())
+                else:
+                    rc = self.lib.wg_step(C.byref(self.topo), C.byref(self.params), C.byref(b), self.num_envs, self._stream())
+        finally:
+            b.noise = None
             b.obs, b.reward, b.done = self._p(self.obs), self._p(self.reward), self._p(self._done_u8)
         _lib.check(rc, "wg_step_x64" if self.x64 else "wg_step")
         self._advance()
@@ -513,13 +523,19 @@ class BatchedPhysicsEnv:
 
     # ---- checkpoint / state.pkl ------------------------------------------------------
     def state_dict(self) -> dict:
-        d = {"pos": self.pos, "vel": self.vel, "mx": self.mx, "steps": self.steps, "obs": self.obs,
-             "step_count": self.step_count}
+        """A complete snapshot (copies, in either layout): state, observation, host and device step counters
+        (``graph_safe``), the float64 muscle state of x64 mode, episode accumulators."""
+        def snap(t):
+            return t.clone() if t is not None else None
+        d = {"pos": snap(self.pos), "vel": snap(self.vel), "mx": snap(self.mx), "steps": snap(self.steps),
+             "obs": snap(self.obs), "step_count": self.step_count}
         if self.ep_ret is not None:
-            d["ep_ret"] = self.ep_ret
-        for k in ("old_a", "fin_stats"):
+            d["ep_ret"] = snap(self.ep_ret)
+        for k in ("old_a", "fin_stats", "mx64", "mx_weak"):
             if getattr(self, k) is not None:
-                d[k] = getattr(self, k)
+                d[k] = snap(getattr(self, k))
+        if self._counter is not None:
+            d["counter"] = snap(self._counter)
         return d
 
     def load_state_dict(self, d: dict) -> None:
@@ -527,8 +543,12 @@ class BatchedPhysicsEnv:
         for k, v in d.items():
             if k == "step_count":
                 self.step_count = int(v)
-            elif k in ("obs", "old_a", "fin_stats") and getattr(self, k, None) is not None:
-                getattr(self, k).copy_(v)
+            elif k == "counter":
+                if self._counter is None:
+                    raise ValueError("the checkpoint comes from a graph_safe env (device step counter); this env has none")
+                self._counter.copy_(torch.as_tensor(v, device=self.device).reshape(1))
+            elif k in ("obs", "old_a", "fin_stats", "mx64", "mx_weak") and getattr(self, k, None) is not None:
+                getattr(self, k).copy_(v)       # after set_state: the saved float64 muscle state wins over its float32 view
 
     def save_state(self, path: str, env_index: int = 0) -> None:
         """Write env ``env_index`` as a reference-compatible ``state.pkl``
@@ -578,7 +598,8 @@ class HostStepPipeline:
             pipe.submit(h_action[t], h_obs[t], h_reward[t], h_done[t])     # pinned host tensors; any result may be None
         pipe.drain()                                                        # all results are in the host tensors
 
-    Results of step t are complete once a later ``submit`` that reuses the same slot (t + 2) or ``drain`` returned."""
+    Only ``drain()`` (all steps) and ``wait_slot(age)`` (one step) guarantee that results are in the host tensors: both
+    block the host.  ``submit`` never blocks; it orders the new step behind whatever the caller queued on its stream."""
 
     def __init__(self, env: BatchedPhysicsEnv):
         if env.act_layout != "row" or env.x64:
@@ -601,6 +622,8 @@ class HostStepPipeline:
         env, k = self.env, self.t & 1
         if self.d_act is None or self.d_act[0].shape != h_action.shape:
             self.d_act = [torch.empty(h_action.shape, dtype=torch.float32, device=env.device) for _ in range(2)]
+        # whatever the caller queued on its stream (reset / step / set_state between drains) happens before this step
+        self.s_step.wait_stream(torch.cuda.current_stream(env.device))
         with torch.cuda.stream(self.s_step):
             if self.t >= 2:
                 self.s_step.wait_event(self.ev_copy[k])           # slot k's previous results have left the device
@@ -634,6 +657,7 @@ class HostStepPipeline:
             self.m_rew = [torch.empty(T, E, dtype=torch.float32, device=dev) for _ in range(2)]
             self.m_done = [torch.empty(T, E, dtype=torch.uint8, device=dev) for _ in range(2)]
             self._many_key = key
+        self.s_step.wait_stream(torch.cuda.current_stream(env.device))    # caller-stream work precedes this block
         with torch.cuda.stream(self.s_up):                       # the upload also overlaps the previous block's kernel
             if self.t >= 2:
                 self.s_up.wait_event(self.ev_step[k])             # the kernel that read slot k's actions has finished
@@ -664,7 +688,19 @@ class HostStepPipeline:
         self.t += 1
 
     def drain(self) -> None:
+        """Block the HOST until every submitted step has finished and its results are in the host tensors; work the
+        caller queues on its stream afterwards is ordered behind the pipeline."""
         cur = torch.cuda.current_stream(self.env.device)
         cur.wait_stream(self.s_up)
         cur.wait_stream(self.s_step)
         cur.wait_stream(self.s_copy)
+        self.s_up.synchronize()
+        self.s_step.synchronize()
+        self.s_copy.synchronize()
+
+    def wait_slot(self, age: int = 1) -> None:
+        """Block the host until the results of the step submitted ``age`` submits ago (1 = the latest) are in its
+        host tensors -- the closed-loop pattern: submit(t), wait_slot(2) -> step t-1's results are readable while
+        step t is in flight."""
+        if 1 <= age <= 2 and self.t >= age:
+            self.ev_copy[(self.t - age) & 1].synchronize()

@@ -202,11 +202,16 @@ class RolloutCollector:
             self._rollout()
         else:
             if self._graph is None:
+                # warm-up outside capture (allocator, cuBLAS handles) on a snapshot: the env, its device step counter and
+                # the finished-episode accumulators are restored, so the first collect() advances the env by exactly
+                # `horizon` steps and its statistics hold only what was returned
+                snap = self.env.state_dict()
                 s = torch.cuda.Stream(device=self.env.device)
                 s.wait_stream(torch.cuda.current_stream(self.env.device))
                 with torch.cuda.stream(s):
-                    self._rollout()                               # warm-up outside capture (allocator, cuBLAS handles)
+                    self._rollout()
                 torch.cuda.current_stream(self.env.device).wait_stream(s)
+                self.env.load_state_dict(snap)
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
                     self._rollout()
