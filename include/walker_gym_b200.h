@@ -362,6 +362,37 @@ int wg_gae(const float* rewards, const float* values, const uint8_t* dones, floa
  */
 int wg_stream_probe(const float* src, float* dst, int64_t n_threads, int32_t vec_reads, int32_t vec_writes, void* cuda_stream);
 
+/*
+ * Pinned (page-locked, portable, device-mapped) host memory for the host-buffer calls above.  The reference keeps
+ * its arrays in pageable NumPy memory (gym/optimized_engine.py:84-89); a caller that feeds wg_step_host from such
+ * arrays copies them into these buffers.  The pages are allocated and first-touched by the CALLING thread, so bind
+ * the thread to the GPU's NUMA node first (walker_gym_b200.host.bind_to_device).  write_combined = 1 suits buffers
+ * the host only writes (actions).  Because the memory is mapped, buf->obs / reward / done may point into it: the
+ * step kernel then writes its results straight over PCIe ("zero-copy"), without a device staging buffer.
+ */
+int wg_host_alloc(void** out, uint64_t bytes, int write_combined);
+int wg_host_free(void* p);
+
+/*
+ * Self-tests of the exact-arithmetic primitives the kernels are built from (csrc/wg_math.cuh), each against the
+ * IEEE operation it replaces; every call ADDS the number of mismatching inputs to *d_mismatches (a device counter
+ * the caller zeroes).  Asynchronous on cuda_stream.
+ *   wg_selftest_div_smallint: x / m through the 3-FMA exact quotient (Point.forced's `f / self.m`,
+ *       gym/optimized_engine.py:104-106, for integer masses and for the division by the number of masses) vs
+ *       IEEE division, for every float32 bit pattern x in [x_begin, x_begin + x_count), x_begin + x_count <= 2^32.
+ *   wg_selftest_forced_list: float32(float64(a) + float64(f) / m) (a python-list force, gym/optimized_env.py:148-172)
+ *       on n_pairs Philox-random (a, f) bit patterns.
+ *   wg_selftest_sqrt: the inline sqrt of np.linalg.norm vs IEEE sqrt for every non-negative float32 and every NaN.
+ *   wg_selftest_div3: `direction / current_dist` with one shared reciprocal (gym/optimized_walker.py:52-54) vs three
+ *       IEEE divisions on n Philox-random inputs; mode 0 = independent bit patterns, 1 = L = norm(d), 2 = exponents
+ *       at the guard boundaries (L near 2^-2 / 2^120 / subnormal / huge, quotients near 2^-100); general = 1 tests
+ *       the variant the package-lineage kernel uses (arbitrary numerators).
+ */
+int wg_selftest_div_smallint(float m, uint64_t x_begin, uint64_t x_count, uint64_t* d_mismatches, void* cuda_stream);
+int wg_selftest_forced_list(double m, uint32_t seed, uint64_t n_pairs, uint64_t* d_mismatches, void* cuda_stream);
+int wg_selftest_sqrt(uint64_t* d_mismatches, void* cuda_stream);
+int wg_selftest_div3(int mode, int general, uint32_t seed, uint64_t n, uint64_t* d_mismatches, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

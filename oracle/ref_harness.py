@@ -38,8 +38,20 @@ DEFAULT_REF = os.environ.get("WALKER_GYM_REFERENCE", "/root/reference")
 _loaded = {}
 
 
+# the byte-compiled copy made by oracle/make_ref.py (bytecode of the unmodified modules; travels to the GPU box)
+COMPILED_REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _module_file(gym_dir: str, stem: str):
+    for ext in (".py", ".pyc"):
+        p = os.path.join(gym_dir, stem + ext)
+        if os.path.isfile(p):
+            return p
+    return None
+
+
 def available(ref_root: str = DEFAULT_REF) -> bool:
-    return os.path.isfile(os.path.join(ref_root, "gym", "optimized_env.py"))
+    return _module_file(os.path.join(ref_root, "gym"), "optimized_env") is not None
 
 
 def load(ref_root: str = DEFAULT_REF):
@@ -58,7 +70,7 @@ def load(ref_root: str = DEFAULT_REF):
     sys.path.insert(0, gym_dir)
     try:
         def by_path(modname, fname):
-            spec = importlib.util.spec_from_file_location(modname, os.path.join(gym_dir, fname))
+            spec = importlib.util.spec_from_file_location(modname, _module_file(gym_dir, fname[:-3]))
             mod = importlib.util.module_from_spec(spec)
             sys.modules[modname] = mod
             spec.loader.exec_module(mod)

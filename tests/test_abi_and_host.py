@@ -276,3 +276,39 @@ def test_config1_walker_py_body_1000_steps_oracle_vs_live_reference():
         g[k] = np.asarray(out[k], np.float32)
     assert replay_trajectory(g, wo) is None
     assert bool(out["done"][-1]) and not out["done"][:-1].any()
+
+
+def test_bind_to_device_picks_a_subset_of_the_allowed_cpus():
+    import os
+    from walker_gym_b200.host import bind_to_device
+    before = os.sched_getaffinity(0)
+    try:
+        info = bind_to_device(0, 2)
+        assert set(info["cpus"]) <= before and len(info["cpus"]) >= 1
+        assert os.sched_getaffinity(0) == set(info["cpus"])
+        other = None
+        os.sched_setaffinity(0, before)
+        other = bind_to_device(1, 2)
+        if len(before) >= 2:
+            assert not (set(info["cpus"]) & set(other["cpus"]))      # two ranks never share a core
+    finally:
+        os.sched_setaffinity(0, before)
+
+
+def test_reference_bytecode_recipe_and_harness(tmp_path):
+    """oracle/make_ref.py byte-compiles the unmodified reference modules; the harness imports them from bytecode and
+    steps the same trajectory as from the sources (only where the read-only checkout exists)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import make_ref
+    import ref_harness as rh
+    if not rh.available(rh.DEFAULT_REF):
+        pytest.skip("reference checkout not present")
+    assert make_ref.make(quiet=True) and rh.available(rh.COMPILED_REF)
+    acts = np.random.default_rng(0).uniform(-1, 1, (30, 2)).astype(np.float32)
+    a = rh.rollout("Balance-v0", acts, env_kwargs=dict(in3d=True), seed=3, ref_root=rh.DEFAULT_REF)
+    b = rh.rollout("Balance-v0", acts, env_kwargs=dict(in3d=True), seed=3, ref_root=rh.COMPILED_REF)
+    for k in ("pos", "vel", "obs", "reward", "done"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    listing = os.listdir(os.path.join(rh.COMPILED_REF, "gym"))
+    assert not [f for f in listing if f.endswith(".py")], "bytecode only: no reference source text in the repo tree"

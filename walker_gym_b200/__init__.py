@@ -12,9 +12,9 @@ gym/optimized_walker.py and gym/optimized_engine.py of the reference):
 from .engine import Config, DingPoint, Point
 from .walker import (BODIES, Creature, Muscle, Skeleton, create_balance_creature, create_box_creature,
                      make_creature)
-from .batched import BatchedPhysicsEnv, HostStepPipeline, creature_from_id, make_params
+from .batched import BatchedPhysicsEnv, HostStepPipeline, StepGraph, creature_from_id, make_params
 from .env import Environment, PhysicsEnv, make_env
 
 __all__ = ["Config", "Point", "DingPoint", "Creature", "Muscle", "Skeleton", "BODIES", "make_creature",
-           "create_balance_creature", "create_box_creature", "BatchedPhysicsEnv", "HostStepPipeline", "creature_from_id",
+           "create_balance_creature", "create_box_creature", "BatchedPhysicsEnv", "HostStepPipeline", "StepGraph", "creature_from_id",
            "make_params", "PhysicsEnv", "Environment", "make_env"]

@@ -287,9 +287,16 @@ class BatchedPhysicsEnv:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _check_f32(self, t: torch.Tensor, shape, what: str) -> torch.Tensor:
-        if t.device != self.obs.device or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
-            raise ValueError(f"{what} must be a contiguous float32 tensor of shape {tuple(shape)} on {self.obs.device}")
+    def _on_device_or_mapped(self, t: torch.Tensor, mapped_ok: bool) -> bool:
+        """On the env's device, or (results only) pinned host memory, which CUDA maps into the device's address
+        space: the kernel then writes it over PCIe directly ("zero-copy")."""
+        return t.device == self.obs.device or (mapped_ok and t.device.type == "cpu" and t.is_pinned())
+
+    def _check_f32(self, t: torch.Tensor, shape, what: str, mapped_ok: bool = False) -> torch.Tensor:
+        if not self._on_device_or_mapped(t, mapped_ok) or t.dtype != torch.float32 or not t.is_contiguous() \
+                or tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{what} must be a contiguous float32 tensor of shape {tuple(shape)} on {self.obs.device}"
+                             + (" (or pinned host memory)" if mapped_ok else ""))
         return t
 
     @property
@@ -341,17 +348,20 @@ class BatchedPhysicsEnv:
         With auto-reset on, ``obs`` of a done env is its post-reset observation while
         ``reward``/``done`` describe the step that ended the episode.
         ``out=(obs, reward, done)``: write this step's results straight into caller-owned tensors (e.g. slot t
-        of a trajectory buffer) instead of the env's own buffers; ``done`` is uint8/bool."""
+        of a trajectory buffer) instead of the env's own buffers; ``done`` is uint8/bool.  The tensors may also be
+        PINNED HOST memory (``walker_gym_b200.host.pinned_empty`` / ``tensor.pin_memory()``): the kernel then writes
+        observation rows, rewards and dones over PCIe itself, with no device staging buffer and no separate copy."""
         b = self._buf
         res_obs, res_rew, res_done = self.obs, self.reward, self.done
         # validate everything before touching the bound buffers: a rejected call must leave the env as it was
         if out is not None:
             res_obs, res_rew, res_done = out
-            self._check_f32(res_obs, self.obs.shape, "out obs")
-            self._check_f32(res_rew, (self.num_envs,), "out reward")
+            self._check_f32(res_obs, self.obs.shape, "out obs", mapped_ok=True)
+            self._check_f32(res_rew, (self.num_envs,), "out reward", mapped_ok=True)
             if res_done.element_size() != 1 or res_done.numel() != self.num_envs or not res_done.is_contiguous() \
-                    or res_done.device != self.obs.device:
-                raise ValueError("out done must be a contiguous 1-byte tensor of length num_envs on the env's device")
+                    or not self._on_device_or_mapped(res_done, True):
+                raise ValueError("out done must be a contiguous 1-byte tensor of length num_envs on the env's device "
+                                 "(or pinned host memory)")
         act_ptr, act64_ptr, act_dim = None, None, 0
         if action is not None:
             env_axis = 0 if self.act_layout == "row" else 1
@@ -641,6 +651,29 @@ class HostStepPipeline:
             self.ev_copy[k].record(self.s_copy)
         self.t += 1
 
+    def submit_zero_copy(self, h_action, h_obs, h_reward, h_done) -> None:
+        """The same step with the results written by the kernel itself into the pinned (device-mapped) host tensors:
+        no device result buffers, no download copies.  The action upload of step t+1 (its own stream) overlaps step
+        t's kernel; the kernels serialise (they share the env state) and run at the PCIe write rate.  Results of a
+        step are readable after ``wait_slot`` / ``drain``."""
+        env, k = self.env, self.t & 1
+        if self.d_act is None or self.d_act[0].shape != h_action.shape:
+            self.d_act = [torch.empty(h_action.shape, dtype=torch.float32, device=env.device) for _ in range(2)]
+        self.s_step.wait_stream(torch.cuda.current_stream(env.device))
+        with torch.cuda.stream(self.s_up):
+            if self.t >= 2:
+                self.s_up.wait_event(self.ev_step[k])             # the kernel that read slot k's actions has finished
+            else:
+                self.s_up.wait_stream(torch.cuda.current_stream(env.device))
+            self.d_act[k].copy_(h_action, non_blocking=True)
+            self.ev_up[k].record(self.s_up)
+        with torch.cuda.stream(self.s_step):
+            self.s_step.wait_event(self.ev_up[k])
+            env.step(self.d_act[k], out=(h_obs, h_reward, h_done))
+            self.ev_step[k].record(self.s_step)
+            self.ev_copy[k].record(self.s_step)                   # wait_slot waits on ev_copy
+        self.t += 1
+
     def submit_many(self, h_actions, h_rewards=None, h_dones=None, h_obs=None, n_steps=None) -> None:
         """The same pipeline for T-step launches (``step_many``): pinned host ``h_actions`` [T, E, M] (or [E, M] with
         ``n_steps``: action repeat) up, per-step ``h_rewards`` / ``h_dones`` [T, E] and, optionally, the observation
@@ -704,3 +737,51 @@ class HostStepPipeline:
         step t is in flight."""
         if 1 <= age <= 2 and self.t >= age:
             self.ev_copy[(self.t - age) & 1].synchronize()
+
+
+class StepGraph:
+    """T closed-loop ``env.step`` calls captured once in a CUDA graph and replayed.
+
+    For shards so small that one step kernel takes a few microseconds (BASELINE config 3 as written: 2^20 envs split
+    over 8 GPUs = 131072 per GPU, about 9 us per step) the Python + ctypes cost of a launch (~15 us) would dominate;
+    a graph replay launches T steps with one host call.  The env must be built with ``graph_safe=True`` (the Philox
+    step index of the in-kernel reset jitter then lives in a device counter that the graph advances by T per replay).
+
+        g = StepGraph(env, actions)        # actions: device float32 [T, E, M]; overwrite in place between replays
+        g.replay()                          # T steps; g.obs [T, E, D] (or the last one only), g.rewards / g.dones [T, E]
+    """
+
+    def __init__(self, env: BatchedPhysicsEnv, actions: torch.Tensor, keep_obs: str = "last"):
+        if env._counter is None:
+            raise ValueError("StepGraph needs BatchedPhysicsEnv(graph_safe=True)")
+        if keep_obs not in ("last", "all"):
+            raise ValueError("keep_obs must be 'last' or 'all'")
+        if actions.dim() != 3 or actions.device != env.obs.device or actions.dtype != torch.float32:
+            raise ValueError("actions must be a device float32 tensor [T, E, A] (or [T, A, E] with act_layout='feature')")
+        self.env, self.actions, self.T = env, actions, int(actions.shape[0])
+        E, dev = env.num_envs, env.device
+        n_obs = self.T if keep_obs == "all" else 1
+        self.obs = torch.empty((n_obs,) + tuple(env.obs.shape), dtype=torch.float32, device=dev)
+        self.rewards = torch.empty(self.T, E, dtype=torch.float32, device=dev)
+        self.dones = torch.empty(self.T, E, dtype=torch.uint8, device=dev)
+        snap = env.state_dict()                                   # warm-up outside capture, on a snapshot
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            self._steps()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        env.load_state_dict(snap)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._steps()
+        env.load_state_dict(snap)                                 # capture does not execute, but keep the contract explicit
+
+    def _steps(self) -> None:
+        env = self.env
+        with env.deferred_steps(self.T):
+            for t in range(self.T):
+                env._step_offset = t
+                env.step(self.actions[t], out=(self.obs[t if self.obs.shape[0] > 1 else 0], self.rewards[t], self.dones[t]))
+
+    def replay(self) -> None:
+        self.graph.replay()

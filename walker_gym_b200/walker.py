@@ -196,6 +196,19 @@ def _quad_balance():
 BODIES["quad_balance"] = _quad_balance()
 
 
+def _quad_balance_chain():
+    """The same four Balance-v0 units CONNECTED into one body: a bone from unit u's right shoulder (its point 1) to
+    unit u+1's left shoulder (its point 0), rest length = the 50-unit gap.  N=16, S=23, M=8 -- BASELINE.json config 4's
+    "enlarged walker morphology (4x masses/springs)" as one connected creature (the size of gym/walker.py's insect,
+    :255-293, N=13, S=23, M=8).  The link bones come after every unit's own bones in the skeleton list."""
+    spec = _quad_balance()
+    spec["skeletons"] = spec["skeletons"] + [(4 * u + 1, 4 * (u + 1), {}) for u in range(3)]
+    return spec
+
+
+BODIES["quad_balance_chain"] = _quad_balance_chain()
+
+
 def make_creature(name: str) -> Creature:
     """Build one of the in-tree morphologies by name (keys of ``BODIES``)."""
     spec = BODIES[name]
@@ -224,3 +237,4 @@ test, leg2, box, box2, balance, balance2, balance3, intrian, humanb, insect, box
     _legacy(n) for n in ("test", "leg2", "box", "box2", "balance", "balance2", "balance3", "intrian",
                          "humanb", "insect", "box4", "leg", "hat"))
 quad_balance = _legacy("quad_balance")
+quad_balance_chain = _legacy("quad_balance_chain")
