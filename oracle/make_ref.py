@@ -6,7 +6,8 @@ The reference (walker-gym) is pure Python with no build system and no package me
 
     gym/optimized_engine.py  gym/optimized_renderer.py  gym/optimized_walker.py  gym/optimized_env.py
 
-from the read-only checkout (default /root/reference) into ``oracle/_ref/gym/*.pyc`` -- bytecode only, the Python
+from the read-only checkout (default /root/reference) into ``oracle/_ref/gym/*.refbc`` (CPython bytecode files under a neutral extension, so that
+snapshot tools that drop ``*.pyc`` still ship them) -- bytecode only, the Python
 analogue of compiling a C reference into ``oracle/_ref/*.so``: no reference source text enters the repository, the
 directory is git-ignored, and it travels to the GPU box with the snapshot (same image, same interpreter, same
 bytecode magic).  ``oracle/ref_harness.py`` imports the modules from there (pygame / turtle stubbed, the six-line
@@ -34,7 +35,7 @@ def make(ref_root: str = "/root/reference", quiet: bool = False) -> bool:
         return False
     os.makedirs(OUT, exist_ok=True)
     for m in MODULES:
-        py_compile.compile(os.path.join(src_dir, m + ".py"), cfile=os.path.join(OUT, m + ".pyc"),
+        py_compile.compile(os.path.join(src_dir, m + ".py"), cfile=os.path.join(OUT, m + ".refbc"),
                            dfile=f"<reference>/gym/{m}.py", doraise=True, optimize=0)
     with open(os.path.join(OUT, "PROVENANCE"), "w") as f:
         f.write(f"bytecode of {', '.join(m + '.py' for m in MODULES)} from {src_dir}, unmodified; "

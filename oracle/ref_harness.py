@@ -43,7 +43,7 @@ COMPILED_REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def _module_file(gym_dir: str, stem: str):
-    for ext in (".py", ".pyc"):
+    for ext in (".py", ".refbc"):
         p = os.path.join(gym_dir, stem + ext)
         if os.path.isfile(p):
             return p
@@ -70,7 +70,13 @@ def load(ref_root: str = DEFAULT_REF):
     sys.path.insert(0, gym_dir)
     try:
         def by_path(modname, fname):
-            spec = importlib.util.spec_from_file_location(modname, _module_file(gym_dir, fname[:-3]))
+            path = _module_file(gym_dir, fname[:-3])
+            if path.endswith(".refbc"):        # bytecode made by oracle/make_ref.py: a .pyc under a neutral extension
+                from importlib.machinery import SourcelessFileLoader
+                loader = SourcelessFileLoader(modname, path)
+                spec = importlib.util.spec_from_loader(modname, loader, origin=path)
+            else:
+                spec = importlib.util.spec_from_file_location(modname, path)
             mod = importlib.util.module_from_spec(spec)
             sys.modules[modname] = mod
             spec.loader.exec_module(mod)

@@ -311,4 +311,4 @@ def test_reference_bytecode_recipe_and_harness(tmp_path):
     for k in ("pos", "vel", "obs", "reward", "done"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
     listing = os.listdir(os.path.join(rh.COMPILED_REF, "gym"))
-    assert not [f for f in listing if f.endswith(".py")], "bytecode only: no reference source text in the repo tree"
+    assert not [f for f in listing if f.endswith((".py", ".pyc"))], "bytecode only: no reference source text in the repo tree"

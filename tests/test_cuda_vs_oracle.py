@@ -86,7 +86,7 @@ def test_ragged_batch_sizes(name, E):
 
 
 @pytest.mark.parametrize("name", ["test", "leg2", "box", "box2", "balance", "balance2", "balance3", "intrian",
-                                  "humanb", "insect", "box4", "leg", "hat", "quad_balance"])
+                                  "humanb", "insect", "box4", "leg", "hat", "quad_balance", "quad_balance_chain"])
 def test_every_walker_py_body(name):
     """BASELINE config 1 bodies (gym/walker.py tables) under the L1 semantics."""
     env, body, prm, st = make_pair(name, 64, env_kw=dict(in3d=True))
@@ -569,6 +569,62 @@ def test_units_kernel_for_bodies_of_identical_disconnected_units(R, masses, in3d
         run_lockstep(env, body, prm, st, 14, np.random.default_rng(R), noise_reset=True)
     finally:
         Point.clear()
+
+
+@pytest.mark.parametrize("R,masses,in3d,layout,auto,link", [
+    (4, (5, 5, 1, 3), True, "row", "template", {}), (2, (5, 5, 1, 3), False, "feature", "jitter", {"k": 700, "dampk": 15}),
+    (8, (5, 5, 1, 3), True, "row", "jitter", {"k": 3000}), (4, (1, 1, 1, 1), False, "row", "template", {"x": 80.0}),
+    (4, (2, 3, 4, 5), True, "feature", "template", {})])
+def test_linked_units_kernel_for_a_connected_chain_of_units(R, masses, in3d, layout, auto, link):
+    """The same units CONNECTED by link bones (unit u's mass 1 -- unit u+1's mass 0, after every unit's own bones in
+    the skeleton list): one lane per unit, the far endpoint of a link over warp shuffles, both owners evaluate the link.
+    Bit-identical to the oracle's one-env-at-a-time evaluation: mass patterns, 2-D / 3-D, layouts, reset modes,
+    substeps, ragged batch, custom link constants."""
+    from walker_gym_b200 import BODIES, BatchedPhysicsEnv, Creature, Muscle, Point, Skeleton, _lib
+    base = BODIES["balance_v0"]
+    pts_s, mus_s, sks_s = [], [], []
+    for u in range(R):
+        off = 150.0 * (u - (R - 1) / 2)
+        pts_s += [(float(masses[n]), (p[0] + off, p[1], p[2]), False) for n, (_, p) in enumerate(base["points"])]
+        mus_s += [(4 * u + i, 4 * u + j, {}) for i, j, _ in base["muscles"]]
+    for u in range(R):
+        sks_s += [(4 * u + i, 4 * u + j, {}) for i, j, _ in base["skeletons"]]
+    sks_s += [(4 * u + 1, 4 * (u + 1), dict(link)) for u in range(R - 1)]
+    spec = {"points": pts_s, "muscles": mus_s, "skeletons": sks_s}
+    Point.clear()
+    try:
+        pts = [Point(m, list(p), [0, 0, 0]) for m, p, _ in pts_s]
+        cr = Creature(pts, [Muscle(pts[i], pts[j]) for i, j, _ in mus_s], [Skeleton(pts[i], pts[j], **kw) for i, j, kw in sks_s])
+        E = 1003
+        kw = dict(in3d=in3d, auto_reset=auto, max_steps=6, k_sub=3, seed=R, obs_layout=layout, keep_old_a=True,
+                  track_info=True, track_contacts=True, initial_reset=False)
+        env = BatchedPhysicsEnv(cr, E, "cuda:0", **kw)
+        body = wo.make_body(spec)
+        prm = wo.make_params(in3d=in3d, auto_reset={"jitter": 1, "template": 2}[auto], max_steps=6, k_sub=3, seed=R)
+        st = wo.init_state(body, E)
+        run_lockstep(env, body, prm, st, 14, np.random.default_rng(R), noise_reset=True)
+        # and against the run-time-topology kernel on the same inputs (kernel agreement at a glance)
+        lib = _lib.load()
+        a, b = BatchedPhysicsEnv(cr, E, "cuda:0", **kw), BatchedPhysicsEnv(cr, E, "cuda:0", **kw)
+        import torch
+        g = torch.Generator(device="cuda:0").manual_seed(5)
+        for t in range(6):
+            act = torch.rand(E, a.M, device="cuda:0", generator=g) * 2 - 1
+            oa = a.step(act)[0].clone()
+            lib.wg_force_generic(1)
+            try:
+                ob = b.step(act)[0].clone()
+            finally:
+                lib.wg_force_generic(0)
+            assert gu.same(oa.cpu().numpy(), ob.cpu().numpy()), t
+    finally:
+        Point.clear()
+
+
+def test_config4_connected_enlarged_body_8_substeps():
+    """BASELINE config 4 on ONE connected creature (quad_balance_chain: N=16, S=23, M=8), 8 substeps."""
+    env, body, prm, st = make_pair("quad_balance_chain", 1024, env_kw=dict(in3d=True), k_sub=8, auto_reset="template", max_steps=12)
+    run_lockstep(env, body, prm, st, 30, np.random.default_rng(4), noise_reset=False)
 
 
 @pytest.mark.parametrize("mode", ["graph_safe_packed", "graph_safe_soa", "x64"])

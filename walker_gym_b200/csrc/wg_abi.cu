@@ -11,6 +11,8 @@
 namespace wg {
 int balance_units(const wg_topology*);
 int launch_balance_units(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int R, cudaStream_t);
+int balance_chain_units(const wg_topology*);
+int launch_balance_chain(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, int R, cudaStream_t);
 bool jit_eligible(const wg_topology*);
 bool jit_runtime_available();
 bool jit_eligible_soa(const wg_topology*);
@@ -190,6 +192,9 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
     if (tuning(WG_TUNE_PART) < 0 && !g_force_generic.load()) {
         const int R = balance_units(topo);
         if (R) return launch_balance_units(topo, prm, buf, n_env, R, s);
+        // the same units chained into ONE connected body by link bones: neighbour endpoints over warp shuffles
+        const int Rc = balance_chain_units(topo);
+        if (Rc) return launch_balance_chain(topo, prm, buf, n_env, Rc, s);
     }
     // larger bodies: several lanes per env (mass partition); automatic choice by body size
     int parts = tuning(WG_TUNE_PART);

@@ -11,9 +11,10 @@
 namespace wg {
 
 // ---- self-test kernels ------------------------------------------------------------------------------------
-__device__ __forceinline__ bool same_f32(float a, float b) {
-    return (a != a && b != b) || __float_as_uint(a) == __float_as_uint(b);
-}
+// equal values (+0 == -0: the kernels' contract is "same bits up to NaN payload and the sign of zero" -- the exact
+// quotient of -0 by a constant comes out as +0, and no operation of the step divides by, or takes the sign of, a zero)
+__device__ __forceinline__ bool same_f32(float a, float b) { return (a != a && b != b) || a == b; }
+__device__ __forceinline__ bool same_bits(float a, float b) { return (a != a && b != b) || __float_as_uint(a) == __float_as_uint(b); }
 __device__ __forceinline__ void count_mismatch(bool bad, unsigned long long* out) {
     const unsigned m = __ballot_sync(0xffffffffu, bad);
     if (m && (threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)__popc(m));
@@ -65,7 +66,7 @@ __global__ void selftest_sqrt_kernel(unsigned long long* out) {
         if (i < n) {
             const float x = __uint_as_float((uint32_t)i);
             if (!(x < 0.0f) && __float_as_uint(x) != 0x80000000u)       // a sum of squares is +0, positive or NaN
-                bad = !same_f32(sqrt_rn(x), __fsqrt_rn(x));
+                bad = !same_bits(sqrt_rn(x), __fsqrt_rn(x));
         }
         count_mismatch(bad, out);
     }
@@ -112,7 +113,7 @@ __global__ void selftest_div3_kernel(int mode, uint32_t seed, uint64_t n, unsign
                 div3_len<GENERAL>(q0, q1, q2, L);
                 float w0 = d[0], w1 = d[1], w2 = d[2];
                 if (L > 0.0f) { w0 = __fdiv_rn(d[0], L); w1 = __fdiv_rn(d[1], L); w2 = __fdiv_rn(d[2], L); }
-                bad = !(same_f32(q0, w0) && same_f32(q1, w1) && same_f32(q2, w2));
+                bad = !(same_bits(q0, w0) && same_bits(q1, w1) && same_bits(q2, w2));
             }
         }
         count_mismatch(bad, out);

@@ -238,7 +238,36 @@ template <class U, int UMM>
 struct UnitsArgs {
     PartArgs P;                        // env-level tables (pt unused)
     BodyVals<U::N, U::S> ubv;          // the unit's constants (identical for every unit: checked on the host)
+    float link_k, link_damp, link_rest;   // LINKED units: the bone joining unit u's mass LA to unit u+1's mass LB
 };
+
+// One endpoint's share of Skeleton.run (gym/optimized_walker.py:84-106) for a bone whose other endpoint lives in a
+// neighbouring lane: p1 = (pi, vi), p2 = (pj, vj) exactly as spring_run reads them; SIDE 0 accumulates p1's two
+// increments (F / m, (-D) / m), SIDE 1 p2's ((-F) / m, D / m) into acc (the mass with local index n of this unit).
+// Both owners evaluate the same operations on the same inputs, so each gets the bits the one-thread kernel computes.
+template <int MM, int SIDE, class U, class BV>
+__device__ __forceinline__ void link_half(const BV& bv, int n, const float (&pi)[3], const float (&vi)[3],
+                                          const float (&pj)[3], const float (&vj)[3], float k, float damp, float rest,
+                                          float (&acc)[3]) {
+    const float L = np_norm3(pi[0] - pj[0], pi[1] - pj[1], pi[2] - pj[2]);
+    const float dx = L - rest;
+    const float fs = (-dx) * k;
+    float d0 = pj[0] - pi[0], d1 = pj[1] - pi[1], d2 = pj[2] - pi[2];
+    div3_len(d0, d1, d2, L);
+    const float F[3] = { fs * d0, fs * d1, fs * d2 };
+    const float dk = np_dot3(vi[0] - vj[0], vi[1] - vj[1], vi[2] - vj[2], d0, d1, d2);
+    const float cd = dk * damp;
+    const float D[3] = { cd * d0, cd * d1, cd * d2 };
+    bool unit = (MM == 0);
+    if constexpr (MM == 3) unit = U::unit(n);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float f1 = SIDE == 0 ? F[c] : -F[c], f2 = SIDE == 0 ? -D[c] : D[c];
+        const float q1 = unit ? f1 : div_smallint(f1, bv.mass_f[n], bv.mass_r[n]);
+        const float q2 = unit ? f2 : div_smallint(f2, bv.mass_f[n], bv.mass_r[n]);
+        acc[c] = (acc[c] + q1) + q2;
+    }
+}
 
 // positions of every mass of an env in the per-env scratch (the env-level tail reads them in NumPy's order)
 struct ScratchPos {
@@ -262,7 +291,12 @@ struct UnitView {
 #ifndef WG_UNITS_THREADS_PER_SM
 #define WG_UNITS_THREADS_PER_SM 768
 #endif
-template <class U, bool IN3D, int P, bool ROWMAJOR, int MM, int KB>
+// LA >= 0: LINKED units -- one connected body.  After every unit's own bones the skeleton list holds P-1 link bones,
+// link u joining unit u's mass LA (its p1) to unit u+1's mass LB (its p2), all with the same constants.  Each substep,
+// after the unit's springs and before the integration, a lane fetches its neighbours' link endpoints with warp
+// shuffles and evaluates its side of the left link (it owns p2 = its LB) and of the right link (it owns p1 = its LA):
+// per-mass accumulation order is the list's (unit springs, then link u-1, then link u).
+template <class U, bool IN3D, int P, bool ROWMAJOR, int MM, int KB, int LA = -1, int LB = -1>
 __global__ void __launch_bounds__(KB, WG_UNITS_THREADS_PER_SM / KB)
 step_units_kernel(const __grid_constant__ UnitsArgs<U, MM> UA) {
     const auto& A = UA.P.A;
@@ -279,6 +313,7 @@ step_units_kernel(const __grid_constant__ UnitsArgs<U, MM> UA) {
     const int64_t e0 = (int64_t)blockIdx.x * EB;
     const int64_t e = e0 + el;
     const bool valid = e < E;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);     // the warp's valid lanes (whole envs): shuffle mask of the links
     float* const scr = smem + el * SCR;
     RegStore<U::N, U::M> rs;
     uint32_t cpre = 0;
@@ -305,7 +340,34 @@ step_units_kernel(const __grid_constant__ UnitsArgs<U, MM> UA) {
         }
         const U utopo;
         uint32_t cu = 0;
-        for (int k = 0; k < A.ec.k_sub; k++) cu = run_physics<IN3D, MM>(utopo, UA.ubv, A.ec, rs);
+        if constexpr (LA < 0) {
+            for (int k = 0; k < A.ec.k_sub; k++) cu = run_physics<IN3D, MM>(utopo, UA.ubv, A.ec, rs);
+        } else {
+            for (int k = 0; k < A.ec.k_sub; k++) {
+                // Creature.run: zero, muscles, this unit's bones (run_physics up to the integration)
+#pragma unroll
+                for (int n = 0; n < U::N; n++) { rs.a_[n][0] = 0.0f; rs.a_[n][1] = 0.0f; rs.a_[n][2] = 0.0f; }
+#pragma unroll
+                for (int sp = 0; sp < U::M; sp++) spring_run<MM>(utopo, UA.ubv, rs, sp, rs.mx(sp), 0u);
+#pragma unroll
+                for (int sp = U::M; sp < U::S; sp++) spring_run<MM>(utopo, UA.ubv, rs, sp, UA.ubv.srest[sp], 0u);
+                // the link bones: neighbours' endpoints over shuffles (pre-integration state of this substep)
+                float lp[3], lv[3], rp[3], rv[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    lp[c] = __shfl_up_sync(vmask, rs.p_[LA][c], 1);          // unit u-1's mass LA
+                    lv[c] = __shfl_up_sync(vmask, rs.v_[LA][c], 1);
+                    rp[c] = __shfl_down_sync(vmask, rs.p_[LB][c], 1);        // unit u+1's mass LB
+                    rv[c] = __shfl_down_sync(vmask, rs.v_[LB][c], 1);
+                }
+                if (u > 0) link_half<MM, 1, U>(UA.ubv, LB, lp, lv, rs.p_[LB], rs.v_[LB], UA.link_k, UA.link_damp, UA.link_rest, rs.a_[LB]);
+                if (u + 1 < P) link_half<MM, 0, U>(UA.ubv, LA, rs.p_[LA], rs.v_[LA], rp, rv, UA.link_k, UA.link_damp, UA.link_rest, rs.a_[LA]);
+                cu = 0;
+#pragma unroll
+                for (int n = 0; n < U::N; n++)
+                    if (point_step<IN3D, MM>(UA.ubv, A.ec, rs, n)) cu |= 1u << n;
+            }
+        }
         cpre = cu << m0;
         // ---- env-level scratch: heights, speeds, positions ----
 #pragma unroll
@@ -345,6 +407,7 @@ step_units_kernel(const __grid_constant__ UnitsArgs<U, MM> UA) {
         do_reset = (o.done && A.ec.auto_reset) ? 1 : 0;
         A.steps[e] = do_reset ? 0 : sn;
     }
+    (void)vmask;
     do_reset = __shfl_sync(0xffffffffu, do_reset, lane - u);
     if (valid && do_reset) {                            // each lane resets its own unit (Philox keyed per global mass)
         const uint32_t si = step_index_of(A);
