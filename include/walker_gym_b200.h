@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define WG_ABI_VERSION 2
+#define WG_ABI_VERSION 3
 #define WG_MAX_MASS 32
 #define WG_MAX_SPRING 96
 
@@ -90,6 +90,32 @@ typedef struct wg_params {
     uint32_t env_offset;    /* global id of env 0 of this shard (multi-GPU invariance) */
 } wg_params;
 
+/*
+ * In-kernel action source for wg_step_multi: the action of every step of the launch is computed on chip from the
+ * env's own step counter (Point-in-episode time), so an n_steps launch reads no action memory at all.
+ *   mode 1, table: the scripted phase-table gait sketched at gym/walker.py:356-366 (`tt = (t // 50) % 3;
+ *           c.act([...row tt...])`): action = table[((steps / hold) % n_rows)][muscle], steps = the env's step
+ *           counter BEFORE the step (0 for the first step of an episode; an auto-reset restarts the gait);
+ *   mode 2, cpg:   the sinusoidal pattern generator of the package lineage's Muscle.act
+ *           (gym/optimized_walker/walker.py:56-90: `t += dt; sin(2 pi freq t + phase)`) as an action source:
+ *           action = amp[m] * sin(2 pi * ((phase0[m] + (steps + 1) * dphase[m]) mod 2^24) / 2^24), the phase kept
+ *           as a 24-bit fraction of a turn (dphase = round(freq * time_step * 2^24)) and the sine evaluated by the
+ *           library's deterministic polynomial (IEEE +, *, fma only), so the oracle reproduces its bits.
+ * Creature.act applies the generated value exactly like an action read from memory (add, then regulation()).
+ */
+#define WG_GEN_MAX_ROWS 32
+#define WG_GEN_MAX_MUSCLE 16
+typedef struct wg_action_gen {
+    int32_t  mode;          /* 0 = off (buf->action is used), 1 = table, 2 = cpg */
+    int32_t  n_rows;        /* table: 1..WG_GEN_MAX_ROWS */
+    int32_t  hold;          /* table: env-steps each row is held (>= 1) */
+    int32_t  reserved;
+    float    table[WG_GEN_MAX_ROWS * WG_GEN_MAX_MUSCLE];   /* [row * WG_GEN_MAX_MUSCLE + muscle] */
+    float    amp[WG_GEN_MAX_MUSCLE];
+    uint32_t phase0[WG_GEN_MAX_MUSCLE];   /* 24-bit fractions of a turn */
+    uint32_t dphase[WG_GEN_MAX_MUSCLE];
+} wg_action_gen;
+
 /* Caller-owned device buffers of one shard.  Optional ones may be NULL. */
 typedef struct wg_buffers {
     float*       pos;           /* in/out */
@@ -121,6 +147,9 @@ typedef struct wg_buffers {
     double*      mx64;          /* in/out: muscle lengths as doubles, [m * E + e] */
     uint8_t*     mx_weak;       /* in/out: 1 = the length is float32-typed (a fresh or just-clamped muscle), [m * E + e] */
     const double* action64;     /* in: float64 actions, laid out like action */
+    /* wg_step_multi only: HOST pointer to an in-kernel action source (copied into the kernel parameters at launch);
+     * when set with mode != 0, action must be NULL and n_action_steps is ignored */
+    const wg_action_gen* action_gen;
 } wg_buffers;
 
 /*
@@ -212,6 +241,8 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
  *   buf->action        [n_action_steps][n_env][n_muscle] float32 (act_layout 0, act_dim == n_muscle), or null;
  *                      n_action_steps == n_steps: one action block per step; n_action_steps == 1: the same block is
  *                      applied at every step (action repeat / frame skip: Creature.act runs n_steps times with it)
+ *   buf->action_gen    optional in-kernel action source (scripted table / CPG, see wg_action_gen) instead of buf->action:
+ *                      the launch then reads no action memory at all
  *   buf->reward        [n_steps][n_env] float32, optional;  buf->done  [n_steps][n_env] uint8, optional
  *   buf->obs           [n_env][obs_dim] row-major observation after the LAST step (obs_layout 0), optional
  *   buf->old_a / contact_pre / contact_post / energy / centroid must be null.
@@ -379,19 +410,24 @@ int wg_host_free(void* p);
  * the caller zeroes).  Asynchronous on cuda_stream.
  *   wg_selftest_div_smallint: x / m through the 3-FMA exact quotient (Point.forced's `f / self.m`,
  *       gym/optimized_engine.py:104-106, for integer masses and for the division by the number of masses) vs
- *       IEEE division, for every float32 bit pattern x in [x_begin, x_begin + x_count), x_begin + x_count <= 2^32.
+ *       IEEE division, for every float32 bit pattern x in [x_begin, x_begin + x_count), x_begin + x_count <= 2^32;
+ *       m = 1, a power of two <= 2048 or an odd integer in [3, 2047] (the divisors that ever take this path).
  *   wg_selftest_forced_list: float32(float64(a) + float64(f) / m) (a python-list force, gym/optimized_env.py:148-172)
  *       on n_pairs Philox-random (a, f) bit patterns.
  *   wg_selftest_sqrt: the inline sqrt of np.linalg.norm vs IEEE sqrt for every non-negative float32 and every NaN.
  *   wg_selftest_div3: `direction / current_dist` with one shared reciprocal (gym/optimized_walker.py:52-54) vs three
  *       IEEE divisions on n Philox-random inputs; mode 0 = independent bit patterns, 1 = L = norm(d), 2 = exponents
  *       at the guard boundaries (L near 2^-2 / 2^120 / subnormal / huge, quotients near 2^-100); general = 1 tests
- *       the variant the package-lineage kernel uses (arbitrary numerators).
+ *       the variant the package-lineage kernel uses (arbitrary numerators; general = 0 assumes |d| <~ L, a direction,
+ *       so mode 0 applies to general = 1 only).  Inputs are numbered first .. first + n - 1.  d_mismatches is
+ *       uint64[2]: [0] += mismatches, [1] = 1 + the number of one failing input (if it was 0); d_dump (optional,
+ *       float[10]) receives that input's d0 d1 d2 L, the three results and the three IEEE quotients.
  */
 int wg_selftest_div_smallint(float m, uint64_t x_begin, uint64_t x_count, uint64_t* d_mismatches, void* cuda_stream);
 int wg_selftest_forced_list(double m, uint32_t seed, uint64_t n_pairs, uint64_t* d_mismatches, void* cuda_stream);
 int wg_selftest_sqrt(uint64_t* d_mismatches, void* cuda_stream);
-int wg_selftest_div3(int mode, int general, uint32_t seed, uint64_t n, uint64_t* d_mismatches, void* cuda_stream);
+int wg_selftest_div3(int mode, int general, uint32_t seed, uint64_t first, uint64_t n, uint64_t* d_mismatches, float* d_dump,
+                     void* cuda_stream);
 
 #ifdef __cplusplus
 }

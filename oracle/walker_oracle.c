@@ -159,6 +159,24 @@ static void det_sincos2pi(uint32_t j, float *sn, float *cs) {
         default: *sn = -c; *cs = s; break;
     }
 }
+/* In-kernel action sources of wg_step_multi, restated: the scripted phase table sketched at gym/walker.py:356-366
+ * (`tt = (t // 50) % 3; c.act([... row tt ...])`) and a sinusoidal pattern generator after the package lineage's
+ * Muscle.act (gym/optimized_walker/walker.py:56-90: `t += dt; sin(2 pi freq t + phase)`) with the phase kept as a
+ * 24-bit fraction of a turn.  steps[e] is env e's step counter BEFORE the step; out is [E][M] row-major.
+ * mode 1: out = table[((steps / hold) % n_rows) * 16 + m];  mode 2: out = amp[m] * sin(2 pi ((phase0 + (steps+1) dphase) mod 2^24) / 2^24) */
+void wgo_gen_actions(int mode, int n_rows, int hold, const float *table, const float *amp, const uint32_t *phase0,
+                     const uint32_t *dphase, const int32_t *steps, int64_t E, int M, float *out) {
+    for (int64_t e = 0; e < E; e++)
+        for (int m = 0; m < M; m++) {
+            if (mode == 1) out[e * M + m] = table[((steps[e] / hold) % n_rows) * 16 + m];
+            else {
+                float sn, cs;
+                det_sincos2pi((phase0[m] + (uint32_t)(steps[e] + 1) * dphase[m]) & 0xffffffu, &sn, &cs);
+                out[e * M + m] = amp[m] * sn;
+            }
+        }
+}
+
 /* three standard normals for (global env id, global step index, mass) */
 void wgo_normal3(uint32_t seed_lo, uint32_t seed_hi, uint32_t env, uint32_t step, uint32_t mass, float out[3]) {
     uint32_t c[4] = { env, step, mass, 0x57474231u };

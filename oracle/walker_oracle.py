@@ -203,6 +203,26 @@ def reset(body: Body, prm: Params, st: dict, *, mode=1, mask=None, noise=None):
     return obs
 
 
+def gen_actions(gen: dict, steps: np.ndarray, M: int) -> np.ndarray:
+    """The in-kernel action sources of wg_step_multi for envs whose step counters (before the step) are ``steps``.
+    gen = {"mode": 1, "table": [T0][M], "hold": h}  or  {"mode": 2, "amp": [M], "phase0": [M] uint32, "dphase": [M] uint32}."""
+    E = int(steps.shape[0])
+    out = np.empty((E, M), np.float32)
+    table = np.zeros((32, 16), np.float32)
+    amp, p0, dp = np.zeros(16, np.float32), np.zeros(16, np.uint32), np.zeros(16, np.uint32)
+    n_rows, hold = 1, 1
+    if gen["mode"] == 1:
+        t = np.asarray(gen["table"], np.float32)
+        n_rows, hold = t.shape[0], int(gen["hold"])
+        table[:n_rows, :t.shape[1]] = t
+    else:
+        amp[:M], p0[:M], dp[:M] = gen["amp"], gen["phase0"], gen["dphase"]
+    lib().wgo_gen_actions(C.c_int(gen["mode"]), C.c_int(n_rows), C.c_int(hold), _ptr(table, C.c_float), _ptr(amp, C.c_float),
+                          _ptr(p0, C.c_uint32), _ptr(dp, C.c_uint32), _ptr(np.ascontiguousarray(steps, np.int32), C.c_int32),
+                          C.c_int64(E), C.c_int(M), _ptr(out, C.c_float))
+    return out
+
+
 def normal3(seed: int, env: int, step: int, mass: int) -> np.ndarray:
     out = (C.c_float * 3)()
     lib().wgo_normal3(C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32((seed >> 32) & 0xFFFFFFFF),

@@ -265,3 +265,79 @@ def test_host_pipeline_submit_many():
         if i % 2 == 0:
             assert gu.same(h_obs[i].numpy(), obs.cpu().numpy()), i
     assert gu.same(a.state.cpu().numpy(), b.state.cpu().numpy())
+
+
+def _gen_cases(M, dt):
+    from walker_gym_b200 import CPGActions, ScriptedActions
+    rng = np.random.default_rng(M)
+    table = rng.uniform(-1, 1, (3, M)).round(2).tolist()
+    return [ScriptedActions(table, hold=2), ScriptedActions([[0.5] * M], hold=1),
+            CPGActions(amp=rng.uniform(0.2, 3.0, M).tolist(), freq=rng.uniform(0.3, 9.0, M).tolist(),
+                       phase=rng.uniform(-3, 3, M).tolist())]
+
+
+@pytest.mark.parametrize("name,in3d", [("balance_v0", True), ("box_v0", False), ("hat", True), ("balance3", True)])
+def test_step_many_with_in_kernel_action_sources_matches_oracle(name, in3d):
+    """Scripted phase table (gym/walker.py:356-366) and sinusoidal CPG (after gym/optimized_walker/walker.py:56-90)
+    evaluated inside the T-steps kernel from each env's own step counter == the oracle stepped with the same generated
+    actions; episodes end and restart the gait inside a block."""
+    import torch
+    E = 2048 + 19
+    for gi in range(3):
+        env, body, prm, st = _pair(name, E, in3d=in3d, auto_reset="template", max_steps=7, seed=31 + gi)
+        src = _gen_cases(env.M, 0.01)[gi]
+        desc = src.describe() if gi < 2 else src.describe(0.01)
+        rng = np.random.default_rng(gi)
+        nz = (rng.standard_normal((3 * env.N, E)) * 0.1).astype(np.float32)
+        env.reset(noise=torch.from_numpy(nz).cuda(), mode="jitter")
+        wo.reset(body, prm, st, mode=1, noise=nz)
+        # desynchronise the step counters so that one launch sees many gait phases
+        steps0 = rng.integers(0, 6, E).astype(np.int32)
+        env.set_state(steps=torch.from_numpy(steps0))
+        st["steps"][:] = steps0
+        for T in (1, 9, 16):
+            first = env.step_count
+            obs, rew, done = env.step_many(src, n_steps=T)
+            for t in range(T):
+                prm.step_index = first + t
+                acts = wo.gen_actions(desc, st["steps"], env.M)
+                out = wo.step(body, prm, st, acts)
+                assert gu.same(rew[t].cpu().numpy(), out["reward"]), (gi, T, t)
+                assert gu.same(done[t].cpu().numpy(), out["done"].astype(bool)), (gi, T, t)
+            assert gu.same(obs.cpu().numpy(), out["obs"]), (gi, T)
+            assert gu.same(env.pos.cpu().numpy(), st["pos"]) and gu.same(env.mx.cpu().numpy(), st["mx"]), (gi, T)
+            assert gu.same(env.steps.cpu().numpy(), st["steps"])
+        assert np.unique(wo.gen_actions(desc, np.arange(64, dtype=np.int32), env.M), axis=0).shape[0] > (1 if gi != 1 else 0)
+
+
+def test_in_kernel_action_sources_on_a_run_time_compiled_body_and_validation():
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv, CPGActions, Creature, Muscle, Point, ScriptedActions, Skeleton
+    Point.clear()
+    try:
+        pts = [Point(1, [0, 0, 0], [0, 0, 0]), Point(1, [60, 0, 0], [0, 0, 0]), Point(1, [30, 50, 0], [0, 0, 0]),
+               Point(1, [30, 100, 0], [0, 0, 0]), Point(1, [80, 90, 0], [0, 0, 0])]
+        mus = [Muscle(pts[0], pts[2]), Muscle(pts[1], pts[2]), Muscle(pts[3], pts[4])]
+        sks = [Skeleton(pts[0], pts[1]), Skeleton(pts[2], pts[3]), Skeleton(pts[2], pts[4])]
+        cr = Creature(pts, mus, sks)
+        E, T = 4096, 12
+        kw = dict(in3d=True, auto_reset="template", max_steps=5, seed=3, state_layout="packed")
+        a, b = BatchedPhysicsEnv(cr, E, DEV, **kw), BatchedPhysicsEnv(cr, E, DEV, **kw)
+        src = CPGActions(amp=[1.0, 2.0, 0.5], freq=[2.0, 3.5, 7.0], phase=[0.0, 1.0, 2.0])
+        obs, rew, done = a.step_many(src, n_steps=T)
+        # the same generator evaluated on the host (float32 ops as written in wg_action_gen) and fed as a tensor
+        import walker_oracle as wo2
+        desc = src.describe(0.01)
+        for t in range(T):
+            acts = wo2.gen_actions(desc, b.steps.cpu().numpy(), 3)
+            o, r, d, _ = b.step(torch.from_numpy(acts).to(DEV))
+            assert gu.same(rew[t].cpu().numpy(), r.cpu().numpy()) and torch.equal(done[t], d), t
+        assert gu.same(obs.cpu().numpy(), o.cpu().numpy())
+        with pytest.raises(ValueError):
+            a.step_many(ScriptedActions([[0.0, 0.0]]), n_steps=2)             # 2 values for 3 muscles
+        with pytest.raises(ValueError):
+            a.step_many(src)                                                   # n_steps missing
+        with pytest.raises(ValueError):
+            ScriptedActions([[0.0]] * 33)
+    finally:
+        Point.clear()

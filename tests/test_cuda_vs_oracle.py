@@ -643,7 +643,7 @@ def test_state_dict_round_trip_is_a_complete_snapshot(mode):
                                 state_layout="packed" if mode.endswith("packed") else "soa", **kw)
     g = torch.Generator(device=DEV).manual_seed(3)
     dt = torch.float64 if x64 else torch.float32
-    acts = [(torch.rand(E, env.M, device=DEV, generator=g, dtype=dt) * (60 if x64 else 2) - (30 if x64 else 1)) for _ in range(2 * T)]
+    acts = [(torch.rand(E, env.M, device=DEV, generator=g, dtype=dt) * (160 if x64 else 2) - (80 if x64 else 1)) for _ in range(2 * T)]
     for t in range(T):
         env.step(acts[t])
     sd = env.state_dict()

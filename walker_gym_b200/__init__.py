@@ -13,8 +13,9 @@ from .engine import Config, DingPoint, Point
 from .walker import (BODIES, Creature, Muscle, Skeleton, create_balance_creature, create_box_creature,
                      make_creature)
 from .batched import BatchedPhysicsEnv, HostStepPipeline, StepGraph, creature_from_id, make_params
+from .actions import CPGActions, ScriptedActions
 from .env import Environment, PhysicsEnv, make_env
 
 __all__ = ["Config", "Point", "DingPoint", "Creature", "Muscle", "Skeleton", "BODIES", "make_creature",
            "create_balance_creature", "create_box_creature", "BatchedPhysicsEnv", "HostStepPipeline", "StepGraph", "creature_from_id",
-           "make_params", "PhysicsEnv", "Environment", "make_env"]
+           "make_params", "PhysicsEnv", "Environment", "make_env", "ScriptedActions", "CPGActions"]

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 MAX_MASS, MAX_SPRING = 32, 96
-ABI_VERSION = 2
+ABI_VERSION = 3
+GEN_MAX_ROWS, GEN_MAX_MUSCLE = 32, 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WG_LIB_PATH", os.path.join(_HERE, "libwalkergym_b200.so"))   # override: tuning experiments
@@ -42,6 +43,14 @@ class WgParams(C.Structure):
     ]
 
 
+class WgActionGen(C.Structure):
+    """``wg_action_gen``: in-kernel action source of wg_step_multi (scripted table gym/walker.py:356-366, or a CPG
+    after gym/optimized_walker/walker.py:56-90)."""
+    _fields_ = [("mode", C.c_int32), ("n_rows", C.c_int32), ("hold", C.c_int32), ("reserved", C.c_int32),
+                ("table", C.c_float * (GEN_MAX_ROWS * GEN_MAX_MUSCLE)), ("amp", C.c_float * GEN_MAX_MUSCLE),
+                ("phase0", C.c_uint32 * GEN_MAX_MUSCLE), ("dphase", C.c_uint32 * GEN_MAX_MUSCLE)]
+
+
 class WgBuffers(C.Structure):
     _fields_ = [
         ("pos", C.c_void_p), ("vel", C.c_void_p), ("old_a", C.c_void_p), ("mx", C.c_void_p), ("steps", C.c_void_p),
@@ -53,6 +62,7 @@ class WgBuffers(C.Structure):
         ("ep_ret", C.c_void_p), ("fin_stats", C.c_void_p), ("noise", C.c_void_p),
         ("step_counter", C.c_void_p), ("state_packed", C.c_void_p),
         ("mx64", C.c_void_p), ("mx_weak", C.c_void_p), ("action64", C.c_void_p),      # x64 mode (wg_step_x64)
+        ("action_gen", C.POINTER(WgActionGen)),                                         # wg_step_multi: in-kernel action source
     ]
 
 
@@ -157,7 +167,7 @@ def load():
     lib.wg_selftest_div_smallint.argtypes = [C.c_float, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.wg_selftest_forced_list.argtypes = [C.c_double, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.wg_selftest_sqrt.argtypes = [C.c_void_p, C.c_void_p]
-    lib.wg_selftest_div3.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.wg_selftest_div3.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in ("wg_host_alloc", "wg_host_free", "wg_selftest_div_smallint", "wg_selftest_forced_list",
                  "wg_selftest_sqrt", "wg_selftest_div3"):
         getattr(lib, name).restype = C.c_int

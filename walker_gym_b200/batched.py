@@ -402,7 +402,9 @@ class BatchedPhysicsEnv:
         front: scripted gaits / open-loop controllers (the phase-table gait sketched at gym/walker.py:356-366), action repeat, replays.
 
         ``actions``: float32 [T, E, M]; or [E, M] with ``n_steps`` = T: the same action at every step (action repeat /
-        frame skip: ``Creature.act`` runs T times with it); or ``None`` with ``n_steps``: T steps without an action.
+        frame skip: ``Creature.act`` runs T times with it); or ``None`` with ``n_steps``: T steps without an action; or
+        an in-kernel action source (``walker_gym_b200.actions.ScriptedActions`` / ``CPGActions``) with ``n_steps``:
+        the action of every step is computed on chip from the env's own step counter (no action memory is read).
         Returns ``(obs, rewards [T, E], dones [T, E])``: ``obs`` is the observation after the last step (the env's own
         buffer), rewards / dones are per step.  Bit-identical to T ``step`` calls; needs ``state_layout="packed"``,
         row-major observations and actions, a body with an ahead-of-time packed kernel, and no per-step info buffers.
@@ -411,7 +413,16 @@ class BatchedPhysicsEnv:
             raise ValueError("step_many needs state_layout='packed', obs_layout='row', act_layout='row' and float32 actions")
         E = self.num_envs
         n_act = 1
-        if actions is not None and actions.dim() == 2:
+        gen = None
+        from .actions import ActionSource
+        if isinstance(actions, ActionSource):
+            # an in-kernel action source (scripted table / CPG): every step's action is computed on chip from the env's
+            # own step counter; the launch reads no action memory
+            if n_steps is None:
+                raise ValueError("n_steps is required with an in-kernel action source")
+            gen = actions.struct(self.M, float(self.params.dt))
+            actions, T = None, int(n_steps)
+        elif actions is not None and actions.dim() == 2:
             if n_steps is None:
                 raise ValueError("n_steps is required with a single [E, M] action block (action repeat)")
             if actions.shape[0] != E or actions.shape[1] != self.M:
@@ -444,15 +455,19 @@ class BatchedPhysicsEnv:
         b.old_a = b.contact_pre = b.contact_post = b.energy = b.centroid = None
         b.action, b.act_dim, b.noise = self._p(actions), (self.M if actions is not None else 0), None
         b.reward, b.done = rew.data_ptr(), done.data_ptr()
+        b.action_gen = C.pointer(gen) if gen is not None else None
         self._stamp()
-        with torch.cuda.device(self.device):
-            if _host is None:
-                rc = self.lib.wg_step_multi(C.byref(self.topo), C.byref(self.params), C.byref(b), E, T, n_act, self._stream())
-            else:
-                rc = self.lib.wg_step_multi_host(C.byref(self.topo), C.byref(self.params), C.byref(b), E, T, n_act,
-                                                 *[self._p(t) for t in _host], self._stream())
-        b.old_a, b.contact_pre, b.contact_post, b.energy, b.centroid = saved
-        b.reward, b.done = self._p(self.reward), self._p(self._done_u8)
+        try:
+            with torch.cuda.device(self.device):
+                if _host is None:
+                    rc = self.lib.wg_step_multi(C.byref(self.topo), C.byref(self.params), C.byref(b), E, T, n_act, self._stream())
+                else:
+                    rc = self.lib.wg_step_multi_host(C.byref(self.topo), C.byref(self.params), C.byref(b), E, T, n_act,
+                                                     *[self._p(t) for t in _host], self._stream())
+        finally:
+            b.old_a, b.contact_pre, b.contact_post, b.energy, b.centroid = saved
+            b.reward, b.done = self._p(self.reward), self._p(self._done_u8)
+            b.action_gen = None
         _lib.check(rc, "wg_step_multi" if _host is None else "wg_step_multi_host")
         if self._counter is not None:
             if not self._defer_advance:

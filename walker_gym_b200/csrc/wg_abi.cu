@@ -231,6 +231,14 @@ int wg_step_multi(const wg_topology* topo, const wg_params* prm, const wg_buffer
     if (buf->obs && buf->obs_layout != 0) return fail(WG_ERR_BAD_ARG, "wg_step_multi writes row-major observations%s");
     if (buf->action && (buf->act_layout != 0 || buf->act_dim != topo->n_muscle))
         return fail(WG_ERR_BAD_ARG, "wg_step_multi reads actions as [n_action_steps][n_env][n_muscle]%s");
+    if (buf->action_gen && buf->action_gen->mode != 0) {
+        const wg_action_gen* g = buf->action_gen;
+        if (buf->action) return fail(WG_ERR_BAD_ARG, "wg_step_multi: action must be null when an in-kernel action source is set%s");
+        if (g->mode != 1 && g->mode != 2) return fail(WG_ERR_BAD_ARG, "wg_action_gen.mode must be 0, 1 (table) or 2 (cpg)%s");
+        if (topo->n_muscle > WG_GEN_MAX_MUSCLE) return fail(WG_ERR_BAD_ARG, "in-kernel action sources drive at most 16 muscles%s");
+        if (g->mode == 1 && (g->n_rows < 1 || g->n_rows > WG_GEN_MAX_ROWS || g->hold < 1))
+            return fail(WG_ERR_BAD_ARG, "wg_action_gen table: n_rows in [1, 32], hold >= 1%s");
+    }
     if (buf->old_a || buf->contact_pre || buf->contact_post || buf->energy || buf->centroid)
         return fail(WG_ERR_BAD_ARG, "wg_step_multi has no per-step info outputs (old_a / contact / energy / centroid must be null)%s");
     if (n_env == 0) return WG_OK;

@@ -80,13 +80,14 @@ __global__ void selftest_sqrt_kernel(unsigned long long* out) {
 // d by a NaN factor derived from the same length (f_size, dk), so both give NaN -- checked at the spring level by
 // the trajectory tests.
 template <bool GENERAL>
-__global__ void selftest_div3_kernel(int mode, uint32_t seed, uint64_t n, unsigned long long* out) {
+__global__ void selftest_div3_kernel(int mode, uint32_t seed, uint64_t first, uint64_t n, unsigned long long* out, float* dump) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t rounds = (n + stride - 1) / stride;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t k = 0; k < rounds; k++, i += stride) {
+    uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t k = 0; k < rounds; k++, i0 += stride) {
         bool bad = false;
-        if (i < n) {
+        if (i0 < n) {
+            const uint64_t i = first + i0;
             uint32_t c[4] = { (uint32_t)i, (uint32_t)(i >> 32), 0x44495633u, (uint32_t)mode };
             philox4x32_10(c, seed, 0x5eedu);
             float d[3] = { __uint_as_float(c[0]), __uint_as_float(c[1]), __uint_as_float(c[2]) };
@@ -114,6 +115,10 @@ __global__ void selftest_div3_kernel(int mode, uint32_t seed, uint64_t n, unsign
                 float w0 = d[0], w1 = d[1], w2 = d[2];
                 if (L > 0.0f) { w0 = __fdiv_rn(d[0], L); w1 = __fdiv_rn(d[1], L); w2 = __fdiv_rn(d[2], L); }
                 bad = !(same_bits(q0, w0) && same_bits(q1, w1) && same_bits(q2, w2));
+                if (bad && atomicCAS(out + 1, 0ull, (unsigned long long)(i + 1)) == 0ull && dump) {
+                    dump[0] = d[0]; dump[1] = d[1]; dump[2] = d[2]; dump[3] = L;
+                    dump[4] = q0; dump[5] = q1; dump[6] = q2; dump[7] = w0; dump[8] = w1; dump[9] = w2;
+                }
             }
         }
         count_mismatch(bad, out);
@@ -152,8 +157,10 @@ int wg_host_free(void* p) {
 }
 
 int wg_selftest_div_smallint(float m, uint64_t x_begin, uint64_t x_count, uint64_t* d_mismatches, void* cuda_stream) {
-    if (!d_mismatches || !(m >= 1.0f) || m > 2048.0f || m != (float)(int)m || x_begin + x_count > (1ull << 32))
-        return fail(WG_ERR_BAD_ARG, "wg_selftest_div_smallint: m must be an integer in [1, 2048], x range within 2^32%s", "");
+    // the divisors the host ever hands to div_smallint: 1, powers of two, odd integers in [3, 2047] (make_const_div)
+    const int kind = (m >= 1.0f && m <= 2048.0f) ? make_const_div(m).kind : 3;
+    if (!d_mismatches || kind == 3 || x_begin + x_count > (1ull << 32))
+        return fail(WG_ERR_BAD_ARG, "wg_selftest_div_smallint: m must be 1, a power of two <= 2048 or an odd integer in [3, 2047]; x range within 2^32%s", "");
     if (x_count == 0) return WG_OK;
     cudaStream_t s = (cudaStream_t)cuda_stream;
     selftest_div_smallint_kernel<<<148 * 16, 256, 0, s>>>(m, 1.0f / m, x_begin, x_count, (unsigned long long*)d_mismatches);
@@ -164,9 +171,7 @@ int wg_selftest_forced_list(double m, uint32_t seed, uint64_t n_pairs, uint64_t*
     if (!d_mismatches || !(m > 0.0)) return fail(WG_ERR_BAD_ARG, "wg_selftest_forced_list: bad argument%s", "");
     if (n_pairs == 0) return WG_OK;
     // the kind the host picks for this mass (fill_args): 0 unit, 1 power of two, 2 integer in [2, 2048], 3 anything else
-    int kind = 3;
-    if (m == 1.0) kind = 0;
-    else if (m == (double)(int)m && m >= 2.0 && m <= 2048.0) kind = (((int)m) & ((int)m - 1)) == 0 ? 1 : 2;
+    const int kind = make_const_div((float)m).kind;
     cudaStream_t s = (cudaStream_t)cuda_stream;
     selftest_forced_list_kernel<<<148 * 16, 256, 0, s>>>(m, 1.0 / m, kind, seed, (n_pairs + 1) / 2, (unsigned long long*)d_mismatches);
     return run_selftest((unsigned long long*)d_mismatches, s, "forced_list");
@@ -179,12 +184,13 @@ int wg_selftest_sqrt(uint64_t* d_mismatches, void* cuda_stream) {
     return run_selftest((unsigned long long*)d_mismatches, s, "sqrt");
 }
 
-int wg_selftest_div3(int mode, int general, uint32_t seed, uint64_t n, uint64_t* d_mismatches, void* cuda_stream) {
+int wg_selftest_div3(int mode, int general, uint32_t seed, uint64_t first, uint64_t n, uint64_t* d_mismatches, float* d_dump,
+                     void* cuda_stream) {
     if (!d_mismatches || mode < 0 || mode > 2) return fail(WG_ERR_BAD_ARG, "wg_selftest_div3: mode must be 0, 1 or 2%s", "");
     if (n == 0) return WG_OK;
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    if (general) selftest_div3_kernel<true><<<148 * 16, 256, 0, s>>>(mode, seed, n, (unsigned long long*)d_mismatches);
-    else selftest_div3_kernel<false><<<148 * 16, 256, 0, s>>>(mode, seed, n, (unsigned long long*)d_mismatches);
+    if (general) selftest_div3_kernel<true><<<148 * 16, 256, 0, s>>>(mode, seed, first, n, (unsigned long long*)d_mismatches, d_dump);
+    else selftest_div3_kernel<false><<<148 * 16, 256, 0, s>>>(mode, seed, first, n, (unsigned long long*)d_mismatches, d_dump);
     return run_selftest((unsigned long long*)d_mismatches, s, "div3_len");
 }
 

@@ -199,7 +199,9 @@ int launch_jit_multi(const wg_topology* t, const wg_params* p, const wg_buffers*
         cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute (jit): %s", cudaGetErrorString(e));
     }
-    void* args[] = { &A, &n_steps, &act_stride };
+    static thread_local ActionGen G;
+    fill_gen(G, b);
+    void* args[] = { &A, &n_steps, &act_stride, &G };
     cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3((unsigned)((E + kMultiBlock - 1) / kMultiBlock)), dim3(kMultiBlock),
                                      args, smem, s);
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (jit, multi) launch: %s", cudaGetErrorString(e));

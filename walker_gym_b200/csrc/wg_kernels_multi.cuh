@@ -35,11 +35,30 @@ __host__ __device__ constexpr int multi_min_blocks(int n_mass) {
     return threads / kMultiBlock > 0 ? threads / kMultiBlock : 1;
 }
 
+// In-kernel action source (mirror of wg_action_gen, include/walker_gym_b200.h): a scripted phase table indexed by the
+// env's step counter (gym/walker.py:356-366) or a sinusoidal pattern generator (gym/optimized_walker/walker.py:56-90)
+constexpr int kGenRows = 32, kGenMuscle = 16;
+struct ActionGen {
+    int32_t mode, n_rows, hold, reserved;
+    float table[kGenRows * kGenMuscle];
+    float amp[kGenMuscle];
+    uint32_t phase0[kGenMuscle], dphase[kGenMuscle];
+};
+// the action of muscle m for an env whose step counter (before the step) is `stp`
+__device__ __forceinline__ float gen_action(const ActionGen& G, int m, int32_t stp) {
+    if (G.mode == 1) return G.table[((stp / G.hold) % G.n_rows) * kGenMuscle + m];
+    float sn, cs;
+    det_sincos2pi((G.phase0[m] + (uint32_t)(stp + 1) * G.dphase[m]) & 0xffffffu, sn, cs);
+    return G.amp[m] * sn;
+}
+
 // action: [T][E][M] row-major (act_stride = E * M), or one [E][M] block applied at every step (act_stride = 0:
-// action repeat); reward: [T][E]; done: [T][E]; obs: [E][D] row-major, after the last step.
+// action repeat), or generated on chip (G.mode != 0); reward: [T][E]; done: [T][E]; obs: [E][D] row-major, after the
+// last step.
 template <class Topo, bool IN3D, int MM, class Args = StepArgs<Topo::N, Topo::S>>
 __global__ void __launch_bounds__(kMultiBlock, multi_min_blocks(Topo::N))
-step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, const int64_t act_stride) {
+step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, const int64_t act_stride,
+                         const __grid_constant__ ActionGen G) {
     constexpr int N = Topo::N, M = Topo::M;
     constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;
     constexpr int R = 6 * N + M + 2, R4 = (R + 3) / 4;
@@ -86,7 +105,15 @@ step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, cons
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(kMultiBlock / 4) : "memory");
 #endif
             // ---- Creature.act ----
-            if (ap) {
+            if (G.mode != 0) {                  // generated on chip from the env's own step counter: no action memory
+#pragma unroll
+                for (int m = 0; m < M; m++) {
+                    float x = st.mx(m) + gen_action(G, m, stp);
+                    if (A.bv.mlo[m] > x) x = A.bv.mlo[m];
+                    if (A.bv.mhi[m] < x) x = A.bv.mhi[m];
+                    st.mx(m) = x;
+                }
+            } else if (ap) {
 #pragma unroll
                 for (int m = 0; m < M; m++) {
                     float x = st.mx(m) + act[m];
@@ -164,6 +191,13 @@ step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, cons
 }
 
 #ifndef __CUDACC_RTC__          // host-side launch helpers (not part of a run-time compiled translation unit)
+static_assert(sizeof(ActionGen) == sizeof(wg_action_gen) && kGenRows == WG_GEN_MAX_ROWS && kGenMuscle == WG_GEN_MAX_MUSCLE,
+              "ActionGen mirrors wg_action_gen");
+inline void fill_gen(ActionGen& G, const wg_buffers* b) {
+    if (b->action_gen && b->action_gen->mode != 0) memcpy(&G, b->action_gen, sizeof(G));
+    else { G.mode = 0; G.n_rows = 1; G.hold = 1; }
+}
+
 template <class Topo, bool IN3D, int MM>
 inline int launch_multi_packed(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int n_steps,
                                int64_t act_stride, cudaStream_t s) {
@@ -177,7 +211,9 @@ inline int launch_multi_packed(const wg_topology* t, const wg_params* p, const w
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<(unsigned)((E + kMultiBlock - 1) / kMultiBlock), kMultiBlock, smem, s>>>(A, n_steps, act_stride);
+    static thread_local ActionGen G;
+    fill_gen(G, b);
+    kern<<<(unsigned)((E + kMultiBlock - 1) / kMultiBlock), kMultiBlock, smem, s>>>(A, n_steps, act_stride, G);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (multi) launch: %s", cudaGetErrorString(e));
     return WG_OK;

@@ -75,7 +75,11 @@ inline ConstDiv make_const_div(float m) {
     const float fr = frexpf(m, &ex);
     if (m == 1.0f) c.kind = 0;
     else if (fr == 0.5f && ex > -100 && ex < 100) c.kind = 1;              // power of two: reciprocal exact
-    else if (m >= 2.0f && m <= 2048.0f && m == floorf(m)) c.kind = 2;       // small integer
+    // odd integers only: for an even m that is not a power of two, x / m can fall exactly halfway between two
+    // SUBNORMAL float32 values (x = (2k+1) * (m/2) * 2^-149), and the 3-FMA quotient, which works with the inexact
+    // RN(1/m), breaks such ties the wrong way (found by wg_selftest_div_smallint: 2 796 202 of the 2^32 x for m = 6);
+    // with an odd m no quotient is ever a tie.  Even non-powers of two take the IEEE division.
+    else if (m >= 3.0f && m <= 2047.0f && m == floorf(m) && fmodf(m, 2.0f) == 1.0f) c.kind = 2;
     return c;
 }
 
