@@ -260,6 +260,19 @@ int wg_step_x64(const wg_topology* topo, const wg_x64* x64, const wg_params* prm
                 int64_t n_env, void* cuda_stream);
 
 /*
+ * Creature.getstat (gym/optimized_walker.py:129-162) with its options, for every env: per point
+ * [(pos - mid)[:d] * pk (midform) or pos[:d] * pk, v[:d] * vk, old_a[:d] * ak], then the centroid `mid` (3 values,
+ * zeros without midform) if conmid, then Muscle.x * mk.  d = in3d ? 3 : 2; out has 3*d*n_mass + n_muscle (+3) entries
+ * per env, row-major [E][D'] (out_layout 0) or [D'][E] (1).  The state is read from buf (SoA or packed); Point.old_a
+ * from buf->old_a or, when that is null, from the acceleration entries of obs_default -- the observation the step
+ * kernel wrote (layout buf->obs_layout, dimensionality env_in3d).  The python scalars pk / vk / ak / mk multiply
+ * float32 arrays, i.e. they act as float32 (NEP 50).
+ */
+int wg_getstat(const wg_topology* topo, const wg_buffers* buf, const float* obs_default, int32_t env_in3d,
+               int32_t in3d, float pk, float vk, float ak, float mk, int32_t midform, int32_t conmid,
+               float* out, int32_t out_layout, int64_t n_env, void* cuda_stream);
+
+/*
  * PhysicsEnv.reset (gym/optimized_env.py:53-68) for the envs whose mask byte is
  * non-zero (mask NULL = all).  mode 1 = jitter only (the reference's reset),
  * mode 2 = restore the template first (what make_env does, :273-294).

@@ -223,6 +223,30 @@ def gen_actions(gen: dict, steps: np.ndarray, M: int) -> np.ndarray:
     return out
 
 
+def getstat(body: Body, st: dict, old_a: np.ndarray, in3d=True, pk=1, vk=1, ak=1, mk=1, midform=True, conmid=False) -> np.ndarray:
+    """Creature.getstat (gym/optimized_walker.py:129-162) for every env of an SoA state: [E, 3*d*N + M (+3)] float32.
+    NumPy float32 arithmetic in the reference's order: sequential `mid += pos`, `mid /= N`, `(pos - mid) * pk`."""
+    N, M = body.n_mass, body.n_muscle
+    E = st["pos"].shape[1]
+    d = 3 if in3d else 2
+    pos, vel = st["pos"].reshape(N, 3, E), st["vel"].reshape(N, 3, E)
+    oa = np.asarray(old_a, np.float32).reshape(N, 3, E)
+    mid = np.zeros((3, E), np.float32)
+    if midform:
+        for n in range(N):
+            mid += pos[n]
+        mid /= N
+    cols = []
+    for n in range(N):
+        cols += [(((pos[n, c] - mid[c]) if midform else pos[n, c]) * np.float32(pk)) for c in range(d)]
+        cols += [vel[n, c] * np.float32(vk) for c in range(d)]
+        cols += [oa[n, c] * np.float32(ak) for c in range(d)]
+    if conmid:
+        cols += [mid[c] for c in range(3)]
+    cols += [st["mx"][m] * np.float32(mk) for m in range(M)]
+    return np.stack(cols, axis=1).astype(np.float32)
+
+
 def normal3(seed: int, env: int, step: int, mass: int) -> np.ndarray:
     out = (C.c_float * 3)()
     lib().wgo_normal3(C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32((seed >> 32) & 0xFFFFFFFF),

@@ -307,9 +307,72 @@ def l2_env_state():
     print("env_state_ref.pkl written by the reference:", os.path.getsize(dst), "bytes")
 
 
+GETSTAT_VARIANTS = [
+    dict(in3d=True, pk=0.5, vk=2.0, ak=0.25, mk=3.0, midform=True, conmid=True),
+    dict(in3d=False, pk=1, vk=1, ak=1, mk=1, midform=False, conmid=False),
+    dict(in3d=True, pk=0.1, vk=0.01, ak=0.001, mk=0.7, midform=False, conmid=True),
+    dict(in3d=True),
+]
+
+
+def main_getstat():
+    """Creature.actdisp (discrete stride actions, gym/optimized_walker.py:37-43,169-172) driving PhysicsEnv.step, and
+    Creature.getstat with non-default options (:129-162) recorded after every step, from the reference itself."""
+    from unittest import mock
+    engine, walker, envmod = rh.load()
+    spec = json.loads(json.dumps(CUSTOM))
+    for (i, j, kw), stride in zip(spec["muscles"], (2, 3, 0.7)):
+        kw["stride"] = stride
+        kw.pop("x", None)       # np.float32 rest lengths: a python-float Muscle.x would make `x * mk` a float64 product
+    spec["points"] = [(m, tuple(p), bool(f)) for m, p, f in spec["points"]]
+    T = 40
+    rng = np.random.default_rng(77)
+    disp = rng.integers(0, 2, (T, len(spec["muscles"]))).astype(np.uint8)
+    noise = (np.random.default_rng(78).standard_normal(64) * 0.1).astype(np.float32)
+    draws = []
+
+    def fake_normal(loc=0.0, scale=1.0, size=None):
+        v = float(noise[len(draws)])
+        draws.append(v)
+        return v
+
+    engine.Point.clear()
+    with mock.patch.object(np.random, "normal", fake_normal):
+        env = envmod.PhysicsEnv(rh.build_creature(spec), in3d=True)
+        cr = env.creature
+        rec = {f"stat{v}": [] for v in range(len(GETSTAT_VARIANTS))}
+        rec.update(pos=[], vel=[], old_a=[], x=[], reward=[], done=[])
+        for t in range(T):
+            cr.actdisp([bool(b) for b in disp[t]])
+            _, r, d, _ = env.step([])                   # an empty action list: Creature.act touches no muscle
+            for v, kw in enumerate(GETSTAT_VARIANTS):
+                rec[f"stat{v}"].append(np.asarray(cr.getstat(**kw), np.float64))
+            sn = rh.snapshot(env)
+            for k in ("pos", "vel", "old_a", "x"):
+                rec[k].append(sn[k])
+            rec["reward"].append(r)
+            rec["done"].append(bool(d))
+    engine.Point.clear()
+    arrs = {}
+    for k, v in rec.items():
+        a = np.stack([np.asarray(x) for x in v])
+        if a.dtype == np.float64:
+            a32 = a.astype(np.float32)
+            assert np.array_equal(a, a32.astype(np.float64), equal_nan=True), f"getstat fixture: {k} not float32-representable"
+            a = a32
+        arrs[k] = a
+    np.savez_compressed(os.path.join(HERE, "getstat_actdisp_custom3d.npz"), disp=disp, reset_noise=np.asarray(draws, np.float32),
+                        spec=np.array(json.dumps(spec)), variants=np.array(json.dumps(GETSTAT_VARIANTS)), **arrs)
+    print(f"getstat_actdisp_custom3d: T={T} draws={len(draws)} done={int(arrs['done'].sum())}")
+
+
 if __name__ == "__main__":
     import warnings
     warnings.filterwarnings("ignore", category=RuntimeWarning)
+    if len(sys.argv) > 1 and sys.argv[1] == "getstat":
+        main_getstat()
+        sys.exit(0)
     main()
     main_f64()
     main_l2()
+    main_getstat()

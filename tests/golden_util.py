@@ -21,7 +21,7 @@ def golden_names(prefix=""):
 
 
 def trajectory_names():
-    return [n for n in golden_names() if not n.startswith(("batch_", "compat_", "l2_", "env_state_", "f64act_"))]
+    return [n for n in golden_names() if not n.startswith(("batch_", "compat_", "l2_", "env_state_", "f64act_", "getstat_"))]
 
 
 def f64_names():

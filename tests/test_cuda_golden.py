@@ -76,3 +76,41 @@ def test_cuda_x64_mode_matches_reference_bit_for_bit(stepper, name, layout):
     auto-reset, substeps."""
     stepper.obs_layout = layout
     assert replay_x64(gu.load(name), stepper) is None
+
+
+@pytest.mark.parametrize("layout,keep_old_a", [("soa", True), ("soa", False), ("auto", False)])
+def test_batched_getstat_options_and_step_disp_against_the_reference_recording(layout, keep_old_a):
+    """BatchedPhysicsEnv.step_disp (Creature.actdisp + PhysicsEnv.step) and BatchedPhysicsEnv.getstat (Creature.getstat
+    with pk / vk / ak / mk / midform / conmid, through wg_getstat) on E copies of the recorded env: every copy reproduces
+    the reference's recording (tests/golden/getstat_actdisp_custom3d.npz) bit for bit, in both observation layouts."""
+    import json
+    import os
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv, Creature, DingPoint, Muscle, Point, Skeleton
+    z = np.load(os.path.join(gu.GOLDEN_DIR, "getstat_actdisp_custom3d.npz"))
+    spec = json.loads(str(z["spec"]))
+    Point.clear()
+    try:
+        pts = [DingPoint(m, list(p)) if f else Point(m, list(p), [0, 0, 0]) for m, p, f in spec["points"]]
+        cr = Creature(pts, [Muscle(pts[i], pts[j], **kw) for i, j, kw in spec["muscles"]],
+                      [Skeleton(pts[i], pts[j], **kw) for i, j, kw in spec["skeletons"]])
+        E, N = 300, len(pts)
+        env = BatchedPhysicsEnv(cr, E, "cuda:0", in3d=True, auto_reset=None, state_layout=layout, keep_old_a=keep_old_a,
+                                initial_reset=False)
+        noise = torch.from_numpy(np.repeat(z["reset_noise"][: 3 * N, None], E, axis=1).copy()).cuda()
+        env.reset(noise=noise, mode="jitter")
+        variants = json.loads(str(z["variants"]))
+        for t in range(z["disp"].shape[0]):
+            disp = torch.from_numpy(np.repeat(z["disp"][t][None], E, axis=0).copy()).cuda()
+            obs, rew, done, _ = env.step_disp(disp)
+            assert gu.same(rew.cpu().numpy(), np.repeat(z["reward"][t], E)), t
+            for v, kw in enumerate(variants):
+                for lay in ("row", "feature"):
+                    got = env.getstat(layout=lay, **kw).cpu().numpy()
+                    got = got if lay == "row" else got.T
+                    assert gu.same(got, np.repeat(z[f"stat{v}"][t][None], E, axis=0)), (t, v, lay)
+            assert gu.same(env.getstat().cpu().numpy(), obs.cpu().numpy())          # the defaults == the step's observation
+        with pytest.raises(ValueError):
+            env.step_disp(torch.zeros(E + 1, 3, dtype=torch.bool, device="cuda:0"))
+    finally:
+        Point.clear()

@@ -1,4 +1,6 @@
 """CPU: the C oracle must reproduce the reference's recorded outputs bit for bit."""
+import os
+
 import numpy as np
 import pytest
 
@@ -272,3 +274,37 @@ def test_x64_fixtures_exercise_the_type_switch():
     assert clamped[:, :3].any(axis=0).all() and (~clamped[:, :3]).any(axis=0).all()    # both types occur per acted muscle
     assert (g["x"][1:, 3] == g["x"][0, 3]).all()                                       # the un-acted muscle never moves
     assert gu.load("f64act_autoreset_box3d")["done"].sum() >= 3
+
+
+def test_getstat_options_and_actdisp_against_the_reference_recording():
+    """Creature.actdisp (discrete +-stride actions) driving PhysicsEnv.step and Creature.getstat with non-default
+    options, recorded from the reference itself (tests/golden/make_golden.py main_getstat): the oracle stepped with
+    actions +-float32(stride) reproduces the trajectory, and its getstat restatement every recorded variant."""
+    import json
+    z = np.load(os.path.join(gu.GOLDEN_DIR, "getstat_actdisp_custom3d.npz"))
+    spec = json.loads(str(z["spec"]))
+    spec = {"points": [(m, tuple(p), bool(f)) for m, p, f in spec["points"]],
+            "muscles": [(i, j, dict(kw)) for i, j, kw in spec["muscles"]],
+            "skeletons": [(i, j, dict(kw)) for i, j, kw in spec["skeletons"]]}
+    strides = np.array([np.float32(kw.get("stride", 2)) for _, _, kw in spec["muscles"]], np.float32)
+    oracle_spec = {"points": spec["points"], "skeletons": spec["skeletons"],
+                   "muscles": [(i, j, {k: v for k, v in kw.items() if k != "stride"}) for i, j, kw in spec["muscles"]]}
+    body = wo.make_body(oracle_spec)
+    prm = wo.make_params(in3d=True)
+    st = wo.init_state(body, 1)
+    N = body.n_mass
+    noise = np.zeros((3 * N, 1), np.float32)
+    k = 0
+    for n in range(N):                                   # PhysicsEnv.reset draws x, y, z per point, in order
+        for c in range(3):
+            noise[n * 3 + c, 0] = z["reset_noise"][k]
+            k += 1
+    wo.reset(body, prm, st, mode=1, noise=noise)
+    variants = json.loads(str(z["variants"]))
+    for t in range(z["disp"].shape[0]):
+        act = np.where(z["disp"][t].astype(bool), strides, -strides).astype(np.float32)[None]
+        out = wo.step(body, prm, st, act)
+        assert gu.same(gu.aos(st["pos"], N)[0], z["pos"][t]) and gu.same(gu.aos(st["vel"], N)[0], z["vel"][t]), t
+        assert gu.same(st["mx"][:, 0], z["x"][t]) and gu.same(out["reward"][0], z["reward"][t]), t
+        for v, kw in enumerate(variants):
+            assert gu.same(wo.getstat(body, st, st["old_a"], **kw)[0], z[f"stat{v}"][t]), (t, v)

@@ -523,6 +523,43 @@ class BatchedPhysicsEnv:
         _lib.check(rc, "wg_step_host")
         self._advance()
 
+    def getstat(self, in3d: Optional[bool] = None, pk=1, vk=1, ak=1, mk=1, midform: bool = True, conmid: bool = False,
+                out: Optional[torch.Tensor] = None, layout: str = "row") -> torch.Tensor:
+        """``Creature.getstat`` (gym/optimized_walker.py:129-162) with its options for every env: a float32 tensor
+        [E, D'] (or [D', E] with ``layout="feature"``), D' = 3*d*N + M (+3 with ``conmid``).  With the defaults this is
+        the observation ``step`` returns.  ``Point.old_a`` comes from the env's ``old_a`` buffer (``keep_old_a=True``)
+        or from the last observation (which needs ``in3d`` <= the env's dimensionality)."""
+        in3d = self.in3d if in3d is None else bool(in3d)
+        Dp = 3 * (3 if in3d else 2) * self.N + self.M + (3 if conmid else 0)
+        shape = (self.num_envs, Dp) if layout == "row" else (Dp, self.num_envs)
+        if layout not in ("row", "feature"):
+            raise ValueError("layout must be 'row' or 'feature'")
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        else:
+            self._check_f32(out, shape, "out")
+        with torch.cuda.device(self.device):
+            rc = self.lib.wg_getstat(C.byref(self.topo), C.byref(self._buf), self.obs.data_ptr(), int(self.in3d), int(in3d),
+                                     float(np.float32(pk)), float(np.float32(vk)), float(np.float32(ak)), float(np.float32(mk)),
+                                     int(bool(midform)), int(bool(conmid)), out.data_ptr(), 0 if layout == "row" else 1,
+                                     self.num_envs, self._stream())
+        _lib.check(rc, "wg_getstat")
+        return out
+
+    def step_disp(self, disp: torch.Tensor, **kw):
+        """``Creature.actdisp`` (gym/optimized_walker.py:169-172; ``Muscle.actdisp`` :37-43) + ``PhysicsEnv.step``:
+        ``disp`` is a bool / uint8 tensor [E, A]; muscle m lengthens by its ``stride`` where disp is true and shortens
+        by it where false, then ``regulation()`` -- i.e. ``x += +-stride``, the same float32 addition ``act`` performs."""
+        if disp.dim() != 2 or disp.shape[0] != self.num_envs or disp.device != self.obs.device:
+            raise ValueError(f"disp must be a bool / uint8 tensor [{self.num_envs}, A] on the env's device")
+        if self.act_layout != "row" or self.x64:
+            raise ValueError("step_disp needs act_layout='row' and float32 muscle state")
+        A = min(int(disp.shape[1]), self.M)
+        if getattr(self, "_stride", None) is None:
+            self._stride = torch.tensor([np.float32(m.stride) for m in self.creature.muscles], dtype=torch.float32, device=self.device)
+        action = torch.where(disp[:, :A].to(torch.bool), self._stride[:A], -self._stride[:A]).contiguous()
+        return self.step(action, **kw)
+
     def get_action_space(self):
         return {"shape": (self.M,), "type": "continuous", "low": -1.0, "high": 1.0}
 

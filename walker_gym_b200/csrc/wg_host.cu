@@ -114,7 +114,7 @@ __global__ void selftest_div3_kernel(int mode, uint32_t seed, uint64_t first, ui
                 div3_len<GENERAL>(q0, q1, q2, L);
                 float w0 = d[0], w1 = d[1], w2 = d[2];
                 if (L > 0.0f) { w0 = __fdiv_rn(d[0], L); w1 = __fdiv_rn(d[1], L); w2 = __fdiv_rn(d[2], L); }
-                bad = !(same_bits(q0, w0) && same_bits(q1, w1) && same_bits(q2, w2));
+                bad = !(same_f32(q0, w0) && same_f32(q1, w1) && same_f32(q2, w2));      // -0 / L comes out as +0: sign of zero
                 if (bad && atomicCAS(out + 1, 0ull, (unsigned long long)(i + 1)) == 0ull && dump) {
                     dump[0] = d[0]; dump[1] = d[1]; dump[2] = d[2]; dump[3] = L;
                     dump[4] = q0; dump[5] = q1; dump[6] = q2; dump[7] = w0; dump[8] = w1; dump[9] = w2;

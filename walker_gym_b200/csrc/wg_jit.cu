@@ -63,7 +63,7 @@ std::mutex g_mu;
 std::map<std::string, JitKernel> g_cache;
 
 std::string key_of(const wg_topology* t, int in3d, int obs_rm, int mm, int kind) {      // kind: 0 SoA, 1 packed, 2 packed T-steps-per-launch
-    std::string k = std::string(kind == 2 ? "M" : kind ? "P" : "S") + std::to_string(t->n_mass) + "," + std::to_string(t->n_spring) + "," + std::to_string(t->n_muscle) + ":";
+    std::string k = std::string(kind == 3 ? "G" : kind == 2 ? "M" : kind ? "P" : "S") + std::to_string(t->n_mass) + "," + std::to_string(t->n_spring) + "," + std::to_string(t->n_muscle) + ":";
     for (int s = 0; s < t->n_spring; s++) k += std::to_string(t->si[s]) + "-" + std::to_string(t->sj[s]) + ",";
     k += "|" + std::to_string(in3d) + std::to_string(obs_rm) + std::to_string(mm);
     if (mm == 1) {                       // mass mode 3 bakes the mass pattern (which masses are 1 / equal) into the code
@@ -82,7 +82,7 @@ JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm, int kind) 
     JitKernel out;
     Nvrtc& nv = nvrtc();
     if (!nv.ok) { out.rc = WG_ERR_UNSUPPORTED; out.err = "libnvrtc not available"; return out; }
-    std::string src = std::string(kind == 2 ? "#include \"wg_kernels_multi.cuh\"\n" : "#include \"wg_kernels_packed.cuh\"\n") + "namespace wg { WG_STATIC_TOPO(TopoJit, 99, " + std::to_string(t->n_mass) + ", " +
+    std::string src = std::string(kind >= 2 ? "#include \"wg_kernels_multi.cuh\"\n" : "#include \"wg_kernels_packed.cuh\"\n") + "namespace wg { WG_STATIC_TOPO(TopoJit, 99, " + std::to_string(t->n_mass) + ", " +
                       std::to_string(t->n_spring) + ", " + std::to_string(t->n_muscle);
     for (int s = 0; s < t->n_spring; s++) src += ", " + std::to_string(t->si[s]) + "," + std::to_string(t->sj[s]);
     src += ")\n";
@@ -105,8 +105,9 @@ JitKernel compile(const wg_topology* t, int in3d, int obs_rm, int mm, int kind) 
     }
     src += "}\n";
     const std::string mm_s = std::to_string(mm == 1 ? 3 : mm), i3 = in3d ? "true" : "false";
-    const std::string name = kind == 2
-        ? "&wg::step_multi_packed_kernel<" + topo_name + ", " + i3 + ", " + mm_s + ", wg::StepArgs<wg::kMaxMass, wg::kMaxSpring>>"
+    const std::string name = kind >= 2          // kind 3: the instance with the in-kernel action sources compiled in
+        ? "&wg::step_multi_packed_kernel<" + topo_name + ", " + i3 + ", " + mm_s + ", wg::StepArgs<wg::kMaxMass, wg::kMaxSpring>, " +
+          (kind == 3 ? "true" : "false") + ">"
         : std::string(packed ? "&wg::step_static_packed_kernel<" : "&wg::step_static_kernel<") + topo_name + ", " + i3 + ", " +
           std::to_string(obs_rm) + (packed ? ", " : ", 1, ") + mm_s + ", wg::StepArgs<wg::kMaxMass, wg::kMaxSpring>>";
     nvrtcProgram prog = nullptr;
@@ -189,7 +190,9 @@ int launch_jit_packed(const wg_topology* t, const wg_params* p, const wg_buffers
 int launch_jit_multi(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, int n_steps, int64_t act_stride,
                      cudaStream_t s) {
     cudaKernel_t kernel = nullptr;
-    int rc = jit_prepare(t, p->in3d, 0, &kernel, 2);
+    static thread_local ActionGen G;
+    fill_gen(G, b);
+    int rc = jit_prepare(t, p->in3d, 0, &kernel, G.mode ? 3 : 2);
     if (rc != WG_OK) return rc;
     static thread_local StepArgs<kMaxMass, kMaxSpring> A;
     fill_args(A, t, p, b, E);
@@ -199,8 +202,6 @@ int launch_jit_multi(const wg_topology* t, const wg_params* p, const wg_buffers*
         cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute (jit): %s", cudaGetErrorString(e));
     }
-    static thread_local ActionGen G;
-    fill_gen(G, b);
     void* args[] = { &A, &n_steps, &act_stride, &G };
     cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3((unsigned)((E + kMultiBlock - 1) / kMultiBlock)), dim3(kMultiBlock),
                                      args, smem, s);

@@ -55,7 +55,9 @@ __device__ __forceinline__ float gen_action(const ActionGen& G, int m, int32_t s
 // action: [T][E][M] row-major (act_stride = E * M), or one [E][M] block applied at every step (act_stride = 0:
 // action repeat), or generated on chip (G.mode != 0); reward: [T][E]; done: [T][E]; obs: [E][D] row-major, after the
 // last step.
-template <class Topo, bool IN3D, int MM, class Args = StepArgs<Topo::N, Topo::S>>
+// GEN: compile-time switch for the in-kernel action sources -- the tensor-action instance (GEN = false) stays exactly
+// the code it was (the loop is instruction-cache sensitive: a run-time branch around the generator cost it 6 %).
+template <class Topo, bool IN3D, int MM, class Args = StepArgs<Topo::N, Topo::S>, bool GEN = false>
 __global__ void __launch_bounds__(kMultiBlock, multi_min_blocks(Topo::N))
 step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, const int64_t act_stride,
                          const __grid_constant__ ActionGen G) {
@@ -105,7 +107,7 @@ step_multi_packed_kernel(const __grid_constant__ Args A, const int n_steps, cons
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(kMultiBlock / 4) : "memory");
 #endif
             // ---- Creature.act ----
-            if (G.mode != 0) {                  // generated on chip from the env's own step counter: no action memory
+            if constexpr (GEN) {                // generated on chip from the env's own step counter: no action memory
 #pragma unroll
                 for (int m = 0; m < M; m++) {
                     float x = st.mx(m) + gen_action(G, m, stp);
@@ -206,13 +208,14 @@ inline int launch_multi_packed(const wg_topology* t, const wg_params* p, const w
     constexpr int D = 3 * (IN3D ? 3 : 2) * Topo::N + Topo::M;
     constexpr bool bulk = gcd_c(D, 32) <= 2;
     const size_t smem = b->obs ? sizeof(float) * kMultiBlock * (bulk ? D : (D | 1)) : 0;
-    auto kern = step_multi_packed_kernel<Topo, IN3D, MM>;
+    static thread_local ActionGen G;
+    fill_gen(G, b);
+    auto kern = G.mode ? step_multi_packed_kernel<Topo, IN3D, MM, StepArgs<Topo::N, Topo::S>, true>
+                       : step_multi_packed_kernel<Topo, IN3D, MM, StepArgs<Topo::N, Topo::S>, false>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    static thread_local ActionGen G;
-    fill_gen(G, b);
     kern<<<(unsigned)((E + kMultiBlock - 1) / kMultiBlock), kMultiBlock, smem, s>>>(A, n_steps, act_stride, G);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (multi) launch: %s", cudaGetErrorString(e));
