@@ -76,8 +76,6 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the sub_configs measurements (configs 3-strong, 4, 5, multi-step)")
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to CPUs next to its GPU")
-    ap.add_argument("--e2e-zero-copy", action="store_true",
-                    help="also measure e2e with the kernel writing its results straight into mapped pinned host memory")
     return ap.parse_args()
 
 
@@ -330,6 +328,7 @@ class Ctx:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         self.affinity = None
+        self.allowed_cpus = host_cpus()
         if not args.no_affinity:
             from walker_gym_b200.host import bind_to_device
             self.affinity = bind_to_device(self.local, int(os.environ.get("LOCAL_WORLD_SIZE", self.world)))
@@ -530,6 +529,37 @@ def measure_e2e(ctx, env, args):
     solo = ctx.gather(my_solo)
     ceiling_gbs = world * d2h_bytes * Ke / (ms_all * 1e-3) / 1e9
     ceiling_steps = ceiling_gbs * 1e9 / d2h_bytes * E       # env-steps/s if the D2H wire were the only cost
+    # the other direction, every rank at once (names the limiter: the links are symmetric, the host's write path is not)
+
+    def h2d(i):
+        for h, d in zip(slots[i & 1], d_res):
+            d.copy_(h, non_blocking=True)
+    for i in range(3):
+        h2d(i)
+    ms_h2d = ctx.timed(h2d, Ke)
+    h2d_all_gbs = world * d2h_bytes * Ke / (ms_h2d * 1e-3) / 1e9
+    # and what the host's own cores copy (rank 0, every allowed core, 512 MiB blocks), while the GPUs idle
+    host_copy_gbs = None
+    ctx.barrier()
+    if ctx.rank == 0:
+        try:
+            saved = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, ctx.allowed_cpus)
+            nthr = torch.get_num_threads()
+            torch.set_num_threads(len(ctx.allowed_cpus))
+            a = torch.empty(1 << 27, dtype=torch.float32)
+            b = torch.empty(1 << 27, dtype=torch.float32)
+            a.fill_(1.0); b.copy_(a)
+            t0 = time.perf_counter()
+            for _ in range(4):
+                b.copy_(a)
+            host_copy_gbs = 4 * 2 * a.numel() * 4 / (time.perf_counter() - t0) / 1e9
+            del a, b
+            torch.set_num_threads(nthr)
+            os.sched_setaffinity(0, saved)
+        except Exception:
+            pass
+    ctx.barrier()
 
     # ---- synchronous C-ABI call: upload, kernel, download back to back on one stream ----
     for _ in range(3):
@@ -555,25 +585,35 @@ def measure_e2e(ctx, env, args):
         ctx.barrier()
         return ctx.max_over_ranks(e0.elapsed_time(e1))
     ms_pipe = run_pipe(Ke, lambda i: pipe.submit(h_act, *slots[i & 1]))
-    value = world * E * Ke / (ms_pipe * 1e-3)
+    copy_value = world * E * Ke / (ms_pipe * 1e-3)
+    # ---- zero-copy: the kernel writes its results into the mapped pinned buffers itself (no staging, no D2H copies) ----
+    for i in range(4):
+        pipe.submit_zero_copy(h_act, *slots[i & 1])
+    pipe.drain()
+    ms_zc = run_pipe(Ke, lambda i: pipe.submit_zero_copy(h_act, *slots[i & 1]))
+    zc_value = world * E * Ke / (ms_zc * 1e-3)
+    value, path = (zc_value, "zero_copy") if zc_value > copy_value else (copy_value, "copy_pipeline")
     e2e = {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": Ke,
-           "what": "HostStepPipeline: every step uploads its pinned host actions and downloads observations, rewards "
-                   "and dones to pinned host memory (wg_host_alloc by the CPU-bound rank); two streams and two result "
-                   "slots overlap step t+1's upload + kernel with step t's download; PCIe-bound by the observation rows",
-           "achieved_d2h_gbs": world * d2h_bytes * Ke / (ms_pipe * 1e-3) / 1e9,
+           "path": path,
+           "what": "every step uploads its pinned host actions (wg_host_alloc by the CPU-bound rank) and delivers "
+                   "observations, rewards and dones into pinned host memory; value = the faster of the two public paths "
+                   "measured below (both move the same bytes over PCIe, which bounds them)",
+           "copy_pipeline": {"value": copy_value, "unit": UNIT,
+                             "what": "HostStepPipeline.submit: two streams and two device result slots overlap step t+1's "
+                                     "upload + kernel with step t's cudaMemcpyAsync downloads"},
+           "zero_copy": {"value": zc_value, "unit": UNIT,
+                         "what": "HostStepPipeline.submit_zero_copy: the step kernel's TMA bulk stores write the observation "
+                                 "rows (and reward / done) straight into the mapped pinned host buffers: no device staging, "
+                                 "no download copy; the next step's upload overlaps the kernel"},
+           "achieved_d2h_gbs": value * d2h_bytes / E / 1e9,
            "d2h_ceiling": {"all_ranks_gbs": ceiling_gbs, "env_steps_per_s": ceiling_steps, "per_rank_solo_gbs": solo,
+                           "h2d_all_ranks_gbs": h2d_all_gbs, "host_memcpy_gbs": host_copy_gbs,
                            "what": f"plain cudaMemcpyAsync device->pinned host of the same {d2h_bytes} bytes per step, "
-                                   f"{Ke} steps, one stream per rank: all {world} rank(s) at once / one rank at a time"},
+                                   f"{Ke} steps, one stream per rank: all {world} rank(s) at once / one rank at a time; "
+                                   "h2d_all_ranks: the same buffers the other way, all ranks at once; host_memcpy: "
+                                   "read+write rate of the host's own cores copying 512 MiB blocks (rank 0, GPUs idle)"},
            "frac_of_d2h_ceiling": value / ceiling_steps,
            "synchronous": sync_e2e}
-    if args.e2e_zero_copy:
-        for i in range(4):
-            pipe.submit_zero_copy(h_act, *slots[i & 1])
-        pipe.drain()
-        ms_zc = run_pipe(Ke, lambda i: pipe.submit_zero_copy(h_act, *slots[i & 1]))
-        e2e["zero_copy"] = {"value": world * E * Ke / (ms_zc * 1e-3), "unit": UNIT, "steps": Ke,
-                            "what": "the step kernel's TMA bulk stores write the observation rows (and reward / done) "
-                                    "straight into the mapped pinned host buffers: no device staging, no D2H copy"}
     # the other usage mode: policy on the device -- observations stay in HBM, only reward/done go to the host
     Kd = max(Ke, 50)
     for i in range(4):

@@ -64,6 +64,11 @@ typedef struct wg_topology {
     float   srest[WG_MAX_SPRING];       /* Skeleton.x / Muscle.originx */
     float   mlo[WG_MAX_SPRING];         /* originx * minl   (Muscle.regulation, :27-30) */
     float   mhi[WG_MAX_SPRING];         /* originx * maxl */
+    uint8_t sstring[WG_MAX_SPRING];     /* 1 = rope-type spring: no elastic force while shorter than its rest length
+                                           (`if dx < 0 and string: f_size = 0`, Point.resilience,
+                                           gym/optimized_engine.py:134-138, applied to Muscle.run / Skeleton.run; the
+                                           damping term is unchanged).  Bodies with such springs step through the
+                                           run-time-topology kernels. */
 } wg_topology;
 
 /*

@@ -41,6 +41,10 @@ typedef struct {
     float sdamp[WGO_MAX_SPRING];             /* float32(dampk)  */
     float srest[WGO_MAX_SPRING];             /* skeleton.x / muscle.originx as float32 */
     float mlo[WGO_MAX_SPRING], mhi[WGO_MAX_SPRING]; /* float32(originx*minl), float32(originx*maxl) */
+    uint8_t sstring[WGO_MAX_SPRING];         /* rope-type spring: no elastic force while shorter than its rest length --
+                                                `if dx < 0 and string: f_size = 0` of Point.resilience
+                                                (optimized_engine.py:134-138) applied to Muscle.run / Skeleton.run;
+                                                the damping term is unchanged */
 } wgo_body;
 
 typedef struct {
@@ -226,6 +230,7 @@ static void spring_run(const wgo_body *b, const wgo_params *p, env_state *s, int
     float dx = L - x;                                          /* :48 */
     float fs = (-dx) * b->sk[sp];                              /* :49  -dx*k: inverted Hooke as written
                                                                   (SURVEY 0.4); physical sign == negative k */
+    if (b->sstring[sp] && dx < 0) fs = 0.0f;                   /* rope-type: f_size = 0 (optimized_engine.py:134-136) */
     for (int c = 0; c < 3; c++) dir[c] = s->pos[j][c] - s->pos[i][c];   /* :52 */
     if (L > 0) for (int c = 0; c < 3; c++) dir[c] = dir[c] / L;         /* :53-54 */
     if (s->xb && sp < b->n_muscle && !s->mxw[sp]) {

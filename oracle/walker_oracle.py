@@ -36,6 +36,7 @@ class Body(C.Structure):
         ("sk", C.c_float * MAX_SPRING), ("sdamp", C.c_float * MAX_SPRING),
         ("srest", C.c_float * MAX_SPRING),
         ("mlo", C.c_float * MAX_SPRING), ("mhi", C.c_float * MAX_SPRING),
+        ("sstring", C.c_uint8 * MAX_SPRING),
     ]
 
 
@@ -109,6 +110,7 @@ def make_body(spec) -> Body:
         if x is None:
             x = np.linalg.norm(P[i] - P[j])                # Muscle.distant (optimized_walker.py:23-25)
         b.srest[s] = np.float32(x)
+        b.sstring[s] = 1 if kw.get("string", False) else 0
         if s < len(mus):
             b.mlo[s] = np.float32(x * kw.get("minl", 0.1))  # regulation (:27-30), python semantics
             b.mhi[s] = np.float32(x * kw.get("maxl", 1.5))

@@ -39,17 +39,21 @@ def test_struct_layouts_match_the_header(tmp_path):
     from walker_gym_b200 import _lib
     prog = tmp_path / "sz.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "walker_gym_b200.h"\n'
-                    'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(wg_topology), sizeof(wg_params), '
+                    'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(wg_topology), sizeof(wg_params), '
                     'sizeof(wg_buffers), offsetof(wg_topology, si), offsetof(wg_params, seed_lo), '
                     'offsetof(wg_buffers, obs), sizeof(wg_x64), sizeof(wg_pkg_system), sizeof(wg_pkg_params), '
-                    'sizeof(wg_mlp_policy), offsetof(wg_buffers, mx64), offsetof(wg_pkg_system, srest)); return 0;}\n')
+                    'sizeof(wg_mlp_policy), offsetof(wg_buffers, mx64), offsetof(wg_pkg_system, srest), '
+                    'offsetof(wg_topology, sstring), offsetof(wg_buffers, action_gen), sizeof(wg_action_gen), '
+                    'offsetof(wg_action_gen, phase0)); return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     out = list(map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()))
     assert out == [C.sizeof(_lib.WgTopology), C.sizeof(_lib.WgParams), C.sizeof(_lib.WgBuffers),
                    _lib.WgTopology.si.offset, _lib.WgParams.seed_lo.offset, _lib.WgBuffers.obs.offset,
                    C.sizeof(_lib.WgX64), C.sizeof(_lib.WgPkgSystem), C.sizeof(_lib.WgPkgParams), C.sizeof(_lib.WgMlpPolicy),
-                   _lib.WgBuffers.mx64.offset, _lib.WgPkgSystem.srest.offset]
+                   _lib.WgBuffers.mx64.offset, _lib.WgPkgSystem.srest.offset,
+                   _lib.WgTopology.sstring.offset, _lib.WgBuffers.action_gen.offset, C.sizeof(_lib.WgActionGen),
+                   _lib.WgActionGen.phase0.offset]
 
 
 def test_argument_validation_needs_no_gpu():

@@ -689,3 +689,39 @@ def test_rejected_step_leaves_the_bound_buffers_alone():
     obs_r, rew_r, done_r, _ = ref.step(a)
     assert obs.data_ptr() == env.obs.data_ptr() and gu.same(obs.cpu().numpy(), obs_r.cpu().numpy())
     assert gu.same(rew.cpu().numpy(), rew_r.cpu().numpy()) and float(out[0].min()) == 7.0 and float(out[1].min()) == 7.0
+
+
+@pytest.mark.parametrize("E,layout,parts", [(1000, "row", -1), (777, "feature", -1), (515, "row", 4)])
+def test_rope_type_springs_match_oracle(E, layout, parts):
+    """Rope-type springs (`string=True`, Point.resilience semantics, gym/optimized_engine.py:134-138) as a per-spring
+    flag of the run-time-topology kernels: random bodies with a mix of rope-type muscles and bones, bit-exact against
+    the oracle; a body with such springs never takes a compile-time specialisation."""
+    from walker_gym_b200 import BatchedPhysicsEnv, Creature, Muscle, Point, Skeleton, _lib
+    rng = np.random.default_rng(E)
+    lib = _lib.load()
+    old = lib.wg_set_tuning(_lib.TUNE_PART, parts)
+    Point.clear()
+    try:
+        # Balance-v0's graph (which has every specialisation) with two rope-type springs, and a random 9-mass body
+        base = [(5, (-50, 100, 0)), (5, (50, 100, 0)), (1, (0, 0, 0)), (3, (0, 100, 0))]
+        bodies = [(base, [(0, 2, {"string": True}), (1, 2, {})], [(0, 1, {}), (0, 3, {"string": True, "x": 60.0}), (1, 3, {})])]
+        pts9 = [(float(rng.integers(1, 6)), tuple(rng.uniform(-80, 80, 3).round(1))) for _ in range(9)]
+        pts9 = [(m, (p[0], abs(p[1]) + 5, p[2])) for m, p in pts9]
+        mus9 = [(int(i), int((i + 1 + rng.integers(0, 7)) % 9), {"string": bool(rng.integers(0, 2))}) for i in range(5)]
+        sks9 = [(int(i), int((i + 1) % 9), {"string": bool(rng.integers(0, 2)), "k": float(rng.choice([300, 1000, -500]))}) for i in range(9)]
+        bodies.append((pts9, [(i, j, kw) for i, j, kw in mus9 if i != j], [(i, j, kw) for i, j, kw in sks9 if i != j]))
+        for pts_s, mus_s, sks_s in bodies:
+            spec = {"points": [(m, p, False) for m, p in pts_s], "muscles": mus_s, "skeletons": sks_s}
+            Point.clear()
+            pts = [Point(m, list(p), [0, 0, 0]) for m, p in pts_s]
+            cr = Creature(pts, [Muscle(pts[i], pts[j], **kw) for i, j, kw in mus_s], [Skeleton(pts[i], pts[j], **kw) for i, j, kw in sks_s])
+            env = BatchedPhysicsEnv(cr, E, "cuda:0", in3d=True, auto_reset="template", max_steps=9, k_sub=2, seed=5,
+                                    obs_layout=layout, keep_old_a=True, track_info=True, track_contacts=True, initial_reset=False)
+            assert env.kernel_variant == 0 and env.state_layout == "soa"
+            body = wo.make_body(spec)
+            prm = wo.make_params(in3d=True, auto_reset=2, max_steps=9, k_sub=2, seed=5)
+            st = wo.init_state(body, E)
+            run_lockstep(env, body, prm, st, 20, rng, noise_reset=True)
+    finally:
+        lib.wg_set_tuning(_lib.TUNE_PART, old)
+        Point.clear()

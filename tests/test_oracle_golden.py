@@ -308,3 +308,38 @@ def test_getstat_options_and_actdisp_against_the_reference_recording():
         assert gu.same(st["mx"][:, 0], z["x"][t]) and gu.same(out["reward"][0], z["reward"][t]), t
         for v, kw in enumerate(variants):
             assert gu.same(wo.getstat(body, st, st["old_a"], **kw)[0], z[f"stat{v}"][t]), (t, v)
+
+
+def test_rope_type_springs_follow_point_resilience():
+    """`string=True` (extension of Muscle / Skeleton; semantics of Point.resilience, gym/optimized_engine.py:134-138):
+    while the spring is shorter than its rest length the elastic term is f_size = 0 and only the damping term acts;
+    once it is longer it is the ordinary spring.  Checked against the reference's own arithmetic written out in NumPy
+    (float32 arrays, python-scalar constants) for one spring, and: a body whose springs never get shorter than their
+    rest lengths steps identically with and without the flag.  (The reference's L1 classes have no such flag, so there is
+    no reference recording for it: parity of this option is pinned to this restatement only.)"""
+    def spec(string, x):
+        return {"points": [(2.0, (0.0, 50.0, 0.0), False), (3.0, (30.0, 90.0, 0.0), False)], "muscles": [],
+                "skeletons": [(0, 1, {"x": x, "k": 700, "dampk": 12, "string": string})]}
+    for x, slack in ((80.0, True), (20.0, False)):            # current distance is 50: shorter / longer than x
+        outs = []
+        for string in (False, True):
+            body = wo.make_body(spec(string, x))
+            prm = wo.make_params(in3d=True, g=0, ground_high=-1000)
+            st = wo.init_state(body, 1)
+            st["vel"][:, 0] = np.array([1, -2, 0.5, -3, 4, 0.25], np.float32)
+            v0 = st["vel"].copy()
+            wo.step(body, prm, st, np.zeros((1, 0), np.float32))
+            outs.append(st["old_a"].copy())
+        p1, p2 = np.array([0, 50, 0], np.float32), np.array([30, 90, 0], np.float32)
+        v1, v2 = v0[:3, 0], v0[3:, 0]
+        L = np.linalg.norm(p1 - p2)
+        direction = (p2 - p1) / L
+        dk = np.dot(v1 - v2, direction)
+        damp = dk * 12 * direction
+        for string, got in zip((False, True), outs):
+            f_size = 0 if (string and L - x < 0) else -(L - x) * 700
+            force = f_size * direction
+            a1 = np.zeros(3, np.float32); a1 += force / 2.0; a1 += (-damp) / 2.0
+            a2 = np.zeros(3, np.float32); a2 += (-force) / 3.0; a2 += damp / 3.0
+            assert gu.same(got[:3, 0], a1) and gu.same(got[3:, 0], a2), (x, string)
+        assert gu.same(outs[0], outs[1]) == (not slack)

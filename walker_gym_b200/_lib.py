@@ -27,6 +27,7 @@ class WgTopology(C.Structure):
         ("si", C.c_int32 * MAX_SPRING), ("sj", C.c_int32 * MAX_SPRING),
         ("sk", C.c_float * MAX_SPRING), ("sdamp", C.c_float * MAX_SPRING), ("srest", C.c_float * MAX_SPRING),
         ("mlo", C.c_float * MAX_SPRING), ("mhi", C.c_float * MAX_SPRING),
+        ("sstring", C.c_uint8 * MAX_SPRING),
     ]
 
 

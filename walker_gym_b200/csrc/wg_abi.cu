@@ -61,6 +61,10 @@ static int topo_id(const wg_topology* t) {
     if (topo_matches<TopoLeg>(t)) return TopoLeg::kId;
     return 0;
 }
+static bool has_strings(const wg_topology* t) {
+    for (int s = 0; s < t->n_spring; s++) if (t->sstring[s]) return true;
+    return false;
+}
 static bool general_masses(const wg_topology* t) {      // arbitrary masses or DingPoints: mass mode 2
     if (mass_mode(t) == 2) return true;
     for (int n = 0; n < t->n_mass; n++) if (t->fixed[n]) return true;
@@ -68,7 +72,7 @@ static bool general_masses(const wg_topology* t) {      // arbitrary masses or D
 }
 
 static int pick_variant(const wg_topology* t) {
-    if (g_force_generic.load()) return 0;
+    if (g_force_generic.load() || has_strings(t)) return 0;      // rope-type springs: a flag of the run-time topology only
     // only the Balance topology's packed kernel carries the general path (full IEEE division, DingPoint masks)
     if (general_masses(t)) return 0;
     return topo_id(t);
@@ -79,7 +83,7 @@ static bool packed_variant(int v) { return v == TopoBalance::kId || v == TopoBox
 // the kernel a packed-state call launches: like pick_variant, plus the Balance topology with general masses
 constexpr int kJitId = 99;     // a kernel compiled at run time for this body's spring graph (wg_jit.cu)
 static int packed_pick(const wg_topology* t) {
-    if (g_force_generic.load()) return 0;
+    if (g_force_generic.load() || has_strings(t)) return 0;
     const int id = topo_id(t);
     if (general_masses(t)) { if (id == TopoBalance::kId) return id; }
     else if (packed_variant(id)) return id;
@@ -189,7 +193,7 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
     }
     // bodies made of identical disconnected Balance units (config 4's enlarged morphology): one lane per unit, the
     // unit's physics register-resident for all substeps (WG_TUNE_PART -1 = automatic; 0 / 2 / 4 / 8 select the older paths)
-    if (tuning(WG_TUNE_PART) < 0 && !g_force_generic.load()) {
+    if (tuning(WG_TUNE_PART) < 0 && !g_force_generic.load() && !has_strings(topo)) {
         const int R = balance_units(topo);
         if (R) return launch_balance_units(topo, prm, buf, n_env, R, s);
         // the same units chained into ONE connected body by link bones: neighbour endpoints over warp shuffles
@@ -214,7 +218,7 @@ int wg_step(const wg_topology* topo, const wg_params* prm, const wg_buffers* buf
             // no ahead-of-time kernel: a kernel compiled for this spring graph at run time (up to 16 masses); if the
             // run-time compiler is missing or fails, the run-time-topology kernel (same bits)
             // (only for batches that amortise the seconds of compilation)
-            if (n_env >= 4096 && !g_force_generic.load() && tuning(WG_TUNE_JIT) && jit_eligible_soa(topo) && jit_runtime_available() &&
+            if (n_env >= 4096 && !g_force_generic.load() && !has_strings(topo) && tuning(WG_TUNE_JIT) && jit_eligible_soa(topo) && jit_runtime_available() &&
                 launch_jit_soa(topo, prm, buf, n_env, s) == WG_OK)
                 return WG_OK;
             return launch_generic_step(topo, prm, buf, n_env, s);

@@ -23,8 +23,14 @@ static_assert(kPackedBlock % 128 == 0, "the packed layout is tiled by 128 envs")
 
 // Args: StepArgs<Topo::N, Topo::S> for the ahead-of-time specialisations; the run-time compiled ones (wg_jit.cu) take
 // the full-size StepArgs<kMaxMass, kMaxSpring> the host can fill for any body.
-template <class Topo, bool IN3D, int OBS, int MM, class Args = StepArgs<Topo::N, Topo::S>>
-__global__ void __launch_bounds__(kPackedBlock, Topo::N <= 4 ? WG_PACKED_MIN_BLOCKS : (Topo::N <= 6 ? 512 : 384) / WG_PACKED_BLOCK)
+// MINB: resident CTAs per SM the compiler must allow (0 = the default for the body size).  The 7-CTA instance (72
+// registers) exists for grids that fit ONE wave at 7 CTAs per SM but not at 6 -- BASELINE config 3 as written, 2^20 envs
+// over 8 GPUs = 1024 CTAs per GPU against 148 x 6 = 888 slots: a second, 14 %-full wave would double the step time.
+__host__ __device__ constexpr int packed_min_blocks(int n_mass, int minb) {
+    return minb > 0 ? minb : (n_mass <= 4 ? WG_PACKED_MIN_BLOCKS : (n_mass <= 6 ? 512 : 384) / WG_PACKED_BLOCK);
+}
+template <class Topo, bool IN3D, int OBS, int MM, class Args = StepArgs<Topo::N, Topo::S>, int MINB = 0>
+__global__ void __launch_bounds__(kPackedBlock, packed_min_blocks(Topo::N, MINB))
 step_static_packed_kernel(const __grid_constant__ Args A) {
     constexpr int N = Topo::N, M = Topo::M;
     constexpr int D = 3 * (IN3D ? 3 : 2) * N + M;

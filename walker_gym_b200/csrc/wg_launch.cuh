@@ -104,6 +104,7 @@ inline void fill_args(StepArgs<MAXN, MAXS>& A, const wg_topology* t, const wg_pa
         bv.si[s] = t->si[s]; bv.sj[s] = t->sj[s];
         bv.sk[s] = t->sk[s]; bv.sdamp[s] = t->sdamp[s]; bv.srest[s] = t->srest[s];
         bv.mlo[s] = t->mlo[s]; bv.mhi[s] = t->mhi[s];
+        if (t->sstring[s]) bv.string_mask[s >> 5] |= 1u << (s & 31);
     }
     bv.ndiv = make_const_div((float)t->n_mass);
     auto& ec = A.ec;
@@ -192,6 +193,18 @@ inline int launch_static_tma(const wg_topology* t, const wg_params* p, const wg_
     return WG_OK;
 }
 
+// SMs of the current device (cached per thread and device)
+inline int sm_count() {
+    static thread_local int dev_cached = -1, sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != dev_cached) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+        dev_cached = dev;
+    }
+    return sms;
+}
+
 // ---- packed state layout: float4 state access --------------------------------------------------------
 template <class Topo, bool IN3D, int OBS, int MM>
 inline int launch_static_packed(const wg_topology* t, const wg_params* p, const wg_buffers* b, int64_t E, cudaStream_t s) {
@@ -201,11 +214,17 @@ inline int launch_static_packed(const wg_topology* t, const wg_params* p, const 
     constexpr bool bulk = (OBS == 1) && gcd_c(D, 32) <= 2;
     const size_t smem = (OBS == 1 && b->obs) ? sizeof(float) * kPackedBlock * (bulk ? D : (D | 1)) : 0;
     auto kern = step_static_packed_kernel<Topo, IN3D, OBS, MM>;
+    const int64_t n_blocks = (E + kPackedBlock - 1) / kPackedBlock;
+    if constexpr (Topo::N <= 4 && IN3D && OBS == 1 && (MM == 0 || MM == 3) && WG_PACKED_MIN_BLOCKS == 6 && WG_PACKED_BLOCK == 128) {
+        // a grid of (6, 7] CTAs per SM: one wave with the 7-CTA instance instead of one full wave plus a sliver
+        const int64_t sms = sm_count();
+        if (n_blocks > 6 * sms && n_blocks <= 7 * sms) kern = step_static_packed_kernel<Topo, IN3D, OBS, MM, StepArgs<Topo::N, Topo::S>, 7>;
+    }
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<(unsigned)((E + kPackedBlock - 1) / kPackedBlock), kPackedBlock, smem, s>>>(A);
+    kern<<<(unsigned)n_blocks, kPackedBlock, smem, s>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (packed) launch: %s", cudaGetErrorString(e));
     return WG_OK;

@@ -33,6 +33,7 @@ struct BodyVals {
     uint32_t unit_mask;     // bit n: m == 1 (x / 1 is exact, float64 division skipped)
     int32_t si[MAXS], sj[MAXS];   // only read by the run-time topology
     int32_t n_mass, n_spring, n_muscle;
+    uint32_t string_mask[(MAXS + 31) / 32];   // rope-type springs (run-time topology only: f_size = 0 while dx < 0)
 };
 
 struct EnvConst {
@@ -140,7 +141,10 @@ __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store
     const float pjx = st.pos(j, 0), pjy = st.pos(j, 1), pjz = st.pos(j, 2);
     const float L = np_norm3(pix - pjx, piy - pjy, piz - pjz);            // distant(p1, p2)
     const float dx = L - x;
-    const float fs = (-dx) * bv.sk[sp];                                   // -dx * k (sign as written)
+    float fs = (-dx) * bv.sk[sp];                                         // -dx * k (sign as written)
+    // rope-type springs (`if dx < 0 and string: f_size = 0`, gym/optimized_engine.py:134-136): a per-spring flag of
+    // the run-time topology only -- bodies with such springs never reach the compile-time specialisations
+    if constexpr (!Topo::kStatic) { if (((bv.string_mask[sp >> 5] >> (sp & 31)) & 1u) && dx < 0.0f) fs = 0.0f; }
     float d0 = pjx - pix, d1 = pjy - piy, d2 = pjz - piz;                 // direction = p2 - p1
     div3_len(d0, d1, d2, L);
     const float F[3] = { fs * d0, fs * d1, fs * d2 };

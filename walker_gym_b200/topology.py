@@ -37,6 +37,7 @@ def topology_from_creature(creature: Creature) -> WgTopology:
             raise ValueError("a spring must join two different points")
         t.sk[s] = np.float32(sp.k)
         t.sdamp[s] = np.float32(sp.dampk)
+        t.sstring[s] = 1 if getattr(sp, "string", False) else 0
         if s < t.n_muscle:
             t.srest[s] = np.float32(sp.originx)
             t.mlo[s] = np.float32(sp.originx * sp.minl)     # Muscle.regulation operands, python semantics

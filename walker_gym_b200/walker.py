@@ -24,13 +24,16 @@ class Muscle:
     """An actuated spring: its rest length ``x`` is the control variable
     (gym/optimized_walker.py:7-43)."""
 
-    def __init__(self, p1: Point, p2: Point, x=None, k=1000, maxl=1.5, minl=0.1, stride=2, dampk=20):
+    def __init__(self, p1: Point, p2: Point, x=None, k=1000, maxl=1.5, minl=0.1, stride=2, dampk=20, string=False):
         self.p1, self.p2 = p1, p2
         self.x = _distance(p1, p2) if x is None else x
         self.originx = self.x
         self.k, self.dampk = k, dampk
         self.minl, self.maxl = minl, maxl
         self.stride = stride
+        # extension (keyword only in spirit; the reference's constructor ends at dampk): rope-type spring, no elastic
+        # force while shorter than its rest length -- Point.resilience's `string` (gym/optimized_engine.py:116-140)
+        self.string = bool(string)
 
     def distant(self, p1: Point, p2: Point):
         return _distance(p1, p2)
@@ -57,10 +60,11 @@ class Muscle:
 class Skeleton:
     """A passive spring (gym/optimized_walker.py:69-82)."""
 
-    def __init__(self, p1: Point, p2: Point, x=None, k=1000, dampk=20):
+    def __init__(self, p1: Point, p2: Point, x=None, k=1000, dampk=20, string=False):
         self.p1, self.p2 = p1, p2
         self.x = _distance(p1, p2) if x is None else x
         self.k, self.dampk = k, dampk
+        self.string = bool(string)      # extension: rope-type (gym/optimized_engine.py:134-138), see Muscle
 
     def distant(self, p1: Point, p2: Point):
         return _distance(p1, p2)
