@@ -76,6 +76,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the sub_configs measurements (configs 3-strong, 4, 5, multi-step)")
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to CPUs next to its GPU")
+    ap.add_argument("--strong-envs-per-gpu", type=int, default=0,
+                    help="sub-config 3_strong: envs per GPU (default 2^20 / n_gpus, BASELINE config 3 as written)")
     return ap.parse_args()
 
 
@@ -647,7 +649,7 @@ def measure_sub_configs(ctx, args):
     # ---- config 3 as written: 2^20 envs TOTAL, split over the GPUs (strong scaling), 1000-step rollout replayed from a
     # CUDA graph of 50 closed-loop steps so that the few-us kernel is not hidden behind Python + ctypes launch cost ----
     def strong():
-        Es = (1 << 20) // world
+        Es = args.strong_envs_per_gpu or (1 << 20) // world
         env = BatchedPhysicsEnv(ENV_ID, Es, dev, in3d=True, auto_reset="template", seed=1234, env_offset=rank * Es,
                                 track_stats=True, graph_safe=True)
         T = 50

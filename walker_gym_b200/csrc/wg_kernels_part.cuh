@@ -249,10 +249,10 @@ template <int MM, int SIDE, class U, class BV>
 __device__ __forceinline__ void link_half(const BV& bv, int n, const float (&pi)[3], const float (&vi)[3],
                                           const float (&pj)[3], const float (&vj)[3], float k, float damp, float rest,
                                           float (&acc)[3]) {
-    const float L = np_norm3(pi[0] - pj[0], pi[1] - pj[1], pi[2] - pj[2]);
+    float d0 = pj[0] - pi[0], d1 = pj[1] - pi[1], d2 = pj[2] - pi[2];
+    const float L = np_norm3(d0, d1, d2);
     const float dx = L - rest;
     const float fs = (-dx) * k;
-    float d0 = pj[0] - pi[0], d1 = pj[1] - pi[1], d2 = pj[2] - pi[2];
     div3_len(d0, d1, d2, L);
     const float F[3] = { fs * d0, fs * d1, fs * d2 };
     const float dk = np_dot3(vi[0] - vj[0], vi[1] - vj[1], vi[2] - vj[2], d0, d1, d2);

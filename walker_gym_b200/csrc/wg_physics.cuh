@@ -139,13 +139,15 @@ __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store
     const int i = topo.si(sp), j = topo.sj(sp);
     const float pix = st.pos(i, 0), piy = st.pos(i, 1), piz = st.pos(i, 2);
     const float pjx = st.pos(j, 0), pjy = st.pos(j, 1), pjz = st.pos(j, 2);
-    const float L = np_norm3(pix - pjx, piy - pjy, piz - pjz);            // distant(p1, p2)
+    float d0 = pjx - pix, d1 = pjy - piy, d2 = pjz - piz;                 // direction = p2 - p1
+    // distant(p1, p2) = norm(p1 - p2): p1 - p2 == -(p2 - p1) exactly and only its squares are used, so the norm is
+    // taken of the direction's components (three subtractions less per spring)
+    const float L = np_norm3(d0, d1, d2);
     const float dx = L - x;
     float fs = (-dx) * bv.sk[sp];                                         // -dx * k (sign as written)
     // rope-type springs (`if dx < 0 and string: f_size = 0`, gym/optimized_engine.py:134-136): a per-spring flag of
     // the run-time topology only -- bodies with such springs never reach the compile-time specialisations
     if constexpr (!Topo::kStatic) { if (((bv.string_mask[sp >> 5] >> (sp & 31)) & 1u) && dx < 0.0f) fs = 0.0f; }
-    float d0 = pjx - pix, d1 = pjy - piy, d2 = pjz - piz;                 // direction = p2 - p1
     div3_len(d0, d1, d2, L);
     const float F[3] = { fs * d0, fs * d1, fs * d2 };
     const float dk = np_dot3(st.vel(i, 0) - st.vel(j, 0), st.vel(i, 1) - st.vel(j, 1),
@@ -209,8 +211,8 @@ __device__ __forceinline__ void spring_run_x64(const Topo& topo, const BV& bv, S
     const int i = topo.si(sp), j = topo.sj(sp);
     const float pix = st.pos(i, 0), piy = st.pos(i, 1), piz = st.pos(i, 2);
     const float pjx = st.pos(j, 0), pjy = st.pos(j, 1), pjz = st.pos(j, 2);
-    const float L = np_norm3(pix - pjx, piy - pjy, piz - pjz);
     float d0 = pjx - pix, d1 = pjy - piy, d2 = pjz - piz;
+    const float L = np_norm3(d0, d1, d2);
     div3_len(d0, d1, d2, L);
     const double fs = (-((double)L - x)) * k_d;
     const double F[3] = { fs * (double)d0, fs * (double)d1, fs * (double)d2 };
