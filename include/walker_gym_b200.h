@@ -222,6 +222,7 @@ int wg_force_generic(int on);
 #define WG_TUNE_PART 1
 #define WG_TUNE_L2_PREFETCH 2
 #define WG_TUNE_JIT 3             /* 1 (default) = bodies without an ahead-of-time kernel get one compiled at run time */
+#define WG_TUNE_POLICY_TC 4       /* wg_policy_act: 1 = the tcgen05 / tensor-memory kernel, 0 = the mma.sync kernel */
 int wg_set_tuning(int key, int value);
 
 /*
@@ -396,6 +397,10 @@ typedef struct wg_mlp_policy {
 int wg_policy_act(const wg_mlp_policy* pol, const float* obs, int32_t obs_layout, float* action, int32_t act_layout, float* logp,
                   float* value, float* mean, int64_t n_env, int32_t sample, uint32_t seed_lo, uint32_t seed_hi,
                   uint32_t step_index, const uint32_t* step_counter, uint32_t env_offset, void* cuda_stream);
+
+/* 1 if a tcgen05 policy kernel ever gave up waiting for its tensor-core work (a diagnostic: synchronises the device;
+ * never set by a correct build), 0 otherwise, -1 on a CUDA error. */
+int wg_policy_tc_status(void);
 
 /*
  * GAE(lambda) over a trajectory: rewards [T][n_env], values [T+1][n_env], dones uint8 [T][n_env] ->

@@ -96,12 +96,12 @@ class WgMlpPolicy(C.Structure):
                 ("obs_scale", C.c_float), ("obs_clip", C.c_float), ("precision", C.c_int32), ("reserved", C.c_int32)]
 
 
-TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH, TUNE_JIT = 0, 1, 2, 3
+TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH, TUNE_JIT, TUNE_POLICY_TC = 0, 1, 2, 3, 4
 
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
            "wg_set_tuning", "wg_packed_state_floats", "wg_packed_available", "wg_jit_prepare",
            "wg_step", "wg_step_multi", "wg_step_x64", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_step_multi_host", "wg_pkg_update_physics", "wg_pkg_kernel_variant",
-           "wg_policy_act", "wg_gae", "wg_stream_probe", "wg_host_alloc", "wg_host_free", "wg_getstat",
+           "wg_policy_act", "wg_gae", "wg_stream_probe", "wg_host_alloc", "wg_host_free", "wg_getstat", "wg_policy_tc_status",
            "wg_selftest_div_smallint", "wg_selftest_forced_list", "wg_selftest_sqrt", "wg_selftest_div3")
 
 _lib = None
@@ -172,7 +172,7 @@ def load():
     lib.wg_selftest_forced_list.argtypes = [C.c_double, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.wg_selftest_sqrt.argtypes = [C.c_void_p, C.c_void_p]
     lib.wg_selftest_div3.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
-    for name in ("wg_host_alloc", "wg_host_free", "wg_getstat", "wg_selftest_div_smallint", "wg_selftest_forced_list",
+    for name in ("wg_host_alloc", "wg_host_free", "wg_getstat", "wg_policy_tc_status", "wg_selftest_div_smallint", "wg_selftest_forced_list",
                  "wg_selftest_sqrt", "wg_selftest_div3"):
         getattr(lib, name).restype = C.c_int
     for name in ("wg_obs_dim", "wg_kernel_variant", "wg_force_generic", "wg_step", "wg_reset",

@@ -21,6 +21,7 @@ int launch_jit_multi(const wg_topology*, const wg_params*, const wg_buffers*, in
 int launch_jit_soa(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_jit_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_policy(const PolicyArgs& A, int precision, cudaStream_t s);
+int policy_tc_error();
 int launch_stream_probe(const float* src, float* dst, int64_t n, int R, int W, cudaStream_t s);
 int launch_gae(const float* rewards, const float* values, const uint8_t* dones, float* adv, float* ret, int T, int64_t E,
                float gamma, float lam, float clip, cudaStream_t s);
@@ -28,8 +29,8 @@ int launch_gae(const float* rewards, const float* values, const uint8_t* dones, 
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_force_generic{0};
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
-static std::atomic<int> g_tune[4] = { {env_int("WG_TMA", 0)}, {env_int("WG_PART", -1)}, {env_int("WG_L2_PREFETCH", 256)},
-                                      {env_int("WG_JIT", 1)} };
+static std::atomic<int> g_tune[5] = { {env_int("WG_TMA", 0)}, {env_int("WG_PART", -1)}, {env_int("WG_L2_PREFETCH", 256)},
+                                      {env_int("WG_JIT", 1)}, {env_int("WG_POLICY_TC", 0)} };
 int tuning(int key) { return g_tune[key].load(std::memory_order_relaxed); }
 
 int fail(int code, const char* fmt, const char* a) {
@@ -163,7 +164,7 @@ int64_t wg_packed_state_floats(const wg_topology* topo, int64_t n_env) {
 }
 
 int wg_set_tuning(int key, int value) {
-    if (key < 0 || key > 3) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
+    if (key < 0 || key > 4) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
     if (key == WG_TUNE_PART && value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
         return fail(WG_ERR_BAD_ARG, "PART must be -1, 0, 2, 4 or 8%s");
     if (key == WG_TUNE_L2_PREFETCH && (value < 0 || value > (1 << 20))) return fail(WG_ERR_BAD_ARG, "L2 prefetch distance out of range%s");
@@ -376,6 +377,8 @@ int wg_policy_act(const wg_mlp_policy* pol, const float* obs, int32_t obs_layout
     A.seed_lo = seed_lo; A.seed_hi = seed_hi; A.step_index = step_index; A.env_offset = env_offset;
     return launch_policy(A, pol->precision, (cudaStream_t)cuda_stream);
 }
+
+int wg_policy_tc_status(void) { return policy_tc_error(); }
 
 int wg_stream_probe(const float* src, float* dst, int64_t n_threads, int32_t vec_reads, int32_t vec_writes, void* cuda_stream) {
     if (!src || !dst || n_threads < 0 || vec_reads < 0 || vec_writes < 0) return fail(WG_ERR_BAD_ARG, "bad argument to wg_stream_probe%s");

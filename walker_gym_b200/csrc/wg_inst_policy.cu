@@ -1,6 +1,7 @@
 // wg_inst_policy.cu -- rollout-side kernels: the fused MLP policy (wg_policy_act) and GAE (wg_gae).
 #include "wg_launch.cuh"
 #include "wg_policy.cuh"
+#include "wg_policy_tc.cuh"
 namespace wg {
 
 #ifndef WG_POLICY_MT
@@ -28,7 +29,50 @@ static int launch_policy_t(const PolicyArgs& A, cudaStream_t s) {
     return WG_OK;
 }
 
+// ---- tcgen05 / TMEM variant (wg_policy_tc.cuh) ----
+__device__ int g_policy_tc_error = 0;          // set by a CTA that gave up waiting for its MMAs (never in a correct build)
+
+template <int K1, bool SPLIT>
+static int launch_policy_tc_t(const PolicyArgs& A, cudaStream_t s) {
+    auto kern = policy_act_tc_kernel<K1, SPLIT>;
+    const size_t smem = TcSmem<K1>::bytes;
+    static thread_local int cached_dev = -1, n_sm = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    int* flag = nullptr;
+    cudaGetSymbolAddress((void**)&flag, g_policy_tc_error);
+    const int64_t n_tiles = (A.E + kTcTile - 1) / kTcTile;
+    const int64_t resident = (int64_t)n_sm * (smem * 2 <= 227 * 1024 ? 2 : 1);      // persistent: weights staged once per CTA
+    kern<<<(unsigned)(n_tiles < resident ? n_tiles : resident), kTcTile, smem, s>>>(A, flag);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "policy kernel (tcgen05) launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
+int policy_tc_error() {
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_policy_tc_error, sizeof(int)) != cudaSuccess) return -1;
+    return v;
+}
+
+static int launch_policy_tc(const PolicyArgs& A, int precision, cudaStream_t s) {
+    const int k1 = ((A.D + 7) / 8) * 8;
+#define WG_POLTC(K) (precision == 0 ? launch_policy_tc_t<K, true>(A, s) : launch_policy_tc_t<K, false>(A, s))
+    if (k1 <= 24) return WG_POLTC(24);
+    if (k1 <= 32) return WG_POLTC(32);
+    if (k1 <= 40) return WG_POLTC(40);
+    return WG_POLTC(64);
+#undef WG_POLTC
+}
+
 int launch_policy(const PolicyArgs& A, int precision, cudaStream_t s) {
+    if (tuning(WG_TUNE_POLICY_TC) > 0) return launch_policy_tc(A, precision, s);
     const int kt = (A.D + 7) / 8;
 #define WG_POL(KT) (precision == 0 ? launch_policy_t<KT, true>(A, s) : launch_policy_t<KT, false>(A, s))
     if (kt <= 3) return WG_POL(3);

@@ -362,10 +362,7 @@ step_units_kernel(const __grid_constant__ UnitsArgs<U, MM> UA) {
                 }
                 if (u > 0) link_half<MM, 1, U>(UA.ubv, LB, lp, lv, rs.p_[LB], rs.v_[LB], UA.link_k, UA.link_damp, UA.link_rest, rs.a_[LB]);
                 if (u + 1 < P) link_half<MM, 0, U>(UA.ubv, LA, rs.p_[LA], rs.v_[LA], rp, rv, UA.link_k, UA.link_damp, UA.link_rest, rs.a_[LA]);
-                cu = 0;
-#pragma unroll
-                for (int n = 0; n < U::N; n++)
-                    if (point_step<IN3D, MM>(UA.ubv, A.ec, rs, n)) cu |= 1u << n;
+                cu = all_point_steps<IN3D, MM>(utopo, UA.ubv, A.ec, rs);
             }
         }
         cpre = cu << m0;

@@ -254,7 +254,9 @@ static __device__ __noinline__ void run2_cold(float3& p, float3& v, float3 a, fl
 
 // Environment forces on mass n (gravity, damping, ground contact: gym/optimized_env.py:146-175) followed by
 // the integrator (Point.run1 / run2).  Returns the force-phase contact flag.
-template <bool IN3D, int MM, class BV, class Store>
+// UNIT: 1 = this mass is known at compile time to be 1 (mass mode 0, or mode 3's unit-mass point), 0 = known not to
+// need the run-time kind (modes 1 and 3: the exact-remainder quotient, which is also right for m == 1), -1 = run time.
+template <bool IN3D, int MM, int UNIT = -1, class BV, class Store>
 __device__ __forceinline__ bool point_step(const BV& bv, const EnvConst& ec, Store& st, int n) {
     const bool fixed = (MM == 2) && ((bv.fixed_mask >> n) & 1u);
     float ax = st.acc(n, 0), ay = st.acc(n, 1), az = st.acc(n, 2);
@@ -272,12 +274,24 @@ __device__ __forceinline__ bool point_step(const BV& bv, const EnvConst& ec, Sto
         }
         if (hit) {
             const double m = bv.mass_d[n], rd = bv.mass_rd[n];
-            const int kd = MM == 0 ? 0 : bv.mass_kind[n];
-            ay = forced_list(ay, ec.nground_k * deep, m, rd, kd);    // ground spring
-            ay = forced_list(ay, ec.nground_damp * vy, m, rd, kd);   // ground damper
             const float ff = fabsf(deep) * ec.friction;             // friction
-            ax = forced_list(ax, (-vx) * ff, m, rd, kd);
-            if (IN3D) az = forced_list(az, (-vz) * ff, m, rd, kd);
+            if constexpr (MM == 0 || UNIT == 1) {                    // unit mass: float32 additions (see forced_list_k)
+                ay = forced_list_k<0>(ay, ec.nground_k * deep, m, rd);       // ground spring
+                ay = forced_list_k<0>(ay, ec.nground_damp * vy, m, rd);      // ground damper
+                ax = forced_list_k<0>(ax, (-vx) * ff, m, rd);
+                if (IN3D) az = forced_list_k<0>(az, (-vz) * ff, m, rd);
+            } else if constexpr (MM == 1 || MM == 3) {               // unit / power-of-two / odd-integer masses: no dispatch
+                ay = forced_list_k<2>(ay, ec.nground_k * deep, m, rd);
+                ay = forced_list_k<2>(ay, ec.nground_damp * vy, m, rd);
+                ax = forced_list_k<2>(ax, (-vx) * ff, m, rd);
+                if (IN3D) az = forced_list_k<2>(az, (-vz) * ff, m, rd);
+            } else {
+                const int kd = bv.mass_kind[n];
+                ay = forced_list(ay, ec.nground_k * deep, m, rd, kd);
+                ay = forced_list(ay, ec.nground_damp * vy, m, rd, kd);
+                ax = forced_list(ax, (-vx) * ff, m, rd, kd);
+                if (IN3D) az = forced_list(az, (-vz) * ff, m, rd, kd);
+            }
         }
     }
     if (ec.integrator == 0) {
@@ -298,6 +312,29 @@ __device__ __forceinline__ bool point_step(const BV& bv, const EnvConst& ec, Sto
     return hit;
 }
 
+// point_step for every mass; returns the force-phase contact mask.  Mass mode 3 (compile-time mass pattern) walks the
+// masses by template recursion so that the unit-mass points get their float32 contact forces.
+template <bool IN3D, int MM, class Topo, int N0, class BV, class Store>
+__device__ __forceinline__ uint32_t point_steps_static(const BV& bv, const EnvConst& ec, Store& st) {
+    if constexpr (N0 >= Topo::N) return 0u;
+    else {
+        const uint32_t c = point_step<IN3D, MM, (Topo::unit(N0) ? 1 : 0)>(bv, ec, st, N0) ? (1u << N0) : 0u;
+        return c | point_steps_static<IN3D, MM, Topo, N0 + 1>(bv, ec, st);
+    }
+}
+template <bool IN3D, int MM, class Topo, class BV, class Store>
+__device__ __forceinline__ uint32_t all_point_steps(const Topo& topo, const BV& bv, const EnvConst& ec, Store& st) {
+    if constexpr (MM == 3) return point_steps_static<IN3D, MM, Topo, 0>(bv, ec, st);
+    else {
+        uint32_t contact = 0;
+        const int N = topo.n();
+#pragma unroll
+        for (int n = 0; n < N; n++)
+            if (point_step<IN3D, MM>(bv, ec, st, n)) contact |= 1u << n;
+        return contact;
+    }
+}
+
 // PhysicsEnv._run_physics + Point.run1: one substep.  Returns the force-phase contact mask.
 template <bool IN3D, int MM, class Topo, class BV, class Store>
 __device__ __forceinline__ uint32_t run_physics(const Topo& topo, const BV& bv, const EnvConst& ec, Store& st) {
@@ -310,9 +347,7 @@ __device__ __forceinline__ uint32_t run_physics(const Topo& topo, const BV& bv, 
 #pragma unroll
     for (int sp = M; sp < S; sp++) spring_run<MM>(topo, bv, st, sp, bv.srest[sp], bv.fixed_mask);
     uint32_t contact = 0;
-#pragma unroll
-    for (int n = 0; n < N; n++)
-        if (point_step<IN3D, MM>(bv, ec, st, n)) contact |= 1u << n;
+    contact = all_point_steps<IN3D, MM>(topo, bv, ec, st);
     return contact;
 }
 

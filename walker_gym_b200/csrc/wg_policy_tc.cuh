@@ -1,0 +1,289 @@
+// wg_policy_tc.cuh -- the rollout policy (BASELINE config 5) on the 5th-generation tensor cores.
+//
+// Same function as policy_act_kernel (wg_policy.cuh): obs -> gaussian MLP (D -> 64 -> 64 -> {M means, 1 value}, tanh)
+// -> sampled action, log-prob, value, one launch per env step, reading the observation as the step kernel wrote it.
+// The three GEMMs run as tcgen05.mma (kind::tf32, M = 128 envs per tile, accumulators in tensor memory):
+//
+//   layer 1   A = the tile's observations [128 x K1] in shared memory (canonical K-major layout, no swizzle),
+//             B = W1 [64 x K1] in shared memory,              D -> TMEM columns [0, 64)
+//   layer 2   A = tanh(layer 1) [128 x 64] in TENSOR MEMORY (written there by the epilogue with tcgen05.st: thread r
+//             owns TMEM lane r = env r, so an activation row never touches shared memory), B = W2 [64 x 64] in smem,
+//             D -> TMEM columns [0, 64)
+//   heads     A = tanh(layer 2) in TMEM, B = [w_mu; w_v; 0] [16 x 64] in smem, D -> TMEM columns [192, 208)
+//
+// With SPLIT every product is the 3-term error-compensated a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (float32-grade, like the
+// mma.sync kernel): three MMAs per k-step into the same accumulator, hi / lo planes of A in TMEM columns [64, 128) /
+// [128, 192) and of B in shared memory.  One thread issues the MMAs of a layer and commits them to an mbarrier; all
+// 128 threads then run that layer's epilogue (tcgen05.ld -> bias, tanh, split -> tcgen05.st).  Two CTAs per SM
+// (2 x 256 TMEM columns, 2 x ~100 KB of shared memory) overlap one tile's epilogue with the other's MMAs.
+// Every mbarrier wait is bounded: a descriptor mistake ends the kernel with an error flag instead of hanging the GPU.
+#pragma once
+#include "wg_policy.cuh"
+
+namespace wg {
+
+constexpr int kTcTile = 128;          // envs per tile = MMA M = TMEM lanes = threads per CTA
+constexpr int kTcCols = 256;          // TMEM columns per CTA: D [0,64)  A_hi [64,128)  A_lo [128,192)  heads [192,208)
+constexpr int kTcHeadN = 16;          // heads MMA N (smallest N for M = 128); rows 0..M-1 means, row M value, rest 0
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: element (r, k) of a [R x K] float matrix lives at byte
+// (k / 4) * (R * 16) + r * 16 + (k % 4) * 4 from the start address, i.e. 16-byte chunks of 4 consecutive k, all R rows of a
+// chunk contiguous: core matrices (8 rows x 16 B) are 128 B apart along the rows (stride byte offset) and R * 16 B apart
+// along k (leading byte offset).  One MMA (K = 8) reads two chunks.
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t rows) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);                 // start address            bits [0, 14)
+    d |= (uint64_t)((rows * 16u) >> 4 & 0x3fffu) << 16;      // leading byte offset      bits [16, 30)
+    d |= (uint64_t)(128u >> 4) << 32;                        // stride byte offset       bits [32, 46)
+    d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
+    return d;                                                // base offset 0, layout type 0 = no swizzle
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N
+__host__ __device__ constexpr uint32_t tc_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait on an mbarrier phase; false = gave up (a fraction of a second)
+__device__ __forceinline__ bool tc_wait_bar(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (int it = 0; it < (1 << 18); it++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+
+// shared memory of one CTA (floats): B planes of the three layers (hi, lo), the A planes of the observation tile (hi, lo)
+template <int K1>
+struct TcSmem {
+    static constexpr int W1 = 64 * K1, W2 = 64 * 64, WH = kTcHeadN * 64, AO = kTcTile * K1;
+    static constexpr int o_w1 = 0, o_w2 = o_w1 + 2 * W1, o_wh = o_w2 + 2 * W2, o_a = o_wh + 2 * WH;
+    static constexpr int o_bias = o_a + 2 * AO;                    // b1[64] b2[64] bh[16] ls[16]
+    static constexpr int floats = o_bias + 64 + 64 + 16 + 16;
+    static constexpr size_t bytes = sizeof(float) * floats + 64;   // + mbarrier, TMEM slot, error flag
+};
+
+// one weight matrix [rows x K] (torch layout w[n * ld + k]; row n_valid from w_last; zero padding) into its hi (and lo)
+// plane in the canonical layout
+template <bool SPLIT>
+__device__ __forceinline__ void tc_fill_b(float* hi, float* lo, int rows, int K, int n_valid, int k_valid,
+                                          const float* __restrict__ w, int ld, const float* __restrict__ w_last) {
+    for (int idx = threadIdx.x; idx < rows * K; idx += blockDim.x) {
+        const int n = idx / K, k = idx - n * K;
+        float v = 0.0f;
+        if (k < k_valid) {
+            if (n < n_valid) v = w[n * ld + k];
+            else if (n == n_valid && w_last) v = w_last[k];
+        }
+        const int off = (k >> 2) * (rows * 4) + n * 4 + (k & 3);
+        const float h = __uint_as_float(to_tf32(v));
+        hi[off] = h;
+        if (SPLIT) lo[off] = v - h;
+    }
+}
+
+// K1 = layer-1 depth (obs_dim rounded up to a multiple of 8), SPLIT = float32-grade 3xTF32
+template <int K1, bool SPLIT>
+__global__ void __launch_bounds__(kTcTile, 2)
+policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ error_flag) {
+    using L = TcSmem<K1>;
+    extern __shared__ __align__(128) float tsm[];
+    float* const W1h = tsm + L::o_w1; float* const W1l = W1h + L::W1;
+    float* const W2h = tsm + L::o_w2; float* const W2l = W2h + L::W2;
+    float* const WHh = tsm + L::o_wh; float* const WHl = WHh + L::WH;
+    float* const AOh = tsm + L::o_a;  float* const AOl = AOh + L::AO;
+    float* const B1 = tsm + L::o_bias; float* const B2 = B1 + 64; float* const BH = B2 + 64; float* const LS = BH + 16;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(tsm + L::floats);
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int D = A.D, M = A.M;
+
+    // ---- one-time setup: weights (hi / lo planes), biases, mbarrier, tensor memory ----
+    tc_fill_b<SPLIT>(W1h, W1l, 64, K1, 64, D, A.w1, D, nullptr);
+    tc_fill_b<SPLIT>(W2h, W2l, 64, 64, 64, 64, A.w2, 64, nullptr);
+    tc_fill_b<SPLIT>(WHh, WHl, kTcHeadN, 64, M, 64, A.w_mu, 64, A.w_v);
+    if (tid < 64) { B1[tid] = A.b1[tid]; B2[tid] = A.b2[tid]; }
+    if (tid < 16) { BH[tid] = tid < M ? A.b_mu[tid] : (tid == M ? A.b_v[0] : 0.0f); LS[tid] = tid < M ? A.log_std[tid] : 0.0f; }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTcCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the weight planes -> visible to the tensor core's reads
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;                                  // lane 0, first column of this CTA's allocation
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 lanes
+    const uint32_t cD = 0, cAh = 64, cAl = 128, cH = 192;
+    uint32_t phase = 0;
+    bool alive = true;
+
+    const int64_t E = A.E;
+    const int64_t n_tiles = (E + kTcTile - 1) / kTcTile;
+    const uint32_t step = A.step_index + (A.step_counter ? __ldg(A.step_counter) : 0u);
+    const uint64_t dW1h = tc_smem_desc(smem_u32(W1h), 64), dW1l = tc_smem_desc(smem_u32(W1l), 64);
+    const uint64_t dW2h = tc_smem_desc(smem_u32(W2h), 64), dW2l = tc_smem_desc(smem_u32(W2l), 64);
+    const uint64_t dWHh = tc_smem_desc(smem_u32(WHh), kTcHeadN), dWHl = tc_smem_desc(smem_u32(WHl), kTcHeadN);
+    const uint64_t dAOh = tc_smem_desc(smem_u32(AOh), kTcTile), dAOl = tc_smem_desc(smem_u32(AOl), kTcTile);
+    // a k-step of 8 advances an operand by two 16-byte chunks = 2 * rows * 16 bytes (descriptor units of 16 bytes)
+    constexpr uint32_t kStepB64 = 2 * 64, kStepBH = 2 * kTcHeadN, kStepA = 2 * kTcTile;
+    constexpr uint32_t id64 = tc_idesc(64), idH = tc_idesc(kTcHeadN);
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles && alive; tile += gridDim.x) {
+        const int64_t e = tile * kTcTile + tid;
+        const bool ev = e < E;
+        // ---- the tile's observations -> sanitise -> hi / lo planes of the layer-1 A operand ----
+#pragma unroll
+        for (int j = 0; j < K1 / 4; j++) {
+            float x[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int f = 4 * j + q;
+                float v = 0.0f;
+                if (ev && f < D) v = __ldg(A.obs + (A.obs_layout ? (int64_t)f * E + e : e * D + f));
+                v = v * A.obs_scale;                               // nan_to_num + clamp of the torch reference
+                x[q] = (v != v) ? 0.0f : fminf(fmaxf(v, -A.obs_clip), A.obs_clip);
+            }
+            float4 h, l;
+            h.x = __uint_as_float(to_tf32(x[0])); h.y = __uint_as_float(to_tf32(x[1]));
+            h.z = __uint_as_float(to_tf32(x[2])); h.w = __uint_as_float(to_tf32(x[3]));
+            l.x = x[0] - h.x; l.y = x[1] - h.y; l.z = x[2] - h.z; l.w = x[3] - h.w;
+            reinterpret_cast<float4*>(AOh)[j * kTcTile + tid] = h;
+            if (SPLIT) reinterpret_cast<float4*>(AOl)[j * kTcTile + tid] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        // ---- layer 1: D[0,64) = obs * W1^T ----
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < K1 / 8; kk++) {
+                tc_mma_ss(tmem + cD, dAOh + kk * kStepA, dW1h + kk * kStepB64, id64, kk > 0);
+                if (SPLIT) {
+                    tc_mma_ss(tmem + cD, dAOl + kk * kStepA, dW1h + kk * kStepB64, id64, 1);
+                    tc_mma_ss(tmem + cD, dAOh + kk * kStepA, dW1l + kk * kStepB64, id64, 1);
+                }
+            }
+            tc_commit(bar);
+        }
+        alive = __syncthreads_and(tc_wait_bar(bar, phase));        // uniform verdict: nobody waits at a barrier others left
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogues 1 and 2: tanh(D + b) -> hi / lo planes of the next layer's A operand, in tensor memory ----
+#pragma unroll 1
+        for (int layer = 0; layer < 2 && alive; layer++) {
+            const float* bias = layer ? B2 : B1;
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                uint32_t v[16], hi[16], lo[16];
+                tc_ld16(t_lane + cD + c0, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float y = pol_tanh<SPLIT>(__uint_as_float(v[i]) + bias[c0 + i]);
+                    hi[i] = to_tf32(y);
+                    lo[i] = __float_as_uint(y - __uint_as_float(hi[i]));
+                }
+                tc_st16(t_lane + cAh + c0, hi);
+                if (SPLIT) tc_st16(t_lane + cAl + c0, lo);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t dcol = layer ? cH : cD;
+                const uint64_t bh = layer ? dWHh : dW2h, bl = layer ? dWHl : dW2l;
+                const uint32_t ks = layer ? kStepBH : kStepB64, id = layer ? idH : id64;
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) {
+                    tc_mma_ts(tmem + dcol, tmem + cAh + 8 * kk, bh + kk * ks, id, kk > 0);
+                    if (SPLIT) {
+                        tc_mma_ts(tmem + dcol, tmem + cAl + 8 * kk, bh + kk * ks, id, 1);
+                        tc_mma_ts(tmem + dcol, tmem + cAh + 8 * kk, bl + kk * ks, id, 1);
+                    }
+                }
+                tc_commit(bar);
+            }
+            alive = __syncthreads_and(tc_wait_bar(bar, phase));
+            phase ^= 1;
+            tc_fence_after();
+        }
+        if (!alive) break;
+        // ---- heads: this thread's env: outputs n < M means, n == M value; gaussian sample, log-prob ----
+        uint32_t hv[16];
+        tc_ld16(t_lane + cH, hv);
+        tc_wait_ld();
+        tc_fence_before();                      // the next tile's layer-1 MMA overwrites D / the A planes after the barrier above
+        if (ev) {
+            float lp = 0.0f;
+#pragma unroll
+            for (int pr = 0; pr < 4; pr++) {
+                if (2 * pr < M) {
+                    float2 z = make_float2(0.0f, 0.0f);
+                    if (A.sample) z = pol_normal2(A.seed_lo, A.seed_hi, A.env_offset + (uint32_t)e, step, (uint32_t)pr);
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const int n = 2 * pr + j;
+                        if (n < M) {
+                            const float mean = __uint_as_float(hv[n]) + BH[n], ls = LS[n], eps = j ? z.y : z.x;
+                            const float act = A.sample ? __fmaf_rn(__expf(ls), eps, mean) : mean;
+                            lp += -0.5f * eps * eps - ls - 0.9189385332046727f;
+                            if (A.mean) A.mean[(int64_t)n * E + e] = mean;
+                            if (A.action) A.action[A.act_layout ? (int64_t)n * E + e : e * M + n] = act;
+                        }
+                    }
+                }
+            }
+            if (A.value) {
+                float val = 0.0f;
+#pragma unroll
+                for (int n = 0; n < 8; n++) if (n == M) val = __uint_as_float(hv[n]) + BH[n];
+                A.value[e] = val;
+            }
+            if (A.logp) A.logp[e] = lp;
+        }
+    }
+    if (!alive && error_flag && tid == 0) atomicExch(error_flag, 1);
+    // ---- teardown: the allocating warp frees the tensor memory once every warp is done with it ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTcCols) : "memory");
+}
+
+}  // namespace wg
