@@ -35,7 +35,7 @@ __device__ int g_policy_tc_error = 0;          // set by a CTA that gave up wait
 template <int K1, bool SPLIT>
 static int launch_policy_tc_t(const PolicyArgs& A, cudaStream_t s) {
     auto kern = policy_act_tc_kernel<K1, SPLIT>;
-    const size_t smem = TcSmem<K1>::bytes;
+    const size_t smem = TcSmem<K1>::bytes(A.D);
     static thread_local int cached_dev = -1, n_sm = 0;
     int dev = 0;
     cudaGetDevice(&dev);

@@ -4,11 +4,12 @@
 // -> sampled action, log-prob, value, one launch per env step, reading the observation as the step kernel wrote it.
 // The three GEMMs run as tcgen05.mma (kind::tf32, M = 128 envs per tile, accumulators in tensor memory):
 //
-//   layer 1   A = the tile's observations [128 x K1] in shared memory (canonical K-major layout, no swizzle),
-//             B = W1 [64 x K1] in shared memory,              D -> TMEM columns [0, 64)
-//   layer 2   A = tanh(layer 1) [128 x 64] in TENSOR MEMORY (written there by the epilogue with tcgen05.st: thread r
-//             owns TMEM lane r = env r, so an activation row never touches shared memory), B = W2 [64 x 64] in smem,
-//             D -> TMEM columns [0, 64)
+//   layer 1   A = the tile's observations [128 x K1] in TENSOR MEMORY: thread r owns TMEM lane r = env r, sanitises its
+//             observation row and writes it with tcgen05.st; B = W1 [64 x K1] in shared memory (canonical K-major
+//             layout, no swizzle); D -> TMEM columns [0, 64).  Row-major observation tiles (one contiguous 128 x D
+//             block) arrive by TMA bulk copy into a double-buffered staging area, one tile ahead.
+//   layer 2   A = tanh(layer 1) [128 x 64] in tensor memory (written there by the epilogue: an activation row never
+//             touches shared memory), B = W2 [64 x 64] in smem, D -> TMEM columns [0, 64)
 //   heads     A = tanh(layer 2) in TMEM, B = [w_mu; w_v; 0] [16 x 64] in smem, D -> TMEM columns [192, 208)
 //
 // With SPLIT every product is the 3-term error-compensated a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (float32-grade, like the
@@ -83,33 +84,57 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16])
                     "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 
-// shared memory of one CTA (floats): B planes of the three layers (hi, lo), the A planes of the observation tile (hi, lo)
+// shared memory of one CTA (floats): B planes of the three layers (hi, lo) and two staging buffers for raw observation
+// tiles (row-major observations: one TMA bulk copy per tile, issued one tile ahead)
 template <int K1>
 struct TcSmem {
-    static constexpr int W1 = 64 * K1, W2 = 64 * 64, WH = kTcHeadN * 64, AO = kTcTile * K1;
-    static constexpr int o_w1 = 0, o_w2 = o_w1 + 2 * W1, o_wh = o_w2 + 2 * W2, o_a = o_wh + 2 * WH;
-    static constexpr int o_bias = o_a + 2 * AO;                    // b1[64] b2[64] bh[16] ls[16]
-    static constexpr int floats = o_bias + 64 + 64 + 16 + 16;
-    static constexpr size_t bytes = sizeof(float) * floats + 64;   // + mbarrier, TMEM slot, error flag
+    static constexpr int W1 = 64 * K1, W2 = 64 * 64, WH = kTcHeadN * 64, ST = kTcTile * 64;   // staging: up to 64 floats per env
+    static constexpr int o_w1 = 0, o_w2 = o_w1 + 2 * W1, o_wh = o_w2 + 2 * W2, o_st = o_wh + 2 * WH;
+    static constexpr int st_floats(int D) { return ((kTcTile * D + 3) / 4) * 4; }
+    static constexpr int o_bias(int D) { return o_st + 2 * st_floats(D); }                  // b1[64] b2[64] bh[16] ls[16]
+    static constexpr size_t bytes(int D) { return sizeof(float) * (o_bias(D) + 64 + 64 + 16 + 16) + 64; }   // + 3 mbarriers, TMEM slot
 };
 
 // one weight matrix [rows x K] (torch layout w[n * ld + k]; row n_valid from w_last; zero padding) into its hi (and lo)
-// plane in the canonical layout
+// plane in the canonical layout; four independent loads in flight per thread
 template <bool SPLIT>
 __device__ __forceinline__ void tc_fill_b(float* hi, float* lo, int rows, int K, int n_valid, int k_valid,
                                           const float* __restrict__ w, int ld, const float* __restrict__ w_last) {
-    for (int idx = threadIdx.x; idx < rows * K; idx += blockDim.x) {
-        const int n = idx / K, k = idx - n * K;
-        float v = 0.0f;
-        if (k < k_valid) {
-            if (n < n_valid) v = w[n * ld + k];
-            else if (n == n_valid && w_last) v = w_last[k];
+    const int total = rows * K;
+    for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
+        float v[4]; int off[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = base + u * blockDim.x;
+            v[u] = 0.0f; off[u] = -1;
+            if (idx < total) {
+                const int n = idx / K, k = idx - n * K;
+                off[u] = (k >> 2) * (rows * 4) + n * 4 + (k & 3);
+                if (k < k_valid) {
+                    if (n < n_valid) v[u] = __ldg(w + n * ld + k);
+                    else if (n == n_valid && w_last) v[u] = __ldg(w_last + k);
+                }
+            }
         }
-        const int off = (k >> 2) * (rows * 4) + n * 4 + (k & 3);
-        const float h = __uint_as_float(to_tf32(v));
-        hi[off] = h;
-        if (SPLIT) lo[off] = v - h;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (off[u] >= 0) {
+                const float h = __uint_as_float(to_tf32(v[u]));
+                hi[off[u]] = h;
+                if (SPLIT) lo[off[u]] = v[u] - h;
+            }
+        }
     }
+}
+
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // K1 = layer-1 depth (obs_dim rounded up to a multiple of 8), SPLIT = float32-grade 3xTF32
@@ -118,26 +143,35 @@ __global__ void __launch_bounds__(kTcTile, 2)
 policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ error_flag) {
     using L = TcSmem<K1>;
     extern __shared__ __align__(128) float tsm[];
+    const int D = A.D, M = A.M;
     float* const W1h = tsm + L::o_w1; float* const W1l = W1h + L::W1;
     float* const W2h = tsm + L::o_w2; float* const W2l = W2h + L::W2;
     float* const WHh = tsm + L::o_wh; float* const WHl = WHh + L::WH;
-    float* const AOh = tsm + L::o_a;  float* const AOl = AOh + L::AO;
-    float* const B1 = tsm + L::o_bias; float* const B2 = B1 + 64; float* const BH = B2 + 64; float* const LS = BH + 16;
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(tsm + L::floats);
-    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    float* const ST0 = tsm + L::o_st;                                   // two raw observation tiles [128][D]
+    const int st_floats = L::st_floats(D);
+    float* const B1 = tsm + L::o_bias(D); float* const B2 = B1 + 64; float* const BH = B2 + 64; float* const LS = BH + 16;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(LS + 16);        // [0] MMA commits, [1], [2] staging buffers full
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int D = A.D, M = A.M;
+    const int64_t E = A.E;
+    const int64_t n_tiles = (E + kTcTile - 1) / kTcTile;
+    // row-major observations whose tiles are whole and 16-byte aligned arrive by TMA bulk copy, one tile ahead
+    const uint32_t tile_bytes = (uint32_t)(kTcTile * D * 4);
+    const bool tma_ok = A.obs_layout == 0 && ((reinterpret_cast<uintptr_t>(A.obs) & 15u) == 0);
+    auto tile_by_tma = [&](int64_t t) { return tma_ok && (t + 1) * kTcTile <= E; };
 
-    // ---- one-time setup: weights (hi / lo planes), biases, mbarrier, tensor memory ----
+    if (tid == 0) {
+        for (int i = 0; i < 3; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar + i)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int64_t t0 = blockIdx.x;                                  // the first tile's observations: in flight during the setup
+        if (t0 < n_tiles && tile_by_tma(t0)) tc_bulk_g2s(ST0, A.obs + t0 * kTcTile * D, tile_bytes, bar + 1);
+    }
+    // ---- one-time setup: weights (hi / lo planes), biases, tensor memory ----
     tc_fill_b<SPLIT>(W1h, W1l, 64, K1, 64, D, A.w1, D, nullptr);
     tc_fill_b<SPLIT>(W2h, W2l, 64, 64, 64, 64, A.w2, 64, nullptr);
     tc_fill_b<SPLIT>(WHh, WHl, kTcHeadN, 64, M, 64, A.w_mu, 64, A.w_v);
     if (tid < 64) { B1[tid] = A.b1[tid]; B2[tid] = A.b2[tid]; }
     if (tid < 16) { BH[tid] = tid < M ? A.b_mu[tid] : (tid == M ? A.b_v[0] : 0.0f); LS[tid] = tid < M ? A.log_std[tid] : 0.0f; }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTcCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -149,59 +183,70 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
     const uint32_t tmem = *tmem_slot;                                  // lane 0, first column of this CTA's allocation
     const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 lanes
     const uint32_t cD = 0, cAh = 64, cAl = 128, cH = 192;
-    uint32_t phase = 0;
+    uint32_t phase = 0, st_phase[2] = { 0, 0 };
     bool alive = true;
 
-    const int64_t E = A.E;
-    const int64_t n_tiles = (E + kTcTile - 1) / kTcTile;
     const uint32_t step = A.step_index + (A.step_counter ? __ldg(A.step_counter) : 0u);
     const uint64_t dW1h = tc_smem_desc(smem_u32(W1h), 64), dW1l = tc_smem_desc(smem_u32(W1l), 64);
     const uint64_t dW2h = tc_smem_desc(smem_u32(W2h), 64), dW2l = tc_smem_desc(smem_u32(W2l), 64);
     const uint64_t dWHh = tc_smem_desc(smem_u32(WHh), kTcHeadN), dWHl = tc_smem_desc(smem_u32(WHl), kTcHeadN);
-    const uint64_t dAOh = tc_smem_desc(smem_u32(AOh), kTcTile), dAOl = tc_smem_desc(smem_u32(AOl), kTcTile);
-    // a k-step of 8 advances an operand by two 16-byte chunks = 2 * rows * 16 bytes (descriptor units of 16 bytes)
-    constexpr uint32_t kStepB64 = 2 * 64, kStepBH = 2 * kTcHeadN, kStepA = 2 * kTcTile;
+    // a k-step of 8 advances a B operand by two 16-byte chunks = 2 * rows * 16 bytes (descriptor units of 16 bytes)
+    constexpr uint32_t kStepB64 = 2 * 64, kStepBH = 2 * kTcHeadN;
     constexpr uint32_t id64 = tc_idesc(64), idH = tc_idesc(kTcHeadN);
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles && alive; tile += gridDim.x) {
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles && alive; tile += gridDim.x, it++) {
+        const int buf = it & 1;
         const int64_t e = tile * kTcTile + tid;
         const bool ev = e < E;
-        // ---- the tile's observations -> sanitise -> hi / lo planes of the layer-1 A operand ----
-#pragma unroll
-        for (int j = 0; j < K1 / 4; j++) {
-            float x[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int f = 4 * j + q;
-                float v = 0.0f;
-                if (ev && f < D) v = __ldg(A.obs + (A.obs_layout ? (int64_t)f * E + e : e * D + f));
-                v = v * A.obs_scale;                               // nan_to_num + clamp of the torch reference
-                x[q] = (v != v) ? 0.0f : fminf(fmaxf(v, -A.obs_clip), A.obs_clip);
-            }
-            float4 h, l;
-            h.x = __uint_as_float(to_tf32(x[0])); h.y = __uint_as_float(to_tf32(x[1]));
-            h.z = __uint_as_float(to_tf32(x[2])); h.w = __uint_as_float(to_tf32(x[3]));
-            l.x = x[0] - h.x; l.y = x[1] - h.y; l.z = x[2] - h.z; l.w = x[3] - h.w;
-            reinterpret_cast<float4*>(AOh)[j * kTcTile + tid] = h;
-            if (SPLIT) reinterpret_cast<float4*>(AOl)[j * kTcTile + tid] = l;
+        // the next tile's observations: its staging buffer was last read two tiles ago (a __syncthreads since)
+        const int64_t nxt = tile + gridDim.x;
+        if (tid == 0 && nxt < n_tiles && tile_by_tma(nxt))
+            tc_bulk_g2s(ST0 + (buf ^ 1) * st_floats, A.obs + nxt * kTcTile * D, tile_bytes, bar + 1 + (buf ^ 1));
+        // ---- this env's observation row -> sanitise -> hi / lo planes of the layer-1 A operand, in tensor memory ----
+        const bool staged = tile_by_tma(tile);
+        if (staged) {
+            alive = tc_wait_bar(bar + 1 + buf, st_phase[buf]);
+            st_phase[buf] ^= 1;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const float* srow = ST0 + buf * st_floats + tid * D;
+#pragma unroll
+        for (int j = 0; j < K1 / 8; j++) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int f = 8 * j + q;
+                float v = 0.0f;
+                if (f < D) {
+                    if (staged) v = srow[f];
+                    else if (ev) v = __ldg(A.obs + (A.obs_layout ? (int64_t)f * E + e : e * D + f));
+                }
+                v = v * A.obs_scale;                               // nan_to_num + clamp of the torch reference
+                v = (v != v) ? 0.0f : fminf(fmaxf(v, -A.obs_clip), A.obs_clip);
+                hi[q] = to_tf32(v);
+                lo[q] = __float_as_uint(v - __uint_as_float(hi[q]));
+            }
+            tc_st8(t_lane + cAh + 8 * j, hi);
+            if (SPLIT) tc_st8(t_lane + cAl + 8 * j, lo);
+        }
+        tc_wait_st();
         tc_fence_before();
-        __syncthreads();
-        // ---- layer 1: D[0,64) = obs * W1^T ----
-        if (tid == 0) {
+        alive = __syncthreads_and(alive);                          // also: every thread is done with staging[buf]
+        // ---- layer 1: D[0,64) = obs * W1^T (A from tensor memory) ----
+        if (tid == 0 && alive) {
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < K1 / 8; kk++) {
-                tc_mma_ss(tmem + cD, dAOh + kk * kStepA, dW1h + kk * kStepB64, id64, kk > 0);
+                tc_mma_ts(tmem + cD, tmem + cAh + 8 * kk, dW1h + kk * kStepB64, id64, kk > 0);
                 if (SPLIT) {
-                    tc_mma_ss(tmem + cD, dAOl + kk * kStepA, dW1h + kk * kStepB64, id64, 1);
-                    tc_mma_ss(tmem + cD, dAOh + kk * kStepA, dW1l + kk * kStepB64, id64, 1);
+                    tc_mma_ts(tmem + cD, tmem + cAl + 8 * kk, dW1h + kk * kStepB64, id64, 1);
+                    tc_mma_ts(tmem + cD, tmem + cAh + 8 * kk, dW1l + kk * kStepB64, id64, 1);
                 }
             }
             tc_commit(bar);
         }
-        alive = __syncthreads_and(tc_wait_bar(bar, phase));        // uniform verdict: nobody waits at a barrier others left
+        if (alive) alive = tc_wait_bar(bar, phase);
+        alive = __syncthreads_and(alive);                          // uniform verdict: nobody waits at a barrier others left
         phase ^= 1;
         tc_fence_after();
         // ---- epilogues 1 and 2: tanh(D + b) -> hi / lo planes of the next layer's A operand, in tensor memory ----
@@ -249,7 +294,7 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
         uint32_t hv[16];
         tc_ld16(t_lane + cH, hv);
         tc_wait_ld();
-        tc_fence_before();                      // the next tile's layer-1 MMA overwrites D / the A planes after the barrier above
+        tc_fence_before();                      // the next tile's MMAs overwrite D / the A planes only after further barriers
         if (ev) {
             float lp = 0.0f;
 #pragma unroll
