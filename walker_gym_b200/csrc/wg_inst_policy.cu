@@ -49,7 +49,7 @@ static int launch_policy_tc_t(const PolicyArgs& A, cudaStream_t s) {
     cudaGetSymbolAddress((void**)&flag, g_policy_tc_error);
     const int64_t n_tiles = (A.E + kTcTile - 1) / kTcTile;
     const int64_t resident = (int64_t)n_sm * (smem * 2 <= 227 * 1024 ? 2 : 1);      // persistent: weights staged once per CTA
-    kern<<<(unsigned)(n_tiles < resident ? n_tiles : resident), kTcTile, smem, s>>>(A, flag);
+    kern<<<(unsigned)(n_tiles < resident ? n_tiles : resident), kTcThreads, smem, s>>>(A, flag);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "policy kernel (tcgen05) launch: %s", cudaGetErrorString(e));
     return WG_OK;
@@ -62,12 +62,13 @@ int policy_tc_error() {
 }
 
 static int launch_policy_tc(const PolicyArgs& A, int precision, cudaStream_t s) {
-    const int k1 = ((A.D + 7) / 8) * 8;
+    const int k1 = ((A.D + 1 + 7) / 8) * 8;          // obs_dim + the bias column, in k-steps of 8
 #define WG_POLTC(K) (precision == 0 ? launch_policy_tc_t<K, true>(A, s) : launch_policy_tc_t<K, false>(A, s))
     if (k1 <= 24) return WG_POLTC(24);
     if (k1 <= 32) return WG_POLTC(32);
     if (k1 <= 40) return WG_POLTC(40);
-    return WG_POLTC(64);
+    if (k1 <= 48) return WG_POLTC(48);
+    return WG_POLTC(72);
 #undef WG_POLTC
 }
 

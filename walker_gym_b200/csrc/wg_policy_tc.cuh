@@ -8,13 +8,16 @@
 //             observation row and writes it with tcgen05.st; B = W1 [64 x K1] in shared memory (canonical K-major
 //             layout, no swizzle); D -> TMEM columns [0, 64).  Row-major observation tiles (one contiguous 128 x D
 //             block) arrive by TMA bulk copy into a double-buffered staging area, one tile ahead.
-//   layer 2   A = tanh(layer 1) [128 x 64] in tensor memory (written there by the epilogue: an activation row never
-//             touches shared memory), B = W2 [64 x 64] in smem, D -> TMEM columns [0, 64)
-//   heads     A = tanh(layer 2) in TMEM, B = [w_mu; w_v; 0] [16 x 64] in smem, D -> TMEM columns [192, 208)
+//   layer 2   A = tanh(layer 1) [128 x 72] in tensor memory (written there by the epilogue: an activation row never
+//             touches shared memory), B = [W2, b2] [64 x 72] in smem, D -> TMEM columns [0, 64)
+//   heads     A = tanh(layer 2) in TMEM, B = [w_mu, b_mu; w_v, b_v; 0] [16 x 72] in smem, D -> TMEM columns [224, 240)
+// The biases ride in the GEMMs: every A operand carries a constant 1 in the column after its last feature and every B
+// operand its bias there, so the epilogues are tanh + split only.  256 threads per tile: two warps share each quarter
+// of the TMEM lanes and split an env row's columns between them.
 //
 // With SPLIT every product is the 3-term error-compensated a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (float32-grade, like the
-// mma.sync kernel): three MMAs per k-step into the same accumulator, hi / lo planes of A in TMEM columns [64, 128) /
-// [128, 192) and of B in shared memory.  One thread issues the MMAs of a layer and commits them to an mbarrier; all
+// mma.sync kernel): three MMAs per k-step into the same accumulator, hi / lo planes of A in TMEM columns [64, 144) /
+// [144, 224) and of B in shared memory.  One thread issues the MMAs of a layer and commits them to an mbarrier; all
 // 128 threads then run that layer's epilogue (tcgen05.ld -> bias, tanh, split -> tcgen05.st).  Two CTAs per SM
 // (2 x 256 TMEM columns, 2 x ~100 KB of shared memory) overlap one tile's epilogue with the other's MMAs.
 // Every mbarrier wait is bounded: a descriptor mistake ends the kernel with an error flag instead of hanging the GPU.
@@ -23,9 +26,11 @@
 
 namespace wg {
 
-constexpr int kTcTile = 128;          // envs per tile = MMA M = TMEM lanes = threads per CTA
-constexpr int kTcCols = 256;          // TMEM columns per CTA: D [0,64)  A_hi [64,128)  A_lo [128,192)  heads [192,208)
+constexpr int kTcTile = 128;          // envs per tile = MMA M = TMEM lanes
+constexpr int kTcThreads = 256;       // two warps per TMEM lane quarter: each thread owns one env row and half of its columns
+constexpr int kTcCols = 256;          // TMEM columns per CTA: D [0,64)  A_hi [64,144)  A_lo [144,224)  heads [224,240)
 constexpr int kTcHeadN = 16;          // heads MMA N (smallest N for M = 128); rows 0..M-1 means, row M value, rest 0
+constexpr int kTcKH = 72;             // depth of layer 2 / the heads: 64 hidden units + the bias column (a constant 1) + padding
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -88,42 +93,37 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16])
 // tiles (row-major observations: one TMA bulk copy per tile, issued one tile ahead)
 template <int K1>
 struct TcSmem {
-    static constexpr int W1 = 64 * K1, W2 = 64 * 64, WH = kTcHeadN * 64, ST = kTcTile * 64;   // staging: up to 64 floats per env
+    static constexpr int W1 = 64 * K1, W2 = 64 * kTcKH, WH = kTcHeadN * kTcKH;
     static constexpr int o_w1 = 0, o_w2 = o_w1 + 2 * W1, o_wh = o_w2 + 2 * W2, o_st = o_wh + 2 * WH;
     static constexpr int st_floats(int D) { return ((kTcTile * D + 3) / 4) * 4; }
-    static constexpr int o_bias(int D) { return o_st + 2 * st_floats(D); }                  // b1[64] b2[64] bh[16] ls[16]
-    static constexpr size_t bytes(int D) { return sizeof(float) * (o_bias(D) + 64 + 64 + 16 + 16) + 64; }   // + 3 mbarriers, TMEM slot
+    static constexpr int o_ls(int D) { return o_st + 2 * st_floats(D); }                    // log_std[16]
+    static constexpr size_t bytes(int D) { return sizeof(float) * (o_ls(D) + 16) + 64; }    // + 3 mbarriers, TMEM slot
 };
 
-// one weight matrix [rows x K] (torch layout w[n * ld + k]; row n_valid from w_last; zero padding) into its hi (and lo)
-// plane in the canonical layout; four independent loads in flight per thread
+// One weight matrix [rows x K] into its hi (and lo) plane in the canonical layout, 16-byte chunk by chunk.  Element
+// (n, k): w[n * ld + k] for k < k_valid (row n_valid from w_last, rows beyond: zero); column k_valid is the BIAS column
+// (bias[n], or bias_last[0] for row n_valid): the A operand carries a constant 1 there, so the tensor core adds the bias.
 template <bool SPLIT>
 __device__ __forceinline__ void tc_fill_b(float* hi, float* lo, int rows, int K, int n_valid, int k_valid,
-                                          const float* __restrict__ w, int ld, const float* __restrict__ w_last) {
-    const int total = rows * K;
-    for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
-        float v[4]; int off[4];
+                                          const float* __restrict__ w, int ld, const float* __restrict__ w_last,
+                                          const float* __restrict__ bias, const float* __restrict__ bias_last) {
+    const int n_chunks = rows * (K / 4);
+    for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+        const int n = c % rows, k4 = c / rows;
+        float v[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int idx = base + u * blockDim.x;
-            v[u] = 0.0f; off[u] = -1;
-            if (idx < total) {
-                const int n = idx / K, k = idx - n * K;
-                off[u] = (k >> 2) * (rows * 4) + n * 4 + (k & 3);
-                if (k < k_valid) {
-                    if (n < n_valid) v[u] = __ldg(w + n * ld + k);
-                    else if (n == n_valid && w_last) v[u] = __ldg(w_last + k);
-                }
-            }
+        for (int q = 0; q < 4; q++) {
+            const int k = 4 * k4 + q;
+            v[q] = 0.0f;
+            if (n < n_valid) { if (k < k_valid) v[q] = __ldg(w + n * ld + k); else if (k == k_valid) v[q] = __ldg(bias + n); }
+            else if (n == n_valid && w_last) { if (k < k_valid) v[q] = __ldg(w_last + k); else if (k == k_valid) v[q] = __ldg(bias_last); }
         }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (off[u] >= 0) {
-                const float h = __uint_as_float(to_tf32(v[u]));
-                hi[off[u]] = h;
-                if (SPLIT) lo[off[u]] = v[u] - h;
-            }
-        }
+        float4 h, l;
+        h.x = __uint_as_float(to_tf32(v[0])); h.y = __uint_as_float(to_tf32(v[1]));
+        h.z = __uint_as_float(to_tf32(v[2])); h.w = __uint_as_float(to_tf32(v[3]));
+        l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
+        reinterpret_cast<float4*>(hi)[k4 * rows + n] = h;          // chunk (n, k4) at (k4 * rows + n) * 16 bytes
+        if (SPLIT) reinterpret_cast<float4*>(lo)[k4 * rows + n] = l;
     }
 }
 
@@ -136,10 +136,18 @@ __device__ __forceinline__ void tc_bulk_g2s(void* dst_smem, const void* src_gmem
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// nan_to_num + clamp of the torch reference, then the hi / lo split of one A element
+template <bool SPLIT>
+__device__ __forceinline__ void tc_obs_elem(float v, float scale, float clip, uint32_t& hi, uint32_t& lo) {
+    v = v * scale;
+    v = (v != v) ? 0.0f : fminf(fmaxf(v, -clip), clip);
+    hi = to_tf32(v);
+    lo = SPLIT ? __float_as_uint(v - __uint_as_float(hi)) : 0u;
+}
 
-// K1 = layer-1 depth (obs_dim rounded up to a multiple of 8), SPLIT = float32-grade 3xTF32
+// K1 = layer-1 depth: obs_dim + 1 (the bias column) rounded up to a multiple of 8; SPLIT = float32-grade 3xTF32
 template <int K1, bool SPLIT>
-__global__ void __launch_bounds__(kTcTile, 2)
+__global__ void __launch_bounds__(kTcThreads, 2)
 policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ error_flag) {
     using L = TcSmem<K1>;
     extern __shared__ __align__(128) float tsm[];
@@ -149,10 +157,11 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
     float* const WHh = tsm + L::o_wh; float* const WHl = WHh + L::WH;
     float* const ST0 = tsm + L::o_st;                                   // two raw observation tiles [128][D]
     const int st_floats = L::st_floats(D);
-    float* const B1 = tsm + L::o_bias(D); float* const B2 = B1 + 64; float* const BH = B2 + 64; float* const LS = BH + 16;
+    float* const LS = tsm + L::o_ls(D);
     uint64_t* const bar = reinterpret_cast<uint64_t*>(LS + 16);        // [0] MMA commits, [1], [2] staging buffers full
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (kTcTile - 1), half = tid >> 7;              // env row of the tile; which half of the columns
     const int64_t E = A.E;
     const int64_t n_tiles = (E + kTcTile - 1) / kTcTile;
     // row-major observations whose tiles are whole and 16-byte aligned arrive by TMA bulk copy, one tile ahead
@@ -166,12 +175,11 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
         const int64_t t0 = blockIdx.x;                                  // the first tile's observations: in flight during the setup
         if (t0 < n_tiles && tile_by_tma(t0)) tc_bulk_g2s(ST0, A.obs + t0 * kTcTile * D, tile_bytes, bar + 1);
     }
-    // ---- one-time setup: weights (hi / lo planes), biases, tensor memory ----
-    tc_fill_b<SPLIT>(W1h, W1l, 64, K1, 64, D, A.w1, D, nullptr);
-    tc_fill_b<SPLIT>(W2h, W2l, 64, 64, 64, 64, A.w2, 64, nullptr);
-    tc_fill_b<SPLIT>(WHh, WHl, kTcHeadN, 64, M, 64, A.w_mu, 64, A.w_v);
-    if (tid < 64) { B1[tid] = A.b1[tid]; B2[tid] = A.b2[tid]; }
-    if (tid < 16) { BH[tid] = tid < M ? A.b_mu[tid] : (tid == M ? A.b_v[0] : 0.0f); LS[tid] = tid < M ? A.log_std[tid] : 0.0f; }
+    // ---- one-time setup: weights with their bias columns (hi / lo planes), tensor memory ----
+    tc_fill_b<SPLIT>(W1h, W1l, 64, K1, 64, D, A.w1, D, nullptr, A.b1, nullptr);
+    tc_fill_b<SPLIT>(W2h, W2l, 64, kTcKH, 64, 64, A.w2, 64, nullptr, A.b2, nullptr);
+    tc_fill_b<SPLIT>(WHh, WHl, kTcHeadN, kTcKH, M, 64, A.w_mu, 64, A.w_v, A.b_mu, A.b_v);
+    if (tid < 16) LS[tid] = tid < M ? A.log_std[tid] : 0.0f;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTcCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -181,9 +189,9 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;                                  // lane 0, first column of this CTA's allocation
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 lanes
-    const uint32_t cD = 0, cAh = 64, cAl = 128, cH = 192;
-    uint32_t phase = 0, st_phase[2] = { 0, 0 };
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's quarter of the lanes
+    constexpr uint32_t cD = 0, cAh = 64, cAl = 144, cH = 224;
+    uint32_t phase = 0, st_phase0 = 0, st_phase1 = 0;
     bool alive = true;
 
     const uint32_t step = A.step_index + (A.step_counter ? __ldg(A.step_counter) : 0u);
@@ -193,38 +201,53 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
     // a k-step of 8 advances a B operand by two 16-byte chunks = 2 * rows * 16 bytes (descriptor units of 16 bytes)
     constexpr uint32_t kStepB64 = 2 * 64, kStepBH = 2 * kTcHeadN;
     constexpr uint32_t id64 = tc_idesc(64), idH = tc_idesc(kTcHeadN);
+    constexpr int NC = K1 / 8, NC0 = (NC + 1) / 2;                     // obs chunks of 8 columns: half 0 takes [0, NC0)
 
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles && alive; tile += gridDim.x, it++) {
         const int buf = it & 1;
-        const int64_t e = tile * kTcTile + tid;
+        const int64_t e = tile * kTcTile + row;
         const bool ev = e < E;
-        // the next tile's observations: its staging buffer was last read two tiles ago (a __syncthreads since)
+        // the next tile's observations: its staging buffer was last read one tile ago (a __syncthreads since)
         const int64_t nxt = tile + gridDim.x;
         if (tid == 0 && nxt < n_tiles && tile_by_tma(nxt))
             tc_bulk_g2s(ST0 + (buf ^ 1) * st_floats, A.obs + nxt * kTcTile * D, tile_bytes, bar + 1 + (buf ^ 1));
-        // ---- this env's observation row -> sanitise -> hi / lo planes of the layer-1 A operand, in tensor memory ----
+        // ---- this env's observation row (this thread's half of it) -> sanitise -> hi / lo planes of the layer-1 A
+        // operand in tensor memory; column D carries the constant 1 that multiplies the bias column of W1 ----
         const bool staged = tile_by_tma(tile);
         if (staged) {
-            alive = tc_wait_bar(bar + 1 + buf, st_phase[buf]);
-            st_phase[buf] ^= 1;
+            alive = tc_wait_bar(bar + 1 + buf, buf ? st_phase1 : st_phase0);
+            if (buf) st_phase1 ^= 1; else st_phase0 ^= 1;
         }
-        const float* srow = ST0 + buf * st_floats + tid * D;
+        const float* srow = ST0 + buf * st_floats + row * D;
 #pragma unroll
-        for (int j = 0; j < K1 / 8; j++) {
+        for (int j = 0; j < NC; j++) {
+            if ((j < NC0) != (half == 0)) continue;                 // warp-uniform
             uint32_t hi[8], lo[8];
+            if (8 * j + 8 <= D) {                                   // a whole chunk of observation entries (warp-uniform)
+                float x[8];
+                if (staged) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int f = 8 * j + q;
-                float v = 0.0f;
-                if (f < D) {
-                    if (staged) v = srow[f];
-                    else if (ev) v = __ldg(A.obs + (A.obs_layout ? (int64_t)f * E + e : e * D + f));
+                    for (int q = 0; q < 8; q++) x[q] = srow[8 * j + q];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        x[q] = ev ? __ldg(A.obs + (A.obs_layout ? (int64_t)(8 * j + q) * E + e : e * D + 8 * j + q)) : 0.0f;
                 }
-                v = v * A.obs_scale;                               // nan_to_num + clamp of the torch reference
-                v = (v != v) ? 0.0f : fminf(fmaxf(v, -A.obs_clip), A.obs_clip);
-                hi[q] = to_tf32(v);
-                lo[q] = __float_as_uint(v - __uint_as_float(hi[q]));
+#pragma unroll
+                for (int q = 0; q < 8; q++) tc_obs_elem<SPLIT>(x[q], A.obs_scale, A.obs_clip, hi[q], lo[q]);
+            } else {                                                // the chunk with the end of the row, the 1 and the padding
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int f = 8 * j + q;
+                    float x = 0.0f;
+                    if (f < D) {
+                        if (staged) x = srow[f];
+                        else if (ev) x = __ldg(A.obs + (A.obs_layout ? (int64_t)f * E + e : e * D + f));
+                    }
+                    tc_obs_elem<SPLIT>(x, A.obs_scale, A.obs_clip, hi[q], lo[q]);
+                    if (f >= D) { hi[q] = f == D ? 0x3f800000u : 0u; lo[q] = 0u; }
+                }
             }
             tc_st8(t_lane + cAh + 8 * j, hi);
             if (SPLIT) tc_st8(t_lane + cAl + 8 * j, lo);
@@ -232,11 +255,11 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
         tc_wait_st();
         tc_fence_before();
         alive = __syncthreads_and(alive);                          // also: every thread is done with staging[buf]
-        // ---- layer 1: D[0,64) = obs * W1^T (A from tensor memory) ----
+        // ---- layer 1: D[0,64) = [obs, 1] * [W1, b1]^T (A from tensor memory) ----
         if (tid == 0 && alive) {
             tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < K1 / 8; kk++) {
+            for (int kk = 0; kk < NC; kk++) {
                 tc_mma_ts(tmem + cD, tmem + cAh + 8 * kk, dW1h + kk * kStepB64, id64, kk > 0);
                 if (SPLIT) {
                     tc_mma_ts(tmem + cD, tmem + cAl + 8 * kk, dW1h + kk * kStepB64, id64, 1);
@@ -249,23 +272,35 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
         alive = __syncthreads_and(alive);                          // uniform verdict: nobody waits at a barrier others left
         phase ^= 1;
         tc_fence_after();
-        // ---- epilogues 1 and 2: tanh(D + b) -> hi / lo planes of the next layer's A operand, in tensor memory ----
+        // ---- epilogues 1 and 2: tanh(D) -> hi / lo planes of the next layer's A operand, in tensor memory; this thread
+        // owns 32 of its env's 64 hidden units; half 1 also writes the chunk with the constant 1 of the bias column ----
 #pragma unroll 1
         for (int layer = 0; layer < 2 && alive; layer++) {
-            const float* bias = layer ? B2 : B1;
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-                uint32_t v[16], hi[16], lo[16];
-                tc_ld16(t_lane + cD + c0, v);
+            uint32_t v[32];
+            {
+                uint32_t a[16], b[16];
+                tc_ld16(t_lane + cD + 32 * half, a);
+                tc_ld16(t_lane + cD + 32 * half + 16, b);
                 tc_wait_ld();
 #pragma unroll
+                for (int i = 0; i < 16; i++) { v[i] = a[i]; v[16 + i] = b[i]; }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const float y = pol_tanh<SPLIT>(__uint_as_float(v[i]) + bias[c0 + i]);
+                    const float y = pol_tanh<SPLIT>(__uint_as_float(v[16 * c + i]));
                     hi[i] = to_tf32(y);
-                    lo[i] = __float_as_uint(y - __uint_as_float(hi[i]));
+                    lo[i] = SPLIT ? __float_as_uint(y - __uint_as_float(hi[i])) : 0u;
                 }
-                tc_st16(t_lane + cAh + c0, hi);
-                if (SPLIT) tc_st16(t_lane + cAl + c0, lo);
+                tc_st16(t_lane + cAh + 32 * half + 16 * c, hi);
+                if (SPLIT) tc_st16(t_lane + cAl + 32 * half + 16 * c, lo);
+            }
+            if (half) {
+                const uint32_t one[8] = { 0x3f800000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u }, zero[8] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u };
+                tc_st8(t_lane + cAh + 64, one);
+                if (SPLIT) tc_st8(t_lane + cAl + 64, zero);
             }
             tc_wait_st();
             tc_fence_before();
@@ -276,7 +311,7 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
                 const uint64_t bh = layer ? dWHh : dW2h, bl = layer ? dWHl : dW2l;
                 const uint32_t ks = layer ? kStepBH : kStepB64, id = layer ? idH : id64;
 #pragma unroll
-                for (int kk = 0; kk < 8; kk++) {
+                for (int kk = 0; kk < kTcKH / 8; kk++) {
                     tc_mma_ts(tmem + dcol, tmem + cAh + 8 * kk, bh + kk * ks, id, kk > 0);
                     if (SPLIT) {
                         tc_mma_ts(tmem + dcol, tmem + cAl + 8 * kk, bh + kk * ks, id, 1);
@@ -290,39 +325,41 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
             tc_fence_after();
         }
         if (!alive) break;
-        // ---- heads: this thread's env: outputs n < M means, n == M value; gaussian sample, log-prob ----
-        uint32_t hv[16];
-        tc_ld16(t_lane + cH, hv);
-        tc_wait_ld();
-        tc_fence_before();                      // the next tile's MMAs overwrite D / the A planes only after further barriers
-        if (ev) {
-            float lp = 0.0f;
+        // ---- heads (one thread per env): outputs n < M means, n == M value (biases included); gaussian sample, log-prob ----
+        if (half == 0) {
+            uint32_t hv[16];
+            tc_ld16(t_lane + cH, hv);
+            tc_wait_ld();
+            if (ev) {
+                float lp = 0.0f;
 #pragma unroll
-            for (int pr = 0; pr < 4; pr++) {
-                if (2 * pr < M) {
-                    float2 z = make_float2(0.0f, 0.0f);
-                    if (A.sample) z = pol_normal2(A.seed_lo, A.seed_hi, A.env_offset + (uint32_t)e, step, (uint32_t)pr);
+                for (int pr = 0; pr < 4; pr++) {
+                    if (2 * pr < M) {
+                        float2 z = make_float2(0.0f, 0.0f);
+                        if (A.sample) z = pol_normal2(A.seed_lo, A.seed_hi, A.env_offset + (uint32_t)e, step, (uint32_t)pr);
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        const int n = 2 * pr + j;
-                        if (n < M) {
-                            const float mean = __uint_as_float(hv[n]) + BH[n], ls = LS[n], eps = j ? z.y : z.x;
-                            const float act = A.sample ? __fmaf_rn(__expf(ls), eps, mean) : mean;
-                            lp += -0.5f * eps * eps - ls - 0.9189385332046727f;
-                            if (A.mean) A.mean[(int64_t)n * E + e] = mean;
-                            if (A.action) A.action[A.act_layout ? (int64_t)n * E + e : e * M + n] = act;
+                        for (int j = 0; j < 2; j++) {
+                            const int n = 2 * pr + j;
+                            if (n < M) {
+                                const float mean = __uint_as_float(hv[n]), ls = LS[n], eps = j ? z.y : z.x;
+                                const float act = A.sample ? __fmaf_rn(__expf(ls), eps, mean) : mean;
+                                lp += -0.5f * eps * eps - ls - 0.9189385332046727f;
+                                if (A.mean) A.mean[(int64_t)n * E + e] = mean;
+                                if (A.action) A.action[A.act_layout ? (int64_t)n * E + e : e * M + n] = act;
+                            }
                         }
                     }
                 }
-            }
-            if (A.value) {
-                float val = 0.0f;
+                if (A.value) {
+                    float val = 0.0f;
 #pragma unroll
-                for (int n = 0; n < 8; n++) if (n == M) val = __uint_as_float(hv[n]) + BH[n];
-                A.value[e] = val;
+                    for (int n = 0; n < 8; n++) if (n == M) val = __uint_as_float(hv[n]);
+                    A.value[e] = val;
+                }
+                if (A.logp) A.logp[e] = lp;
             }
-            if (A.logp) A.logp[e] = lp;
         }
+        tc_fence_before();                      // the next tile's MMAs overwrite the heads' columns only after further barriers
     }
     if (!alive && error_flag && tid == 0) atomicExch(error_flag, 1);
     // ---- teardown: the allocating warp frees the tensor memory once every warp is done with it ----
