@@ -50,14 +50,28 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// Activation -> TF32 operand(s) WITHOUT the conversion unit: cvt.rna.tf32 issues on the XU pipe (16 lanes / clock / SM),
+// which it shares with the tanh's MUFU operations and which ncu showed to be the busiest pipe of both policy kernels
+// (45 %).  SPLIT: hi = the float32 rounded to 11 significant bits by integer arithmetic (add half an ulp of TF32 to the
+// magnitude, clear the 13 low bits: round-to-nearest, ties away from zero == cvt.rna for every finite value whose
+// rounding does not overflow -- activations are clipped observations and tanh outputs), lo = x - hi exactly (left as
+// float32: the MMA reads only its TF32 bits, residual ~2^-22 |x|); a NaN activation stays NaN through lo.  Plain TF32:
+// Veltkamp's split (three float32 operations on the FMA pipe; NaN-preserving, no integer wrap-around of a NaN).
+template <bool SPLIT>
+__device__ __forceinline__ void act_split(float x, uint32_t& hi, uint32_t& lo) {
+    if (SPLIT) {
+        hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+        lo = __float_as_uint(__fsub_rn(x, __uint_as_float(hi)));
+    } else {
+        const float c = __fmul_rn(x, 8193.0f);                 // 2^13 + 1: keeps 24 - 13 = 11 significant bits
+        hi = __float_as_uint(__fadd_rn(c, __fsub_rn(x, c)));
+        lo = 0u;
+    }
+}
 template <bool SPLIT>
 __device__ __forceinline__ void split4(const float (&x)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        hi[i] = to_tf32(x[i]);
-        // the low part is left as float32: the MMA reads only its TF32 bits (truncation), residual ~2^-22 |x|
-        lo[i] = SPLIT ? __float_as_uint(x[i] - __uint_as_float(hi[i])) : 0u;
-    }
+    for (int i = 0; i < 4; i++) act_split<SPLIT>(x[i], hi[i], lo[i]);
 }
 // c += A * B with A given as float32 values (split on the fly) and B as pre-split hi / lo planes
 template <bool SPLIT>

@@ -2,7 +2,7 @@
 //
 // Same function as policy_act_kernel (wg_policy.cuh): obs -> gaussian MLP (D -> 64 -> 64 -> {M means, 1 value}, tanh)
 // -> sampled action, log-prob, value, one launch per env step, reading the observation as the step kernel wrote it.
-// The three GEMMs run as tcgen05.mma (kind::tf32, M = 128 envs per tile, accumulators in tensor memory):
+// The two wide GEMMs run as tcgen05.mma (kind::tf32, M = 128 envs per tile, accumulators in tensor memory):
 //
 //   layer 1   A = the tile's observations [128 x K1] in TENSOR MEMORY: thread r owns TMEM lane r = env r, sanitises its
 //             observation row and writes it with tcgen05.st; B = W1 [64 x K1] in shared memory (canonical K-major
@@ -10,27 +10,45 @@
 //             block) arrive by TMA bulk copy into a double-buffered staging area, one tile ahead.
 //   layer 2   A = tanh(layer 1) [128 x 72] in tensor memory (written there by the epilogue: an activation row never
 //             touches shared memory), B = [W2, b2] [64 x 72] in smem, D -> TMEM columns [0, 64)
-//   heads     A = tanh(layer 2) in TMEM, B = [w_mu, b_mu; w_v, b_v; 0] [16 x 72] in smem, D -> TMEM columns [224, 240)
+//   heads     M + 1 <= 9 outputs of depth 64: 192 MACs per env.  As MMAs they cost a third accumulate / commit / wait
+//             round trip per tile plus the split and tcgen05.st of the second activation; instead the layer-2 epilogue
+//             multiplies its 32 activations (in registers, float32) with the head weights (broadcast reads from shared
+//             memory) and the two threads of an env add their halves through shared memory.
 // The biases ride in the GEMMs: every A operand carries a constant 1 in the column after its last feature and every B
 // operand its bias there, so the epilogues are tanh + split only.  256 threads per tile: two warps share each quarter
 // of the TMEM lanes and split an env row's columns between them.
 //
 // With SPLIT every product is the 3-term error-compensated a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (float32-grade, like the
-// mma.sync kernel): three MMAs per k-step into the same accumulator, hi / lo planes of A in TMEM columns [64, 144) /
-// [144, 224) and of B in shared memory.  One thread issues the MMAs of a layer and commits them to an mbarrier; all
-// 128 threads then run that layer's epilogue (tcgen05.ld -> bias, tanh, split -> tcgen05.st).  Two CTAs per SM
-// (2 x 256 TMEM columns, 2 x ~100 KB of shared memory) overlap one tile's epilogue with the other's MMAs.
+// mma.sync kernel): three MMAs per k-step into the same accumulator, hi / lo planes of A in TMEM columns [64, 136) /
+// [144, 216) and of B in shared memory.
+//
+// What the measurements on B200 said (gpurun_scratch/mma_rate*.cu, tc_trace.cu):
+//  * one tcgen05.mma M128 N64 K8 costs its 32-cycle floor (N16: 9) when issued from WARP-UNIFORM code (warp 0, one
+//    elected lane); issued under `if (threadIdx.x == 0)` the compiler wraps every instruction in a lane-election loop and
+//    the issue alone costs 60-70 cycles per MMA -- 4000 of the first version's 10800 cycles per tile;
+//  * the epilogues are bound by the XU pipe (ex2 + rcp per float32-grade tanh, 16 lanes / clock / SM), so the hi / lo
+//    split uses integer rounding instead of cvt.rna.tf32 (also XU);
+//  * Philox + Box-Muller (a ~150-instruction dependent chain per env) is evaluated by the threads that would otherwise
+//    only wait for the layer-2 MMAs, and handed to the sampling threads through shared memory.
+// Two CTAs per SM (2 x 256 TMEM columns, 2 x ~107 KB of shared memory) overlap one tile's epilogue with the other's MMAs.
 // Every mbarrier wait is bounded: a descriptor mistake ends the kernel with an error flag instead of hanging the GPU.
 #pragma once
 #include "wg_policy.cuh"
 
 namespace wg {
 
+// development aid (gpurun_scratch/tc_trace.cu): thread 0 of CTA 0 stamps the clock at the phase boundaries of its tiles
+#ifdef WG_TC_TRACE
+__device__ long long g_tc_trace[16 * 64];
+#define WG_TC_STAMP(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && it < 64) g_tc_trace[it * 16 + (slot)] = clock64(); } while (0)
+#else
+#define WG_TC_STAMP(slot) do { } while (0)
+#endif
+
 constexpr int kTcTile = 128;          // envs per tile = MMA M = TMEM lanes
 constexpr int kTcThreads = 256;       // two warps per TMEM lane quarter: each thread owns one env row and half of its columns
-constexpr int kTcCols = 256;          // TMEM columns per CTA: D [0,64)  A_hi [64,144)  A_lo [144,224)  heads [224,240)
-constexpr int kTcHeadN = 16;          // heads MMA N (smallest N for M = 128); rows 0..M-1 means, row M value, rest 0
-constexpr int kTcKH = 72;             // depth of layer 2 / the heads: 64 hidden units + the bias column (a constant 1) + padding
+constexpr int kTcCols = 256;          // TMEM columns per CTA: D [0,64)  A_hi [64,136)  A_lo [144,216)
+constexpr int kTcKH = 72;             // depth of layer 2: 64 hidden units + the bias column (a constant 1) + padding
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -89,44 +107,11 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16])
                     "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 
-// shared memory of one CTA (floats): B planes of the three layers (hi, lo) and two staging buffers for raw observation
-// tiles (row-major observations: one TMA bulk copy per tile, issued one tile ahead)
-template <int K1>
-struct TcSmem {
-    static constexpr int W1 = 64 * K1, W2 = 64 * kTcKH, WH = kTcHeadN * kTcKH;
-    static constexpr int o_w1 = 0, o_w2 = o_w1 + 2 * W1, o_wh = o_w2 + 2 * W2, o_st = o_wh + 2 * WH;
-    static constexpr int st_floats(int D) { return ((kTcTile * D + 3) / 4) * 4; }
-    static constexpr int o_ls(int D) { return o_st + 2 * st_floats(D); }                    // log_std[16]
-    static constexpr size_t bytes(int D) { return sizeof(float) * (o_ls(D) + 16) + 64; }    // + 3 mbarriers, TMEM slot
-};
-
-// One weight matrix [rows x K] into its hi (and lo) plane in the canonical layout, 16-byte chunk by chunk.  Element
-// (n, k): w[n * ld + k] for k < k_valid (row n_valid from w_last, rows beyond: zero); column k_valid is the BIAS column
-// (bias[n], or bias_last[0] for row n_valid): the A operand carries a constant 1 there, so the tensor core adds the bias.
-template <bool SPLIT>
-__device__ __forceinline__ void tc_fill_b(float* hi, float* lo, int rows, int K, int n_valid, int k_valid,
-                                          const float* __restrict__ w, int ld, const float* __restrict__ w_last,
-                                          const float* __restrict__ bias, const float* __restrict__ bias_last) {
-    const int n_chunks = rows * (K / 4);
-    for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
-        const int n = c % rows, k4 = c / rows;
-        float v[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int k = 4 * k4 + q;
-            v[q] = 0.0f;
-            if (n < n_valid) { if (k < k_valid) v[q] = __ldg(w + n * ld + k); else if (k == k_valid) v[q] = __ldg(bias + n); }
-            else if (n == n_valid && w_last) { if (k < k_valid) v[q] = __ldg(w_last + k); else if (k == k_valid) v[q] = __ldg(bias_last); }
-        }
-        float4 h, l;
-        h.x = __uint_as_float(to_tf32(v[0])); h.y = __uint_as_float(to_tf32(v[1]));
-        h.z = __uint_as_float(to_tf32(v[2])); h.w = __uint_as_float(to_tf32(v[3]));
-        l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
-        reinterpret_cast<float4*>(hi)[k4 * rows + n] = h;          // chunk (n, k4) at (k4 * rows + n) * 16 bytes
-        if (SPLIT) reinterpret_cast<float4*>(lo)[k4 * rows + n] = l;
-    }
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
-
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
@@ -136,13 +121,61 @@ __device__ __forceinline__ void tc_bulk_g2s(void* dst_smem, const void* src_gmem
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+constexpr int kTcMaxHeads = 9;        // M <= 8 action means + the value
+
+// shared memory of one CTA (floats): B planes of the two layers (hi, lo), the head weights in float32, two staging buffers
+// for raw observation tiles (row-major observations: one TMA bulk copy per tile, issued one tile ahead), the gaussian
+// noise of the tile (float2 per env and action pair) and the column-half partial sums of the heads
+template <int K1>
+struct TcSmem {
+    static constexpr int W1 = 64 * K1, W2 = 64 * kTcKH, WH = kTcMaxHeads * 64;
+    static constexpr int o_w1 = 0, o_w2 = o_w1 + 2 * W1, o_wh = o_w2 + 2 * W2, o_zs = o_wh + WH + 4 /* pad to 16 B */;
+    static constexpr int o_hx = o_zs + 4 * 2 * kTcTile, o_ls = o_hx + kTcMaxHeads * kTcTile, o_st = o_ls + 32;
+    static constexpr int st_floats(int D) { return ((kTcTile * D + 3) / 4) * 4; }
+    static constexpr int o_bar(int D) { return o_st + 2 * st_floats(D); }
+    static constexpr size_t bytes(int D) { return sizeof(float) * o_bar(D) + 64; }          // + 3 mbarriers, TMEM slot
+};
+
+// One weight matrix [64 x K] into its hi (and lo) plane in the canonical layout, 16-byte chunk by chunk.  Element
+// (n, k): w[n * ld + k] for k < k_valid; column k_valid is the BIAS column (the A operand carries a constant 1 there, so
+// the tensor core adds the bias); zero beyond.  All of a thread's loads are issued before the first conversion (the
+// 296 CTAs read the same few KB from L2 at the same time: one round trip instead of one per chunk).
+template <bool SPLIT, int K>
+__device__ __forceinline__ void tc_fill_b(float* hi, float* lo, int k_valid, const float* __restrict__ w, int ld,
+                                          const float* __restrict__ bias) {
+    constexpr int n_chunks = 64 * (K / 4), NPT = (n_chunks + kTcThreads - 1) / kTcThreads;
+    float v[NPT][4];
+#pragma unroll
+    for (int i = 0; i < NPT; i++) {
+        const int c = threadIdx.x + i * kTcThreads, n = c & 63, k4 = c >> 6;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = 4 * k4 + q;
+            v[i][q] = 0.0f;
+            if (c < n_chunks) { if (k < k_valid) v[i][q] = __ldg(w + n * ld + k); else if (k == k_valid) v[i][q] = __ldg(bias + n); }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NPT; i++) {
+        const int c = threadIdx.x + i * kTcThreads;
+        if (c < n_chunks) {
+            float4 h, l;
+            h.x = __uint_as_float(to_tf32(v[i][0])); h.y = __uint_as_float(to_tf32(v[i][1]));
+            h.z = __uint_as_float(to_tf32(v[i][2])); h.w = __uint_as_float(to_tf32(v[i][3]));
+            l.x = v[i][0] - h.x; l.y = v[i][1] - h.y; l.z = v[i][2] - h.z; l.w = v[i][3] - h.w;
+            reinterpret_cast<float4*>(hi)[c] = h;                  // chunk (n, k4) at (k4 * 64 + n) * 16 bytes
+            if (SPLIT) reinterpret_cast<float4*>(lo)[c] = l;
+        }
+    }
+}
+
 // nan_to_num + clamp of the torch reference, then the hi / lo split of one A element
 template <bool SPLIT>
 __device__ __forceinline__ void tc_obs_elem(float v, float scale, float clip, uint32_t& hi, uint32_t& lo) {
     v = v * scale;
     v = (v != v) ? 0.0f : fminf(fmaxf(v, -clip), clip);
-    hi = to_tf32(v);
-    lo = SPLIT ? __float_as_uint(v - __uint_as_float(hi)) : 0u;
+    act_split<SPLIT>(v, hi, lo);
 }
 
 // K1 = layer-1 depth: obs_dim + 1 (the bias column) rounded up to a multiple of 8; SPLIT = float32-grade 3xTF32
@@ -154,14 +187,18 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
     const int D = A.D, M = A.M;
     float* const W1h = tsm + L::o_w1; float* const W1l = W1h + L::W1;
     float* const W2h = tsm + L::o_w2; float* const W2l = W2h + L::W2;
-    float* const WHh = tsm + L::o_wh; float* const WHl = WHh + L::WH;
+    float* const WH = tsm + L::o_wh;                                    // [M + 1][64] float32: rows < M means, row M value
+    float2* const ZS = reinterpret_cast<float2*>(tsm + L::o_zs);        // [4 pairs][128 envs] gaussian noise of the tile
+    float* const HX = tsm + L::o_hx;                                    // [9][128] head partial sums of column half 1
+    float* const LS = tsm + L::o_ls;                                    // log_std[16], head biases[16]
+    float* const HB = LS + 16;
     float* const ST0 = tsm + L::o_st;                                   // two raw observation tiles [128][D]
     const int st_floats = L::st_floats(D);
-    float* const LS = tsm + L::o_ls(D);
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(LS + 16);        // [0] MMA commits, [1], [2] staging buffers full
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(tsm + L::o_bar(D));   // [0] MMA commits, [1], [2] staging buffers full
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = tid & (kTcTile - 1), half = tid >> 7;              // env row of the tile; which half of the columns
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform for the compiler too (MMA issue below)
+    const int row = tid & (kTcTile - 1), half = warp >> 2;             // env row of the tile; which half of the columns
     const int64_t E = A.E;
     const int64_t n_tiles = (E + kTcTile - 1) / kTcTile;
     // row-major observations whose tiles are whole and 16-byte aligned arrive by TMA bulk copy, one tile ahead
@@ -175,11 +212,11 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
         const int64_t t0 = blockIdx.x;                                  // the first tile's observations: in flight during the setup
         if (t0 < n_tiles && tile_by_tma(t0)) tc_bulk_g2s(ST0, A.obs + t0 * kTcTile * D, tile_bytes, bar + 1);
     }
-    // ---- one-time setup: weights with their bias columns (hi / lo planes), tensor memory ----
-    tc_fill_b<SPLIT>(W1h, W1l, 64, K1, 64, D, A.w1, D, nullptr, A.b1, nullptr);
-    tc_fill_b<SPLIT>(W2h, W2l, 64, kTcKH, 64, 64, A.w2, 64, nullptr, A.b2, nullptr);
-    tc_fill_b<SPLIT>(WHh, WHl, kTcHeadN, kTcKH, M, 64, A.w_mu, 64, A.w_v, A.b_mu, A.b_v);
-    if (tid < 16) LS[tid] = tid < M ? A.log_std[tid] : 0.0f;
+    // ---- one-time setup: weights with their bias columns (hi / lo planes), head weights, tensor memory ----
+    tc_fill_b<SPLIT, K1>(W1h, W1l, D, A.w1, D, A.b1);
+    tc_fill_b<SPLIT, kTcKH>(W2h, W2l, 64, A.w2, 64, A.b2);
+    for (int i = tid; i < (M + 1) * 64; i += kTcThreads) WH[i] = i < M * 64 ? __ldg(A.w_mu + i) : __ldg(A.w_v + (i - M * 64));
+    if (tid < 16) { LS[tid] = tid < M ? A.log_std[tid] : 0.0f; HB[tid] = tid < M ? A.b_mu[tid] : (tid == M ? A.b_v[0] : 0.0f); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTcCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -190,28 +227,27 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;                                  // lane 0, first column of this CTA's allocation
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's quarter of the lanes
-    constexpr uint32_t cD = 0, cAh = 64, cAl = 144, cH = 224;
+    constexpr uint32_t cD = 0, cAh = 64, cAl = 144;
     uint32_t phase = 0, st_phase0 = 0, st_phase1 = 0;
     bool alive = true;
 
     const uint32_t step = A.step_index + (A.step_counter ? __ldg(A.step_counter) : 0u);
     const uint64_t dW1h = tc_smem_desc(smem_u32(W1h), 64), dW1l = tc_smem_desc(smem_u32(W1l), 64);
     const uint64_t dW2h = tc_smem_desc(smem_u32(W2h), 64), dW2l = tc_smem_desc(smem_u32(W2l), 64);
-    const uint64_t dWHh = tc_smem_desc(smem_u32(WHh), kTcHeadN), dWHl = tc_smem_desc(smem_u32(WHl), kTcHeadN);
-    // a k-step of 8 advances a B operand by two 16-byte chunks = 2 * rows * 16 bytes (descriptor units of 16 bytes)
-    constexpr uint32_t kStepB64 = 2 * 64, kStepBH = 2 * kTcHeadN;
-    constexpr uint32_t id64 = tc_idesc(64), idH = tc_idesc(kTcHeadN);
+    // a k-step of 8 advances a B operand by two 16-byte chunks = 2 * 64 * 16 bytes (descriptor units of 16 bytes)
+    constexpr uint32_t kStepB = 2 * 64;
+    constexpr uint32_t id64 = tc_idesc(64);
     constexpr int NC = K1 / 8, NC0 = (NC + 1) / 2;                     // obs chunks of 8 columns: half 0 takes [0, NC0)
+    const int n_pairs = A.sample ? (M + 1) / 2 : 0;
+    const bool even_d = (D & 1) == 0;                                  // staged rows are then 8-byte aligned: 64-bit reads
 
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles && alive; tile += gridDim.x, it++) {
         const int buf = it & 1;
+        WG_TC_STAMP(0);
         const int64_t e = tile * kTcTile + row;
         const bool ev = e < E;
-        // the next tile's observations: its staging buffer was last read one tile ago (a __syncthreads since)
         const int64_t nxt = tile + gridDim.x;
-        if (tid == 0 && nxt < n_tiles && tile_by_tma(nxt))
-            tc_bulk_g2s(ST0 + (buf ^ 1) * st_floats, A.obs + nxt * kTcTile * D, tile_bytes, bar + 1 + (buf ^ 1));
         // ---- this env's observation row (this thread's half of it) -> sanitise -> hi / lo planes of the layer-1 A
         // operand in tensor memory; column D carries the constant 1 that multiplies the bias column of W1 ----
         const bool staged = tile_by_tma(tile);
@@ -219,6 +255,7 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
             alive = tc_wait_bar(bar + 1 + buf, buf ? st_phase1 : st_phase0);
             if (buf) st_phase1 ^= 1; else st_phase0 ^= 1;
         }
+        WG_TC_STAMP(1);
         const float* srow = ST0 + buf * st_floats + row * D;
 #pragma unroll
         for (int j = 0; j < NC; j++) {
@@ -227,8 +264,16 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
             if (8 * j + 8 <= D) {                                   // a whole chunk of observation entries (warp-uniform)
                 float x[8];
                 if (staged) {
+                    if (even_d) {
 #pragma unroll
-                    for (int q = 0; q < 8; q++) x[q] = srow[8 * j + q];
+                        for (int q = 0; q < 4; q++) {
+                            const float2 t = reinterpret_cast<const float2*>(srow + 8 * j)[q];
+                            x[2 * q] = t.x; x[2 * q + 1] = t.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) x[q] = srow[8 * j + q];
+                    }
                 } else {
 #pragma unroll
                     for (int q = 0; q < 8; q++)
@@ -254,45 +299,50 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
         }
         tc_wait_st();
         tc_fence_before();
+        WG_TC_STAMP(2);
         alive = __syncthreads_and(alive);                          // also: every thread is done with staging[buf]
-        // ---- layer 1: D[0,64) = [obs, 1] * [W1, b1]^T (A from tensor memory) ----
-        if (tid == 0 && alive) {
-            tc_fence_after();
+        WG_TC_STAMP(3);
+        // ---- layer 1: D[0,64) = [obs, 1] * [W1, b1]^T (A from tensor memory); issued by one elected lane of warp 0 in
+        // warp-uniform control flow (straight-line UTCHMMA, no lane-election loop around each instruction) ----
+        if (warp == 0) {
+            if (alive && tc_elect_one()) {
+                tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < NC; kk++) {
-                tc_mma_ts(tmem + cD, tmem + cAh + 8 * kk, dW1h + kk * kStepB64, id64, kk > 0);
-                if (SPLIT) {
-                    tc_mma_ts(tmem + cD, tmem + cAl + 8 * kk, dW1h + kk * kStepB64, id64, 1);
-                    tc_mma_ts(tmem + cD, tmem + cAh + 8 * kk, dW1l + kk * kStepB64, id64, 1);
+                for (int kk = 0; kk < NC; kk++) {
+                    tc_mma_ts(tmem + cD, tmem + cAh + 8 * kk, dW1h + kk * kStepB, id64, kk > 0);
+                    if (SPLIT) {
+                        tc_mma_ts(tmem + cD, tmem + cAl + 8 * kk, dW1h + kk * kStepB, id64, 1);
+                        tc_mma_ts(tmem + cD, tmem + cAh + 8 * kk, dW1l + kk * kStepB, id64, 1);
+                    }
                 }
+                tc_commit(bar);
+                // the next tile's observations: its staging buffer was last read one tile ago (several barriers since)
+                if (nxt < n_tiles && tile_by_tma(nxt))
+                    tc_bulk_g2s(ST0 + (buf ^ 1) * st_floats, A.obs + nxt * kTcTile * D, tile_bytes, bar + 1 + (buf ^ 1));
             }
-            tc_commit(bar);
+            __syncwarp();
         }
+        WG_TC_STAMP(4);
         if (alive) alive = tc_wait_bar(bar, phase);
+        WG_TC_STAMP(5);
         alive = __syncthreads_and(alive);                          // uniform verdict: nobody waits at a barrier others left
         phase ^= 1;
         tc_fence_after();
-        // ---- epilogues 1 and 2: tanh(D) -> hi / lo planes of the next layer's A operand, in tensor memory; this thread
-        // owns 32 of its env's 64 hidden units; half 1 also writes the chunk with the constant 1 of the bias column ----
-#pragma unroll 1
-        for (int layer = 0; layer < 2 && alive; layer++) {
-            uint32_t v[32];
-            {
-                uint32_t a[16], b[16];
-                tc_ld16(t_lane + cD + 32 * half, a);
-                tc_ld16(t_lane + cD + 32 * half + 16, b);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 16; i++) { v[i] = a[i]; v[16 + i] = b[i]; }
-            }
+        if (!alive) break;
+        // ---- epilogue 1: tanh(D) -> hi / lo planes of layer 2's A operand, in tensor memory; this thread owns 32 of its
+        // env's 64 hidden units; half 1 also writes the chunk with the constant 1 of the bias column ----
+        {
+            uint32_t a[16], b[16];
+            tc_ld16(t_lane + cD + 32 * half, a);
+            tc_ld16(t_lane + cD + 32 * half + 16, b);
+            tc_wait_ld();
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const float y = pol_tanh<SPLIT>(__uint_as_float(v[16 * c + i]));
-                    hi[i] = to_tf32(y);
-                    lo[i] = SPLIT ? __float_as_uint(y - __uint_as_float(hi[i])) : 0u;
+                    const float y = pol_tanh<SPLIT>(__uint_as_float(c ? b[i] : a[i]));
+                    act_split<SPLIT>(y, hi[i], lo[i]);
                 }
                 tc_st16(t_lane + cAh + 32 * half + 16 * c, hi);
                 if (SPLIT) tc_st16(t_lane + cAl + 32 * half + 16 * c, lo);
@@ -302,64 +352,109 @@ policy_act_tc_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
                 tc_st8(t_lane + cAh + 64, one);
                 if (SPLIT) tc_st8(t_lane + cAl + 64, zero);
             }
-            tc_wait_st();
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
+        }
+        WG_TC_STAMP(6);
+        tc_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        WG_TC_STAMP(7);
+        // ---- layer 2: D[0,64) = [tanh(h1), 1] * [W2, b2]^T ----
+        if (warp == 0) {
+            if (tc_elect_one()) {
                 tc_fence_after();
-                const uint32_t dcol = layer ? cH : cD;
-                const uint64_t bh = layer ? dWHh : dW2h, bl = layer ? dWHl : dW2l;
-                const uint32_t ks = layer ? kStepBH : kStepB64, id = layer ? idH : id64;
 #pragma unroll
                 for (int kk = 0; kk < kTcKH / 8; kk++) {
-                    tc_mma_ts(tmem + dcol, tmem + cAh + 8 * kk, bh + kk * ks, id, kk > 0);
+                    tc_mma_ts(tmem + cD, tmem + cAh + 8 * kk, dW2h + kk * kStepB, id64, kk > 0);
                     if (SPLIT) {
-                        tc_mma_ts(tmem + dcol, tmem + cAl + 8 * kk, bh + kk * ks, id, 1);
-                        tc_mma_ts(tmem + dcol, tmem + cAh + 8 * kk, bl + kk * ks, id, 1);
+                        tc_mma_ts(tmem + cD, tmem + cAl + 8 * kk, dW2h + kk * kStepB, id64, 1);
+                        tc_mma_ts(tmem + cD, tmem + cAh + 8 * kk, dW2l + kk * kStepB, id64, 1);
                     }
                 }
                 tc_commit(bar);
             }
-            alive = __syncthreads_and(tc_wait_bar(bar, phase));
-            phase ^= 1;
-            tc_fence_after();
+            __syncwarp();
         }
+        WG_TC_STAMP(8);
+        // ---- while the tensor core works: the tile's gaussian noise (Philox + Box-Muller per env and action pair); pair p
+        // is evaluated by the thread of column half (p + 1) & 1 and handed to the sampling thread through shared memory ----
+#pragma unroll
+        for (int pr = 0; pr < 4; pr++)
+            if (pr < n_pairs && half == ((pr + 1) & 1) && ev)
+                ZS[pr * kTcTile + row] = pol_normal2(A.seed_lo, A.seed_hi, A.env_offset + (uint32_t)e, step, (uint32_t)pr);
+        alive = __syncthreads_and(tc_wait_bar(bar, phase));
+        WG_TC_STAMP(9);
+        phase ^= 1;
+        tc_fence_after();
         if (!alive) break;
-        // ---- heads (one thread per env): outputs n < M means, n == M value (biases included); gaussian sample, log-prob ----
-        if (half == 0) {
-            uint32_t hv[16];
-            tc_ld16(t_lane + cH, hv);
+        // ---- epilogue 2 + heads: y = tanh(D); output n = b_n + sum_k y_k W_n[k] in float32 on the CUDA cores, this
+        // thread's 32 columns first, the two halves of an env added through shared memory ----
+        float hs[kTcMaxHeads];
+        {
+            uint32_t a[16], b[16];
+            tc_ld16(t_lane + cD + 32 * half, a);
+            tc_ld16(t_lane + cD + 32 * half + 16, b);
             tc_wait_ld();
-            if (ev) {
-                float lp = 0.0f;
+            float y[32];
 #pragma unroll
-                for (int pr = 0; pr < 4; pr++) {
-                    if (2 * pr < M) {
-                        float2 z = make_float2(0.0f, 0.0f);
-                        if (A.sample) z = pol_normal2(A.seed_lo, A.seed_hi, A.env_offset + (uint32_t)e, step, (uint32_t)pr);
+            for (int i = 0; i < 16; i++) { y[i] = pol_tanh<SPLIT>(__uint_as_float(a[i])); y[16 + i] = pol_tanh<SPLIT>(__uint_as_float(b[i])); }
+            WG_TC_STAMP(13);
 #pragma unroll
-                        for (int j = 0; j < 2; j++) {
-                            const int n = 2 * pr + j;
-                            if (n < M) {
-                                const float mean = __uint_as_float(hv[n]), ls = LS[n], eps = j ? z.y : z.x;
-                                const float act = A.sample ? __fmaf_rn(__expf(ls), eps, mean) : mean;
-                                lp += -0.5f * eps * eps - ls - 0.9189385332046727f;
-                                if (A.mean) A.mean[(int64_t)n * E + e] = mean;
-                                if (A.action) A.action[A.act_layout ? (int64_t)n * E + e : e * M + n] = act;
-                            }
+            for (int n = 0; n < kTcMaxHeads; n++) {
+                hs[n] = 0.0f;
+                if (n <= M) {                                       // warp-uniform
+                    const float4* wn = reinterpret_cast<const float4*>(WH + n * 64 + 32 * half);
+                    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < 8; q += 2) {
+                        const float4 w0 = wn[q], w1 = wn[q + 1];
+                        s0 = __fmaf_rn(y[4 * q + 0], w0.x, s0); s0 = __fmaf_rn(y[4 * q + 1], w0.y, s0);
+                        s0 = __fmaf_rn(y[4 * q + 2], w0.z, s0); s0 = __fmaf_rn(y[4 * q + 3], w0.w, s0);
+                        s1 = __fmaf_rn(y[4 * q + 4], w1.x, s1); s1 = __fmaf_rn(y[4 * q + 5], w1.y, s1);
+                        s1 = __fmaf_rn(y[4 * q + 6], w1.z, s1); s1 = __fmaf_rn(y[4 * q + 7], w1.w, s1);
+                    }
+                    hs[n] = s0 + s1;
+                    if (half) HX[n * kTcTile + row] = hs[n];
+                }
+            }
+        }
+        tc_fence_before();                      // the next tile's MMAs overwrite D only after this thread's loads (and barriers)
+        WG_TC_STAMP(10);
+        __syncthreads();
+        WG_TC_STAMP(11);
+        // ---- heads (one thread per env): outputs n < M means, n == M value; gaussian sample, log-prob ----
+        if (half == 0 && ev) {
+            float lp = 0.0f, mean[8], act[8], val = 0.0f;
+#pragma unroll
+            for (int pr = 0; pr < 4; pr++) {
+                if (2 * pr < M) {
+                    float2 z = make_float2(0.0f, 0.0f);
+                    if (A.sample) z = ZS[pr * kTcTile + row];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const int n = 2 * pr + j;
+                        if (n < M) {
+                            const float ls = LS[n], eps = j ? z.y : z.x;
+                            mean[n] = hs[n] + HX[n * kTcTile + row] + HB[n];
+                            act[n] = A.sample ? __fmaf_rn(__expf(ls), eps, mean[n]) : mean[n];
+                            lp += -0.5f * eps * eps - ls - 0.9189385332046727f;
                         }
                     }
                 }
-                if (A.value) {
-                    float val = 0.0f;
-#pragma unroll
-                    for (int n = 0; n < 8; n++) if (n == M) val = __uint_as_float(hv[n]);
-                    A.value[e] = val;
-                }
-                if (A.logp) A.logp[e] = lp;
             }
+#pragma unroll
+            for (int n = 0; n < kTcMaxHeads; n++) if (n == M) val = hs[n] + HX[n * kTcTile + row] + HB[n];
+            WG_TC_STAMP(12);
+#pragma unroll
+            for (int n = 0; n < 8; n++) {
+                if (n < M) {
+                    if (A.mean) A.mean[(int64_t)n * E + e] = mean[n];
+                    if (A.action) A.action[A.act_layout ? (int64_t)n * E + e : e * M + n] = act[n];
+                }
+            }
+            if (A.value) A.value[e] = val;
+            if (A.logp) A.logp[e] = lp;
         }
-        tc_fence_before();                      // the next tile's MMAs overwrite the heads' columns only after further barriers
+        WG_TC_STAMP(14);
     }
     if (!alive && error_flag && tid == 0) atomicExch(error_flag, 1);
     // ---- teardown: the allocating warp frees the tensor memory once every warp is done with it ----
