@@ -27,6 +27,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+POLICY_KERNELS = {2: "wg::policy_act_ws_kernel (warp-specialised tcgen05 / TMEM pipeline, TMA-staged observations)",
+                  1: "wg::policy_act_tc_kernel (monolithic tcgen05 / TMEM kernel)", 0: "wg::policy_act_kernel (mma.sync TF32)"}
 METRIC = "env-steps/sec (whole box)"
 UNIT = "env-steps/s"
 ENV_ID = "Balance-v0"
@@ -748,7 +750,7 @@ def measure_sub_configs(ctx, args):
         return {"what": f"BASELINE config 5: PPO rollout collection, MLP {env.obs_dim}->64->64->{env.M} policy kernel (wg_policy_act, "
                         f"float32-grade) + step kernel + GAE, {E} envs per GPU, T={T} per CUDA-graph replay",
                 "steps": n * T, "us_per_env_step": us, "value": world * E / (us * 1e-6), "unit": UNIT,
-                "policy_kernel": col.policy_kernel_name if hasattr(col, "policy_kernel_name") else "wg::policy_act_kernel",
+                "policy_kernel": POLICY_KERNELS[int(os.environ.get("WG_POLICY_TC", "2"))],
                 "clocks": clk}
     entry("5", rollout)
     return out
@@ -934,7 +936,8 @@ def run_rollout(args, ctx):
                                    f"(tanh, gaussian head, value head) + fused step kernel, {ENV_ID} in3d, {E} envs per GPU, "
                                    f"T={T} steps per CUDA-graph replay, GAE on device, {lay}-major obs/actions",
                        "policy": {"fused-fp32": "wg_policy_act: the torch module's weights evaluated by one CUDA kernel per step, "
-                                                "error-compensated 3xTF32 mma.sync (float32-grade, 1e-5 vs torch fp32)",
+                                                "error-compensated 3xTF32 products (float32-grade, 1e-5 vs torch fp32); kernel: "
+                                                + POLICY_KERNELS[int(os.environ.get("WG_POLICY_TC", "2"))],
                                   "fused-tf32": "wg_policy_act with plain TF32 products and tanh.approx",
                                   "torch": "torch eager ops captured in the CUDA graph"}[args.policy],
                        "baseline_config": 5, "envs_per_gpu": E, "global_envs": world * E,

@@ -222,7 +222,8 @@ int wg_force_generic(int on);
 #define WG_TUNE_PART 1
 #define WG_TUNE_L2_PREFETCH 2
 #define WG_TUNE_JIT 3             /* 1 (default) = bodies without an ahead-of-time kernel get one compiled at run time */
-#define WG_TUNE_POLICY_TC 4       /* wg_policy_act: 1 = the tcgen05 / tensor-memory kernel, 0 = the mma.sync kernel */
+#define WG_TUNE_POLICY_TC 4       /* wg_policy_act: 2 (default) = the warp-specialised tcgen05 / tensor-memory pipeline, 1 = the monolithic
+                                   tcgen05 kernel, 0 = the mma.sync kernel (env WG_POLICY_TC) */
 int wg_set_tuning(int key, int value);
 
 /*

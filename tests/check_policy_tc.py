@@ -1,5 +1,6 @@
-"""Stand-alone first-contact check of the tcgen05 / tensor-memory policy kernel (run it under `timeout`): the same
-policy through the mma.sync kernel and through the tcgen05 kernel, on the same observations and seeds.
+"""Stand-alone first-contact check of the tcgen05 / tensor-memory policy kernels (run it under `timeout`): the same
+policy through the mma.sync kernel (0), the monolithic tcgen05 kernel (1) and the warp-specialised tcgen05 pipeline (2), on
+the same observations and seeds; device time per call from CUDA events.
     python tests/check_policy_tc.py [E]
 Exit code 0 = both agree within the float32-grade tolerance and the kernel never gave up waiting for its MMAs."""
 import os
@@ -29,26 +30,30 @@ for D, M, E in [(38, 2, 128), (38, 2, 4096 + 77), (40, 4, 1000), (26, 2, 33), (1
     obs[3::11, 1 % D] = float("inf")
     for prec, tol in (("fp32", 3e-5), ("tf32", 3e-2)):
         res = {}
-        for impl in (0, 1):
+        for impl in (0, 1, 2):
             lib.wg_set_tuning(_lib.TUNE_POLICY_TC, impl)
             out = dict(action=torch.zeros(E, M, device=DEV), logp=torch.zeros(E, device=DEV), value=torch.zeros(E, device=DEV),
                        mean=torch.zeros(M, E, device=DEV))
             fp = FusedPolicy(pol, prec)
             fp.act(obs, obs_layout="row", act_layout="row", seed=3, step_index=9, **out)
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             for _ in range(20):
                 fp.act(obs, obs_layout="row", act_layout="row", seed=3, step_index=9, **out)
+            e1.record()
             torch.cuda.synchronize()
-            res[impl] = (out, (time.perf_counter() - t0) / 20 * 1e6)
-        lib.wg_set_tuning(_lib.TUNE_POLICY_TC, 0)
-        a, b = res[0][0], res[1][0]
-        err = {k: (a[k] - b[k]).abs().max().item() for k in a}
+            res[impl] = (out, e0.elapsed_time(e1) / 20 * 1e3)
+        lib.wg_set_tuning(_lib.TUNE_POLICY_TC, 2)
         status = lib.wg_policy_tc_status()
-        good = status == 0 and all(v < tol for v in err.values()) and all(torch.isfinite(b[k]).all().item() for k in b)
-        ok = ok and good
-        print(f"D={D} M={M} E={E} {prec}: max |mma.sync - tcgen05| = " + ", ".join(f"{k} {v:.2e}" for k, v in err.items()) +
-              f"; us per call {res[0][1]:.1f} -> {res[1][1]:.1f}; tc_status {status}; {'OK' if good else 'MISMATCH'}", flush=True)
+        a = res[0][0]
+        for impl in (1, 2):
+            b = res[impl][0]
+            err = {k: (a[k] - b[k]).abs().max().item() for k in a}
+            good = status == 0 and all(v < tol for v in err.values()) and all(torch.isfinite(b[k]).all().item() for k in b)
+            ok = ok and good
+            print(f"D={D} M={M} E={E} {prec} impl {impl}: max |mma.sync - tcgen05| = " + ", ".join(f"{k} {v:.2e}" for k, v in err.items()) +
+                  f"; us per call {res[0][1]:.1f} -> {res[impl][1]:.1f}; tc_status {status}; {'OK' if good else 'MISMATCH'}", flush=True)
         if status != 0:
             print("the tcgen05 kernel gave up waiting for its MMAs: stopping", flush=True)
             sys.exit(2)

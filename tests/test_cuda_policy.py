@@ -10,6 +10,18 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(params=[2, 1, 0], ids=["tcgen05-pipeline", "tcgen05-monolithic", "mma.sync"])
+def policy_impl(request):
+    """wg_policy_act has three implementations behind one knob (include/walker_gym_b200.h WG_TUNE_POLICY_TC); the default
+    is the warp-specialised tcgen05 pipeline."""
+    from walker_gym_b200 import _lib
+    lib = _lib.load()
+    lib.wg_set_tuning(_lib.TUNE_POLICY_TC, request.param)
+    yield request.param
+    assert lib.wg_policy_tc_status() == 0, "a tcgen05 policy kernel gave up waiting on one of its barriers"
+    lib.wg_set_tuning(_lib.TUNE_POLICY_TC, 2)
+
+
 def make_policy(D, M, seed=0):
     from walker_gym_b200.rollout import FeatureMajorMLP
     torch.manual_seed(seed)
@@ -42,7 +54,7 @@ def reference(pol, obs):
 
 @pytest.mark.parametrize("D,M,E", [(38, 2, 4096), (40, 4, 1000), (26, 2, 33), (17, 1, 257), (64, 7, 5000), (9, 3, 128)])
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("tf32", 2e-2)])
-def test_policy_matches_torch_fp32(D, M, E, precision, tol):
+def test_policy_matches_torch_fp32(D, M, E, precision, tol, policy_impl):
     """mean / value of the fused kernel vs the torch module (float32, TF32 off) and vs a float64 evaluation.
     Tolerance: fp32 mode 2e-5 absolute (outputs are O(1)); tf32 mode 2e-2."""
     from walker_gym_b200.rollout import FusedPolicy
@@ -70,7 +82,7 @@ def test_policy_matches_torch_fp32(D, M, E, precision, tol):
         assert err_ours < max(4 * err_torch, 5e-6), (err_ours, err_torch)
 
 
-def test_policy_sampling_and_logp():
+def test_policy_sampling_and_logp(policy_impl):
     """action = mean + std * eps with eps ~ N(0,1) (Philox per env / step / action), logp = log N(action; mean, std);
     reproducible, independent of how envs are sharded, different for every step."""
     from walker_gym_b200.rollout import FusedPolicy

@@ -30,7 +30,7 @@ static thread_local char g_err[512] = "";
 static std::atomic<int> g_force_generic{0};
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 static std::atomic<int> g_tune[5] = { {env_int("WG_TMA", 0)}, {env_int("WG_PART", -1)}, {env_int("WG_L2_PREFETCH", 256)},
-                                      {env_int("WG_JIT", 1)}, {env_int("WG_POLICY_TC", 0)} };
+                                      {env_int("WG_JIT", 1)}, {env_int("WG_POLICY_TC", 2)} };
 int tuning(int key) { return g_tune[key].load(std::memory_order_relaxed); }
 
 int fail(int code, const char* fmt, const char* a) {

@@ -2,6 +2,7 @@
 #include "wg_launch.cuh"
 #include "wg_policy.cuh"
 #include "wg_policy_tc.cuh"
+#include "wg_policy_ws.cuh"
 namespace wg {
 
 #ifndef WG_POLICY_MT
@@ -55,15 +56,38 @@ static int launch_policy_tc_t(const PolicyArgs& A, cudaStream_t s) {
     return WG_OK;
 }
 
+template <int K1, bool SPLIT>
+static int launch_policy_ws_t(const PolicyArgs& A, cudaStream_t s) {
+    auto kern = policy_act_ws_kernel<K1, SPLIT>;
+    const size_t smem = WsSmem<K1>::bytes(A.D);
+    static thread_local int cached_dev = -1, n_sm = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    int* flag = nullptr;
+    cudaGetSymbolAddress((void**)&flag, g_policy_tc_error);
+    const int64_t n_tiles = (A.E + kTcTile - 1) / kTcTile;
+    kern<<<(unsigned)(n_tiles < n_sm ? n_tiles : n_sm), kWsThreads, smem, s>>>(A, flag);      // one persistent CTA per SM
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(WG_ERR_CUDA, "policy kernel (tcgen05, warp-specialised) launch: %s", cudaGetErrorString(e));
+    return WG_OK;
+}
+
 int policy_tc_error() {
     int v = 0;
     if (cudaMemcpyFromSymbol(&v, g_policy_tc_error, sizeof(int)) != cudaSuccess) return -1;
     return v;
 }
 
-static int launch_policy_tc(const PolicyArgs& A, int precision, cudaStream_t s) {
+static int launch_policy_tc(const PolicyArgs& A, int precision, int variant, cudaStream_t s) {
     const int k1 = ((A.D + 1 + 7) / 8) * 8;          // obs_dim + the bias column, in k-steps of 8
-#define WG_POLTC(K) (precision == 0 ? launch_policy_tc_t<K, true>(A, s) : launch_policy_tc_t<K, false>(A, s))
+#define WG_POLTC(K) (variant == 2 ? (precision == 0 ? launch_policy_ws_t<K, true>(A, s) : launch_policy_ws_t<K, false>(A, s)) \
+                                  : (precision == 0 ? launch_policy_tc_t<K, true>(A, s) : launch_policy_tc_t<K, false>(A, s)))
     if (k1 <= 24) return WG_POLTC(24);
     if (k1 <= 32) return WG_POLTC(32);
     if (k1 <= 40) return WG_POLTC(40);
@@ -73,7 +97,7 @@ static int launch_policy_tc(const PolicyArgs& A, int precision, cudaStream_t s) 
 }
 
 int launch_policy(const PolicyArgs& A, int precision, cudaStream_t s) {
-    if (tuning(WG_TUNE_POLICY_TC) > 0) return launch_policy_tc(A, precision, s);
+    if (tuning(WG_TUNE_POLICY_TC) > 0) return launch_policy_tc(A, precision, tuning(WG_TUNE_POLICY_TC), s);
     const int kt = (A.D + 7) / 8;
 #define WG_POL(KT) (precision == 0 ? launch_policy_t<KT, true>(A, s) : launch_policy_t<KT, false>(A, s))
     if (kt <= 3) return WG_POL(3);

@@ -87,11 +87,15 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 // bounded wait on an mbarrier phase; false = gave up (a fraction of a second)
 __device__ __forceinline__ bool tc_wait_bar(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
+#pragma unroll 1
     for (int it = 0; it < (1 << 18); it++) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
         if (ok) return true;
+#ifdef WG_TC_WAIT_SLEEP
+        __nanosleep(WG_TC_WAIT_SLEEP);          // a polling warp competes for issue slots with the warps that do the work
+#endif
     }
     return false;
 }
