@@ -728,8 +728,17 @@ def measure_sub_configs(ctx, args):
         n = 20
         ms, clk = ctx.timed(lambda t: env.step_many(ring[t % 2], out=res), n, clocks=True)
         us = ms * 1e3 / (n * T)
+        # the same launch with the actions generated in the kernel (sinusoidal CPG): no per-step HBM read at all
+        from walker_gym_b200.actions import CPGActions
+        cpg = CPGActions(amp=[0.8] * env.M, freq=[1.5 + 0.5 * m for m in range(env.M)], phase=[0.7 * m for m in range(env.M)])
+        for t in range(4):
+            env.step_many(cpg, n_steps=T, out=res)
+        ms_g = ctx.timed(lambda t: env.step_many(cpg, n_steps=T, out=res), n)
+        us_g = ms_g * 1e3 / (n * T)
         return {"what": f"{T} env-steps per launch (wg_step_multi, actions [T,E,M] known up front), Balance-v0, {E} envs per GPU",
                 "steps": n * T, "kernel_us": us, "value": world * E / (us * 1e-6), "unit": UNIT,
+                "in_kernel_cpg": {"kernel_us": us_g, "value": world * E / (us_g * 1e-6),
+                                  "what": "actions generated in the kernel (CPGActions): the launch reads no action memory"},
                 "bound": "fp32 / fp64 instruction issue (state read and written once per 16 env-steps)", "clocks": clk}
     entry("multi16", multi)
 
