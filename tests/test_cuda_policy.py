@@ -113,6 +113,53 @@ def test_policy_sampling_and_logp(policy_impl):
     assert torch.equal(arow.t().contiguous(), out["a"])
 
 
+def test_policy_unaligned_and_ragged_observations(policy_impl):
+    """Row-major observations that are NOT 16-byte aligned (a view 4 bytes into a buffer) cannot be fetched by TMA bulk
+    copies: the kernels gather those rows themselves; the last, ragged tile always takes that path.  Same results as
+    the aligned call, bit for bit."""
+    from walker_gym_b200.rollout import FusedPolicy
+    D, M, E = 38, 2, 128 * 5 + 17
+    pol = make_policy(D, M, seed=3)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    big = torch.randn(E * D + 1, device=DEV, generator=g) * 120.0
+    aligned = big[:E * D].clone().view(E, D)
+    shifted = big[1:]                                                   # data_ptr() % 16 == 4
+    shifted.copy_(aligned.reshape(-1))
+    shifted = shifted.view(E, D)
+    assert shifted.data_ptr() % 16 == 4 and shifted.is_contiguous()
+    out = {}
+    for name, obs in (("aligned", aligned), ("shifted", shifted)):
+        o = dict(action=torch.zeros(E, M, device=DEV), logp=torch.zeros(E, device=DEV), value=torch.zeros(E, device=DEV),
+                 mean=torch.zeros(M, E, device=DEV))
+        FusedPolicy(pol, "fp32").act(obs, obs_layout="row", act_layout="row", seed=5, step_index=2, **o)
+        out[name] = o
+    torch.cuda.synchronize()
+    for k in out["aligned"]:
+        assert torch.equal(out["aligned"][k], out["shifted"][k]), k
+    mean_t, value_t, _, _ = reference(pol, aligned.t().contiguous())
+    assert (out["aligned"]["mean"] - mean_t).abs().max().item() < 2e-5
+    assert (out["aligned"]["value"] - value_t).abs().max().item() < 2e-5
+
+
+def test_policy_back_to_back_launches_are_deterministic(policy_impl):
+    """200 back-to-back launches on 2^16 envs (the pipeline's barriers, tensor-memory allocation and teardown under
+    load): every launch returns the bits of the first."""
+    from walker_gym_b200.rollout import FusedPolicy
+    D, M, E = 38, 2, 1 << 16
+    pol = make_policy(D, M, seed=4)
+    obs = torch.randn(E, D, device=DEV) * 120.0
+    fp = FusedPolicy(pol, "fp32")
+    first = dict(action=torch.zeros(E, M, device=DEV), logp=torch.zeros(E, device=DEV), value=torch.zeros(E, device=DEV))
+    fp.act(obs, obs_layout="row", act_layout="row", seed=1, step_index=7, **first)
+    cur = {k: torch.zeros_like(v) for k, v in first.items()}
+    bad = torch.zeros((), dtype=torch.int64, device=DEV)
+    for _ in range(200):
+        fp.act(obs, obs_layout="row", act_layout="row", seed=1, step_index=7, **cur)
+        for k in cur:
+            bad += (cur[k] != first[k]).sum()
+    assert bad.item() == 0
+
+
 def test_gae_matches_torch():
     from walker_gym_b200.rollout import gae
     T, E = 32, 3001
