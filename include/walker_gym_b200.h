@@ -224,6 +224,10 @@ int wg_force_generic(int on);
 #define WG_TUNE_JIT 3             /* 1 (default) = bodies without an ahead-of-time kernel get one compiled at run time */
 #define WG_TUNE_POLICY_TC 4       /* wg_policy_act: 2 (default) = the warp-specialised tcgen05 / tensor-memory pipeline, 1 = the monolithic
                                    tcgen05 kernel, 0 = the mma.sync kernel (env WG_POLICY_TC) */
+#define WG_TUNE_PDL 5             /* 1 (default) = the packed-state step kernel is launched with programmatic stream serialisation
+                                   (cudaLaunchAttributeProgrammaticStreamSerialization): its CTAs may be scheduled while the
+                                   previous kernel of the stream drains and wait (griddepcontrol.wait) before their first global
+                                   access, so back-to-back steps lose no launch gap; 0 = plain launches (env WG_PDL) */
 int wg_set_tuning(int key, int value);
 
 /*

@@ -249,3 +249,43 @@ def test_host_step_pipeline_matches_synchronous_host_steps():
     b.step_host(acts[0], d_act, h_obs, h_rew, h_done)
     torch.cuda.synchronize()
     assert gu.same(obs_a[0].numpy(), h_obs.numpy()) and gu.same(rew_a[0].numpy(), h_rew.numpy())
+
+
+def test_programmatic_dependent_launch_changes_nothing():
+    """The packed step kernel is launched with programmatic stream serialisation by default (WG_TUNE_PDL): its CTAs may
+    be scheduled while the previous kernel of the stream drains and wait before their first global access.  Driven by
+    actions that a kernel launched IMMEDIATELY before each step writes (the dependency the wait protects), eagerly and
+    through a CUDA graph, the trajectory is bit-identical to plain launches."""
+    import torch
+    from walker_gym_b200 import BatchedPhysicsEnv, _lib
+    lib = _lib.load()
+    E, T = 1 << 16, 40
+    out = {}
+    for pdl in (1, 0):
+        old = lib.wg_set_tuning(_lib.TUNE_PDL, pdl)
+        try:
+            env = BatchedPhysicsEnv("Balance-v0", E, "cuda:0", in3d=True, auto_reset="template", max_steps=25, seed=3,
+                                    state_layout="packed", graph_safe=True)
+            g = torch.Generator(device="cuda:0").manual_seed(11)
+            base = torch.rand(E, env.M, device="cuda:0", generator=g) * 2 - 1
+            act = torch.empty_like(base)
+            rews = torch.zeros(T, E, device="cuda:0")
+            for t in range(T // 2):                                     # eager: producer kernel, then the step
+                torch.mul(base, 1.0 - 0.02 * t, out=act)
+                _, r, _, _ = env.step(act)
+                rews[t].copy_(r)
+            graph = torch.cuda.CUDAGraph()                              # the same pair captured and replayed
+            scale = torch.ones((), device="cuda:0")
+            with torch.cuda.graph(graph):
+                torch.mul(base, scale, out=act)
+                env.step(act)
+            for t in range(T // 2, T):
+                scale.fill_(1.0 - 0.02 * t)
+                graph.replay()
+                rews[t].copy_(env.reward)
+            torch.cuda.synchronize()
+            out[pdl] = (rews.clone(), env.obs.clone(), env.steps.clone())
+        finally:
+            lib.wg_set_tuning(_lib.TUNE_PDL, old)
+    for a, b in zip(out[1], out[0]):
+        assert torch.equal(torch.nan_to_num(a.float()), torch.nan_to_num(b.float()))

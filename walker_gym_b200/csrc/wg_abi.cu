@@ -29,8 +29,8 @@ int launch_gae(const float* rewards, const float* values, const uint8_t* dones, 
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_force_generic{0};
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
-static std::atomic<int> g_tune[5] = { {env_int("WG_TMA", 0)}, {env_int("WG_PART", -1)}, {env_int("WG_L2_PREFETCH", 256)},
-                                      {env_int("WG_JIT", 1)}, {env_int("WG_POLICY_TC", 2)} };
+static std::atomic<int> g_tune[6] = { {env_int("WG_TMA", 0)}, {env_int("WG_PART", -1)}, {env_int("WG_L2_PREFETCH", 256)},
+                                      {env_int("WG_JIT", 1)}, {env_int("WG_POLICY_TC", 2)}, {env_int("WG_PDL", 1)} };
 int tuning(int key) { return g_tune[key].load(std::memory_order_relaxed); }
 
 int fail(int code, const char* fmt, const char* a) {
@@ -164,7 +164,7 @@ int64_t wg_packed_state_floats(const wg_topology* topo, int64_t n_env) {
 }
 
 int wg_set_tuning(int key, int value) {
-    if (key < 0 || key > 4) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
+    if (key < 0 || key > 5) return fail(WG_ERR_BAD_ARG, "unknown tuning key%s");
     if (key == WG_TUNE_PART && value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
         return fail(WG_ERR_BAD_ARG, "PART must be -1, 0, 2, 4 or 8%s");
     if (key == WG_TUNE_L2_PREFETCH && (value < 0 || value > (1 << 20))) return fail(WG_ERR_BAD_ARG, "L2 prefetch distance out of range%s");

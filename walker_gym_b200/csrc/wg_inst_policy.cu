@@ -72,8 +72,19 @@ static int launch_policy_ws_t(const PolicyArgs& A, cudaStream_t s) {
     int* flag = nullptr;
     cudaGetSymbolAddress((void**)&flag, g_policy_tc_error);
     const int64_t n_tiles = (A.E + kTcTile - 1) / kTcTile;
-    kern<<<(unsigned)(n_tiles < n_sm ? n_tiles : n_sm), kWsThreads, smem, s>>>(A, flag);      // one persistent CTA per SM
-    e = cudaGetLastError();
+    const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);                       // one persistent CTA per SM
+    if (tuning(WG_TUNE_PDL)) {           // programmatic dependent launch: the kernel's prologue overlaps the previous kernel's tail
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kWsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, A, flag);
+    } else {
+        kern<<<grid, kWsThreads, smem, s>>>(A, flag);
+        e = cudaGetLastError();
+    }
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "policy kernel (tcgen05, warp-specialised) launch: %s", cudaGetErrorString(e));
     return WG_OK;
 }

@@ -49,6 +49,12 @@ step_static_packed_kernel(const __grid_constant__ Args A) {
     const int64_t tile_idx = (int64_t)blockIdx.x * (kPackedBlock / kBlock) + (tid >> 7);
     float4* const base = reinterpret_cast<float4*>(A.state_packed) + tile_idx * (R4 * kBlock) + (tid & 127);
 
+    // Programmatic dependent launch: let the NEXT kernel of the stream be scheduled as soon as every CTA of this grid has
+    // started (its CTAs then sit in freed slots, past their prologue), and wait here for the PREVIOUS kernel's memory
+    // before the first global access -- back-to-back steps lose no launch gap.  Both are no-ops without the launch attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     // L2 prefetch: a tile is one contiguous block, so one thread can ask the copy engine to pull the tile that a
     // CTA launched `pf_dist` blocks later will read (CTAs are dispatched in index order) from HBM into L2 with a
     // single cp.async.bulk.prefetch; that CTA's loads then pay L2 instead of DRAM latency.

@@ -224,8 +224,19 @@ inline int launch_static_packed(const wg_topology* t, const wg_params* p, const 
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(WG_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<(unsigned)n_blocks, kPackedBlock, smem, s>>>(A);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (tuning(WG_TUNE_PDL)) {            // programmatic dependent launch: see the top of step_static_packed_kernel
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_blocks); cfg.blockDim = dim3(kPackedBlock); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, A);
+    } else {
+        kern<<<(unsigned)n_blocks, kPackedBlock, smem, s>>>(A);
+        e = cudaGetLastError();
+    }
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "step kernel (packed) launch: %s", cudaGetErrorString(e));
     return WG_OK;
 }

@@ -147,20 +147,28 @@ policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
         for (int i = 0; i < kBarCount; i++)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar + i)), "r"(counts[i]) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // Programmatic dependent launch (the launch carries cudaLaunchAttributeProgrammaticStreamSerialization): this CTA may
+    // have been scheduled while the previous kernel of the stream -- the env step that writes the observations -- was still
+    // draining.  Barrier initialisation, the zero fill of the weight planes and the tensor-memory allocation touch no
+    // global memory and run ahead; everything else waits for the previous kernel's memory here.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int i = tid; i < (2 * L::W1 + 2 * L::W2) / 4; i += kWsThreads) reinterpret_cast<float4*>(tsm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
         for (int i = 0; i < 2 && i < n_my; i++)                        // the first two tiles' observations: in flight during the setup
             if (tile_by_tma(tile_of(i))) tc_bulk_g2s(ST0 + i * st_floats, A.obs + tile_of(i) * kTcTile * D, tile_bytes, bar + kBarObsFull + i);
     }
-    for (int i = tid; i < (2 * L::W1 + 2 * L::W2) / 4; i += kWsThreads) reinterpret_cast<float4*>(tsm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
     constexpr float kPre = SPLIT ? 2.8853900817779268f : 1.0f;         // 2 log2(e), see ws_tanh
     ws_fill_b<SPLIT, K1>(W1h, W1l, D, A.w1, A.b1, kPre);
     ws_fill_b<SPLIT, kTcKH>(W2h, W2l, 64, A.w2, A.b2, kPre);
     for (int i = tid; i < (M + 1) * 64; i += kWsThreads) WH[i] = i < M * 64 ? __ldg(A.w_mu + i) : __ldg(A.w_v + (i - M * 64));
     if (tid < 16) { LS[tid] = tid < M ? A.log_std[tid] : 0.0f; HB[tid] = tid < M ? A.b_mu[tid] : (tid == M ? A.b_v[0] : 0.0f); }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the weight planes -> visible to the tensor core's reads
     tc_fence_before();
     __syncthreads();
