@@ -22,7 +22,7 @@
 // mma.sync kernel): three MMAs per k-step into the same accumulator, hi / lo planes of A in TMEM columns [64, 136) /
 // [144, 216) and of B in shared memory.
 //
-// What the measurements on B200 said (gpurun_scratch/mma_rate*.cu, tc_trace.cu):
+// What the measurements on B200 said (profiles/microbench/mma_rate*.cu, tc_trace.cu):
 //  * one tcgen05.mma M128 N64 K8 costs its 32-cycle floor (N16: 9) when issued from WARP-UNIFORM code (warp 0, one
 //    elected lane); issued under `if (threadIdx.x == 0)` the compiler wraps every instruction in a lane-election loop and
 //    the issue alone costs 60-70 cycles per MMA -- 4000 of the first version's 10800 cycles per tile;
@@ -37,7 +37,7 @@
 
 namespace wg {
 
-// development aid (gpurun_scratch/tc_trace.cu): thread 0 of CTA 0 stamps the clock at the phase boundaries of its tiles
+// development aid (profiles/microbench/tc_trace.cu): thread 0 of CTA 0 stamps the clock at the phase boundaries of its tiles
 #ifdef WG_TC_TRACE
 __device__ long long g_tc_trace[16 * 64];
 #define WG_TC_STAMP(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && it < 64) g_tc_trace[it * 16 + (slot)] = clock64(); } while (0)

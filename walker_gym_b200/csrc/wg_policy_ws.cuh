@@ -1,19 +1,20 @@
 // wg_policy_ws.cuh -- the rollout policy (BASELINE config 5) as a WARP-SPECIALISED tcgen05 pipeline: one persistent CTA
-// per SM, 21 warps in four roles, three tiles (128 envs each) in flight in different stages, all hand-offs through
+// per SM, 25 warps in five roles, three to four tiles (128 envs each) in flight in different stages, all hand-offs through
 // mbarriers, tensor memory (all 512 columns of the SM) as the only inter-stage storage for activations.
 //
 //   role            warps    per tile
 //   P   producers   0..3     observation row of env r (TMA-staged in shared memory) -> nan_to_num / clip -> hi / lo TF32
 //                            planes of the layer-1 A operand in tensor memory (tcgen05.st); thread 0 issues the TMA bulk
 //                            copy of the tile two ahead
-//   MMA             20       one elected lane: layer 1 of tile i+1, then layer 2 of tile i (tcgen05.mma kind::tf32, M 128,
+//   E1  epilogue 1  4..11    D1 (tcgen05.ld) -> tanh -> hi / lo planes of the layer-2 A operand (tcgen05.st)
+//   E2  epilogue 2  12..19   D2 -> tanh -> heads (M + 1 <= 9 outputs of depth 64) as float32 FMAs against the head weights
+//                            in shared memory; each thread's 32-column partial sums go to shared memory (double buffered)
+//   O   output      20..23   one thread per env: Philox + Box-Muller noise of the first action pair (evaluated while the
+//                            tile is still upstream), heads = the two halves + bias -> gaussian sample, log-prob, value
+//                            -> global memory
+//   MMA             24       one elected lane: layer 1 of tile i, then layer 2 of tile i-1 (tcgen05.mma kind::tf32, M 128,
 //                            N 64, A from tensor memory, B = weight planes in shared memory, biases folded in as an extra
 //                            k-column); tcgen05.commit -> the consumers' "full" and the producers' "free" barriers
-//   E1  epilogue 1  4..11    D1 (tcgen05.ld) -> tanh -> hi / lo planes of the layer-2 A operand (tcgen05.st)
-//   E2  epilogue 2  12..19   D2 -> tanh -> heads (M + 1 <= 9 outputs of depth 64, float32 FMAs against the head weights in
-//                            shared memory; the two column halves of an env meet in shared memory) -> gaussian sample
-//                            (Philox + Box-Muller, evaluated by the half that does not write the outputs), log-prob,
-//                            value -> global memory
 //
 // Tensor-memory columns: obs planes [0, 2 K1) | D1 x 2 | layer-2 A planes 2 x 72 | D2 x 2 (x 1 when K1 > 48).  D1 and D2
 // are double buffered so that the tensor core runs one tile ahead of each epilogue; the layer-2 A planes are single
@@ -22,17 +23,21 @@
 // thread walks obs -> MMA -> tanh -> MMA -> tanh -> heads, two CTAs per SM) is latency bound -- 27 % issue-slot
 // utilisation, each phase waiting for the previous one -- while no single resource is busy more than a third of the
 // time (XU pipe 2100 cycles per tile for the float32-grade tanh, tensor pipe 1350, instruction issue 2000, against
-// 7800 cycles per tile achieved).  With the stages decoupled the slowest resource sets the pace.
+// 7800 cycles per tile achieved).  With the stages decoupled the slowest resource sets the pace -- provided the code of
+// the five roles fits the instruction caches together: loops over heads, action pairs and outputs are ROLLED on purpose
+// (the first, fully unrolled version had 6600 SASS instructions and lost a quarter to half of every role's issue slots to
+// instruction fetch).
 //
-// With SPLIT every product is the 3-term error-compensated a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (float32-grade); without,
-// plain TF32 (hi planes only).  Every mbarrier wait is bounded; a role that gives up raises the error flag, stops
-// touching memory and only keeps its group's named barriers company until the loop ends.
+// With SPLIT every product is the 3-term error-compensated a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (float32-grade) and the
+// factor 2 log2(e) of tanh = 1 - 2 / (2^(2 log2(e) x) + 1) is folded into weights and biases; without, plain TF32 (hi planes
+// only) and tanh.approx.  Every mbarrier wait is bounded; a role that gives up raises the error flag and stops touching
+// memory (the producers keep their named barrier company until their loop ends).
 #pragma once
 #include "wg_policy_tc.cuh"
 
 namespace wg {
 
-// development aid (gpurun_scratch/ws_trace.cu): one thread per role of CTA 0 stamps the clock at its phase boundaries
+// development aid (profiles/microbench/ws_trace.cu): one thread per role of CTA 0 stamps the clock at its phase boundaries
 #ifdef WG_WS_TRACE
 __device__ long long g_ws_trace[4 * 16 * 8];
 #define WG_WS_STAMP(role, who, slot) do { if (blockIdx.x == 0 && (who) && i < 16) g_ws_trace[((role) * 16 + i) * 8 + (slot)] = clock64(); } while (0)
