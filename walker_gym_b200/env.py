@@ -25,6 +25,67 @@ from .walker import Creature
 _f32 = np.float32
 
 
+class _Arena:
+    """Every per-step tensor of an E = 1 core re-homed into ONE device buffer with a pinned host mirror, so that a facade
+    step is one host-to-device copy (state + action), one kernel and one device-to-host copy (state + results) instead
+    of a dozen small torch operations and as many synchronisations.  Layout: [inputs / state | results], 8-byte slots."""
+
+    def __init__(self, core: BatchedPhysicsEnv, max_act: int):
+        f32, n3, M = torch.float32, 3 * core.N, core.M
+        fields = [("pos", n3, f32), ("vel", n3, f32), ("old_a", n3, f32), ("mx", M, f32), ("steps", 1, torch.int32),
+                  ("action", max_act, f32), ("noise", n3, f32)]
+        if core.x64:
+            fields += [("mx64", M, torch.float64), ("mx_weak", M, torch.uint8), ("action64", max_act, torch.float64)]
+        n_in = len(fields)
+        fields += [("obs", core.obs_dim, f32), ("reward", 1, f32), ("done", 1, torch.uint8), ("energy", 1, f32),
+                   ("centroid", 3, f32), ("contact_pre", 1, torch.int32), ("contact_post", 1, torch.int32)]
+        off, self._slots = 0, {}
+        for i, (name, n, dt) in enumerate(fields):
+            if i == n_in:
+                self.in_bytes = off
+            size = n * torch.empty(0, dtype=dt).element_size()
+            self._slots[name] = (off, size, dt)
+            off += (max(size, 1) + 7) // 8 * 8
+        self.dev = torch.zeros(off, dtype=torch.uint8, device=core.device)
+        self.host = torch.zeros(off, dtype=torch.uint8).pin_memory()
+        self.np = {k: self.host[o:o + sz].view(dt).numpy() for k, (o, sz, dt) in self._slots.items()}
+        self.stream_device = core.device
+
+    def view(self, name: str, shape) -> torch.Tensor:
+        o, sz, dt = self._slots[name]
+        return self.dev[o:o + sz].view(dt).view(shape)
+
+    def push(self) -> None:
+        self.dev[:self.in_bytes].copy_(self.host[:self.in_bytes], non_blocking=True)
+
+    def pull(self) -> None:
+        self.host.copy_(self.dev, non_blocking=True)
+        torch.cuda.current_stream(self.stream_device).synchronize()
+
+
+def _rehome(core: BatchedPhysicsEnv, max_act: int) -> _Arena:
+    """Move ``core``'s (SoA, E = 1) tensors into an arena, keeping their current values."""
+    ar = _Arena(core, max_act)
+    n3, M = 3 * core.N, core.M
+
+    def move(attr, name, shape):
+        old = getattr(core, attr)
+        new = ar.view(name, shape)
+        new.copy_(old.reshape(shape))
+        setattr(core, attr, new)
+
+    move("_pos", "pos", (n3, 1)); move("_vel", "vel", (n3, 1)); move("old_a", "old_a", (n3, 1)); move("_mx", "mx", (M, 1))
+    move("_steps", "steps", (1,))
+    move("obs", "obs", tuple(core.obs.shape)); move("reward", "reward", (1,)); move("_done_u8", "done", (1,))
+    core.done = core._done_u8.view(torch.bool)
+    move("energy", "energy", (1,)); move("centroid", "centroid", (3, 1))
+    move("contact_pre", "contact_pre", (1,)); move("contact_post", "contact_post", (1,))
+    if core.x64:
+        move("mx64", "mx64", (M, 1)); move("mx_weak", "mx_weak", (M, 1))
+    core._bind()
+    return ar
+
+
 class _DeviceBody:
     """One creature mirrored on the device (E = 1)."""
 
@@ -33,57 +94,79 @@ class _DeviceBody:
         self.core = BatchedPhysicsEnv(creature, 1, device, auto_reset=None, keep_old_a=True, track_info=True,
                                       track_contacts=True, track_stats=False, initial_reset=False, state_layout="soa",
                                       **env_kwargs)
-        c = self.core
-        self.noise = torch.zeros(3 * c.N, 1, dtype=torch.float32, device=c.device)
+        self._max_act = max(self.core.M, 1) + 8               # the reference accepts more actions than muscles
+        self.arena = _rehome(self.core, self._max_act)
+        self.noise = self.arena.view("noise", (3 * self.core.N, 1))
         self._env_kwargs, self._device = dict(env_kwargs), device
-        self.core64 = None                  # x64 twin (float64 actions), built on first use
+        self.core64, self.arena64 = None, None               # x64 twin (float64 actions), built on first use
 
     def x64_core(self) -> BatchedPhysicsEnv:
         if self.core64 is None:
             self.core64 = BatchedPhysicsEnv(self.creature, 1, self._device, auto_reset=None, keep_old_a=True, track_info=True,
                                             track_contacts=True, track_stats=False, initial_reset=False, x64=True,
                                             **self._env_kwargs)
+            self.arena64 = _rehome(self.core64, self._max_act)
         return self.core64
 
-    def upload(self, steps: int, x64: bool = False) -> None:
+    def upload(self, steps: int, x64: bool = False, action=None, noise=None):
+        """Python objects -> pinned arena -> ONE host-to-device copy.  Returns the device view of the action (or None)."""
         c, cr = (self.x64_core() if x64 else self.core), self.creature
-        host = np.concatenate([np.asarray(p.pos, _f32) for p in cr.phys] + [np.asarray(p.v, _f32) for p in cr.phys]
-                              + [np.asarray(p.old_a, _f32) for p in cr.phys] + [_f32([m.x for m in cr.muscles])])
-        dev = torch.from_numpy(host).to(c.device)
+        ar = self.arena64 if x64 else self.arena
+        h = ar.np
         n3 = 3 * c.N
-        c.pos[:, 0], c.vel[:, 0], c.old_a[:, 0] = dev[:n3], dev[n3:2 * n3], dev[2 * n3:3 * n3]
+        h["pos"][:] = np.concatenate([np.asarray(p.pos, _f32) for p in cr.phys])
+        h["vel"][:] = np.concatenate([np.asarray(p.v, _f32) for p in cr.phys])
+        h["old_a"][:] = np.concatenate([np.asarray(p.old_a, _f32) for p in cr.phys])
         if c.M:
-            c.mx[:, 0] = dev[3 * n3:]
+            h["mx"][:] = [m.x for m in cr.muscles]
             if x64:     # the Muscle objects are the state: their python type is the "weak" bit (np.float64 = strong)
-                c.mx64[:, 0] = torch.tensor([float(m.x) for m in cr.muscles], dtype=torch.float64)
-                c.mx_weak[:, 0] = torch.tensor([0 if isinstance(m.x, np.float64) else 1 for m in cr.muscles], dtype=torch.uint8)
-        c.steps.fill_(int(steps))
+                h["mx64"][:] = [float(m.x) for m in cr.muscles]
+                h["mx_weak"][:] = [0 if isinstance(m.x, np.float64) else 1 for m in cr.muscles]
+        h["steps"][0] = int(steps)
+        if noise is not None:
+            h["noise"][:] = noise
+        act_view = None
+        if action is not None:
+            key = "action64" if x64 else "action"
+            a = np.asarray(action, dtype=np.float64 if x64 else _f32).reshape(-1)
+            if a.size > self._max_act:
+                a = a[:self._max_act]                         # only the first min(len, M) drive muscles anyway
+            h[key][:a.size] = a
+            act_view = ar.view(key, (self._max_act,))[:a.size].view(1, a.size)
+        ar.push()
+        return act_view
 
-    def download(self, refresh_contact: bool, x64: bool = False, muscles: bool = True) -> None:
+    def download(self, refresh_contact: bool, x64: bool = False, muscles: bool = True) -> dict:
+        """ONE device-to-host copy of state + results, then the Point / Muscle objects are refreshed from it.
+        Returns the host views (obs, reward, done, energy, centroid) of this step."""
         c, cr = (self.core64 if x64 else self.core), self.creature
-        n3 = 3 * c.N
-        host = torch.cat([c.pos[:, 0], c.vel[:, 0], c.old_a[:, 0], c.mx[:, 0]]).cpu().numpy()
-        cpre = int(c.contact_pre.item()) if refresh_contact else 0
+        ar = self.arena64 if x64 else self.arena
+        ar.pull()
+        h = ar.np
+        pos, vel, old_a = h["pos"], h["vel"], h["old_a"]
+        cpre = int(h["contact_pre"][0]) if refresh_contact else 0
         for n, p in enumerate(cr.phys):
-            p.pos[:] = host[3 * n:3 * n + 3]
-            p.v[:] = host[n3 + 3 * n:n3 + 3 * n + 3]
-            p.old_a = host[2 * n3 + 3 * n:2 * n3 + 3 * n + 3].copy()
+            p.pos[:] = pos[3 * n:3 * n + 3]
+            p.v[:] = vel[3 * n:3 * n + 3]
+            p.old_a = old_a[3 * n:3 * n + 3].copy()
             p.zero()
             if refresh_contact:             # colour / radius side effects (gym/optimized_env.py:155-156,174-175)
                 hit = (cpre >> n) & 1
                 p.color, p.r = ("red", 3) if hit else ("black", 1)
         if not muscles:                     # reset() does not touch Muscle.x (value or type)
-            return
+            return h
         if x64 and c.M:
-            x64v, weak = c.mx64[:, 0].cpu().numpy(), c.mx_weak[:, 0].cpu().numpy()
+            x64v, weak = h["mx64"], h["mx_weak"]
             for i, m in enumerate(cr.muscles):
                 v = float(x64v[i])
                 # strong = np.float64 (after `x += np.float64`); weak = the limit / constructor object: np.float32
                 # when representable, else the python float the user passed
                 m.x = np.float64(v) if not weak[i] else (_f32(v) if float(_f32(v)) == v else v)
-            return
+            return h
+        mx = h["mx"]
         for i, m in enumerate(cr.muscles):
-            m.x = _f32(host[3 * n3 + i])
+            m.x = _f32(mx[i])
+        return h
 
 
 class PhysicsEnv:
@@ -109,15 +192,20 @@ class PhysicsEnv:
 
     # the reference reads its attributes on every call, so they can be changed between steps
     def _refresh_params(self, time_step=None):
-        p = make_params(in3d=self.in3d, g=self.g, dampk=self.dampk, ground_high=self.ground, ground_k=self.ground_k,
-                        ground_damp=self.ground_damp, friction=self.friction, rand_sigma=self.sigma,
-                        time_step=self.time_step if time_step is None else time_step, max_steps=self.max_steps,
-                        k_sub=1, auto_reset=0)
-        self._body.core.params = p
+        key = (self.in3d, self.g, self.dampk, self.ground, self.ground_k, self.ground_damp, self.friction, self.sigma,
+               self.time_step if time_step is None else time_step, self.max_steps)
+        cache = self.__dict__.setdefault("_params_cache", {})
+        if cache.get("key") != key:          # rebuilt only when the caller changed an attribute between steps
+            cache["key"] = key
+            cache["params"] = make_params(in3d=key[0], g=key[1], dampk=key[2], ground_high=key[3], ground_k=key[4],
+                                          ground_damp=key[5], friction=key[6], rand_sigma=key[7], time_step=key[8],
+                                          max_steps=key[9], k_sub=1, auto_reset=0)
+        self._body.core.params = cache["params"]
 
     def _obs_array(self, x64: bool = False) -> np.ndarray:
+        ar = self._body.arena64 if x64 else self._body.arena
         core = self._body.core64 if x64 else self._body.core
-        obs = core.obs[0].cpu().numpy().astype(np.float64)
+        obs = ar.np["obs"].astype(np.float64)                 # the host mirror the last download() filled
         if core.M:                          # the reference's observation carries Muscle.x at its own precision
             obs[-core.M:] = [float(m.x) for m in self.creature.muscles]
         return obs
@@ -134,8 +222,7 @@ class PhysicsEnv:
             for c in range(d):
                 nz[n, c] = np.random.normal(0, self.sigma)
         self._refresh_params()
-        body.upload(0)
-        body.noise.copy_(torch.from_numpy(nz.reshape(-1, 1)))
+        body.upload(0, noise=nz.reshape(-1))
         core.reset(noise=body.noise, mode="jitter")
         body.download(refresh_contact=False, muscles=False)
         self.steps = 0
@@ -146,27 +233,29 @@ class PhysicsEnv:
         min(len(action), M) muscles.  NumPy's promotion rules decide the arithmetic exactly as in the
         reference: python floats and float32 arrays keep ``Muscle.x`` in float32; a float64 ndarray (what
         ``np.random.uniform`` returns, gym/performance_demo.py:241-262) turns it into an np.float64 and the
-        muscle's spring term into double (x64 mode, ``wg_step_x64``) -- both are bit-identical to the reference."""
+        muscle's spring term into double (x64 mode, ``wg_step_x64``) -- both are bit-identical to the reference.
+        One host-to-device copy, one kernel, one device-to-host copy per call (``_Arena``)."""
         body = self._body
-        x64 = ((isinstance(action, np.ndarray) and action.dtype == np.float64)
-               or any(isinstance(v, np.float64) for v in np.asarray(action, dtype=object).reshape(-1))
-               or any(isinstance(m.x, np.float64) for m in self.creature.muscles))
+        if isinstance(action, np.ndarray) and action.dtype != object:
+            x64 = action.dtype == np.float64
+        else:
+            x64 = any(isinstance(v, np.float64) for v in np.asarray(action, dtype=object).reshape(-1))
+        x64 = x64 or any(isinstance(m.x, np.float64) for m in self.creature.muscles)
         core = body.x64_core() if x64 else body.core
         self._refresh_params()
         if x64:
             core.params = body.core.params
-        body.upload(self.steps, x64)
-        act = np.asarray(action, dtype=np.float64 if x64 else _f32).reshape(1, -1)
-        core.step(torch.from_numpy(act).to(core.device))
-        body.download(refresh_contact=True, x64=x64)
+        act = body.upload(self.steps, x64, action=action)
+        core.step(act)
+        h = body.download(refresh_contact=True, x64=x64)
         self.steps += 1
-        reward = _f32(core.reward.item())
-        done = bool(core.done.item())
+        reward = _f32(h["reward"][0])
+        done = bool(h["done"][0])
         if self.renderer is not None and not self.renderer.is_running():
             done = True
         info = {"steps": self.steps,
-                "centroid_position": core.centroid[:, 0].cpu().numpy().tolist(),
-                "total_energy": _f32(core.energy.item())}
+                "centroid_position": h["centroid"].tolist(),
+                "total_energy": _f32(h["energy"][0])}
         return self._obs_array(x64), reward, done, info
 
     def render(self, mode: str = "human") -> Optional[np.ndarray]:
