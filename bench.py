@@ -449,7 +449,7 @@ def run_ours(args):
         tr, tr_src = ncu_traffic_per_env_step() if (args.config == 3 and args.obs_layout == "row" and not args.generic
                                                     and args.body == "balance") else (None, None)
         kernel = {"balance": "wg::step_static_packed_kernel<TopoBalanceV0, in3d, row-major obs via TMA bulk store, packed "
-                             "float4 state, L2 bulk prefetch, mass pattern [k,k,1,j] at compile time>",
+                             "float4 state, L2 bulk prefetch, mass pattern [k,k,1,j] at compile time, programmatic dependent launch>",
                   "quad": "wg::step_units_kernel<TopoBalanceV0, in3d, P=4 lanes per env (one per Balance unit), row-major obs via TMA bulk store, MM=3>",
                   "quad_chain": "wg::step_units_kernel<TopoBalanceV0, ..., LINK=1> (4 linked Balance units, neighbour masses over warp shuffles)"
                   }.get(args.body if args.config == 3 or args.body in ("quad", "quad_chain") else "quad",
