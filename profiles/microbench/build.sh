@@ -8,3 +8,4 @@ nvcc $F -o mma_rate mma_rate.cu          # cycles per tcgen05.mma issued under `
 nvcc $F -o mma_rate2 mma_rate2.cu        # the same from warp-uniform code (elect.sync), several issuing warps; tcgen05.ld / st throughput
 nvcc $F -fmad=false --expt-relaxed-constexpr -I ../../include -o tc_trace tc_trace.cu     # monolithic kernel: phase stamps of CTA 0
 nvcc $F -fmad=false --expt-relaxed-constexpr -I ../../include -o ws_trace ws_trace.cu     # pipeline: one thread per role
+nvcc $F -fmad=false -o divtest divtest.cu    # is the 3-FMA exact-remainder quotient IEEE-exact for non-integer divisors?  (no: r02_divtest.log)
