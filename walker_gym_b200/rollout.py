@@ -220,5 +220,9 @@ class RolloutCollector:
                 "rewards": self.rewards, "dones": self.dones, "advantages": self.advantages, "returns": self.returns}
 
     def episode_stats(self, all_reduce: bool = True) -> dict:
-        """Finished-episode return statistics of all ranks: K3 reduction + one NCCL all-reduce of 8 doubles."""
+        """Finished-episode return statistics of all ranks: K3 reduction + one NCCL all-reduce of 8 doubles.  Also the
+        point where the tcgen05 policy kernel's diagnostic flag is read (it synchronises the device anyway): a kernel
+        that ever gave up on one of its bounded barrier waits produced garbage, and that must not go unnoticed."""
+        if self.fused and _lib.load().wg_policy_tc_status() != 0:
+            raise _lib.WalkerGymError("a tcgen05 policy kernel gave up waiting on one of its barriers (wg_policy_tc_status)")
         return self.env.episode_stats(all_reduce=all_reduce)
