@@ -403,6 +403,22 @@ int wg_policy_act(const wg_mlp_policy* pol, const float* obs, int32_t obs_layout
                   float* value, float* mean, int64_t n_env, int32_t sample, uint32_t seed_lo, uint32_t seed_hi,
                   uint32_t step_index, const uint32_t* step_counter, uint32_t env_offset, void* cuda_stream);
 
+/*
+ * wg_policy_act immediately followed by wg_step with that action -- one env step of a PPO rollout (the caller of the hot
+ * path, gym/performance_demo.py:241-262 with a policy instead of random actions) -- in ONE launch: the output warps of
+ * the policy pipeline run PhysicsEnv.step of the env whose action they have just sampled, with the device functions of
+ * the packed step kernel (the results are the bits of the two separate calls).  obs [n_env][38] row-major is this step's
+ * observation; action [n_env][2] (row-major), logp, value, mean as in wg_policy_act (any may be NULL); buf as in wg_step:
+ * buf->obs receives the NEXT observation, buf->reward / done / state_packed / fin_stats ... the step's results; buf->action is
+ * ignored; the policy's Philox counter is step_index + *buf->step_counter, the env's prm->step_index + *buf->step_counter.
+ * Exists for BASELINE config 5's environment -- Balance-v0's spring graph with the mass pattern [k, k, 1, j] (unit /
+ * power-of-two / odd-integer masses), 3-D, packed state, row-major observations, WG_TUNE_POLICY_TC == 2; anything else
+ * returns WG_ERR_UNSUPPORTED and the caller makes the two calls.
+ */
+int wg_policy_step(const wg_mlp_policy* pol, const wg_topology* topo, const wg_params* prm, const wg_buffers* buf,
+                   const float* obs, float* action, float* logp, float* value, float* mean, int64_t n_env, int32_t sample,
+                   uint32_t seed_lo, uint32_t seed_hi, uint32_t step_index, uint32_t env_offset, void* cuda_stream);
+
 /* 1 if a tcgen05 policy kernel ever gave up waiting for its tensor-core work (a diagnostic: synchronises the device;
  * never set by a correct build), 0 otherwise, -1 on a CUDA error. */
 int wg_policy_tc_status(void);

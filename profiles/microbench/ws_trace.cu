@@ -14,7 +14,7 @@ template <bool SPLIT> void run(const PolicyArgs& A) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int rep = 0; rep < 3; rep++) {
         cudaEventRecord(e0);
-        kern<<<148, kWsThreads, smem>>>(A, flag);
+        kern<<<148, kWsThreads, smem>>>(A, flag, NoStep{});
         cudaEventRecord(e1);
         cudaError_t e = cudaDeviceSynchronize();
         float ms; cudaEventElapsedTime(&ms, e0, e1);

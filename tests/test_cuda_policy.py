@@ -198,15 +198,20 @@ def test_fused_rollout_collector(graph, layout):
     env = BatchedPhysicsEnv("Balance-v0", E, DEV, **kw)
     torch.manual_seed(1)
     pol = FeatureMajorMLP(env.obs_dim, env.M).to(DEV)
-    col = RolloutCollector(env, pol, T, use_cuda_graph=graph, fused=True, seed=9)
-    assert col.fused and col.kernel_launches_per_rollout == 2 * T + 2
+    col = RolloutCollector(env, pol, T, use_cuda_graph=graph, fused=True, seed=9, fuse_step=True)
+    # row-major Balance-v0 on the packed state: policy + env step in ONE launch (wg_policy_step, opt-in); else two launches
+    assert col.fused and col.fused_step == (layout == "row")
+    assert col.kernel_launches_per_rollout == (T if col.fused_step else 2 * T) + 2
     for _ in range(3 if graph else 1):               # graph: warm-up rollout, capture, replays
         out = {k: v.clone() for k, v in col.collect().items()}
     torch.cuda.synchronize()
     if not graph:
         # the same seeds through a second, identical env + collector: bit-identical trajectory
         env2 = BatchedPhysicsEnv("Balance-v0", E, DEV, **kw)
-        ref = RolloutCollector(env2, pol, T, use_cuda_graph=False, fused=True, seed=9).collect()
+        # ... with the two separate launches (policy kernel, step kernel): the fused launch returns the same bits
+        ref = RolloutCollector(env2, pol, T, use_cuda_graph=False, fused=True, seed=9, fuse_step=False)
+        assert not ref.fused_step
+        ref = ref.collect()
         for k in ("obs", "actions", "rewards", "dones", "values", "logp", "advantages"):
             assert torch.equal(torch.nan_to_num(out[k].float()), torch.nan_to_num(ref[k].float())), k
         # and the physics inside it is the step kernel: replay the actions through a third env, step by step

@@ -101,7 +101,7 @@ TUNE_TMA, TUNE_PART, TUNE_L2_PREFETCH, TUNE_JIT, TUNE_POLICY_TC, TUNE_PDL = 0, 1
 EXPORTS = ("wg_abi_version", "wg_last_error_string", "wg_obs_dim", "wg_kernel_variant", "wg_force_generic",
            "wg_set_tuning", "wg_packed_state_floats", "wg_packed_available", "wg_jit_prepare",
            "wg_step", "wg_step_multi", "wg_step_x64", "wg_reset", "wg_stats_reduce", "wg_step_host", "wg_step_multi_host", "wg_pkg_update_physics", "wg_pkg_kernel_variant",
-           "wg_policy_act", "wg_gae", "wg_stream_probe", "wg_host_alloc", "wg_host_free", "wg_getstat", "wg_policy_tc_status",
+           "wg_policy_act", "wg_policy_step", "wg_gae", "wg_stream_probe", "wg_host_alloc", "wg_host_free", "wg_getstat", "wg_policy_tc_status",
            "wg_selftest_div_smallint", "wg_selftest_forced_list", "wg_selftest_sqrt", "wg_selftest_div3")
 
 _lib = None
@@ -159,6 +159,10 @@ def load():
     lib.wg_policy_act.argtypes = [P(WgMlpPolicy), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
                                   C.c_void_p]
+    lib.wg_policy_step.argtypes = [P(WgMlpPolicy), P(WgTopology), P(WgParams), P(WgBuffers), C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                   C.c_void_p]
+    lib.wg_policy_step.restype = C.c_int
     lib.wg_stream_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.wg_stream_probe.restype = C.c_int
     lib.wg_gae.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,

@@ -22,6 +22,8 @@ int launch_jit_soa(const wg_topology*, const wg_params*, const wg_buffers*, int6
 int launch_jit_packed(const wg_topology*, const wg_params*, const wg_buffers*, int64_t E, cudaStream_t);
 int launch_policy(const PolicyArgs& A, int precision, cudaStream_t s);
 int policy_tc_error();
+int launch_policy_step(const PolicyArgs& A, int precision, const wg_topology* t, const wg_params* p, const wg_buffers* b,
+                       int64_t E, cudaStream_t s);
 int launch_stream_probe(const float* src, float* dst, int64_t n, int R, int W, cudaStream_t s);
 int launch_gae(const float* rewards, const float* values, const uint8_t* dones, float* adv, float* ret, int T, int64_t E,
                float gamma, float lam, float clip, cudaStream_t s);
@@ -376,6 +378,35 @@ int wg_policy_act(const wg_mlp_policy* pol, const float* obs, int32_t obs_layout
     A.obs_scale = pol->obs_scale; A.obs_clip = pol->obs_clip;
     A.seed_lo = seed_lo; A.seed_hi = seed_hi; A.step_index = step_index; A.env_offset = env_offset;
     return launch_policy(A, pol->precision, (cudaStream_t)cuda_stream);
+}
+
+int wg_policy_step(const wg_mlp_policy* pol, const wg_topology* topo, const wg_params* prm, const wg_buffers* buf,
+                   const float* obs, float* action, float* logp, float* value, float* mean, int64_t n_env, int32_t sample,
+                   uint32_t seed_lo, uint32_t seed_hi, uint32_t step_index, uint32_t env_offset, void* cuda_stream) {
+    if (!pol || !obs) return fail(WG_ERR_BAD_ARG, "null argument%s");
+    if (!pol->w1 || !pol->b1 || !pol->w2 || !pol->b2 || !pol->w_mu || !pol->b_mu || !pol->w_v || !pol->b_v || !pol->log_std)
+        return fail(WG_ERR_BAD_ARG, "wg_mlp_policy: every weight pointer must be set%s");
+    if (pol->precision != 0 && pol->precision != 1) return fail(WG_ERR_BAD_ARG, "precision must be 0 or 1%s");
+    int rc = validate(topo, prm, buf, n_env);
+    if (rc != WG_OK) return rc;
+    // the fused kernel exists for BASELINE config 5's environment: Balance-v0's spring graph and mass pattern [k, k, 1, j]
+    // (unit / power-of-two / odd-integer masses), 3-D, packed state, row-major observations, two muscles
+    const bool body_ok = !g_force_generic.load() && !has_strings(topo) && !general_masses(topo) && topo_id(topo) == TopoBalance::kId &&
+                         mass_mode(topo) == 1 && topo->mass[2] == 1.0 && topo->mass[0] == topo->mass[1] && topo->mass[0] != 1.0 &&
+                         topo->mass[3] != 1.0;
+    if (!body_ok || !prm->in3d || !buf->state_packed || buf->obs_layout != 0 || pol->obs_dim != 38 || pol->act_dim != 2 ||
+        tuning(WG_TUNE_POLICY_TC) != 2)
+        return fail(WG_ERR_UNSUPPORTED, "wg_policy_step: fused policy + step exists for Balance-v0 (3-D, packed state, row-major observations) with the tcgen05 pipeline%s");
+    if (n_env == 0) return WG_OK;
+    PolicyArgs A;
+    A.obs_layout = 0;
+    A.w1 = pol->w1; A.b1 = pol->b1; A.w2 = pol->w2; A.b2 = pol->b2; A.w_mu = pol->w_mu; A.b_mu = pol->b_mu;
+    A.w_v = pol->w_v; A.b_v = pol->b_v; A.log_std = pol->log_std;
+    A.obs = obs; A.action = action; A.logp = logp; A.value = value; A.mean = mean; A.step_counter = buf->step_counter;
+    A.E = n_env; A.D = 38; A.M = 2; A.act_layout = 0; A.sample = sample ? 1 : 0;
+    A.obs_scale = pol->obs_scale; A.obs_clip = pol->obs_clip;
+    A.seed_lo = seed_lo; A.seed_hi = seed_hi; A.step_index = step_index; A.env_offset = env_offset;
+    return launch_policy_step(A, pol->precision, topo, prm, buf, n_env, (cudaStream_t)cuda_stream);
 }
 
 int wg_policy_tc_status(void) { return policy_tc_error(); }

@@ -56,10 +56,10 @@ static int launch_policy_tc_t(const PolicyArgs& A, cudaStream_t s) {
     return WG_OK;
 }
 
-template <int K1, bool SPLIT>
-static int launch_policy_ws_t(const PolicyArgs& A, cudaStream_t s) {
-    auto kern = policy_act_ws_kernel<K1, SPLIT>;
-    const size_t smem = WsSmem<K1>::bytes(A.D);
+template <int K1, bool SPLIT, class SA = NoStep>
+static int launch_policy_ws_t(const PolicyArgs& A, cudaStream_t s, const SA& S = SA{}) {
+    auto kern = policy_act_ws_kernel<K1, SPLIT, SA>;
+    const size_t smem = WsSmem<K1, SA::kObsFloats>::bytes(A.D);
     static thread_local int cached_dev = -1, n_sm = 0;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -80,13 +80,24 @@ static int launch_policy_ws_t(const PolicyArgs& A, cudaStream_t s) {
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kern, A, flag);
+        e = cudaLaunchKernelEx(&cfg, kern, A, flag, S);
     } else {
-        kern<<<grid, kWsThreads, smem, s>>>(A, flag);
+        kern<<<grid, kWsThreads, smem, s>>>(A, flag, S);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "policy kernel (tcgen05, warp-specialised) launch: %s", cudaGetErrorString(e));
     return WG_OK;
+}
+
+// wg_policy_step: the policy pipeline with the env step fused into its output warps (Balance-v0's body and mass pattern,
+// 3-D, packed state, row-major observations and actions -- BASELINE config 5's environment)
+int launch_policy_step(const PolicyArgs& A, int precision, const wg_topology* t, const wg_params* p, const wg_buffers* b,
+                       int64_t E, cudaStream_t s) {
+    using SA = FusedStep<TopoBalanceV0, true, 3>;
+    static_assert(SA::D == 38 && SA::M == 2, "Balance-v0 in 3-D");
+    SA S;
+    fill_args(S.A, t, p, b, E);
+    return precision == 0 ? launch_policy_ws_t<40, true, SA>(A, s, S) : launch_policy_ws_t<40, false, SA>(A, s, S);
 }
 
 int policy_tc_error() {

@@ -34,6 +34,7 @@
 // memory (the producers keep their named barrier company until their loop ends).
 #pragma once
 #include "wg_policy_tc.cuh"
+#include "wg_policy_step.cuh"
 
 namespace wg {
 
@@ -53,11 +54,12 @@ constexpr int kWsWarpE1 = kWsWarpsP, kWsWarpE2 = kWsWarpE1 + kWsWarpsE, kWsWarpO
 enum { kBarObsFull = 0 /* x2 */, kBarA1Ready = 2, kBarA1Free = 3, kBarD1Full = 4 /* x2 */, kBarE1Done = 6, kBarHFree = 7,
        kBarD2Full = 8 /* x2 */, kBarD2Free = 10 /* x2 */, kBarHxFull = 12 /* x2 */, kBarHxFree = 14 /* x2 */, kBarCount = 16 };
 
-template <int K1>
+template <int K1, int OBS_OUT_FLOATS = 0>
 struct WsSmem {
     static constexpr int W1 = 64 * K1, W2 = 64 * kTcKH, WH = kTcMaxHeads * 64;
     static constexpr int o_w1 = 0, o_w2 = o_w1 + 2 * W1, o_wh = o_w2 + 2 * W2, o_hx = o_wh + WH + 4;
-    static constexpr int o_ls = o_hx + 2 * 2 * kTcMaxHeads * kTcTile, o_st = o_ls + 32;
+    static constexpr int o_ls = o_hx + 2 * 2 * kTcMaxHeads * kTcTile, o_ot = o_ls + 32;      // o_ot: fused step, next observations
+    static constexpr int o_st = o_ot + ((OBS_OUT_FLOATS + 3) / 4) * 4;
     static constexpr int st_floats(int D) { return ((kTcTile * D + 3) / 4) * 4 + 8; }     // + 8: the last row's tail chunk reads past its end
     static constexpr int o_bar(int D) { return o_st + 2 * st_floats(D); }
     static constexpr size_t bytes(int D) { return sizeof(float) * o_bar(D) + 8 * kBarCount + 16; }
@@ -115,11 +117,12 @@ __device__ __forceinline__ float ws_tanh(float x) {
     return __fmaf_rn(-2.0f, r, 1.0f);
 }
 
-// K1 = layer-1 depth: obs_dim + 1 (the bias column) rounded up to a multiple of 8; SPLIT = float32-grade 3xTF32
-template <int K1, bool SPLIT>
+// K1 = layer-1 depth: obs_dim + 1 (the bias column) rounded up to a multiple of 8; SPLIT = float32-grade 3xTF32;
+// SA = NoStep (the policy alone) or FusedStep<...> (the output warps also run the env step, wg_policy_step.cuh)
+template <int K1, bool SPLIT, class SA = NoStep>
 __global__ void __launch_bounds__(kWsThreads, 1)
-policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ error_flag) {
-    using L = WsSmem<K1>;
+policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ error_flag, const __grid_constant__ SA S) {
+    using L = WsSmem<K1, SA::kObsFloats>;
     constexpr int ND2 = (2 * K1 + 128 + 2 * kTcKH + 128 <= 512) ? 2 : 1;         // D2 buffers that fit next to the rest
     constexpr uint32_t cOh = 0, cOl = K1, cD1 = 2 * K1, cHh = cD1 + 128, cHl = cHh + kTcKH, cD2 = cHl + kTcKH;
     static_assert(cD2 + 64 * ND2 <= 512, "tensor memory budget");
@@ -383,6 +386,10 @@ policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
             const int hb = i & 1;
             const int64_t e = tile_of(i) * kTcTile + row;
             const bool ev = e < E;
+            // fused env step: the env's packed state is requested before anything else (latency under the noise + wait)
+            float sv[SA::kStateRegs];
+            float act_reg[2] = { 0.0f, 0.0f };
+            if constexpr (SA::kFused) { if (ev) S.load(sv, tile_of(i), row); }
             // the first action pair's noise does not depend on the network: evaluated while the tile is still upstream
             float2 z0 = make_float2(0.0f, 0.0f);
             if (A.sample) z0 = pol_normal2(A.seed_lo, A.seed_hi, A.env_offset + (uint32_t)e, step, 0u);
@@ -401,6 +408,7 @@ policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
                 const float a0 = A.sample ? __fmaf_rn(__expf(l0), z.x, m0) : m0, a1 = A.sample ? __fmaf_rn(__expf(l1), z.y, m1) : m1;
                 lp += -0.5f * z.x * z.x - l0 - 0.9189385332046727f;
                 if (n0 + 1 < M) lp += -0.5f * z.y * z.y - l1 - 0.9189385332046727f;
+                if constexpr (SA::kFused) { if (pr == 0) { act_reg[0] = a0; act_reg[1] = a1; } }      // fused bodies have M == 2
                 if (ev) {
                     if (A.mean) { A.mean[(int64_t)n0 * E + e] = m0; if (n0 + 1 < M) A.mean[(int64_t)n1 * E + e] = m1; }
                     if (A.action) {
@@ -414,6 +422,28 @@ policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
             if (ev) {
                 if (A.value) A.value[e] = val;
                 if (A.logp) A.logp[e] = lp;
+            }
+            if constexpr (SA::kFused) {
+                // ---- PhysicsEnv.step of this env with the action just sampled (wg_policy_step.cuh); the next observation
+                // rows of the warp's 32 envs leave with one TMA bulk store, like the stand-alone step kernel's ----
+                float* const OT = tsm + L::o_ot;
+                constexpr int DO = SA::D;
+                if (ev) S.step(sv, act_reg, tile_of(i), row, e, OT + row * DO);
+                __syncwarp();
+                const int64_t ew = tile_of(i) * kTcTile + (row & ~31);                 // first env of this warp
+                const int64_t remw = E - ew;
+                if (remw > 0 && S.A.obs) {
+                    float* wt = OT + (row & ~31) * DO;
+                    if (remw >= 32 && ((reinterpret_cast<uintptr_t>(S.A.obs) & 15u) == 0)) {
+                        fence_proxy_async();
+                        __syncwarp();
+                        if ((tid & 31) == 0) { bulk_s2g(S.A.obs + ew * DO, wt, (uint32_t)(32 * DO * 4)); bulk_commit(); bulk_wait_read0(); }
+                    } else {
+                        const int total = (remw < 32 ? (int)remw : 32) * DO;
+                        for (int idx = tid & 31; idx < total; idx += 32) S.A.obs[ew * DO + idx] = wt[idx];
+                    }
+                }
+                __syncwarp();                                           // the tile's rows may be overwritten by the next tile
             }
         }
     }

@@ -122,7 +122,7 @@ class RolloutCollector:
 
     def __init__(self, env: BatchedPhysicsEnv, policy: torch.nn.Module, horizon: int, *, gamma: float = 0.99,
                  lam: float = 0.95, use_cuda_graph: bool = True, reward_clip: float = 1e3, fused: Optional[bool] = None,
-                 precision: str = "fp32", seed: int = 0):
+                 precision: str = "fp32", seed: int = 0, fuse_step: bool = False):
         row = env.obs_layout == "row" or env.act_layout == "row"
         if row and fused is False:
             raise ValueError("the torch-op collector needs obs_layout='feature' and act_layout='feature'")
@@ -150,7 +150,43 @@ class RolloutCollector:
         self.fused = can_fuse if fused is None else bool(fused)
         self._fp = FusedPolicy(policy, precision) if self.fused else None
         self.seed = int(seed)
-        self.kernel_launches_per_rollout = (2 * self.T + 2) if self.fused else self.T   # ours only; torch's not counted
+        # fuse_step=True: one launch per env step where the library has the env step fused into the policy pipeline
+        # (wg_policy_step: Balance-v0, 3-D, packed state, row-major observations / actions; probed with an empty call).
+        # Bit-identical to the two launches but measured SLOWER on B200 (96 vs 53 us per 2^18-env step: the four output
+        # warps that carry the step are one warp per scheduler), hence off by default -- see DESIGN.md, K5.
+        self.fused_step = bool(self.fused and fuse_step and not env.x64 and env.state_layout == "packed"
+                               and env.obs_layout == "row" and env.act_layout == "row" and self._policy_step(0, probe=True))
+        self.kernel_launches_per_rollout = ((self.T if self.fused_step else 2 * self.T) + 2) if self.fused else self.T   # ours only
+
+    def _policy_step(self, t: int, probe: bool = False) -> bool:
+        """``wg_policy_step``: policy evaluation of ``obs[t]`` + ``env.step`` with the sampled action in ONE launch; results
+        in ``actions[t]``, ``logp[t]``, ``values[t]``, ``obs[t + 1]``, ``rewards[t]``, ``dones[t]``.  False = the library has
+        no fused kernel for this env / policy (the caller makes the two calls)."""
+        env, fp = self.env, self._fp
+        lib, b = fp.lib, env._buf
+        pol = fp._struct()
+        p = (lambda x: x.data_ptr())
+        saved = (b.action, b.act_dim, b.noise, b.obs, b.reward, b.done)
+        b.action, b.act_dim, b.noise = None, 0, None
+        if not probe:
+            b.obs, b.reward, b.done = p(self.obs[t + 1]), p(self.rewards[t]), p(self.dones.view(torch.uint8)[t])
+            env._stamp()
+        try:
+            with torch.cuda.device(env.device):
+                rc = lib.wg_policy_step(C.byref(pol), C.byref(env.topo), C.byref(env.params), C.byref(b),
+                                        p(self.obs[0 if probe else t]), p(self.actions[0 if probe else t]),
+                                        p(self.logp[0 if probe else t]), p(self.values[0 if probe else t]), None,
+                                        0 if probe else env.num_envs, 1, self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF,
+                                        (t if env._counter is not None else env.step_count) & 0xFFFFFFFF,
+                                        int(env.params.env_offset) & 0xFFFFFFFF, env._stream())
+        finally:
+            b.action, b.act_dim, b.noise, b.obs, b.reward, b.done = saved
+        if rc == -2:
+            return False
+        _lib.check(rc, "wg_policy_step")
+        if not probe:
+            env._advance()
+        return True
 
     @torch.no_grad()
     def _rollout_fused(self) -> None:
@@ -162,6 +198,8 @@ class RolloutCollector:
         with env.deferred_steps(self.T):             # graph-safe mode: one counter update per rollout, not per step
             for t in range(self.T):
                 env._step_offset = t
+                if self.fused_step and self._policy_step(t):
+                    continue
                 fp.act(self.obs[t], action=self.actions[t], logp=self.logp[t], value=self.values[t], sample=True,
                        step_index=t if env._counter is not None else env.step_count, **kw)
                 env.step(self.actions[t], out=(self.obs[t + 1], self.rewards[t], dones_u8[t]))
