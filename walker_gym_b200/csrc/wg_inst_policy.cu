@@ -59,7 +59,7 @@ static int launch_policy_tc_t(const PolicyArgs& A, cudaStream_t s) {
 template <int K1, bool SPLIT, class SA = NoStep>
 static int launch_policy_ws_t(const PolicyArgs& A, cudaStream_t s, const SA& S = SA{}) {
     auto kern = policy_act_ws_kernel<K1, SPLIT, SA>;
-    const size_t smem = WsSmem<K1, SA::kObsFloats>::bytes(A.D);
+    const size_t smem = WsSmem<K1, SA::kObsFloats * WsCfg<SA>::kGroupsO>::bytes(A.D);
     static thread_local int cached_dev = -1, n_sm = 0;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -75,14 +75,14 @@ static int launch_policy_ws_t(const PolicyArgs& A, cudaStream_t s, const SA& S =
     const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);                       // one persistent CTA per SM
     if (tuning(WG_TUNE_PDL)) {           // programmatic dependent launch: the kernel's prologue overlaps the previous kernel's tail
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kWsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WsCfg<SA>::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, kern, A, flag, S);
     } else {
-        kern<<<grid, kWsThreads, smem, s>>>(A, flag, S);
+        kern<<<grid, WsCfg<SA>::kThreads, smem, s>>>(A, flag, S);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return fail(WG_ERR_CUDA, "policy kernel (tcgen05, warp-specialised) launch: %s", cudaGetErrorString(e));

@@ -47,8 +47,15 @@ __device__ long long g_ws_trace[4 * 16 * 8];
 #endif
 
 constexpr int kWsWarpsP = 4, kWsWarpsE = 8, kWsWarpsO = 4;
-constexpr int kWsThreads = 32 * (kWsWarpsP + 2 * kWsWarpsE + kWsWarpsO + 1);      // 800
-constexpr int kWsWarpE1 = kWsWarpsP, kWsWarpE2 = kWsWarpE1 + kWsWarpsE, kWsWarpO = kWsWarpE2 + kWsWarpsE, kWsWarpMma = kWsWarpO + kWsWarpsO;
+constexpr int kWsThreads = 32 * (kWsWarpsP + 2 * kWsWarpsE + kWsWarpsO + 1);      // 800 (the policy alone)
+constexpr int kWsWarpE1 = kWsWarpsP, kWsWarpE2 = kWsWarpE1 + kWsWarpsE, kWsWarpO = kWsWarpE2 + kWsWarpsE;
+// the fused kernel (wg_policy_step.cuh) has TWO groups of output warps that take alternate tiles: the env step they carry
+// is ~1400 instructions per env, too long for one warp per scheduler to keep the pipeline's pace
+template <class SA> struct WsCfg {
+    static constexpr int kGroupsO = SA::kFused ? 2 : 1;
+    static constexpr int kWarpMma = kWsWarpO + kWsWarpsO * kGroupsO;
+    static constexpr int kThreads = 32 * (kWarpMma + 1);
+};
 
 // barriers (uint64_t each)
 enum { kBarObsFull = 0 /* x2 */, kBarA1Ready = 2, kBarA1Free = 3, kBarD1Full = 4 /* x2 */, kBarE1Done = 6, kBarHFree = 7,
@@ -77,21 +84,21 @@ __device__ __forceinline__ void ws_group_sync(int id, int threads) {
 // global reads are coalesced and all in flight at once; the planes were zeroed before (padding columns).
 // `pre` scales weights and bias: the float32-grade tanh is 1 - 2 / (2^(x * 2 log2 e) + 1), and the constant factor rides in
 // the GEMM instead of costing a multiplication per activation.
-template <bool SPLIT, int K>
+template <bool SPLIT, int K, int NT>
 __device__ __forceinline__ void ws_fill_b(float* hi, float* lo, int k_valid, const float* __restrict__ w,
                                           const float* __restrict__ bias, float pre) {
-    constexpr int NPT = (64 * K + kWsThreads - 1) / kWsThreads;
+    constexpr int NPT = (64 * K + NT - 1) / NT;
     const int total = 64 * k_valid;
     float v[NPT];
 #pragma unroll
     for (int j = 0; j < NPT; j++) {
-        const int i = threadIdx.x + j * kWsThreads;
+        const int i = threadIdx.x + j * NT;
         v[j] = i < total ? __ldg(w + i) * pre : 0.0f;
     }
     const float bv = threadIdx.x < 64 ? __ldg(bias + threadIdx.x) * pre : 0.0f;
 #pragma unroll
     for (int j = 0; j < NPT; j++) {
-        const int i = threadIdx.x + j * kWsThreads;
+        const int i = threadIdx.x + j * NT;
         if (i < total) {
             const int n = i / k_valid, k = i - n * k_valid, idx = ((k >> 2) * 64 + n) * 4 + (k & 3);
             const float h = __uint_as_float(to_tf32(v[j]));
@@ -120,9 +127,10 @@ __device__ __forceinline__ float ws_tanh(float x) {
 // K1 = layer-1 depth: obs_dim + 1 (the bias column) rounded up to a multiple of 8; SPLIT = float32-grade 3xTF32;
 // SA = NoStep (the policy alone) or FusedStep<...> (the output warps also run the env step, wg_policy_step.cuh)
 template <int K1, bool SPLIT, class SA = NoStep>
-__global__ void __launch_bounds__(kWsThreads, 1)
+__global__ void __launch_bounds__(WsCfg<SA>::kThreads, 1)
 policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ error_flag, const __grid_constant__ SA S) {
-    using L = WsSmem<K1, SA::kObsFloats>;
+    using L = WsSmem<K1, SA::kObsFloats * WsCfg<SA>::kGroupsO>;
+    constexpr int NT = WsCfg<SA>::kThreads, kWarpMma = WsCfg<SA>::kWarpMma;
     constexpr int ND2 = (2 * K1 + 128 + 2 * kTcKH + 128 <= 512) ? 2 : 1;         // D2 buffers that fit next to the rest
     constexpr uint32_t cOh = 0, cOl = K1, cD1 = 2 * K1, cHh = cD1 + 128, cHl = cHh + kTcKH, cD2 = cHl + kTcKH;
     static_assert(cD2 + 64 * ND2 <= 512, "tensor memory budget");
@@ -161,7 +169,7 @@ policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
     // draining.  Barrier initialisation, the zero fill of the weight planes and the tensor-memory allocation touch no
     // global memory and run ahead; everything else waits for the previous kernel's memory here.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    for (int i = tid; i < (2 * L::W1 + 2 * L::W2) / 4; i += kWsThreads) reinterpret_cast<float4*>(tsm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < (2 * L::W1 + 2 * L::W2) / 4; i += NT) reinterpret_cast<float4*>(tsm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -173,9 +181,9 @@ policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
             if (tile_by_tma(tile_of(i))) tc_bulk_g2s(ST0 + i * st_floats, A.obs + tile_of(i) * kTcTile * D, tile_bytes, bar + kBarObsFull + i);
     }
     constexpr float kPre = SPLIT ? 2.8853900817779268f : 1.0f;         // 2 log2(e), see ws_tanh
-    ws_fill_b<SPLIT, K1>(W1h, W1l, D, A.w1, A.b1, kPre);
-    ws_fill_b<SPLIT, kTcKH>(W2h, W2l, 64, A.w2, A.b2, kPre);
-    for (int i = tid; i < (M + 1) * 64; i += kWsThreads) WH[i] = i < M * 64 ? __ldg(A.w_mu + i) : __ldg(A.w_v + (i - M * 64));
+    ws_fill_b<SPLIT, K1, NT>(W1h, W1l, D, A.w1, A.b1, kPre);
+    ws_fill_b<SPLIT, kTcKH, NT>(W2h, W2l, 64, A.w2, A.b2, kPre);
+    for (int i = tid; i < (M + 1) * 64; i += NT) WH[i] = i < M * 64 ? __ldg(A.w_mu + i) : __ldg(A.w_v + (i - M * 64));
     if (tid < 16) { LS[tid] = tid < M ? A.log_std[tid] : 0.0f; HB[tid] = tid < M ? A.b_mu[tid] : (tid == M ? A.b_v[0] : 0.0f); }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the weight planes -> visible to the tensor core's reads
     tc_fence_before();
@@ -240,7 +248,7 @@ policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
             if (tid == 0 && alive && i + 2 < n_my && tile_by_tma(tile_of(i + 2)))
                 tc_bulk_g2s(ST0 + buf * st_floats, A.obs + tile_of(i + 2) * kTcTile * D, tile_bytes, bar + kBarObsFull + buf);
         }
-    } else if (warp == kWsWarpMma) {
+    } else if (warp == kWarpMma) {
         // ================= MMA: layer 1 of tile i, then layer 2 of tile i - 1 =================
         if (tc_elect_one()) {
             const uint64_t dW1h = tc_smem_desc(smem_u32(W1h), 64), dW1l = tc_smem_desc(smem_u32(W1l), 64);
@@ -382,7 +390,8 @@ policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
         // ================= O: heads -> gaussian sample, log-prob, value -> global memory (one thread per env) =================
         const uint32_t step = A.step_index + (A.step_counter ? __ldg(A.step_counter) : 0u);
         const int n_pairs = (M + 1) / 2;
-        for (int i = 0; i < n_my && alive; i++) {
+        const int og = SA::kFused ? (warp - kWsWarpO) >> 2 : 0;        // fused: output group og takes the tiles of its parity
+        for (int i = og; i < n_my && alive; i += WsCfg<SA>::kGroupsO) {
             const int hb = i & 1;
             const int64_t e = tile_of(i) * kTcTile + row;
             const bool ev = e < E;
@@ -426,7 +435,7 @@ policy_act_ws_kernel(const __grid_constant__ PolicyArgs A, int* __restrict__ err
             if constexpr (SA::kFused) {
                 // ---- PhysicsEnv.step of this env with the action just sampled (wg_policy_step.cuh); the next observation
                 // rows of the warp's 32 envs leave with one TMA bulk store, like the stand-alone step kernel's ----
-                float* const OT = tsm + L::o_ot;
+                float* const OT = tsm + L::o_ot + og * SA::kObsFloats;
                 constexpr int DO = SA::D;
                 if (ev) S.step(sv, act_reg, tile_of(i), row, e, OT + row * DO);
                 __syncwarp();

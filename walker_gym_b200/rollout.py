@@ -152,8 +152,9 @@ class RolloutCollector:
         self.seed = int(seed)
         # fuse_step=True: one launch per env step where the library has the env step fused into the policy pipeline
         # (wg_policy_step: Balance-v0, 3-D, packed state, row-major observations / actions; probed with an empty call).
-        # Bit-identical to the two launches but measured SLOWER on B200 (96 vs 53 us per 2^18-env step: the four output
-        # warps that carry the step are one warp per scheduler), hence off by default -- see DESIGN.md, K5.
+        # Bit-identical to the two launches but measured SLOWER on B200 (71 vs 53 us per 2^18-env step: the output warps
+        # that carry the step run its long straight-line body almost alone on their schedulers), hence off by default --
+        # see DESIGN.md, K5.
         self.fused_step = bool(self.fused and fuse_step and not env.x64 and env.state_layout == "packed"
                                and env.obs_layout == "row" and env.act_layout == "row" and self._policy_step(0, probe=True))
         self.kernel_launches_per_rollout = ((self.T if self.fused_step else 2 * self.T) + 2) if self.fused else self.T   # ours only
