@@ -266,7 +266,9 @@ __device__ __forceinline__ bool point_step(const BV& bv, const EnvConst& ec, Sto
     if (!fixed) {
         ay = (float)((double)ay + bv.gm[n]);                 // forced([0, -g, 0])
         if (ec.dampk_is_zero) {                               // forced(-0 * v): +-0, or NaN for non-finite v
-            ax = ax + ec.ndampk * vx; ay = ay + ec.ndampk * vy; az = az + ec.ndampk * vz;
+            // one FMA per component: the product is an exact zero (or NaN), so fma(-0, v, a) == a + (-0 * v) bit for bit,
+            // signs of zero included
+            ax = __fmaf_rn(ec.ndampk, vx, ax); ay = __fmaf_rn(ec.ndampk, vy, ay); az = __fmaf_rn(ec.ndampk, vz, az);
         } else {                                              // forced(-k * v): float32 force / m  (cold: dampk defaults to 0)
             const float3 r = damp_cold(make_float3(ax, ay, az), make_float3(vx, vy, vz), ec.ndampk,
                                        bv.mass_f[n], bv.mass_r[n], bv.mass_kind[n]);
