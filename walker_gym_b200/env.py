@@ -48,7 +48,7 @@ class _Arena:
             off += (max(size, 1) + 7) // 8 * 8
         self.dev = torch.zeros(off, dtype=torch.uint8, device=core.device)
         self.host = torch.zeros(off, dtype=torch.uint8).pin_memory()
-        self.np = {k: self.host[o:o + sz].view(dt).numpy() for k, (o, sz, dt) in self._slots.items()}
+        self.h = {k: self.host[o:o + sz].view(dt).numpy() for k, (o, sz, dt) in self._slots.items()}    # numpy views of the mirror
         self.stream_device = core.device
 
     def view(self, name: str, shape) -> torch.Tensor:
@@ -112,7 +112,7 @@ class _DeviceBody:
         """Python objects -> pinned arena -> ONE host-to-device copy.  Returns the device view of the action (or None)."""
         c, cr = (self.x64_core() if x64 else self.core), self.creature
         ar = self.arena64 if x64 else self.arena
-        h = ar.np
+        h = ar.h
         n3 = 3 * c.N
         h["pos"][:] = np.concatenate([np.asarray(p.pos, _f32) for p in cr.phys])
         h["vel"][:] = np.concatenate([np.asarray(p.v, _f32) for p in cr.phys])
@@ -142,7 +142,7 @@ class _DeviceBody:
         c, cr = (self.core64 if x64 else self.core), self.creature
         ar = self.arena64 if x64 else self.arena
         ar.pull()
-        h = ar.np
+        h = ar.h
         pos, vel, old_a = h["pos"], h["vel"], h["old_a"]
         cpre = int(h["contact_pre"][0]) if refresh_contact else 0
         for n, p in enumerate(cr.phys):
@@ -205,7 +205,7 @@ class PhysicsEnv:
     def _obs_array(self, x64: bool = False) -> np.ndarray:
         ar = self._body.arena64 if x64 else self._body.arena
         core = self._body.core64 if x64 else self._body.core
-        obs = ar.np["obs"].astype(np.float64)                 # the host mirror the last download() filled
+        obs = ar.h["obs"].astype(np.float64)                 # the host mirror the last download() filled
         if core.M:                          # the reference's observation carries Muscle.x at its own precision
             obs[-core.M:] = [float(m.x) for m in self.creature.muscles]
         return obs
