@@ -103,92 +103,100 @@ struct RuntimeTopo {
 // all), 1 = every mass is 1, a power of two or a small integer (exact 3-instruction division),
 // 2 = arbitrary masses.  The per-mass choice is a warp-uniform branch on a kernel parameter.
 template <int MM, class BV>
-__device__ __forceinline__ void forced2(float (&a)[3], const float (&f)[3], const float (&g)[3], const BV& bv, int n) {
+__device__ __forceinline__ void forced2(V3& a, const V3& f, const V3& g, const BV& bv, int n) {
     if (MM == 0) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) a[c] = (a[c] + f[c]) + g[c];
+        a = v3_add_prod(v3_add_prod(a, f), g);            // f and g are packed products: scalar additions
         return;
     }
-    if (MM == 1 || MM == 3) {           // (mode 3 is handled in spring_run; this instance is never reached)
-        // one straight-line path for every mass of the body: with m == 1 (r == 1) the sequence degenerates to
-        // q0 = x, rem = 0, q = x, so unit masses need no branch -- a few redundant FMAs are cheaper than the
-        // instruction-cache footprint of a second code variant per endpoint
-        const float m = bv.mass_f[n], r = bv.mass_r[n];
-#pragma unroll
-        for (int c = 0; c < 3; c++) a[c] = (a[c] + div_smallint(f[c], m, r)) + div_smallint(g[c], m, r);
-        return;
-    }
-    const int kind = bv.mass_kind[n];
+    int kind = 2;
+    if (MM == 2) kind = bv.mass_kind[n];
     if (kind == 0) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) a[c] = (a[c] + f[c]) + g[c];
+        a = v3_add_prod(v3_add_prod(a, f), g);
     } else if (kind <= 2) {
+        // one straight-line path for every mass of the body (MM 1: with m == 1 (r == 1) the sequence degenerates to
+        // q0 = x, rem = 0, q = x, so unit masses need no branch).  Three packed quotients: (f.x, f.y), (g.x, g.y) and the
+        // two z components together -- they share the divisor
         const float m = bv.mass_f[n], r = bv.mass_r[n];
-#pragma unroll
-        for (int c = 0; c < 3; c++) a[c] = (a[c] + div_smallint(f[c], m, r)) + div_smallint(g[c], m, r);
+        const float2 qf = div_smallint2(f.xy, m, r), qg = div_smallint2(g.xy, m, r), qz = div_smallint2(make_float2(f.z, g.z), m, r);
+        a.xy = __fadd2_rn(__fadd2_rn(a.xy, qf), qg);
+        a.z = (a.z + qz.x) + qz.y;
     } else {
         const float m = bv.mass_f[n];
-#pragma unroll
-        for (int c = 0; c < 3; c++) a[c] = (a[c] + div_rn(f[c], m)) + div_rn(g[c], m);
+        a.xy = make_float2((a.xy.x + div_rn(f.xy.x, m)) + div_rn(g.xy.x, m), (a.xy.y + div_rn(f.xy.y, m)) + div_rn(g.xy.y, m));
+        a.z = (a.z + div_rn(f.z, m)) + div_rn(g.z, m);
     }
 }
 
 // Muscle.run / Skeleton.run (optimized_walker.py:45-67 == :84-106)
+template <class Store>
+__device__ __forceinline__ V3 load_acc(Store& st, int n) { return v3(st.acc(n, 0), st.acc(n, 1), st.acc(n, 2)); }
+template <class Store>
+__device__ __forceinline__ void store_acc(Store& st, int n, const V3& a) { st.acc(n, 0) = a.xy.x; st.acc(n, 1) = a.xy.y; st.acc(n, 2) = a.z; }
+
 template <int MM, bool USE_SKIP = (MM == 2), class Topo, class BV, class Store>
 __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store& st, int sp, float x, uint32_t skip_mask) {
     const int i = topo.si(sp), j = topo.sj(sp);
-    const float pix = st.pos(i, 0), piy = st.pos(i, 1), piz = st.pos(i, 2);
-    const float pjx = st.pos(j, 0), pjy = st.pos(j, 1), pjz = st.pos(j, 2);
-    float d0 = pjx - pix, d1 = pjy - piy, d2 = pjz - piz;                 // direction = p2 - p1
+    const V3 pi = v3(st.pos(i, 0), st.pos(i, 1), st.pos(i, 2)), pj = v3(st.pos(j, 0), st.pos(j, 1), st.pos(j, 2));
+    V3 d = v3_sub(pj, pi);                                                  // direction = p2 - p1
     // distant(p1, p2) = norm(p1 - p2): p1 - p2 == -(p2 - p1) exactly and only its squares are used, so the norm is
     // taken of the direction's components (three subtractions less per spring)
-    const float L = np_norm3(d0, d1, d2);
+    const float L = np_norm3(d);
     const float dx = L - x;
     float fs = (-dx) * bv.sk[sp];                                         // -dx * k (sign as written)
     // rope-type springs (`if dx < 0 and string: f_size = 0`, gym/optimized_engine.py:134-136): a per-spring flag of
     // the run-time topology only -- bodies with such springs never reach the compile-time specialisations
     if constexpr (!Topo::kStatic) { if (((bv.string_mask[sp >> 5] >> (sp & 31)) & 1u) && dx < 0.0f) fs = 0.0f; }
-    div3_len(d0, d1, d2, L);
-    const float F[3] = { fs * d0, fs * d1, fs * d2 };
-    const float dk = np_dot3(st.vel(i, 0) - st.vel(j, 0), st.vel(i, 1) - st.vel(j, 1),
-                             st.vel(i, 2) - st.vel(j, 2), d0, d1, d2);
+    div3_len(d, L);
+    const V3 F = v3_scale(d, fs);
+    const V3 vd = v3_sub(v3(st.vel(i, 0), st.vel(i, 1), st.vel(i, 2)), v3(st.vel(j, 0), st.vel(j, 1), st.vel(j, 2)));
+    const float dk = np_dot3(vd, d);
     const float cd = dk * bv.sdamp[sp];
-    const float D[3] = { cd * d0, cd * d1, cd * d2 };
-    const float nF[3] = { -F[0], -F[1], -F[2] }, nD[3] = { -D[0], -D[1], -D[2] };
+    const V3 D = v3_scale(d, cd);
+    const V3 nF = v3_neg(F), nD = v3_neg(D);
     // skip_mask: masses whose accumulator this thread must not touch -- DingPoints (forced() is a no-op)
     // and, in the mass-partitioned kernel, masses owned by another lane.  Compiled out (USE_SKIP false)
     // in the one-thread-per-env kernels for bodies without DingPoints.
     if constexpr (MM == 3) {
         // mass pattern known at compile time (Topo::unit / Topo::same, constant-folded after unrolling): a unit mass
         // needs no division, and two endpoints of equal mass share the quotients -- (-F)/m == -(F/m) and
-        // D/m == -((-D)/m) exactly, so p2's increments are the negated increments of p1
+        // D/m == -((-D)/m) exactly, so p2's increments are the negated increments of p1.  Per endpoint three packed
+        // quotients: (F.x, F.y), (-D.x, -D.y) and the two z components together.
         const bool ui = Topo::unit(i), uj = Topo::unit(j);
-        float qF[3], qD[3];                                                 // F / m_i, (-D) / m_i
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            qF[c] = ui ? F[c] : div_smallint(F[c], bv.mass_f[i], bv.mass_r[i]);
-            qD[c] = ui ? nD[c] : div_smallint(nD[c], bv.mass_f[i], bv.mass_r[i]);
-            st.acc(i, c) = (st.acc(i, c) + qF[c]) + qD[c];
+        float2 qF = F.xy, qD = nD.xy, qz = make_float2(F.z, nD.z);          // F / m_i, (-D) / m_i
+        if (!ui) {
+            qF = div_smallint2(qF, bv.mass_f[i], bv.mass_r[i]);
+            qD = div_smallint2(qD, bv.mass_f[i], bv.mass_r[i]);
+            qz = div_smallint2(qz, bv.mass_f[i], bv.mass_r[i]);
         }
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            float pF, pD;                                                   // (-F) / m_j, D / m_j
-            if (Topo::same(i, j)) { pF = -qF[c]; pD = -qD[c]; }
-            else if (uj) { pF = nF[c]; pD = D[c]; }
-            else { pF = div_smallint(nF[c], bv.mass_f[j], bv.mass_r[j]); pD = div_smallint(D[c], bv.mass_f[j], bv.mass_r[j]); }
-            st.acc(j, c) = (st.acc(j, c) + pF) + pD;
+        V3 ai = load_acc(st, i);
+        // unit mass: qF / qD are the packed PRODUCTS themselves and must be added with scalar additions (wg_math.cuh CAUTION)
+        ai.xy = ui ? add2_prod(add2_prod(ai.xy, qF), qD) : __fadd2_rn(__fadd2_rn(ai.xy, qF), qD);
+        ai.z = (ai.z + qz.x) + qz.y;
+        store_acc(st, i, ai);
+        float2 pF, pD, pz;                                                  // (-F) / m_j, D / m_j
+        if (Topo::same(i, j)) { pF = neg2(qF); pD = neg2(qD); pz = neg2(qz); }
+        else if (uj) { pF = nF.xy; pD = D.xy; pz = make_float2(nF.z, D.z); }
+        else {
+            pF = div_smallint2(nF.xy, bv.mass_f[j], bv.mass_r[j]);
+            pD = div_smallint2(D.xy, bv.mass_f[j], bv.mass_r[j]);
+            pz = div_smallint2(make_float2(nF.z, D.z), bv.mass_f[j], bv.mass_r[j]);
         }
+        V3 aj = load_acc(st, j);
+        const bool j_raw = Topo::same(i, j) ? ui : uj;                      // p2's increments are (negated) raw products
+        aj.xy = j_raw ? add2_prod(add2_prod(aj.xy, pF), pD) : __fadd2_rn(__fadd2_rn(aj.xy, pF), pD);
+        aj.z = (aj.z + pz.x) + pz.y;
+        store_acc(st, j, aj);
         return;
     }
     if (!USE_SKIP || !((skip_mask >> i) & 1u)) {                            // p1.forced(force); p1.forced(-damp)
-        float a[3] = { st.acc(i, 0), st.acc(i, 1), st.acc(i, 2) };
+        V3 a = load_acc(st, i);
         forced2<MM>(a, F, nD, bv, i);
-        st.acc(i, 0) = a[0]; st.acc(i, 1) = a[1]; st.acc(i, 2) = a[2];
+        store_acc(st, i, a);
     }
     if (!USE_SKIP || !((skip_mask >> j) & 1u)) {                            // p2.forced(-force); p2.forced(damp)
-        float a[3] = { st.acc(j, 0), st.acc(j, 1), st.acc(j, 2) };
+        V3 a = load_acc(st, j);
         forced2<MM>(a, nF, D, bv, j);
-        st.acc(j, 0) = a[0]; st.acc(j, 1) = a[1]; st.acc(j, 2) = a[2];
+        store_acc(st, j, a);
     }
 }
 
@@ -268,7 +276,8 @@ __device__ __forceinline__ bool point_step(const BV& bv, const EnvConst& ec, Sto
         if (ec.dampk_is_zero) {                               // forced(-0 * v): +-0, or NaN for non-finite v
             // one FMA per component: the product is an exact zero (or NaN), so fma(-0, v, a) == a + (-0 * v) bit for bit,
             // signs of zero included
-            ax = __fmaf_rn(ec.ndampk, vx, ax); ay = __fmaf_rn(ec.ndampk, vy, ay); az = __fmaf_rn(ec.ndampk, vz, az);
+            const float2 axy = __ffma2_rn(bc2(ec.ndampk), make_float2(vx, vy), make_float2(ax, ay));
+            ax = axy.x; ay = axy.y; az = __fmaf_rn(ec.ndampk, vz, az);
         } else {                                              // forced(-k * v): float32 force / m  (cold: dampk defaults to 0)
             const float3 r = damp_cold(make_float3(ax, ay, az), make_float3(vx, vy, vz), ec.ndampk,
                                        bv.mass_f[n], bv.mass_r[n], bv.mass_kind[n]);
@@ -298,10 +307,13 @@ __device__ __forceinline__ bool point_step(const BV& bv, const EnvConst& ec, Sto
     }
     if (ec.integrator == 0) {
         // Point.run1: v += a*t; pos += v*t   (old_a = a stays in acc)
-        const float nvx = vx + ax * ec.dt, nvy = vy + ay * ec.dt, nvz = vz + az * ec.dt;
-        st.vel(n, 0) = nvx; st.vel(n, 1) = nvy; st.vel(n, 2) = nvz;
-        st.pos(n, 0) = st.pos(n, 0) + nvx * ec.dt;
-        st.pos(n, 1) = st.pos(n, 1) + nvy * ec.dt;
+        // products packed, additions scalar (a packed addition of a packed product would be contracted: wg_math.cuh CAUTION)
+        const float2 dt2v = bc2(ec.dt);
+        const float2 nvxy = add2_prod(make_float2(vx, vy), __fmul2_rn(make_float2(ax, ay), dt2v));        // v + a * t
+        const float nvz = vz + az * ec.dt;
+        st.vel(n, 0) = nvxy.x; st.vel(n, 1) = nvxy.y; st.vel(n, 2) = nvz;
+        const float2 npxy = add2_prod(make_float2(st.pos(n, 0), st.pos(n, 1)), __fmul2_rn(nvxy, dt2v));   // pos + v * t
+        st.pos(n, 0) = npxy.x; st.pos(n, 1) = npxy.y;
         st.pos(n, 2) = st.pos(n, 2) + nvz * ec.dt;
     } else {
         // Point.run2 (gym/optimized_engine.py:274-288): pos += v*t + (0.5*a)*t**2; then v += a*t  (cold path)
