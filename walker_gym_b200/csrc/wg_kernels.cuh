@@ -134,7 +134,7 @@ __device__ __forceinline__ void epilogue(const Topo& topo, const BV& bv, const E
 #pragma unroll
     for (int n = 0; n < N; n++) {                               // _get_reward (optimized_env.py:189-205)
         ys(n) = st.pos(n, 1);
-        sp(n) = np_norm3(st.vel(n, 0), st.vel(n, 1), st.vel(n, 2));
+        sp(n) = np_norm3(v3(st.vel(n, 0), st.vel(n, 1), st.vel(n, 2)));
     }
     epilogue_reduce(N, bv, ec, st, steps_now, want_energy, want_centroid, ys, sp, o);
 }

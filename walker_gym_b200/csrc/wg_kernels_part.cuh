@@ -249,24 +249,30 @@ template <int MM, int SIDE, class U, class BV>
 __device__ __forceinline__ void link_half(const BV& bv, int n, const float (&pi)[3], const float (&vi)[3],
                                           const float (&pj)[3], const float (&vj)[3], float k, float damp, float rest,
                                           float (&acc)[3]) {
-    float d0 = pj[0] - pi[0], d1 = pj[1] - pi[1], d2 = pj[2] - pi[2];
-    const float L = np_norm3(d0, d1, d2);
+    // the same operations as spring_run, x / y halves packed (wg_math.cuh)
+    V3 d = v3_sub(v3(pj[0], pj[1], pj[2]), v3(pi[0], pi[1], pi[2]));
+    const float L = np_norm3(d);
     const float dx = L - rest;
     const float fs = (-dx) * k;
-    div3_len(d0, d1, d2, L);
-    const float F[3] = { fs * d0, fs * d1, fs * d2 };
-    const float dk = np_dot3(vi[0] - vj[0], vi[1] - vj[1], vi[2] - vj[2], d0, d1, d2);
+    div3_len(d, L);
+    const V3 F = v3_scale(d, fs);
+    const float dk = np_dot3(v3_sub(v3(vi[0], vi[1], vi[2]), v3(vj[0], vj[1], vj[2])), d);
     const float cd = dk * damp;
-    const float D[3] = { cd * d0, cd * d1, cd * d2 };
+    const V3 D = v3_scale(d, cd);
     bool unit = (MM == 0);
     if constexpr (MM == 3) unit = U::unit(n);
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const float f1 = SIDE == 0 ? F[c] : -F[c], f2 = SIDE == 0 ? -D[c] : D[c];
-        const float q1 = unit ? f1 : div_smallint(f1, bv.mass_f[n], bv.mass_r[n]);
-        const float q2 = unit ? f2 : div_smallint(f2, bv.mass_f[n], bv.mass_r[n]);
-        acc[c] = (acc[c] + q1) + q2;
+    const V3 f1 = SIDE == 0 ? F : v3_neg(F), f2 = SIDE == 0 ? v3_neg(D) : D;
+    float2 axy = make_float2(acc[0], acc[1]);
+    if (unit) {                                         // raw packed products: scalar additions (wg_math.cuh CAUTION)
+        axy = add2_prod(add2_prod(axy, f1.xy), f2.xy);
+        acc[2] = (acc[2] + f1.z) + f2.z;
+    } else {
+        const float m = bv.mass_f[n], r = bv.mass_r[n];
+        const float2 q1 = div_smallint2(f1.xy, m, r), q2 = div_smallint2(f2.xy, m, r), qz = div_smallint2(make_float2(f1.z, f2.z), m, r);
+        axy = __fadd2_rn(__fadd2_rn(axy, q1), q2);
+        acc[2] = (acc[2] + qz.x) + qz.y;
     }
+    acc[0] = axy.x; acc[1] = axy.y;
 }
 
 // positions of every mass of an env in the per-env scratch (the env-level tail reads them in NumPy's order)

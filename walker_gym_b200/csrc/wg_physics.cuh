@@ -432,16 +432,20 @@ __device__ __forceinline__ void get_obs(const Topo& topo, const ConstDiv& nd, St
     const int N = topo.n(), M = topo.m();
     constexpr int d = IN3D ? 3 : 2;
     float mid[3] = { 0.0f, 0.0f, 0.0f };
+    float2 mxy = make_float2(0.0f, 0.0f);                    // np.mean(axis=0): sequential sums, x / y packed
 #pragma unroll
-    for (int n = 0; n < N; n++) { mid[0] = mid[0] + st.pos(n, 0); mid[1] = mid[1] + st.pos(n, 1); mid[2] = mid[2] + st.pos(n, 2); }
-    mid[0] = div_const(mid[0], nd.m, nd.r, nd.kind);
-    mid[1] = div_const(mid[1], nd.m, nd.r, nd.kind);
+    for (int n = 0; n < N; n++) { mxy = __fadd2_rn(mxy, make_float2(st.pos(n, 0), st.pos(n, 1))); mid[2] = mid[2] + st.pos(n, 2); }
+    mid[0] = div_const(mxy.x, nd.m, nd.r, nd.kind);
+    mid[1] = div_const(mxy.y, nd.m, nd.r, nd.kind);
     mid[2] = div_const(mid[2], nd.m, nd.r, nd.kind);
+    const float2 nmid = make_float2(-mid[0], -mid[1]);
     int k = 0;
 #pragma unroll
     for (int n = 0; n < N; n++) {
+        const float2 rel = __fadd2_rn(make_float2(st.pos(n, 0), st.pos(n, 1)), nmid);        // pos - mid
+        emit(k++, rel.x); emit(k++, rel.y);
 #pragma unroll
-        for (int c = 0; c < d; c++) emit(k++, st.pos(n, c) - mid[c]);
+        for (int c = 2; c < d; c++) emit(k++, st.pos(n, c) - mid[c]);
 #pragma unroll
         for (int c = 0; c < d; c++) emit(k++, st.vel(n, c));
 #pragma unroll
