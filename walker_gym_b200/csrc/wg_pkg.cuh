@@ -43,31 +43,34 @@ struct PkgRuntimeTopo {
     __device__ __forceinline__ int sj(int k) const { return sj_[k]; }
 };
 
+// Point.forced: a += f / m for a force that is NOT a raw packed product (the quotients of div3_len)
+template <class Store>
+__device__ __forceinline__ void pkg_forced(const PkgArgs& A, Store& st, int n, const V3& f) {
+    const float m = A.mass_f[n], r = A.mass_r[n]; const int kd = A.mass_kind[n];
+    float2 axy = make_float2(st.acc(n, 0), st.acc(n, 1));
+    float az = st.acc(n, 2);
+    if (kd == 0) { axy = make_float2(axy.x + f.xy.x, axy.y + f.xy.y); az = az + f.z; }
+    else if (kd <= 2) { axy = __fadd2_rn(axy, div_smallint2(f.xy, m, r)); az = az + div_smallint(f.z, m, r); }
+    else { axy = make_float2(axy.x + div_rn(f.xy.x, m), axy.y + div_rn(f.xy.y, m)); az = az + div_rn(f.z, m); }
+    st.acc(n, 0) = axy.x; st.acc(n, 1) = axy.y; st.acc(n, 2) = az;
+}
+
 template <class Topo, class Store>
 __device__ __forceinline__ void pkg_spring(const Topo& topo, const PkgArgs& A, Store& st, int sp, uint32_t skip_mask) {
     const int i = topo.si(sp), j = topo.sj(sp);
-    const float d0 = st.pos(i, 0) - st.pos(j, 0), d1 = st.pos(i, 1) - st.pos(j, 1), d2 = st.pos(i, 2) - st.pos(j, 2);
-    const float L = np_norm3(d0, d1, d2);
+    // x / y halves packed (wg_math.cuh): the same IEEE operations, two instructions per 3-vector operation
+    const V3 d = v3_sub(v3(st.pos(i, 0), st.pos(i, 1), st.pos(i, 2)), v3(st.pos(j, 0), st.pos(j, 1), st.pos(j, 2)));
+    const float L = np_norm3(d);
     const float dx = L - A.srest[sp];
     const bool slack = (dx < 0.0f) && ((A.string_mask[sp >> 5] >> (sp & 31)) & 1u);
     const float nfs = slack ? 0.0f : -((-dx) * A.sk[sp]);                 // -f_size
     const float dist = (A.min_dist > L) ? A.min_dist : L;                  // python max(norm, Config.r)
-    float f0 = nfs * d0, f1 = nfs * d1, f2 = nfs * d2;                     // force on p2 (dir = d)
-    div3_len<true>(f0, f1, f2, dist);                                           // dist > 0 or NaN: always a division
+    V3 f = v3_scale(d, nfs);                                               // force on p2 (dir = d)
+    div3_len<true>(f, dist);                                               // dist > 0 or NaN: always a division
     // skip_mask: points whose accumulator this thread must not touch -- DingPoints (forced() is a no-op) and, in the
     // partitioned kernel, points owned by another lane
-    if (!((skip_mask >> i) & 1u)) {
-        const float m = A.mass_f[i], r = A.mass_r[i]; const int kd = A.mass_kind[i];
-        st.acc(i, 0) = st.acc(i, 0) + div_const(-f0, m, r, kd);
-        st.acc(i, 1) = st.acc(i, 1) + div_const(-f1, m, r, kd);
-        st.acc(i, 2) = st.acc(i, 2) + div_const(-f2, m, r, kd);
-    }
-    if (!((skip_mask >> j) & 1u)) {
-        const float m = A.mass_f[j], r = A.mass_r[j]; const int kd = A.mass_kind[j];
-        st.acc(j, 0) = st.acc(j, 0) + div_const(f0, m, r, kd);
-        st.acc(j, 1) = st.acc(j, 1) + div_const(f1, m, r, kd);
-        st.acc(j, 2) = st.acc(j, 2) + div_const(f2, m, r, kd);
-    }
+    if (!((skip_mask >> i) & 1u)) pkg_forced(A, st, i, v3_neg(f));
+    if (!((skip_mask >> j) & 1u)) pkg_forced(A, st, j, f);
 }
 
 // Everything update_physics does to one point after the springs: damping (:153-154), quadratic drag
@@ -79,16 +82,21 @@ __device__ __forceinline__ void pkg_point(const PkgArgs& A, Store& st, int n) {
     float ax = st.acc(n, 0), ay = st.acc(n, 1), az = st.acc(n, 2);
     const bool fixed = (A.fixed_mask >> n) & 1u;
     if (!fixed) {
-        vx = vx * A.damping; vy = vy * A.damping; vz = vz * A.damping;
-        const float cs = A.drag_c * np_norm3(vx, vy, vz);
+        const float2 vxy = __fmul2_rn(make_float2(vx, vy), bc2(A.damping));
+        vx = vxy.x; vy = vxy.y; vz = vz * A.damping;
+        const float cs = A.drag_c * np_norm3(v3(vx, vy, vz));
         const float m = A.mass_f[n], r = A.mass_r[n]; const int kd = A.mass_kind[n];
-        ax = ax + div_const(cs * vx, m, r, kd);
-        ay = ay + div_const(cs * vy, m, r, kd);
+        const float2 dxy = __fmul2_rn(vxy, bc2(cs));                       // cs * v: packed products, then scalar / quotient adds
+        ax = ax + div_const(dxy.x, m, r, kd);
+        ay = ay + div_const(dxy.y, m, r, kd);
         az = az + div_const(cs * vz, m, r, kd);
         st.acc(n, 0) = ax; st.acc(n, 1) = ay; st.acc(n, 2) = az;
     }
-    vx = vx + ax * A.dt; vy = vy + ay * A.dt; vz = vz + az * A.dt;         // run1: every point, DingPoints drift
-    float px = st.pos(n, 0) + vx * A.dt, py = st.pos(n, 1) + vy * A.dt, pz = st.pos(n, 2) + vz * A.dt;
+    // run1: every point, DingPoints drift; products packed, additions scalar (wg_math.cuh CAUTION)
+    const float2 avt = __fmul2_rn(make_float2(ax, ay), bc2(A.dt));
+    vx = vx + avt.x; vy = vy + avt.y; vz = vz + az * A.dt;
+    const float2 pvt = __fmul2_rn(make_float2(vx, vy), bc2(A.dt));
+    float px = st.pos(n, 0) + pvt.x, py = st.pos(n, 1) + pvt.y, pz = st.pos(n, 2) + vz * A.dt;
     if (!fixed && A.ground && py <= A.ground_level) {
         py = A.ground_level;
         if (vy < 0.0f) { vy = (-vy) * A.restitution; vx = vx * A.friction; vz = vz * A.friction; }
