@@ -16,3 +16,4 @@ $U4 > gpurun_out/r02_plain_units.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:step_units -s 250 -c 1 -f -o gpurun_out/r02_step_units $U4 > gpurun_out/r02_ncu_units.log 2>&1
 echo "units full rc=$?"
 ls -la gpurun_out/*.ncu-rep | tail -5
+# (the units capture under profiles/ was retaken after the packed-pair arithmetic: gpurun_scratch/run_o.sh = the U4 block above)
