@@ -452,6 +452,8 @@ int wg_host_free(void* p);
  * Self-tests of the exact-arithmetic primitives the kernels are built from (csrc/wg_math.cuh), each against the
  * IEEE operation it replaces; every call ADDS the number of mismatching inputs to *d_mismatches (a device counter
  * the caller zeroes).  Asynchronous on cuda_stream.
+ *   (The kernels evaluate the x / y halves of their 3-vectors with the packed twins of these primitives -- FMUL2 / FFMA2 /
+ *   FADD2 -- and wg_selftest_div_smallint / wg_selftest_div3 check those twins on the same inputs, in both halves.)
  *   wg_selftest_div_smallint: x / m through the 3-FMA exact quotient (Point.forced's `f / self.m`,
  *       gym/optimized_engine.py:104-106, for integer masses and for the division by the number of masses) vs
  *       IEEE division, for every float32 bit pattern x in [x_begin, x_begin + x_count), x_begin + x_count <= 2^32;

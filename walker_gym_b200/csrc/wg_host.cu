@@ -30,6 +30,10 @@ __global__ void selftest_div_smallint_kernel(float m, float r, uint64_t x0, uint
         if (i < n) {
             const float x = __uint_as_float((uint32_t)(x0 + i));
             bad = !same_f32(div_smallint(x, m, r), __fdiv_rn(x, m));
+            // the packed twin the kernels use (FMUL2 / FFMA2): x in one half, a bijective scramble of it in the other
+            const float y = __uint_as_float(((uint32_t)(x0 + i) * 0x9E3779B1u) ^ 0x5bd1e995u);
+            const float2 q2 = div_smallint2(make_float2(x, y), m, r), p2 = div_smallint2(make_float2(y, x), m, r);
+            bad = bad || !same_f32(q2.x, __fdiv_rn(x, m)) || !same_f32(q2.y, __fdiv_rn(y, m)) || !same_f32(p2.y, __fdiv_rn(x, m));
         }
         count_mismatch(bad, out);
     }
@@ -112,9 +116,12 @@ __global__ void selftest_div3_kernel(int mode, uint32_t seed, uint64_t first, ui
             if (L == L) {
                 float q0 = d[0], q1 = d[1], q2 = d[2];
                 div3_len<GENERAL>(q0, q1, q2, L);
+                V3 pk = v3(d[0], d[1], d[2]);                    // the packed twin the kernels use: must return the same bits
+                div3_len<GENERAL>(pk, L);
+                const bool twin = same_f32(pk.xy.x, q0) && same_f32(pk.xy.y, q1) && same_f32(pk.z, q2);
                 float w0 = d[0], w1 = d[1], w2 = d[2];
                 if (L > 0.0f) { w0 = __fdiv_rn(d[0], L); w1 = __fdiv_rn(d[1], L); w2 = __fdiv_rn(d[2], L); }
-                bad = !(same_f32(q0, w0) && same_f32(q1, w1) && same_f32(q2, w2));      // -0 / L comes out as +0: sign of zero
+                bad = !(twin && same_f32(q0, w0) && same_f32(q1, w1) && same_f32(q2, w2));      // -0 / L comes out as +0: sign of zero
                 if (bad && atomicCAS(out + 1, 0ull, (unsigned long long)(i + 1)) == 0ull && dump) {
                     dump[0] = d[0]; dump[1] = d[1]; dump[2] = d[2]; dump[3] = L;
                     dump[4] = q0; dump[5] = q1; dump[6] = q2; dump[7] = w0; dump[8] = w1; dump[9] = w2;
