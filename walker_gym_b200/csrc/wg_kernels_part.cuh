@@ -251,10 +251,9 @@ __device__ __forceinline__ void link_half(const BV& bv, int n, const float (&pi)
                                           float (&acc)[3]) {
     // the same operations as spring_run, x / y halves packed (wg_math.cuh)
     V3 d = v3_sub(v3(pj[0], pj[1], pj[2]), v3(pi[0], pi[1], pi[2]));
-    const float L = np_norm3(d);
+    const float L = unit_dir(d);
     const float dx = L - rest;
     const float fs = (-dx) * k;
-    div3_len(d, L);
     const V3 F = v3_scale(d, fs);
     const float dk = np_dot3(v3_sub(v3(vi[0], vi[1], vi[2]), v3(vj[0], vj[1], vj[2])), d);
     const float cd = dk * damp;

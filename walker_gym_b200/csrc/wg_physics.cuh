@@ -140,13 +140,12 @@ __device__ __forceinline__ void spring_run(const Topo& topo, const BV& bv, Store
     V3 d = v3_sub(pj, pi);                                                  // direction = p2 - p1
     // distant(p1, p2) = norm(p1 - p2): p1 - p2 == -(p2 - p1) exactly and only its squares are used, so the norm is
     // taken of the direction's components (three subtractions less per spring)
-    const float L = np_norm3(d);
+    const float L = unit_dir(d);                                            // L = |d|, then d /= L (one rare-path region)
     const float dx = L - x;
     float fs = (-dx) * bv.sk[sp];                                         // -dx * k (sign as written)
     // rope-type springs (`if dx < 0 and string: f_size = 0`, gym/optimized_engine.py:134-136): a per-spring flag of
     // the run-time topology only -- bodies with such springs never reach the compile-time specialisations
     if constexpr (!Topo::kStatic) { if (((bv.string_mask[sp >> 5] >> (sp & 31)) & 1u) && dx < 0.0f) fs = 0.0f; }
-    div3_len(d, L);
     const V3 F = v3_scale(d, fs);
     const V3 vd = v3_sub(v3(st.vel(i, 0), st.vel(i, 1), st.vel(i, 2)), v3(st.vel(j, 0), st.vel(j, 1), st.vel(j, 2)));
     const float dk = np_dot3(vd, d);
