@@ -118,7 +118,12 @@ __global__ void selftest_div3_kernel(int mode, uint32_t seed, uint64_t first, ui
                 div3_len<GENERAL>(q0, q1, q2, L);
                 V3 pk = v3(d[0], d[1], d[2]);                    // the packed twin the kernels use: must return the same bits
                 div3_len<GENERAL>(pk, L);
-                const bool twin = same_f32(pk.xy.x, q0) && same_f32(pk.xy.y, q1) && same_f32(pk.z, q2);
+                bool twin = same_f32(pk.xy.x, q0) && same_f32(pk.xy.y, q1) && same_f32(pk.z, q2);
+                if (!GENERAL && mode == 1) {                     // L == norm(d): the fused routine the springs call
+                    V3 ud = v3(d[0], d[1], d[2]);
+                    const float uL = unit_dir(ud);
+                    twin = twin && same_f32(uL, L) && same_f32(ud.xy.x, q0) && same_f32(ud.xy.y, q1) && same_f32(ud.z, q2);
+                }
                 float w0 = d[0], w1 = d[1], w2 = d[2];
                 if (L > 0.0f) { w0 = __fdiv_rn(d[0], L); w1 = __fdiv_rn(d[1], L); w2 = __fdiv_rn(d[2], L); }
                 bad = !(twin && same_f32(q0, w0) && same_f32(q1, w1) && same_f32(q2, w2));      // -0 / L comes out as +0: sign of zero
